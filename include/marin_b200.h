@@ -1,0 +1,86 @@
+/*
+ * marin_b200.h -- C ABI of the B200-native Marin engine (libmarin_b200.so).
+ *
+ * Drop-in boundary for PrMers' register engine: every entry point states the reference interface
+ * it replaces.  The shape (opaque handle, int return 1 = ok / 0 = failed, thread-local last-error
+ * string, nothing thrown across the boundary) follows the reference's own plugin precedent,
+ * third_party/aevum/src/EngineApi.h:28-62 (loader: src/aevum/EngineAevum.cpp:89-128).
+ *
+ * Semantics (include/marin/engine.h:16-303): an engine owns `reg_count` device-resident registers
+ * holding residues modulo 2^p - 1.  Calls are asynchronous and in order on the engine's stream; only
+ * the get_, equal and sync calls block.  Not thread-safe: one thread per engine.
+ * Digits are "encoded": low 32 bits = value, high 32 bits = width of the digit's base.
+ */
+#ifndef MARIN_B200_H
+#define MARIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *mb200_version(void);
+const char *mb200_last_error(void);                         /* thread-local; "" if none */
+
+/* ibdwt::transform_size (include/marin/ibdwt.h:17-43); (size_t)-1 if the exponent is too large */
+size_t mb200_transform_size_for(uint32_t p);
+
+/* engine::create_gpu(q, reg_count, device, verbose) (src/marin/gpu.cpp:52-150, engine.h:301) */
+void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose);
+void mb200_destroy(void *eng);                              /* delete eng */
+size_t mb200_transform_size(void *eng);                     /* engine::get_size, engine.h:40 */
+size_t mb200_register_count(void *eng);
+uint32_t mb200_max_multiplier(void *eng);                   /* largest `a` square_mul / mul accept */
+int mb200_sync(void *eng);                                  /* engine::sync, engine.h:45 */
+
+int mb200_set_u32(void *eng, size_t dst, uint32_t a);               /* engine::set(Reg, uint32), engine.h:47 */
+int mb200_copy(void *eng, size_t dst, size_t src);                  /* engine::copy, engine.h:49 */
+int mb200_square_mul(void *eng, size_t r, uint32_t a);              /* engine::square_mul, engine.h:51 */
+int mb200_set_multiplicand(void *eng, size_t dst, size_t src);      /* engine::set_multiplicand, engine.h:53 */
+int mb200_mul(void *eng, size_t dst, size_t src, uint32_t a);       /* engine::mul, engine.h:60 */
+int mb200_sub_u32(void *eng, size_t r, uint32_t a);                 /* engine::sub, engine.h:62 */
+int mb200_add(void *eng, size_t dst, size_t src);                   /* engine::add, engine.h:64 */
+int mb200_sub_reg(void *eng, size_t dst, size_t src);               /* engine::sub_reg, engine.h:71 */
+
+/* fused helpers with the semantics of the default compositions in engine.h:54-131 */
+int mb200_mul_add(void *eng, size_t dst, size_t mul_src, size_t add_src, uint32_t a);       /* engine.h:65-69 */
+int mb200_addsub(void *eng, size_t sum_out, size_t diff_out, size_t a, size_t b);           /* engine.h:72-80 */
+int mb200_addsub_copy(void *eng, size_t sum, size_t diff, size_t sum_copy, size_t diff_copy, size_t a, size_t b); /* engine.h:124-130 */
+int mb200_square_mul_copy(void *eng, size_t r, size_t dst_copy, uint32_t a);                /* engine.h:82-86 */
+int mb200_mul_copy(void *eng, size_t dst, size_t src, size_t dst_copy, uint32_t a);         /* engine.h:92-96 */
+
+/* engine::is_equal (engine.h:148-157): residues compared modulo 2^p - 1 */
+int mb200_equal(void *eng, size_t lhs, size_t rhs, int *out);
+
+/* engine::get / engine::set(Reg, uint64*) (engine.h:24-25; engine_gpu.h:1452-1561): canonical digits,
+   unweighted and fully carried; n = transform size entries */
+int mb200_get_digits(void *eng, size_t src, uint64_t *enc, size_t n);
+int mb200_set_digits(void *eng, size_t dst, const uint64_t *enc, size_t n);
+
+/* engine::get_data / set_data / get_checkpoint / set_checkpoint (engine.h:133-146): raw register
+   images, n * 8 bytes each (layout is private to this engine: backend tag 3, never Marin-OpenCL's) */
+size_t mb200_register_data_size(void *eng);
+int mb200_get_raw(void *eng, size_t src, void *buf, size_t bytes);
+int mb200_set_raw(void *eng, size_t dst, const void *buf, size_t bytes);
+size_t mb200_checkpoint_size(void *eng);
+int mb200_get_checkpoint(void *eng, void *buf, size_t bytes);
+int mb200_set_checkpoint(void *eng, const void *buf, size_t bytes);
+
+/* the reference's `-bench` loop (src/core/App.cpp:715-746) on the engine's own stream: `count`
+   back-to-back square_mul(r, a), timed with CUDA events and a final synchronise; *ms = elapsed */
+int mb200_bench_square_mul(void *eng, size_t r, uint32_t a, uint32_t count, float *ms);
+/* same loop without timing (asynchronous) */
+int mb200_square_mul_repeat(void *eng, size_t r, uint32_t a, uint32_t count);
+/* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
+uint64_t mb200_launch_count(void *eng);
+
+/* pinned host buffers for fast get_/set_ transfers */
+void *mb200_host_alloc(size_t bytes);
+void mb200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -94,3 +94,23 @@ def mersenne_chain(p, x0, steps, mul_small=None, sub_small=0):
         _f.set(X, T)
     v = int(x)
     return 0 if v == m else v % m
+
+
+def mulmod_mersenne(x, y, p):
+    """x * y mod 2^p - 1 for huge operands (GMP product + fold); Python ints in and out."""
+    m = (1 << p) - 1
+    if _g is None or p < 200000:
+        t = x * y
+        while t >> p:
+            t = (t & m) + (t >> p)
+        return 0 if t == m else t
+    a, b, t, hi = Z(x), Z(y), Z(), Z()
+    T, H = C.byref(t.z), C.byref(hi.z)
+    _f.mul(T, C.byref(a.z), C.byref(b.z))
+    pp = C.c_ulong(p)
+    while _f.sizeinbase(T, 2) > p:
+        _f.tdiv_q_2exp(H, T, pp)
+        _f.tdiv_r_2exp(T, T, pp)
+        _f.add(T, T, H)
+    v = int(t)
+    return 0 if v == m else v

@@ -77,3 +77,8 @@ def pm1_stage2(p, b1, b2, base=3):
             acc = acc * (pow(h, q, m) - 1) % m
     g = gcd(acc, m)
     return g if 1 < g < m else None
+
+
+def mulmod(x, y, p):
+    """x * y mod 2^p - 1 (GMP-backed for large p)."""
+    return _gmp.mulmod_mersenne(x, y, p)

@@ -1,0 +1,215 @@
+// marin_engine.cu -- CUDA backend and C ABI of the B200 Marin engine (sm_100a only).
+//
+// Replaces src/marin/gpu.cpp + include/marin/ocl.h + the launch plumbing of class gpu
+// (include/marin/engine_gpu.h:36-1249): context/queue -> one CUDA stream per engine, JIT'd OpenCL
+// program -> the kernels below (compiled ahead of time for sm_100a), cl_mem slabs -> one cudaMalloc
+// slab of reg_count * n words.  There is no CPU fallback: without a CUDA device creation fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include "marin_engine_core.hpp"
+#include "../../include/marin_b200.h"
+
+using namespace marin;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::runtime_error(std::string("cuda error: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
+
+// ------------------------------------------------------------------ kernels
+
+__global__ void __launch_bounds__(512) k_mid(const __grid_constant__ MidArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	u64 *smc = reinterpret_cast<u64 *>(sm + smem_pairs_lin(A.S));
+	const u32 nph = mid_num_phases(A);
+	for (u32 ph = 0; ph < nph; ++ph)
+	{
+		mid_phase(A, blockIdx.x, ph, threadIdx.x, blockDim.x, sm, smc);
+		__syncthreads();
+	}
+}
+
+template <bool INV> __global__ void __launch_bounds__(512) k_strided(const __grid_constant__ StridedArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	const u32 nph = strided_num_phases(A, INV);
+	for (u32 ph = 0; ph < nph; ++ph)
+	{
+		strided_phase<INV>(A, blockIdx.x, ph, threadIdx.x, blockDim.x, sm);
+		__syncthreads();
+	}
+}
+
+__global__ void k_fixup(const __grid_constant__ FixArgs A, u32 count)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) fixup_thread(A, i);
+}
+__global__ void k_lin_p1(const __grid_constant__ LinArgs A, u32 count)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) lin_p1_thread(A, i);
+}
+__global__ void k_lin_p2(const __grid_constant__ LinArgs A, u32 count)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) lin_p2_thread(A, i);
+}
+__global__ void k_unweight(const __grid_constant__ Tables t, const u64 *x, u64 *out, u32 n)
+{
+	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < n) unweight_thread(t, x, out, j);
+}
+__global__ void k_weights(const __grid_constant__ WeightArgs A, u32 n)
+{
+	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < n) weight_thread(A, j);
+}
+
+// ------------------------------------------------------------------ backend
+
+struct CudaBackend
+{
+	int dev;
+	cudaStream_t st = nullptr;
+	uint64_t launches = 0;
+
+	explicit CudaBackend(int device) : dev(device)
+	{
+		int cnt = 0;
+		if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) throw std::runtime_error("marin_b200: no CUDA device (this engine has no CPU path)");
+		if (device < 0 || device >= cnt) throw std::runtime_error("marin_b200: device index out of range");
+		CK(cudaSetDevice(dev));
+		cudaDeviceProp pr;
+		CK(cudaGetDeviceProperties(&pr, dev));
+		if (pr.major < 10) throw std::runtime_error("marin_b200: built for sm_100a (Blackwell B200) only");
+		CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		const int maxsm = (int)pr.sharedMemPerBlockOptin;
+		CK(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+	}
+	~CudaBackend() { if (st) { cudaSetDevice(dev); cudaStreamDestroy(st); } }
+
+	void use() { CK(cudaSetDevice(dev)); }
+	void *alloc(size_t b) { use(); void *p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); return p; }
+	void free(void *p) { cudaSetDevice(dev); cudaFree(p); }
+	void memset0(void *p, size_t b) { use(); CK(cudaMemsetAsync(p, 0, b, st)); }
+	void h2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+	void d2h(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
+	void sync() { use(); CK(cudaStreamSynchronize(st)); }
+	void post() { ++launches; CK(cudaGetLastError()); }
+
+	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_mid<<<grid, thr, smem, st>>>(A); post(); }
+	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<false><<<grid, thr, smem, st>>>(A); post(); }
+	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<true><<<grid, thr, smem, st>>>(A); post(); }
+	void fixup(const FixArgs &A, u32 count) { use(); k_fixup<<<(count + 255) / 256, 256, 0, st>>>(A, count); post(); }
+	void lin_p1(const LinArgs &A, u32 count) { use(); k_lin_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
+	void lin_p2(const LinArgs &A, u32 count) { use(); k_lin_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
+	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }
+	void weights(const WeightArgs &A, u32 n) { use(); k_weights<<<(n + 255) / 256, 256, 0, st>>>(A, n); post(); }
+};
+
+typedef EngineCore<CudaBackend> Eng;
+
+// ------------------------------------------------------------------ C ABI
+
+static thread_local std::string g_err;
+#define E(h) (static_cast<Eng *>(h))
+#define GUARD(body) do { if (!eng) { g_err = "null engine"; return 0; } try { g_err.clear(); body; return 1; } \
+	catch (const std::exception &ex) { g_err = ex.what(); return 0; } catch (...) { g_err = "unknown error"; return 0; } } while (0)
+
+extern "C" {
+
+const char *mb200_version(void) { return "marin_b200 0.1 (sm_100a)"; }
+const char *mb200_last_error(void) { return g_err.c_str(); }
+size_t mb200_transform_size_for(uint32_t p) { return transform_size(p); }
+
+void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose)
+{
+	try
+	{
+		g_err.clear();
+		u32 force_S = 0;
+		if (const char *s = getenv("MARIN_B200_FORCE_S")) force_S = (u32)atoi(s); // test hook: force the 3-pass path
+		Eng *e = new Eng(p, reg_count, (int)device, force_S);
+		if (verbose)
+			fprintf(stderr, "marin_b200: p = %u, n = %u, %s, R = %u, S = %u, %zu registers, device %u\n", p, e->pl.n,
+				e->pl.small ? "single-CTA path" : "3-pass path", e->pl.R, e->pl.S, reg_count, device);
+		return e;
+	}
+	catch (const std::exception &ex) { g_err = ex.what(); return nullptr; }
+	catch (...) { g_err = "unknown error"; return nullptr; }
+}
+
+void mb200_destroy(void *eng) { try { delete E(eng); } catch (...) {} }
+size_t mb200_transform_size(void *eng) { return eng ? E(eng)->size() : 0; }
+size_t mb200_register_count(void *eng) { return eng ? E(eng)->regs() : 0; }
+uint32_t mb200_max_multiplier(void *eng) { return eng ? E(eng)->pl.a_max : 0; }
+int mb200_sync(void *eng) { GUARD(E(eng)->sync()); }
+
+int mb200_set_u32(void *eng, size_t dst, uint32_t a) { GUARD(E(eng)->set_u32(dst, a)); }
+int mb200_copy(void *eng, size_t dst, size_t src) { GUARD(E(eng)->copy(dst, src)); }
+int mb200_square_mul(void *eng, size_t r, uint32_t a) { GUARD(E(eng)->square_mul(r, a)); }
+int mb200_set_multiplicand(void *eng, size_t dst, size_t src) { GUARD(E(eng)->set_multiplicand(dst, src)); }
+int mb200_mul(void *eng, size_t dst, size_t src, uint32_t a) { GUARD(E(eng)->mul(dst, src, a)); }
+int mb200_sub_u32(void *eng, size_t r, uint32_t a) { GUARD(E(eng)->sub_u32(r, a)); }
+int mb200_add(void *eng, size_t dst, size_t src) { GUARD(E(eng)->add(dst, src)); }
+int mb200_sub_reg(void *eng, size_t dst, size_t src) { GUARD(E(eng)->sub_reg(dst, src)); }
+
+int mb200_mul_add(void *eng, size_t dst, size_t mul_src, size_t add_src, uint32_t a)
+{ GUARD(E(eng)->mul(dst, mul_src, a); E(eng)->add(dst, add_src)); }
+int mb200_addsub(void *eng, size_t s, size_t d, size_t a, size_t b)
+{ GUARD(E(eng)->copy(s, a); E(eng)->copy(d, a); E(eng)->add(s, b); E(eng)->sub_reg(d, b)); }
+int mb200_addsub_copy(void *eng, size_t s, size_t d, size_t sc, size_t dc, size_t a, size_t b)
+{ GUARD(E(eng)->copy(s, a); E(eng)->copy(d, a); E(eng)->add(s, b); E(eng)->sub_reg(d, b); E(eng)->copy(sc, s); E(eng)->copy(dc, d)); }
+int mb200_square_mul_copy(void *eng, size_t r, size_t c, uint32_t a) { GUARD(E(eng)->square_mul(r, a); E(eng)->copy(c, r)); }
+int mb200_mul_copy(void *eng, size_t dst, size_t src, size_t c, uint32_t a) { GUARD(E(eng)->mul(dst, src, a); E(eng)->copy(c, dst)); }
+
+int mb200_equal(void *eng, size_t l, size_t r, int *out) { GUARD(*out = E(eng)->equal(l, r) ? 1 : 0); }
+
+int mb200_get_digits(void *eng, size_t src, uint64_t *enc, size_t n)
+{ GUARD(if (n != E(eng)->size()) throw std::runtime_error("marin_b200: digit count must equal the transform size"); E(eng)->get_digits(src, (u64 *)enc)); }
+int mb200_set_digits(void *eng, size_t dst, const uint64_t *enc, size_t n)
+{ GUARD(if (n != E(eng)->size()) throw std::runtime_error("marin_b200: digit count must equal the transform size"); E(eng)->set_digits(dst, (const u64 *)enc)); }
+
+size_t mb200_register_data_size(void *eng) { return eng ? E(eng)->size() * 8 : 0; }
+int mb200_get_raw(void *eng, size_t src, void *buf, size_t bytes)
+{ if (!eng || bytes != E(eng)->size() * 8) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->get_raw(src, buf)); }
+int mb200_set_raw(void *eng, size_t dst, const void *buf, size_t bytes)
+{ if (!eng || bytes != E(eng)->size() * 8) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->set_raw(dst, buf)); }
+size_t mb200_checkpoint_size(void *eng) { return eng ? E(eng)->size() * 8 * E(eng)->regs() : 0; }
+int mb200_get_checkpoint(void *eng, void *buf, size_t bytes)
+{ if (!eng || bytes != mb200_checkpoint_size(eng)) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->get_all(buf)); }
+int mb200_set_checkpoint(void *eng, const void *buf, size_t bytes)
+{ if (!eng || bytes != mb200_checkpoint_size(eng)) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->set_all(buf)); }
+
+int mb200_square_mul_repeat(void *eng, size_t r, uint32_t a, uint32_t count)
+{ GUARD(for (uint32_t i = 0; i < count; ++i) E(eng)->square_mul(r, a)); }
+
+static void bench_square_mul(Eng *e, size_t r, uint32_t a, uint32_t count, float *ms)
+{
+	e->be.use();
+	cudaEvent_t t0;
+	cudaEvent_t t1;
+	CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+	CK(cudaEventRecord(t0, e->be.st));
+	for (uint32_t i = 0; i < count; ++i) e->square_mul(r, a);
+	CK(cudaEventRecord(t1, e->be.st));
+	CK(cudaEventSynchronize(t1));
+	CK(cudaEventElapsedTime(ms, t0, t1));
+	cudaEventDestroy(t0); cudaEventDestroy(t1);
+}
+
+int mb200_bench_square_mul(void *eng, size_t r, uint32_t a, uint32_t count, float *ms) { GUARD(bench_square_mul(E(eng), r, a, count, ms)); }
+
+uint64_t mb200_launch_count(void *eng) { return eng ? E(eng)->be.launches : 0; }
+
+void *mb200_host_alloc(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
+void mb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}

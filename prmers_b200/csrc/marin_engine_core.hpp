@@ -1,0 +1,223 @@
+// marin_engine_core.hpp -- the register engine: which kernels run, in which order, for each call of
+// the reference's engine API (include/marin/engine.h:37-170; per-op kernel sequences of
+// engine_gpu_flat, include/marin/engine_gpu.h:1432-2164).  Templated on a Backend that owns memory
+// and launches: the CUDA backend in marin_engine.cu is the product; tests/emu instantiates the same
+// template with a CPU emulator of the kernels to check the host logic without a GPU.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "marin_plan.hpp"
+
+namespace marin {
+
+template <class Backend> class EngineCore
+{
+public:
+	Plan pl;
+	Backend be;
+
+	EngineCore(u32 p, size_t regs, int device, u32 force_S = 0) : be(device), _regs(regs)
+	{
+		std::string err;
+		if (regs == 0) throw std::runtime_error("marin_b200: register count must be >= 1");
+		if (!make_plan(p, pl, err, force_S)) throw std::runtime_error("marin_b200: " + err);
+		HostTables h;
+		build_tables(pl, h);
+		_wbits = h.wbits;
+		const size_t n = pl.n;
+		_reg = (u64 *)be.alloc(regs * n * 8);
+		be.memset0(_reg, regs * n * 8);
+		const size_t ncarry = std::max<size_t>(n / pl.D, n / RUN + 1);
+		_carry = (u64 *)be.alloc(ncarry * 8);
+		_scratch = (u64 *)be.alloc(n * 8);
+		Tables &t = _t;
+		std::memset(&t, 0, sizeof(t));
+		t.p = pl.p; t.n = pl.n; t.m = pl.m; t.wbase = pl.wbase; t.inv_m = h.inv_m;
+		t.wbits = (const u32 *)upload(h.wbits.data(), h.wbits.size() * 4);
+		t.twS = (const u64 *)upload(h.twS.data(), h.twS.size() * 8); t.S = pl.S;
+		t.twR = (const u64 *)upload(h.twR.data(), h.twR.size() * 8); t.R = pl.R;
+		t.bl_lo = (const u64 *)upload(h.bl_lo.data(), h.bl_lo.size() * 8);
+		t.bl_hi = (const u64 *)upload(h.bl_hi.data(), h.bl_hi.size() * 8); t.bl_h = h.bl_h;
+		t.rowK = (const u32 *)upload(h.rowK.data(), h.rowK.size() * 4);
+		t.rowroot = (const u64 *)upload(h.rowroot.data(), h.rowroot.size() * 8);
+		t.colroot = (const u64 *)upload(h.colroot.data(), h.colroot.size() * 8);
+		for (int i = 0; i < 4; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
+		u64 *w_nat = (u64 *)be.alloc(n * 8), *winv_nat = (u64 *)be.alloc(n * 8), *w_perm = nullptr, *winvs_perm = nullptr;
+		_owned.push_back(w_nat); _owned.push_back(winv_nat);
+		if (!pl.small) { w_perm = (u64 *)be.alloc(n * 8); winvs_perm = (u64 *)be.alloc(n * 8); _owned.push_back(w_perm); _owned.push_back(winvs_perm); }
+		WeightArgs W{pl.p, pl.n, pl.m, pl.R, pl.S, pl.S / TILE_C, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, w_perm, winvs_perm, pl.small ? 0u : 1u};
+		be.weights(W, pl.n);
+		t.w_nat = w_nat; t.winv_nat = winv_nat; t.w_perm = w_perm; t.winvs_perm = winvs_perm;
+		be.sync();
+	}
+
+	~EngineCore()
+	{
+		be.sync();
+		for (void *p : _owned) be.free(p);
+		be.free(_reg); be.free(_carry); be.free(_scratch);
+	}
+
+	size_t size() const { return pl.n; }
+	size_t regs() const { return _regs; }
+	void sync() { be.sync(); }
+
+	void set_u32(size_t dst, u32 a)
+	{
+		check(dst);
+		if (pl.p < 32) a = (u32)((u64)a % (((u64)1 << pl.p) - 1));
+		lin(LIN_SETSMALL, dst, dst, a, nullptr);
+	}
+
+	void copy(size_t dst, size_t src) { check(dst); check(src); if (dst != src) be.d2d(R(dst), R(src), pl.n * 8); }
+
+	void square_mul(size_t r, u32 a)
+	{
+		check(r); check_a(a);
+		if (pl.small) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M); return; }
+		strided(false, R(r), R(r), 1);
+		MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M);
+		strided(true, R(r), R(r), a);
+	}
+
+	void set_multiplicand(size_t dst, size_t src)
+	{
+		check(dst); check(src);
+		if (pl.small) { MidArgs M = mid_args(R(src), nullptr, R(dst), MODE_FWD, 1); launch_mid(M); return; }
+		strided(false, R(src), R(dst), 1);
+		MidArgs M = mid_args(R(dst), nullptr, R(dst), MODE_FWD, 1); launch_mid(M);
+	}
+
+	void mul(size_t dst, size_t src, u32 a)
+	{
+		check(dst); check(src); check_a(a);
+		if (dst == src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
+		if (pl.small) { MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M); return; }
+		strided(false, R(dst), R(dst), 1);
+		MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M);
+		strided(true, R(dst), R(dst), a);
+	}
+
+	void sub_u32(size_t r, u32 a)
+	{
+		check(r);
+		if (pl.p < 32) a = (u32)((u64)a % (((u64)1 << pl.p) - 1));
+		lin(LIN_SUBSMALL, r, r, a, nullptr);
+	}
+	void add(size_t dst, size_t src) { check(dst); check(src); lin(LIN_ADD, dst, src, 0, nullptr); }
+	void sub_reg(size_t dst, size_t src) { check(dst); check(src); lin(LIN_SUBREG, dst, src, 0, nullptr); }
+
+	// canonical digits, value | width << 32: unweight on the device, strong carry on the host exactly as
+	// engine_gpu_flat::get does (engine_gpu.h:1534-1561)
+	void get_digits(size_t src, u64 *enc)
+	{
+		check(src);
+		const u32 n = pl.n;
+		be.unweight(_t, R(src), _scratch, n);
+		be.d2h(enc, _scratch, (size_t)n * 8);
+		u64 c = 0;
+		for (u32 k = 0; k < n; ++k) enc[k] = adc(enc[k], width(k), c);
+		while (c != 0)
+			for (u32 k = 0; k < n; ++k) { enc[k] = adc(enc[k], width(k), c); if (c == 0) break; }
+		for (u32 k = 0; k < n; ++k) enc[k] = (u32)enc[k] | ((u64)width(k) << 32);
+	}
+
+	void set_digits(size_t dst, const u64 *enc)
+	{
+		check(dst);
+		be.h2d(_scratch, enc, (size_t)pl.n * 8);
+		lin(LIN_SETDIGITS, dst, dst, 0, _scratch);
+	}
+
+	bool equal(size_t l, size_t r)
+	{
+		std::vector<u64> a(pl.n), b(pl.n);
+		get_digits(l, a.data()); get_digits(r, b.data());
+		normalize_zero(a); normalize_zero(b);
+		return a == b;
+	}
+
+	void get_raw(size_t src, void *buf) { check(src); be.d2h(buf, R(src), (size_t)pl.n * 8); }
+	void set_raw(size_t dst, const void *buf) { check(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
+	void get_all(void *buf) { be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
+	void set_all(const void *buf) { be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
+
+	u32 width(u32 k) const { return pl.wbase + ((_wbits[k >> 5] >> (k & 31)) & 1u); }
+	u64 *R(size_t r) { return _reg + r * (size_t)pl.n; }
+	const Tables &tables() const { return _t; }
+
+private:
+	size_t _regs;
+	u64 *_reg = nullptr, *_carry = nullptr, *_scratch = nullptr;
+	Tables _t;
+	std::vector<u32> _wbits;
+	std::vector<void *> _owned;
+
+	void *upload(const void *src, size_t bytes)
+	{
+		void *d = be.alloc(bytes ? bytes : 8);
+		if (bytes) be.h2d(d, src, bytes);
+		_owned.push_back(d);
+		return d;
+	}
+
+	void check(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }
+	void check_a(u32 a) const
+	{
+		if (a == 0 || a > pl.a_max)
+			throw std::runtime_error("marin_b200: multiplier a = " + std::to_string(a) + " outside [1, " + std::to_string(pl.a_max) + "] for this transform");
+	}
+
+	// arith.h:75-81
+	static u32 adc(u64 lhs, u32 w, u64 &carry)
+	{
+		const u64 s = lhs + carry, c = (s < lhs) ? 1 : 0;
+		carry = (s >> w) + (c << (64 - w));
+		return (u32)s & ((1u << w) - 1);
+	}
+
+	void normalize_zero(std::vector<u64> &d) const
+	{
+		// 2^p - 1 (all ones) and 0 are the same residue (engine.h:181-196)
+		for (u32 k = 0; k < pl.n; ++k) if ((u32)d[k] != (1u << width(k)) - 1) return;
+		for (u32 k = 0; k < pl.n; ++k) d[k] &= ~(u64)0xffffffffu;
+	}
+
+	MidArgs mid_args(u64 *x, const u64 *y, u64 *dst, int mode, u32 a)
+	{
+		MidArgs M;
+		std::memset(&M, 0, sizeof(M));
+		fill_mid_args(pl, M);
+		M.t = _t; M.x = (pair_t *)x; M.y = (const pair_t *)y; M.dst = (pair_t *)dst; M.mode = mode; M.a = a; M.carry = _carry;
+		return M;
+	}
+
+	void launch_mid(const MidArgs &M)
+	{
+		const size_t smem = (size_t)smem_pairs_lin(pl.S) * 16 + (pl.small ? ((size_t)pl.n / pl.D) * 8 : 0);
+		be.mid(M, pl.m / pl.S, pl.thrMid, smem);
+	}
+
+	void strided(bool inv, const u64 *src, u64 *dst, u32 a)
+	{
+		StridedArgs A;
+		std::memset(&A, 0, sizeof(A));
+		fill_strided_args(pl, A);
+		A.t = _t; A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.carry = _carry; A.with_carry = inv ? 1 : 0;
+		const size_t smem = (size_t)pl.R * TILE_C * 16;
+		if (!inv) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return; }
+		be.strided_inv(A, A.tiles, pl.thrStr, smem);
+		FixArgs F{_t, dst, _carry, pl.R, pl.S, A.tiles};
+		be.fixup(F, pl.R * A.tiles);
+	}
+
+	void lin(int op, size_t dst, size_t src, u32 a, const u64 *digits)
+	{
+		LinArgs L{_t, R(dst), R(src), digits, _carry, op, a, pl.D};
+		be.lin_p1(L, pl.n / pl.D);
+		be.lin_p2(L, pl.n / pl.D);
+	}
+};
+
+} // namespace marin

@@ -1,0 +1,664 @@
+// marin_kernels.cuh -- device code of the B200 Marin engine (sm_100a), written from scratch.
+//
+// What it replaces, by function (not by name): the NTT pass kernels, pointwise square/multiply and
+// carry kernels of kernels/marin.cl:475-2365, re-derived for Blackwell:
+//   * a register is n weighted IBDWT digits (u64, natural order), viewed as m = n/2 pairs; the
+//     transform is a length-m NTT applied lane-wise to pairs, the last radix-2 level being replaced
+//     by the 2-term product modulo (t^2 - u)  (same algebra as marin.cl:378-392);
+//   * one squaring is THREE out-of-core passes (strided forward / contiguous middle / strided
+//     inverse + unweight + carry + reweight) instead of the reference's six, each pass a chain of
+//     radix-16 butterflies on 128-bit pairs held in registers with shared-memory exchanges between;
+//   * twiddles inside a radix-16 butterfly are shifts (2^12 is a 16th root of unity for our
+//     generator), the ones between stages come from small L1-resident tables.
+// Everything here is __host__ __device__ and free of threadIdx/blockIdx so that tests/emu can run the
+// very same phase functions on a CPU, thread by thread (test infrastructure; never a product path).
+#pragma once
+#include "gl64.cuh"
+
+#if defined(__CUDACC__)
+typedef ulonglong2 pair_t;
+#else
+struct alignas(16) pair_t { u64 x, y; };
+#endif
+
+namespace marin {
+
+static constexpr int MAX_STAGES = 8;
+static constexpr int TILE_C = 8;          // pair columns per strided tile (8 * 16 B = one 128 B line)
+static constexpr int RUN = 16;            // digits per carry run in the strided inverse pass (= 2 * TILE_C)
+
+enum Mode : int { MODE_SQR = 0, MODE_MUL = 1, MODE_FWD = 2 };
+
+struct Stage { u32 radix, L, s; };        // block length L = radix * s
+
+// Constant tables of one engine (device pointers).
+struct Tables
+{
+	u32 p, n, m;                 // exponent, digits, pairs
+	u32 wbase;                   // floor(p / n); digit j has wbase + bit_j(wbits) bits
+	const u32 *wbits;            // n bits, natural order
+	const u64 *w_nat, *winv_nat; // weight, 1/weight (natural digit order)
+	const u64 *w_perm, *winvs_perm; // weight, 1/(weight m) in strided-inverse tile order (see perm_index)
+	u64 inv_m;                   // 1/m
+	// block transforms
+	const u64 *twS; u32 S;       // S powers of the S-th root (contiguous pass), S a power of two
+	const u64 *twR; u32 R;       // R powers of the R-th root (strided pass), R = 2^a or 5 2^a
+	const u64 *bl_lo, *bl_hi; u32 bl_h; // m-th root: w^e = bl_lo[e & (2^h - 1)] * bl_hi[e >> h]
+	const u32 *rowK;             // frequency index of row rho after the strided pass
+	const u64 *rowroot;          // w_m^rowK[rho]
+	const u64 *colroot;          // w_S^freq(sigma), position order inside a contiguous block
+	u64 w5[4];                   // radix-5 constants (c1, c2, s1, s2), see dft5
+	u64 w5i[4];
+};
+
+// ------------------------------------------------------------------ small helpers
+
+HD u32 digit_width(const Tables &t, u32 j) { return t.wbase + ((t.wbits[j >> 5] >> (j & 31)) & 1u); }
+
+// index of digit i (0..15) of run (row, g) in the permuted weight tables: coalesced over rows
+HD size_t perm_index(u32 R, u32 g, u32 i, u32 row) { return ((size_t)g * RUN + i) * R + row; }
+
+HD u64 boundary_tw(const Tables &t, u64 e, bool inv)
+{
+	if (inv) e = e ? (u64)t.m - e : 0;
+	return gl::mul(t.bl_lo[e & ((1u << t.bl_h) - 1)], t.bl_hi[e >> t.bl_h]);
+}
+
+// ------------------------------------------------------------------ views
+
+// Addressing of one FFT dimension.  kind 0: global/linear with element stride; kind 1: shared, padded
+// one pair per 16 (contiguous pass); kind 2: shared tile [row][8] with XOR-swizzled columns.
+struct View
+{
+	pair_t *p; u32 kind; u32 stride; u32 col;
+	HD size_t idx(u32 i) const
+	{
+		if (kind == 0) return (size_t)i * stride;
+		if (kind == 1) return i + (i >> 4);
+		return (size_t)i * TILE_C + (col ^ (i & (TILE_C - 1)));
+	}
+	HD pair_t ld(u32 i) const { return p[idx(i)]; }
+	HD void st(u32 i, pair_t v) const { p[idx(i)] = v; }
+};
+
+HD u32 smem_pairs_lin(u32 S) { return S + (S >> 4) + 1; }
+
+// ------------------------------------------------------------------ butterflies (scalar lanes)
+
+HD void addsub(u64 &a, u64 &b) // (a, b) <- (a + b, a - b)
+{
+	const u64 nb = gl::P - b; // in (0, P]; P itself is a valid subtrahend for gl::sub
+	const u64 d = gl::sub(a, b);
+	a = gl::sub(a, nb);
+	b = d;
+}
+
+// 4-point DFT, natural order in and out; the 4th root of unity is 2^48 (forward) / -2^48 (inverse)
+template <bool INV> HD void dft4(u64 &x0, u64 &x1, u64 &x2, u64 &x3)
+{
+	addsub(x0, x2);                  // x0 = t0, x2 = t1
+	addsub(x1, x3);                  // x1 = t2, x3 = b - d
+	x3 = gl::mul_pow2<48>(x3);       // t3 = i (b - d)
+	addsub(x0, x1);                  // x0 = y0, x1 = y2
+	addsub(x2, x3);                  // x2 = t1 + t3, x3 = t1 - t3
+	const u64 y2 = x1;
+	if (!INV) { x1 = x2; x2 = y2; }             // y1 = t1 + t3, y3 = t1 - t3
+	else { x1 = x3; x3 = x2; x2 = y2; }         // conjugate: y1 = t1 - t3, y3 = t1 + t3
+}
+
+template <bool INV> HD void dft2(u64 &x0, u64 &x1) { addsub(x0, x1); }
+
+// twiddle 2^(12 e) (forward) or its inverse, e = q0 * k0 in {1,2,3,4,6,9}
+template <bool INV, int E> HD u64 tw16(u64 v)
+{
+	if (!INV) return gl::mul_pow2<(12 * E) % 192>(v);
+	else return gl::mul_pow2<(192 - 12 * E) % 192>(v);
+}
+
+// 16-point DFT.  Forward: natural slots in, output k in slot sw(k) = 4 (k & 3) + (k >> 2).
+// Inverse: input y[k] in slot sw(k), natural slots out.  Unnormalised.
+HD constexpr u32 sw16(u32 k) { return ((k & 3) << 2) | (k >> 2); }
+
+template <bool INV> HD void dft16(u64 *x)
+{
+	if (!INV)
+	{
+		for (int q = 0; q < 4; ++q) dft4<false>(x[q], x[q + 4], x[q + 8], x[q + 12]);
+		x[5] = tw16<false, 1>(x[5]); x[9] = tw16<false, 2>(x[9]); x[13] = tw16<false, 3>(x[13]);
+		x[6] = tw16<false, 2>(x[6]); x[10] = tw16<false, 4>(x[10]); x[14] = tw16<false, 6>(x[14]);
+		x[7] = tw16<false, 3>(x[7]); x[11] = tw16<false, 6>(x[11]); x[15] = tw16<false, 9>(x[15]);
+		for (int k = 0; k < 4; ++k) dft4<false>(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+	}
+	else
+	{
+		for (int k = 0; k < 4; ++k) dft4<true>(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+		x[5] = tw16<true, 1>(x[5]); x[9] = tw16<true, 2>(x[9]); x[13] = tw16<true, 3>(x[13]);
+		x[6] = tw16<true, 2>(x[6]); x[10] = tw16<true, 4>(x[10]); x[14] = tw16<true, 6>(x[14]);
+		x[7] = tw16<true, 3>(x[7]); x[11] = tw16<true, 6>(x[11]); x[15] = tw16<true, 9>(x[15]);
+		for (int q = 0; q < 4; ++q) dft4<true>(x[q], x[q + 4], x[q + 8], x[q + 12]);
+	}
+}
+
+// 5-point DFT (the only odd radix the Goldilocks IBDWT admits, ibdwt.h:17-22): symmetric form with
+// 8 multiplications; c = (c1, c2, s1, s2) = ((w+w^4)/2, (w^2+w^3)/2, (w-w^4)/2, (w^2-w^3)/2).
+HD void dft5(u64 *x, const u64 *c)
+{
+	const u64 a = gl::add(x[1], x[4]), b = gl::sub(x[1], x[4]);
+	const u64 cc = gl::add(x[2], x[3]), d = gl::sub(x[2], x[3]);
+	const u64 r1 = gl::add(x[0], gl::add(gl::mul(a, c[0]), gl::mul(cc, c[1])));
+	const u64 r2 = gl::add(x[0], gl::add(gl::mul(a, c[1]), gl::mul(cc, c[0])));
+	const u64 i1 = gl::add(gl::mul(b, c[2]), gl::mul(d, c[3]));
+	const u64 i2 = gl::sub(gl::mul(b, c[3]), gl::mul(d, c[2]));
+	x[0] = gl::add(x[0], gl::add(a, cc));
+	x[1] = gl::add(r1, i1); x[4] = gl::sub(r1, i1);
+	x[2] = gl::add(r2, i2); x[3] = gl::sub(r2, i2);
+}
+
+// ------------------------------------------------------------------ one butterfly of one stage
+
+// Twiddle source of a stage: table of X powers of the X-th root, exponent scale = X / L.
+struct Tw { const u64 *tab; u32 X; u32 scale; };
+
+HD u64 tw_get(const Tw &tw, u32 j, u32 k, bool inv)
+{
+	u32 e = j * k * tw.scale;
+	if (inv) e = e ? tw.X - e : 0;
+	return tw.tab[e];
+}
+
+// Forward (DIF): y_k = sum_q x_q w_R^(qk), then y_k *= w_L^(jk); element q/k lives at base + s q/k.
+// Inverse: the exact mirror (conjugate twiddle first, then conjugate DFT), unnormalised.
+// PRE/POST: optional per-element factor applied to loaded inputs / stored outputs (boundary twiddles).
+// Boundary: per-row factor w_m^(+-rowK[row] * colscale) applied to loaded inputs (inverse) or stored
+// outputs (forward) of the stage that touches global memory in a strided pass.
+struct Boundary { const Tables *t; u64 colscale; };
+
+template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
+
+template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 base, u32 s, u32 j, const Tw &tw,
+	const u64 *c5, const Boundary *bd)
+{
+	u64 a[R], b[R];
+	if (R == 16)
+	{
+		for (u32 q = 0; q < R; ++q)
+		{
+			const pair_t v = in.ld(base + s * q);
+			const u32 slot = INV ? sw16(q) : q;
+			a[slot] = v.x; b[slot] = v.y;
+		}
+	}
+	else for (u32 q = 0; q < R; ++q) { const pair_t v = in.ld(base + s * q); a[q] = v.x; b[q] = v.y; }
+
+	if (INV && bd)
+		for (u32 q = 0; q < R; ++q)
+		{
+			const u64 f = boundary_tw(*bd->t, (u64)bd->t->rowK[base + s * q] * bd->colscale, true);
+			const u32 sl = slot_of<R>(q); a[sl] = gl::mul(a[sl], f); b[sl] = gl::mul(b[sl], f);
+		}
+
+	if (INV && j != 0 && tw.tab)
+		for (u32 k = 1; k < R; ++k) { const u64 t = tw_get(tw, j, k, true); const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], t); b[sl] = gl::mul(b[sl], t); }
+
+	if (R == 16) { dft16<INV>(a); dft16<INV>(b); }
+	else if (R == 4) { dft4<INV>(a[0], a[1], a[2], a[3]); dft4<INV>(b[0], b[1], b[2], b[3]); }
+	else if (R == 2) { dft2<INV>(a[0], a[1]); dft2<INV>(b[0], b[1]); }
+	else if (R == 5) { dft5(a, c5); dft5(b, c5); }
+
+	if (!INV && j != 0 && tw.tab)
+		for (u32 k = 1; k < R; ++k) { const u64 t = tw_get(tw, j, k, false); const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], t); b[sl] = gl::mul(b[sl], t); }
+
+	if (!INV && bd)
+		for (u32 k = 0; k < R; ++k)
+		{
+			const u64 f = boundary_tw(*bd->t, (u64)bd->t->rowK[base + s * k] * bd->colscale, false);
+			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f); b[sl] = gl::mul(b[sl], f);
+		}
+
+	for (u32 k = 0; k < R; ++k)
+	{
+		const u32 sl = INV ? k : slot_of<R>(k);
+		pair_t v; v.x = a[sl]; v.y = b[sl];
+		out.st(base + s * k, v);
+	}
+}
+
+// ------------------------------------------------------------------ pointwise, modulo (t^2 - u)
+
+HD pair_t sqr22(pair_t v, u64 u)
+{
+	pair_t r;
+	const u64 ab = gl::mul(v.x, v.y);
+	r.x = gl::add(gl::sqr(v.x), gl::mul(gl::sqr(v.y), u));
+	r.y = gl::add(ab, ab);
+	return r;
+}
+
+HD pair_t mul22(pair_t v, pair_t y, u64 u)
+{
+	pair_t r;
+	r.x = gl::add(gl::mul(v.x, y.x), gl::mul(gl::mul(v.y, y.y), u));
+	r.y = gl::add(gl::mul(v.x, y.y), gl::mul(v.y, y.x));
+	return r;
+}
+
+// Last forward stage + pointwise + first inverse stage on one block of R consecutive positions
+// (s = 1, so no twiddles).  MODE_FWD stops after the forward butterfly (multiplicand form).
+template <int R> HD void bfly_mid(const View &in, const View &out, u32 base, int mode, const u64 *colroot /* at base */,
+	u64 rowroot, bool use_rowroot, const pair_t *ymul /* at base, or null */, const u64 *c5, const u64 *c5i)
+{
+	u64 a[R], b[R];
+	for (u32 q = 0; q < R; ++q) { const pair_t v = in.ld(base + q); a[q] = v.x; b[q] = v.y; }
+	if (R == 16) { dft16<false>(a); dft16<false>(b); }
+	else if (R == 4) { dft4<false>(a[0], a[1], a[2], a[3]); dft4<false>(b[0], b[1], b[2], b[3]); }
+	else if (R == 2) { dft2<false>(a[0], a[1]); dft2<false>(b[0], b[1]); }
+	else if (R == 5) { dft5(a, c5); dft5(b, c5); }
+	if (mode == MODE_FWD)
+	{
+		for (u32 k = 0; k < R; ++k) { const u32 sl = slot_of<R>(k); pair_t v; v.x = a[sl]; v.y = b[sl]; out.st(base + k, v); }
+		return;
+	}
+	// output k sits in slot_of(k); its position is base + k
+	for (u32 k = 0; k < R; ++k)
+	{
+		const u32 sl = slot_of<R>(k);
+		const u64 u = use_rowroot ? gl::mul(rowroot, colroot[k]) : colroot[k];
+		pair_t v; v.x = a[sl]; v.y = b[sl];
+		v = (mode == MODE_SQR) ? sqr22(v, u) : mul22(v, ymul[k], u);
+		a[sl] = v.x; b[sl] = v.y;
+	}
+	if (R == 16) { dft16<true>(a); dft16<true>(b); }
+	else if (R == 4) { dft4<true>(a[0], a[1], a[2], a[3]); dft4<true>(b[0], b[1], b[2], b[3]); }
+	else if (R == 2) { dft2<true>(a[0], a[1]); dft2<true>(b[0], b[1]); }
+	else if (R == 5) { dft5(a, c5i); dft5(b, c5i); }
+	for (u32 q = 0; q < R; ++q) { pair_t v; v.x = a[q]; v.y = b[q]; out.st(base + q, v); }
+}
+
+// ------------------------------------------------------------------ carry
+
+// Turn exact convolution values v[0..D) (integers < P) times `a` into digits of the given widths;
+// returns the carry out of the run.  Restates adc / adc_mul (arith.h:75-91) on a run of digits.
+HD u64 carry_run(u64 *v, u32 D, u32 wbase, u32 bits, u32 a, u64 cin)
+{
+	if (a == 1)
+	{
+		u64 c = cin;
+		for (u32 i = 0; i < D; ++i)
+		{
+			const u32 w = wbase + ((bits >> i) & 1u);
+			const u64 s = v[i] + c;
+			const u64 co = (s < c) ? 1 : 0;
+			c = (s >> w) | (co << (64 - w));
+			v[i] = s & (((u64)1 << w) - 1);
+		}
+		return c;
+	}
+	unsigned __int128 c = cin;
+	for (u32 i = 0; i < D; ++i)
+	{
+		const u32 w = wbase + ((bits >> i) & 1u);
+		c += (unsigned __int128)v[i] * a;
+		v[i] = (u64)c & (((u64)1 << w) - 1);
+		c >>= w;
+	}
+	return (u64)c;
+}
+
+// Add an incoming carry to the first digits of a run; the last one absorbs what is left without
+// renormalising (the reference's adc4 does the same, marin.cl:203-212).
+HD void carry_absorb(u64 *d, u32 cnt, u32 wbase, u32 bits, u64 c)
+{
+	for (u32 i = 0; i + 1 < cnt; ++i)
+	{
+		const u32 w = wbase + ((bits >> i) & 1u);
+		const u64 s = d[i] + c;
+		d[i] = s & (((u64)1 << w) - 1);
+		c = s >> w;
+	}
+	d[cnt - 1] += c;
+}
+
+HD u32 run_bits(const Tables &t, u32 j0, u32 D) { return (t.wbits[j0 >> 5] >> (j0 & 31)) & ((D >= 32) ? 0xffffffffu : ((1u << D) - 1)); }
+
+// ------------------------------------------------------------------ kernel argument blocks
+
+struct MidArgs     // contiguous pass: one CTA = one block of S pairs (or the whole register when small)
+{
+	Tables t;
+	pair_t *x;          // register to transform (in place)
+	const pair_t *y;    // multiplicand (MODE_MUL)
+	pair_t *dst;        // output register (MODE_FWD), may equal x
+	int mode;
+	u32 S, nst;
+	Stage st[MAX_STAGES];
+	u32 use_rowroot;    // 0: colroot alone is the pointwise root (single-block engines)
+	// fused carry for single-block engines (small n)
+	u32 small; u32 a; u32 D;
+	u64 *carry;
+};
+
+struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
+{
+	Tables t;
+	const pair_t *src; pair_t *dst; // src == dst for in-place
+	u32 R, nst;
+	Stage st[MAX_STAGES];
+	u32 Lb;             // block length in pairs (= R * stride)
+	u32 stride;         // pairs between rows
+	u32 escale;         // m / Lb
+	u32 tiles;          // stride / 8 tiles per block
+	u32 a;              // multiplier for the carry
+	u64 *carry;         // carry[g * R + row]
+	u32 with_carry;
+};
+
+// ------------------------------------------------------------------ phase functions
+// A kernel is a sequence of phases separated by block-wide barriers.  phase(ph, tid) does thread
+// tid's share of phase ph.  GPU: `for ph: phase(ph, threadIdx.x); __syncthreads();`  Emulator:
+// `for ph: for tid: phase(ph, tid)`.
+
+template <int R, bool INV> HD void run_stage_lin(const View &in, const View &out, const Stage &sg, const Tw &tw, u32 S, u32 tid, u32 nthr, const Tables &t)
+{
+	const u32 nb = S / R;
+	for (u32 b = tid; b < nb; b += nthr)
+	{
+		const u32 blk = b / sg.s, j = b % sg.s;
+		bfly<R, INV>(in, out, blk * sg.L + j, sg.s, j, tw, INV ? t.w5i : t.w5, nullptr);
+	}
+}
+
+// ---- contiguous pass -------------------------------------------------------------------------
+// phases: 0 .. nst-2 forward stages, nst-1 middle, nst .. 2 nst - 2 inverse stages,
+// then for small engines: carry, absorb+store.
+HD u32 mid_num_phases(const MidArgs &A) { return (A.mode == MODE_FWD) ? A.nst : (2 * A.nst - 1 + (A.small ? 2 : 0)); }
+
+HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc)
+{
+	const Tables &t = A.t;
+	const u32 S = A.S, nst = A.nst;
+	pair_t *xg = A.x + (size_t)blk * S;
+	View G{xg, 0, 1, 0}, Sv{sm, 1, 1, 0};
+	if (ph + 1 < nst)
+	{
+		const Stage &sg = A.st[ph];
+		const Tw tw{t.twS, t.S, t.S / sg.L};
+		const View &in = (ph == 0) ? G : Sv;
+		switch (sg.radix)
+		{
+		case 16: run_stage_lin<16, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
+		case 4: run_stage_lin<4, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
+		case 2: run_stage_lin<2, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
+		case 5: run_stage_lin<5, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
+		}
+		return;
+	}
+	if (ph == nst - 1)
+	{
+		const Stage &sg = A.st[nst - 1];
+		const View &in = (nst == 1) ? G : Sv;
+		View Gd{A.dst + (size_t)blk * S, 0, 1, 0};
+		const View &out = (A.mode == MODE_FWD) ? Gd : ((nst == 1 && !A.small) ? G : Sv);
+		const u32 R = sg.radix, nb = S / R;
+		const u64 rr = A.use_rowroot ? t.rowroot[blk] : 1;
+		for (u32 b = tid; b < nb; b += nthr)
+		{
+			const u64 *cr = t.colroot + b * R;
+			const pair_t *ym = (A.mode == MODE_MUL) ? A.y + (size_t)blk * S + b * R : nullptr;
+			const bool ur = A.use_rowroot != 0;
+			switch (R)
+			{
+			case 16: bfly_mid<16>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
+			case 4: bfly_mid<4>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
+			case 2: bfly_mid<2>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
+			case 5: bfly_mid<5>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
+			}
+		}
+		return;
+	}
+	if (ph < 2 * nst - 1)
+	{
+		const u32 si = 2 * nst - 2 - ph; // nst-2 .. 0
+		const Stage &sg = A.st[si];
+		const Tw tw{t.twS, t.S, t.S / sg.L};
+		const View &out = (si == 0 && !A.small) ? G : Sv;
+		switch (sg.radix)
+		{
+		case 16: run_stage_lin<16, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
+		case 4: run_stage_lin<4, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
+		case 2: run_stage_lin<2, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
+		case 5: run_stage_lin<5, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
+		}
+		return;
+	}
+	// ---- small engines only: whole register is in shared memory (natural order)
+	const u32 D = A.D, nruns = t.n / D;
+	if (ph == 2 * nst - 1)
+	{
+		for (u32 r = tid; r < nruns; r += nthr)
+		{
+			u64 v[RUN];
+			const u32 j0 = r * D;
+			for (u32 i = 0; i < D; i += 2)
+			{
+				const pair_t pv = Sv.ld((j0 + i) >> 1);
+				v[i] = gl::mul(gl::mul(pv.x, t.winv_nat[j0 + i]), t.inv_m);
+				v[i + 1] = gl::mul(gl::mul(pv.y, t.winv_nat[j0 + i + 1]), t.inv_m);
+			}
+			smc[r] = carry_run(v, D, t.wbase, run_bits(t, j0, D), A.a, 0);
+			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; Sv.st((j0 + i) >> 1, pv); }
+		}
+		return;
+	}
+	for (u32 r = tid; r < nruns; r += nthr)
+	{
+		u64 v[RUN];
+		const u32 j0 = r * D;
+		for (u32 i = 0; i < D; i += 2) { const pair_t pv = Sv.ld((j0 + i) >> 1); v[i] = pv.x; v[i + 1] = pv.y; }
+		carry_absorb(v, (D < 4) ? D : 4, t.wbase, run_bits(t, j0, D), smc[(r == 0) ? nruns - 1 : r - 1]);
+		for (u32 i = 0; i < D; i += 2)
+		{
+			pair_t pv;
+			pv.x = gl::mul(v[i], t.w_nat[j0 + i]); pv.y = gl::mul(v[i + 1], t.w_nat[j0 + i + 1]);
+			xg[(j0 + i) >> 1] = pv;
+		}
+	}
+}
+
+// ---- strided passes ----------------------------------------------------------------------------
+// Tile = R rows x 8 pair columns; butterfly id b -> column c = b & 7 (fastest: 128 B rows), row-butterfly b >> 3.
+
+template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, u32 blockbase /*pairs*/, u32 c0,
+	pair_t *sm, u32 tid, u32 nthr, bool out_smem_always)
+{
+	const Tables &t = A.t;
+	const u32 nb = (A.R / R) * TILE_C;
+	const Tw tw{t.twR, t.R, t.R / sg.L};
+	for (u32 b = tid; b < nb; b += nthr)
+	{
+		const u32 c = b & (TILE_C - 1), rb = b >> 3;
+		const u32 blk = rb / sg.s, j = rb % sg.s;
+		const u32 base = blk * sg.L + j;
+		View Gi{const_cast<pair_t *>(A.src) + blockbase + c0 + c, 0, A.stride, 0};
+		View Go{A.dst + blockbase + c0 + c, 0, A.stride, 0};
+		View Sv{sm, 2, 0, c};
+		const Boundary bd{&t, (u64)(c0 + c) * A.escale};
+		if (!INV)
+		{
+			const View &in = first ? Gi : Sv;
+			const View &out = last ? Go : Sv;
+			bfly<R, false>(in, out, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
+		}
+		else
+		{
+			// inverse order: the stage that is `last` in forward order comes first and reads global
+			const View &in = last ? Gi : Sv;
+			const View &out = (first && !out_smem_always) ? Go : Sv;
+			bfly<R, true>(in, out, base, sg.s, j, tw, t.w5i, last ? &bd : nullptr);
+		}
+	}
+}
+
+HD u32 strided_num_phases(const StridedArgs &A, bool inv) { return A.nst + ((inv && A.with_carry) ? 2 : 0); }
+
+template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 ph, u32 tid, u32 nthr, pair_t *sm)
+{
+	const Tables &t = A.t;
+	const u32 ob = blkid / A.tiles, g = blkid % A.tiles; // outer block, tile
+	const u32 blockbase = ob * A.Lb, c0 = g * TILE_C;
+	if (ph < A.nst)
+	{
+		const u32 si = INV ? (A.nst - 1 - ph) : ph;
+		const Stage &sg = A.st[si];
+		const bool first = (si == 0), last = (si == A.nst - 1);
+		switch (sg.radix)
+		{
+		case 16: run_stage_tile<16, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
+		case 4: run_stage_tile<4, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
+		case 2: run_stage_tile<2, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
+		case 5: run_stage_tile<5, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
+		}
+		return;
+	}
+	if (!INV) return;
+	if (ph == A.nst)
+	{
+		// unweight (x 1/m), carry, reweight: one thread per row = one run of 16 consecutive digits
+		for (u32 row = tid; row < A.R; row += nthr)
+		{
+			u64 v[RUN];
+			View Sv{sm, 2, 0, 0};
+			for (u32 c = 0; c < TILE_C; ++c)
+			{
+				Sv.col = c;
+				const pair_t pv = Sv.ld(row);
+				v[2 * c] = gl::mul(pv.x, t.winvs_perm[perm_index(A.R, g, 2 * c, row)]);
+				v[2 * c + 1] = gl::mul(pv.y, t.winvs_perm[perm_index(A.R, g, 2 * c + 1, row)]);
+			}
+			const u32 j0 = 2 * (row * A.stride + c0);
+			const u64 cout = carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
+			A.carry[(size_t)g * A.R + row] = cout;
+			for (u32 c = 0; c < TILE_C; ++c)
+			{
+				pair_t pv;
+				pv.x = gl::mul(v[2 * c], t.w_perm[perm_index(A.R, g, 2 * c, row)]);
+				pv.y = gl::mul(v[2 * c + 1], t.w_perm[perm_index(A.R, g, 2 * c + 1, row)]);
+				Sv.col = c;
+				Sv.st(row, pv);
+			}
+		}
+		return;
+	}
+	// coalesced store of the tile
+	for (u32 e = tid; e < A.R * TILE_C; e += nthr)
+	{
+		const u32 row = e >> 3, c = e & 7;
+		View Sv{sm, 2, 0, c};
+		A.dst[blockbase + (size_t)row * A.stride + c0 + c] = Sv.ld(row);
+	}
+}
+
+// ---- carry fix-up after the strided inverse pass: run (row, g) takes the carry of the run before it
+struct FixArgs { Tables t; u64 *x; const u64 *carry; u32 R, stride, tiles; };
+
+HD void fixup_thread(const FixArgs &A, u32 id)
+{
+	const Tables &t = A.t;
+	const u32 g = id / A.R, row = id % A.R; // rows fastest: coalesced carry / weight reads
+	if (g >= A.tiles) return;
+	u64 c;
+	if (g > 0) c = A.carry[(size_t)(g - 1) * A.R + row];
+	else c = A.carry[(size_t)(A.tiles - 1) * A.R + ((row == 0) ? A.R - 1 : row - 1)];
+	if (c == 0) return;
+	const size_t j0 = 2 * ((size_t)row * A.stride + (size_t)g * TILE_C);
+	const u64 mm = (u64)t.m;
+	u64 d[4];
+	for (u32 i = 0; i < 4; ++i) d[i] = gl::mul(gl::mul(A.x[j0 + i], t.winvs_perm[perm_index(A.R, g, i, row)]), mm);
+	carry_absorb(d, 4, t.wbase, run_bits(t, (u32)j0, 4), c);
+	for (u32 i = 0; i < 4; ++i) A.x[j0 + i] = gl::mul(d[i], t.w_perm[perm_index(A.R, g, i, row)]);
+}
+
+// ---- linear operations on digits (natural order, runs of D digits) -----------------------------
+enum LinOp : int { LIN_ADD = 0, LIN_SUBREG = 1, LIN_SUBSMALL = 2, LIN_SETDIGITS = 3, LIN_SETSMALL = 4 };
+
+struct LinArgs
+{
+	Tables t;
+	u64 *dst; const u64 *src; // registers (weighted digits); src unused for SUBSMALL / SETSMALL
+	const u64 *digits;        // LIN_SETDIGITS: encoded digits (low 32 bits used)
+	u64 *carry;               // one per run
+	int op; u32 a; u32 D;
+};
+
+// digits of the small constant `a` that fall in digit j (a < 2^32)
+HD u64 small_digit(const Tables &t, u32 j, u32 a)
+{
+	u32 pos = 0;
+	for (u32 i = 0; i < j; ++i) { pos += digit_width(t, i); if (pos >= 32) return 0; }
+	const u32 w = digit_width(t, j);
+	return ((u64)a >> pos) & (((u64)1 << w) - 1);
+}
+
+HD void lin_p1_thread(const LinArgs &A, u32 r)
+{
+	const Tables &t = A.t;
+	const u32 D = A.D, nruns = t.n / D;
+	if (r >= nruns) return;
+	const u32 j0 = r * D;
+	const u32 bits = run_bits(t, j0, D);
+	u64 v[RUN];
+	for (u32 i = 0; i < D; ++i)
+	{
+		const u32 j = j0 + i;
+		const u32 w = t.wbase + ((bits >> i) & 1u);
+		const u64 mask = ((u64)1 << w) - 1;
+		switch (A.op)
+		{
+		case LIN_ADD: v[i] = gl::mul(gl::add(A.dst[j], A.src[j]), t.winv_nat[j]); break;
+		// y - x + 2 (2^w - 1) per digit keeps every digit non-negative (marin.cl:244-257,1876)
+		case LIN_SUBREG: v[i] = gl::mul(gl::sub(A.dst[j], A.src[j]), t.winv_nat[j]); v[i] = gl::add(v[i], 2 * mask); break;
+		// x - a == x + (2^p - 1 - a): digit-wise mask - a_j, never negative
+		case LIN_SUBSMALL: v[i] = gl::mul(A.dst[j], t.winv_nat[j]) + (mask - ((j < 64) ? small_digit(t, j, A.a) : 0)); break;
+		case LIN_SETDIGITS: v[i] = (u32)A.digits[j]; break;
+		default: v[i] = (j < 64) ? small_digit(t, j, A.a) : 0; break;
+		}
+	}
+	A.carry[r] = carry_run(v, D, t.wbase, bits, 1, 0);
+	for (u32 i = 0; i < D; ++i) A.dst[j0 + i] = gl::mul(v[i], t.w_nat[j0 + i]);
+}
+
+HD void lin_p2_thread(const LinArgs &A, u32 r)
+{
+	const Tables &t = A.t;
+	const u32 D = A.D, nruns = t.n / D;
+	if (r >= nruns) return;
+	const u64 c = A.carry[(r == 0) ? nruns - 1 : r - 1];
+	if (c == 0) return;
+	const u32 j0 = r * D, cnt = (D < 4) ? D : 4;
+	u64 d[4];
+	for (u32 i = 0; i < cnt; ++i) d[i] = gl::mul(A.dst[j0 + i], t.winv_nat[j0 + i]);
+	carry_absorb(d, cnt, t.wbase, run_bits(t, j0, D), c);
+	for (u32 i = 0; i < cnt; ++i) A.dst[j0 + i] = gl::mul(d[i], t.w_nat[j0 + i]);
+}
+
+// unweighted digit values (not carried) for the host-side canonical export (engine_gpu.h:1534-1561)
+HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
+
+// weight tables: digit j has weight r^((n - p j mod n) mod n), r the n-th root of two (ibdwt.h:111-147)
+struct WeightArgs { u32 p, n, m, R, stride, tiles; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *w_perm, *winvs_perm; u32 have_perm; };
+
+HD void weight_thread(const WeightArgs &A, u32 j)
+{
+	if (j >= A.n) return;
+	const u64 r = ((u64)A.p * j) % A.n;
+	const u64 e = r ? (u64)A.n - r : 0;
+	const u64 w = gl::pow(A.nr2, e), wi = gl::pow(A.nr2_inv, e);
+	A.w_nat[j] = w; A.winv_nat[j] = wi;
+	if (A.have_perm)
+	{
+		const u32 pairidx = j >> 1, row = pairidx / A.stride, c = pairidx % A.stride, g = c / TILE_C, i = 2 * (c % TILE_C) + (j & 1);
+		const size_t k = perm_index(A.R, g, i, row);
+		A.w_perm[k] = w; A.winvs_perm[k] = gl::mul(wi, A.inv_m);
+	}
+}
+
+} // namespace marin

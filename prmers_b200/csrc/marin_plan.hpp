@@ -1,0 +1,186 @@
+// marin_plan.hpp -- host-side planning for the B200 Marin engine: transform size, pass/stage
+// decomposition, launch shapes and the small constant tables.  Pure C++ (no CUDA) so the kernel
+// emulator in tests/emu shares it with the engine.
+//
+// Replaces ibdwt::transform_size / roots (include/marin/ibdwt.h:17-43,79-108) and the per-n kernel
+// selection tables of engine_gpu_flat (include/marin/engine_gpu.h:108-129,551-691,1568-1630).
+#pragma once
+#include <string>
+#include <vector>
+#include <cstring>
+#include "marin_kernels.cuh"
+
+namespace marin {
+
+// Smallest n in {2^k, 5 2^k}, k <= 26, with 2 (w + 1) + log2 n < 64, w = floor(p / n): the digits
+// of a product must not overflow P.  Same rule (and the same 2.4 for log2 5) as ibdwt.h:17-43, so
+// that residues, digit widths and checkpoints line up with the reference digit for digit.
+inline size_t transform_size(uint32_t exponent)
+{
+	uint32_t w = 0, l2 = 1, l5 = 2;
+	do { ++l2; w = exponent >> l2; } while ((w + 1) * 2 + l2 >= 64);
+	do { ++l5; w = exponent / (5u << l5); } while ((w + 1) * 2 + (l5 + 2.4) >= 64);
+	const size_t bad = (size_t)-1;
+	const size_t n2 = (l2 <= 26) ? ((size_t)1 << l2) : bad, n5 = (l5 <= 26) ? ((size_t)5 << l5) : bad;
+	return n2 < n5 ? n2 : n5;
+}
+
+static constexpr u32 SMALL_MAX_PAIRS = 8192;  // whole register in one CTA's shared memory (128 KiB + pad)
+static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
+static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 8 pairs * 16 B = 160 KiB
+
+struct Plan
+{
+	u32 p = 0, n = 0, m = 0;
+	bool small = false;
+	u32 S = 0, R = 1;            // m = R * S
+	u32 nstS = 0, nstR = 0;
+	Stage stS[MAX_STAGES], stR[MAX_STAGES];
+	u32 thrMid = 0, thrStr = 0;  // threads per CTA
+	u32 D = 0;                   // digits per carry run of the linear / small kernels
+	u32 wbase = 0;
+	u32 a_max = 1;               // largest multiplier `a` the carry chain supports without overflow
+};
+
+inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
+{
+	// radices: optional 5 first, then 2, 4 and 16s (or 16s first) with product len
+	u32 r[MAX_STAGES], k = 0, rest = len;
+	if (rest % 5 == 0) { r[k++] = 5; rest /= 5; }
+	u32 l2 = 0; while ((1u << l2) < rest) ++l2;
+	u32 n16 = l2 / 4, rem = l2 % 4;
+	u32 small_r[2], ns = 0;
+	if (rem & 1) small_r[ns++] = 2;
+	if (rem & 2) small_r[ns++] = 4;
+	if (sixteen_last) { for (u32 i = 0; i < ns; ++i) r[k++] = small_r[i]; for (u32 i = 0; i < n16; ++i) r[k++] = 16; }
+	else { for (u32 i = 0; i < n16; ++i) r[k++] = 16; for (u32 i = ns; i > 0; --i) r[k++] = small_r[i - 1]; }
+	u32 L = len;
+	for (u32 i = 0; i < k; ++i) { st[i].radix = r[i]; st[i].L = L; st[i].s = L / r[i]; L /= r[i]; }
+	return k;
+}
+
+inline u32 round_threads(u32 t, u32 cap) { t = (t + 31) / 32 * 32; if (t < 32) t = 32; return t > cap ? cap : t; }
+
+inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0)
+{
+	if (p < 3) { err = "exponent must be >= 3"; return false; }
+	const size_t n = transform_size(p);
+	if (n == (size_t)-1) { err = "exponent too large for the Goldilocks IBDWT (n would exceed 5*2^26)"; return false; }
+	pl.p = p; pl.n = (u32)n; pl.m = pl.n / 2; pl.wbase = p / pl.n;
+	const u32 m = pl.m;
+	if (m <= SMALL_MAX_PAIRS && !force_S)
+	{
+		pl.small = true; pl.S = m; pl.R = 1;
+		pl.nstS = factor_stages(m, pl.stS, true);
+		pl.nstR = 0;
+		pl.thrMid = round_threads(m / 16, 512);
+	}
+	else
+	{
+		pl.small = false;
+		const u32 five = (m % 5 == 0) ? 5 : 1;
+		if (force_S) { pl.S = force_S; pl.R = m / force_S; }
+		else if (m / five >= ((five == 5) ? 16u : 64u) * MID_S) { pl.S = MID_S; pl.R = m / MID_S; }
+		else { pl.R = (five == 5) ? 80 : 64; pl.S = m / pl.R; }
+		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || (pl.S & (pl.S - 1)) != 0 || pl.R < 2) { err = "bad forced split"; return false; }
+		if (pl.R > MAX_R || pl.S > MID_S)
+		{
+			err = "transform size n = " + std::to_string(n) + " needs a second strided pass (not built yet; n <= 2^23 and 5*2^21 are)";
+			return false;
+		}
+		pl.nstS = factor_stages(pl.S, pl.stS, true);
+		pl.nstR = factor_stages(pl.R, pl.stR, false);
+		pl.thrMid = round_threads(pl.S / 16, 512);
+		const u32 bf = pl.R * TILE_C / 16; // radix-16 butterflies per stage
+		pl.thrStr = (bf <= 512) ? round_threads(bf, 512) : round_threads(bf / 2, 512);
+	}
+	pl.D = (n % 16 == 0 && n >= 256) ? 16 : ((n % 8 == 0 && n >= 16) ? 8 : 4);
+	// a * conv < 2^(64 + w) keeps the carry out of a run below 2^64, and the carry left after three
+	// digits must stay below 2^(w - 1): a <= 2^min(61 - w - log2 n, 3 w - 3 - log2 n)
+	u32 l2n = 0; while ((1ull << l2n) < n) ++l2n;
+	const int w = (int)pl.wbase;
+	int e = 61 - w - (int)l2n; const int e2 = 3 * w - 3 - (int)l2n; if (e2 < e) e = e2;
+	if (e < 0) e = 0; if (e > 31) e = 31;
+	pl.a_max = 1u << e;
+	return true;
+}
+
+// frequency index of the element that ends at position pos after the DIF stages st[0..nst)
+inline u32 freq_of_pos(const Stage *st, u32 nst, u32 pos)
+{
+	u32 K = 0, mult = 1, rem = pos;
+	for (u32 i = 0; i < nst; ++i) { const u32 k = rem / st[i].s; rem %= st[i].s; K += k * mult; mult *= st[i].radix; }
+	return K;
+}
+
+struct HostTables
+{
+	std::vector<u32> wbits, rowK;
+	std::vector<u64> twS, twR, bl_lo, bl_hi, rowroot, colroot;
+	u64 inv_m = 0, nr2 = 0, nr2_inv = 0, w5[4], w5i[4];
+	u32 bl_h = 0;
+};
+
+inline void powers(std::vector<u64> &v, u64 root, size_t cnt)
+{
+	v.resize(cnt);
+	u64 x = 1;
+	for (size_t i = 0; i < cnt; ++i) { v[i] = x; x = gl::mul(x, root); }
+}
+
+inline void build_tables(const Plan &pl, HostTables &h)
+{
+	const u32 n = pl.n, m = pl.m, p = pl.p;
+	// digit widths: width[j] = ceil(p (j+1) / n) - ceil(p j / n)  (ibdwt.h:122-133), as one bit each
+	h.wbits.assign((n + 31) / 32, 0);
+	u32 prev = 0;
+	for (u32 j = 1; j <= n; ++j)
+	{
+		const u64 qj = (u64)p * j;
+		const u32 c = (u32)((qj - 1) / n + 1);
+		if (c - prev == pl.wbase + 1) h.wbits[(j - 1) >> 5] |= 1u << ((j - 1) & 31);
+		prev = c;
+	}
+	// n-th root of two: 554^((P-1)/192/n)  (ibdwt.h:116; 554^((P-1)/192) = 2)
+	h.nr2 = gl::pow(554, (gl::P - 1) / 192 / n);
+	h.nr2_inv = gl::inv(h.nr2);
+	h.inv_m = gl::inv((u64)m);
+	powers(h.twS, gl::root_of_unity(pl.S), pl.S);
+	powers(h.twR, gl::root_of_unity(pl.R), pl.R);
+	h.bl_h = 11;
+	const u64 rm = gl::root_of_unity(m);
+	powers(h.bl_lo, rm, (size_t)1 << h.bl_h);
+	powers(h.bl_hi, gl::pow(rm, (u64)1 << h.bl_h), (m >> h.bl_h) + 1);
+	h.rowK.resize(pl.R); h.rowroot.resize(pl.R);
+	for (u32 r = 0; r < pl.R; ++r)
+	{
+		h.rowK[r] = pl.nstR ? freq_of_pos(pl.stR, pl.nstR, r) : 0;
+		h.rowroot[r] = gl::pow(rm, h.rowK[r]);
+	}
+	h.colroot.resize(pl.S);
+	const u64 rS = gl::root_of_unity(pl.S);
+	for (u32 s = 0; s < pl.S; ++s) h.colroot[s] = gl::pow(rS, freq_of_pos(pl.stS, pl.nstS, s));
+	// radix-5 constants
+	const u64 w = gl::root_of_unity(5), w2 = gl::mul(w, w), w3 = gl::mul(w2, w), w4 = gl::mul(w3, w);
+	h.w5[0] = gl::half(gl::add(w, w4)); h.w5[1] = gl::half(gl::add(w2, w3));
+	h.w5[2] = gl::half(gl::sub(w, w4)); h.w5[3] = gl::half(gl::sub(w2, w3));
+	h.w5i[0] = h.w5[0]; h.w5i[1] = h.w5[1]; h.w5i[2] = gl::neg(h.w5[2]); h.w5i[3] = gl::neg(h.w5[3]);
+}
+
+inline void fill_mid_args(const Plan &pl, MidArgs &A)
+{
+	A.S = pl.S; A.nst = pl.nstS;
+	for (u32 i = 0; i < pl.nstS; ++i) A.st[i] = pl.stS[i];
+	A.use_rowroot = pl.small ? 0 : 1;
+	A.small = pl.small ? 1 : 0;
+	A.D = pl.D; A.a = 1;
+}
+
+inline void fill_strided_args(const Plan &pl, StridedArgs &A)
+{
+	A.R = pl.R; A.nst = pl.nstR;
+	for (u32 i = 0; i < pl.nstR; ++i) A.st[i] = pl.stR[i];
+	A.Lb = pl.m; A.stride = pl.S; A.escale = 1; A.tiles = pl.S / TILE_C; A.a = 1; A.with_carry = 0;
+}
+
+} // namespace marin

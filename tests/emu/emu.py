@@ -1,0 +1,87 @@
+"""ctypes wrapper of tests/emu/libmarin_emu.so (TEST INFRASTRUCTURE: CPU emulation of the CUDA kernels)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmarin_emu.so")
+_SRC = os.path.join(_HERE, "emu_engine.cpp")
+_CSRC = os.path.join(_HERE, "..", "..", "prmers_b200", "csrc")
+
+
+def build():
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("gl64.cuh", "marin_kernels.cuh", "marin_plan.hpp", "marin_engine_core.hpp")]
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", _SO, _SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        r = subprocess.run([c for c in cmd if c != "-fopenmp"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
+        L.emu_last_error.restype = C.c_char_p
+        L.emu_create.restype = vp; L.emu_create.argtypes = [u32, sz, u32]
+        L.emu_destroy.argtypes = [vp]
+        L.emu_size.restype = sz; L.emu_size.argtypes = [vp]
+        for f in ("emu_is_small", "emu_plan_R", "emu_plan_S", "emu_a_max"):
+            getattr(L, f).argtypes = [vp]; getattr(L, f).restype = u32
+        for f, a in (("emu_set_u32", [vp, sz, u32]), ("emu_copy", [vp, sz, sz]), ("emu_square_mul", [vp, sz, u32]),
+                     ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_sub_u32", [vp, sz, u32]),
+                     ("emu_add", [vp, sz, sz]), ("emu_sub_reg", [vp, sz, sz]), ("emu_get_digits", [vp, sz, vp]),
+                     ("emu_set_digits", [vp, sz, vp]), ("emu_equal", [vp, sz, sz, vp])):
+            getattr(L, f).argtypes = a; getattr(L, f).restype = C.c_int
+        L.emu_transform_size.restype = sz; L.emu_transform_size.argtypes = [u32]
+        _lib = L
+    return _lib
+
+
+class EmuEngine:
+    def __init__(self, p, regs, force_S=0):
+        L = lib()
+        self._h = L.emu_create(p, regs, force_S)
+        if not self._h:
+            raise ValueError(L.emu_last_error().decode())
+        self.p, self.n = p, L.emu_size(self._h)
+        self.small = bool(L.emu_is_small(self._h))
+        self.R, self.S = L.emu_plan_R(self._h), L.emu_plan_S(self._h)
+        self.a_max = L.emu_a_max(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().emu_destroy(self._h); self._h = None
+
+    def _ck(self, ok):
+        if not ok:
+            raise RuntimeError(lib().emu_last_error().decode())
+
+    def set(self, d, a): self._ck(lib().emu_set_u32(self._h, d, a))
+    def copy(self, d, s): self._ck(lib().emu_copy(self._h, d, s))
+    def square_mul(self, r, a=1): self._ck(lib().emu_square_mul(self._h, r, a))
+    def set_multiplicand(self, d, s): self._ck(lib().emu_set_multiplicand(self._h, d, s))
+    def mul(self, d, s, a=1): self._ck(lib().emu_mul(self._h, d, s, a))
+    def sub(self, r, a): self._ck(lib().emu_sub_u32(self._h, r, a))
+    def add(self, d, s): self._ck(lib().emu_add(self._h, d, s))
+    def sub_reg(self, d, s): self._ck(lib().emu_sub_reg(self._h, d, s))
+
+    def get_digits(self, s):
+        out = np.zeros(self.n, dtype=np.uint64)
+        self._ck(lib().emu_get_digits(self._h, s, out.ctypes.data))
+        return out
+
+    def set_digits(self, d, enc):
+        enc = np.ascontiguousarray(enc, dtype=np.uint64)
+        self._ck(lib().emu_set_digits(self._h, d, enc.ctypes.data))

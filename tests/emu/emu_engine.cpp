@@ -1,0 +1,90 @@
+// emu_engine.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the product's own kernel phase functions
+// (prmers_b200/csrc/marin_kernels.cuh) and host logic (marin_engine_core.hpp) on the CPU, one
+// emulated thread after the other with a barrier between phases, so that indexing, twiddles and
+// carry logic can be checked against the oracle in the CPU-only test tier.  It is never built into
+// or loaded by the product library; the product has no CPU path.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../prmers_b200/csrc/marin_engine_core.hpp"
+
+using namespace marin;
+
+struct CpuBackend
+{
+	explicit CpuBackend(int) {}
+	void *alloc(size_t bytes) { void *p = nullptr; if (posix_memalign(&p, 64, bytes ? bytes : 64)) throw std::bad_alloc(); return p; }
+	void free(void *p) { ::free(p); }
+	void memset0(void *p, size_t b) { std::memset(p, 0, b); }
+	void h2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+	void d2h(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+	void d2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+	void sync() {}
+
+	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem)
+	{
+		std::vector<pair_t> sm(smem / 16 + 1);
+		u64 *smc = (u64 *)(sm.data() + smem_pairs_lin(A.S));
+		const u32 nph = mid_num_phases(A);
+		for (u32 b = 0; b < grid; ++b)
+			for (u32 ph = 0; ph < nph; ++ph)
+				for (u32 t = 0; t < thr; ++t) mid_phase(A, b, ph, t, thr, sm.data(), smc);
+	}
+	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
+	{
+		std::vector<pair_t> sm(smem / 16 + 1);
+		const u32 nph = strided_num_phases(A, false);
+		for (u32 b = 0; b < grid; ++b)
+			for (u32 ph = 0; ph < nph; ++ph)
+				for (u32 t = 0; t < thr; ++t) strided_phase<false>(A, b, ph, t, thr, sm.data());
+	}
+	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
+	{
+		std::vector<pair_t> sm(smem / 16 + 1);
+		const u32 nph = strided_num_phases(A, true);
+		for (u32 b = 0; b < grid; ++b)
+			for (u32 ph = 0; ph < nph; ++ph)
+				for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, b, ph, t, thr, sm.data());
+	}
+	void fixup(const FixArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) fixup_thread(A, i); }
+	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
+	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
+	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { for (u32 j = 0; j < n; ++j) unweight_thread(t, x, out, j); }
+	void weights(const WeightArgs &A, u32 n)
+	{
+		#pragma omp parallel for schedule(static)
+		for (u32 j = 0; j < n; ++j) weight_thread(A, j);
+	}
+};
+
+typedef EngineCore<CpuBackend> Emu;
+static thread_local std::string g_err;
+
+#define GUARD(expr) try { expr; return 1; } catch (const std::exception &e) { g_err = e.what(); return 0; }
+
+extern "C" {
+const char *emu_last_error() { return g_err.c_str(); }
+void *emu_create(uint32_t p, size_t regs, uint32_t force_S)
+{
+	try { return new Emu(p, regs, 0, force_S); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void emu_destroy(void *h) { delete (Emu *)h; }
+size_t emu_size(void *h) { return ((Emu *)h)->size(); }
+int emu_is_small(void *h) { return ((Emu *)h)->pl.small ? 1 : 0; }
+uint32_t emu_plan_R(void *h) { return ((Emu *)h)->pl.R; }
+uint32_t emu_plan_S(void *h) { return ((Emu *)h)->pl.S; }
+uint32_t emu_a_max(void *h) { return ((Emu *)h)->pl.a_max; }
+int emu_set_u32(void *h, size_t d, uint32_t a) { GUARD(((Emu *)h)->set_u32(d, a)) }
+int emu_copy(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->copy(d, s)) }
+int emu_square_mul(void *h, size_t r, uint32_t a) { GUARD(((Emu *)h)->square_mul(r, a)) }
+int emu_set_multiplicand(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->set_multiplicand(d, s)) }
+int emu_mul(void *h, size_t d, size_t s, uint32_t a) { GUARD(((Emu *)h)->mul(d, s, a)) }
+int emu_sub_u32(void *h, size_t r, uint32_t a) { GUARD(((Emu *)h)->sub_u32(r, a)) }
+int emu_add(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->add(d, s)) }
+int emu_sub_reg(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->sub_reg(d, s)) }
+int emu_get_digits(void *h, size_t s, uint64_t *enc) { GUARD(((Emu *)h)->get_digits(s, (u64 *)enc)) }
+int emu_set_digits(void *h, size_t d, const uint64_t *enc) { GUARD(((Emu *)h)->set_digits(d, (const u64 *)enc)) }
+int emu_equal(void *h, size_t l, size_t r, int *out) { GUARD(*out = ((Emu *)h)->equal(l, r) ? 1 : 0) }
+size_t emu_transform_size(uint32_t p) { return transform_size(p); }
+}

@@ -1,0 +1,131 @@
+"""CPU tier: the product's kernel phase functions and host logic (prmers_b200/csrc) executed by the
+thread-by-thread emulator in tests/emu, checked against the oracle and big-int arithmetic.  This
+validates indexing / twiddles / carries without a GPU; the GPU tier (test_gpu_parity.py) repeats the
+same comparisons through the C-ABI on the real kernels."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import marin_oracle as mo
+from oracle import mersenne_ref as mr
+from tests.emu.emu import EmuEngine, lib
+
+
+def val(e, r):
+    v = mo.digits_to_int(e.get_digits(r))
+    return v % ((1 << e.p) - 1)
+
+
+def put(e, r, x, wd):
+    e.set_digits(r, mo.int_to_digits(x, wd))
+
+
+# (exponent, forced contiguous block S; 0 = planner's choice)
+CASES = [(31, 0), (89, 0), (127, 0), (521, 0), (701, 0), (1279, 0), (3217, 0), (9941, 0), (86243, 0), (216091, 0),
+         (9941, 16), (86243, 8), (86243, 64), (86243, 256), (216091, 64), (216091, 128), (1362763, 0)]
+
+
+@pytest.mark.parametrize("p,force_S", CASES)
+def test_register_ops_match_bigint(p, force_S):
+    e = EmuEngine(p, 6, force_S)
+    assert e.n == mo.transform_size(p)
+    wd = mo.widths(e.n, p)
+    m = mr.mp(p)
+    rng = random.Random(p * 7 + force_S)
+    x, y = rng.randrange(m), rng.randrange(m)
+    put(e, 0, x, wd); put(e, 1, y, wd)
+    assert val(e, 0) == x and val(e, 1) == y
+    e.set_multiplicand(2, 1)
+    assert val(e, 1) == y                                   # src untouched
+    a = min(3, e.a_max)
+    e.mul(0, 2, a); x = x * y * a % m
+    assert val(e, 0) == x
+    e.mul(0, 2); x = x * y % m                                # multiplicand reusable
+    assert val(e, 0) == x
+    e.square_mul(0, a); x = x * x * a % m
+    assert val(e, 0) == x
+    e.square_mul(0); x = x * x % m
+    assert val(e, 0) == x
+    e.add(0, 1); x = (x + y) % m
+    assert val(e, 0) == x
+    e.sub_reg(0, 1); e.sub_reg(0, 1); x = (x - 2 * y) % m
+    assert val(e, 0) == x
+    e.sub(0, 2); x = (x - 2) % m
+    assert val(e, 0) == x
+    e.add(0, 0); x = 2 * x % m
+    assert val(e, 0) == x
+    e.copy(3, 0); e.set(4, 0); e.sub(4, 5)
+    assert val(e, 3) == x and val(e, 4) == (m - 5) % m
+    e.set(5, 0xFFFFFFFF)
+    assert val(e, 5) == 0xFFFFFFFF % m
+    e.set_multiplicand(3, 3)                                  # in place (engine.h:162)
+    e.set(4, 1); e.mul(4, 3)
+    assert val(e, 4) == x
+    e.square_mul(0); x = x * x % m                            # still fine after the linear ops
+    assert val(e, 0) == x
+
+
+@pytest.mark.parametrize("p,force_S", [(127, 0), (9941, 0), (9941, 16), (86243, 64), (216091, 64)])
+def test_digits_bit_exact_vs_oracle(p, force_S):
+    """Canonical digits (value | width << 32) equal the oracle's digit for digit."""
+    e, o = EmuEngine(p, 2, force_S), mo.OracleEngine(p, 2)
+    e.set(0, 3); o.set(0, 3)
+    for i in range(40):
+        a = 3 if (i % 3 == 0 and e.a_max >= 3) else 1
+        e.square_mul(0, a); o.square_mul(0, a)
+    assert np.array_equal(e.get_digits(0), o.get_digits(0))
+    e.sub(0, 2); o.sub(0, 2)
+    assert np.array_equal(e.get_digits(0), o.get_digits(0))
+
+
+def test_extreme_digits_do_not_overflow():
+    """All-ones digits (value 2^p - 1 == 0) and the largest canonical values: the headroom rule
+    n (2^(w+1) - 1)^2 < P of ibdwt.h:28-30 must hold through the transform and carry."""
+    for p, fs in [(127, 0), (86243, 0), (86243, 64), (216091, 64), (161051, 0)]:
+        e = EmuEngine(p, 3, fs)
+        wd = mo.widths(e.n, p)
+        m = mr.mp(p)
+        ones = (np.uint64(1) << wd.astype(np.uint64)) - np.uint64(1)
+        e.set_digits(0, ones | (wd.astype(np.uint64) << np.uint64(32)))
+        e.square_mul(0)
+        assert val(e, 0) == 0
+        x = m - 1
+        put(e, 1, x, wd)
+        e.square_mul(1)
+        assert val(e, 1) == 1
+        e.set_multiplicand(2, 1); e.mul(1, 2)
+        assert val(e, 1) == 1
+
+
+def test_m127_lucas_lehmer_and_prp():
+    e = EmuEngine(127, 2)
+    e.set(0, 4)
+    for _ in range(125):
+        e.square_mul(0); e.sub(0, 2)
+    assert val(e, 0) == 0
+    e.set(1, 3)
+    for _ in range(127):
+        e.square_mul(1)
+    assert val(e, 1) == 9
+
+
+def test_m11213_interim_res64_first_thousand():
+    e = EmuEngine(11213, 1)
+    e.set(0, 3)
+    for _ in range(1000):
+        e.square_mul(0)
+    assert mr.res64_hex(val(e, 0)) == "FBA631FBCB73A011"        # unit_tests.sh:164-187
+
+
+def test_planner_and_limits():
+    L = lib()
+    for p in (31, 127, 701, 86243, 1362763, 136279841, 175000001, 205271257):
+        assert L.emu_transform_size(p) == mo.transform_size(p)
+    e = EmuEngine(127, 2)
+    with pytest.raises(RuntimeError):
+        e.square_mul(0, 0)
+    with pytest.raises(RuntimeError):
+        e.copy(0, 9)
+    with pytest.raises(ValueError):
+        EmuEngine(2, 1)
