@@ -18,7 +18,7 @@ using namespace marin;
 
 // ------------------------------------------------------------------ kernels
 
-__global__ void __launch_bounds__(512) k_mid(const __grid_constant__ MidArgs A)
+__global__ void __launch_bounds__(512, 2) k_mid(const __grid_constant__ MidArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(512) k_mid(const __grid_constant__ MidArgs A)
 	}
 }
 
-template <bool INV> __global__ void __launch_bounds__(512) k_strided(const __grid_constant__ StridedArgs A)
+template <bool INV> __global__ void __launch_bounds__(1024, 1) k_strided(const __grid_constant__ StridedArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
@@ -206,6 +206,24 @@ static void bench_square_mul(Eng *e, size_t r, uint32_t a, uint32_t count, float
 }
 
 int mb200_bench_square_mul(void *eng, size_t r, uint32_t a, uint32_t count, float *ms) { GUARD(bench_square_mul(E(eng), r, a, count, ms)); }
+
+static void bench_pass(Eng *e, size_t r, int which, uint32_t count, float *ms)
+{
+	e->be.use();
+	cudaEvent_t t0;
+	cudaEvent_t t1;
+	CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+	if (!e->run_pass(r, which)) throw std::runtime_error("marin_b200: this engine has no such pass");
+	CK(cudaEventRecord(t0, e->be.st));
+	for (uint32_t i = 0; i < count; ++i) e->run_pass(r, which);
+	CK(cudaEventRecord(t1, e->be.st));
+	CK(cudaEventSynchronize(t1));
+	CK(cudaEventElapsedTime(ms, t0, t1));
+	cudaEventDestroy(t0); cudaEventDestroy(t1);
+}
+
+int mb200_bench_pass(void *eng, size_t r, int which, uint32_t count, float *ms) { GUARD(bench_pass(E(eng), r, which, count, ms)); }
+int mb200_is_single_cta(void *eng) { return (eng && E(eng)->pl.small) ? 1 : 0; }
 
 uint64_t mb200_launch_count(void *eng) { return eng ? E(eng)->be.launches : 0; }
 

@@ -143,6 +143,24 @@ public:
 	void get_all(void *buf) { be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
 	void set_all(const void *buf) { be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
 
+	// single passes of square_mul, for per-kernel timing (3-pass engines only): 0 strided forward,
+	// 1 contiguous middle, 2 strided inverse + carry, 3 carry fix-up
+	bool run_pass(size_t r, int which)
+	{
+		check(r);
+		if (pl.small) { if (which != 1) return false; MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
+		StridedArgs A;
+		std::memset(&A, 0, sizeof(A));
+		fill_strided_args(pl, A);
+		A.t = _t; A.src = (const pair_t *)R(r); A.dst = (pair_t *)R(r); A.a = 1; A.carry = _carry;
+		const size_t smem = (size_t)pl.R * TILE_C * 16;
+		if (which == 0) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return true; }
+		if (which == 1) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
+		if (which == 2) { A.with_carry = 1; be.strided_inv(A, A.tiles, pl.thrStr, smem); return true; }
+		if (which == 3) { FixArgs F{_t, R(r), _carry, pl.R, pl.S, A.tiles}; be.fixup(F, pl.R * A.tiles); return true; }
+		return false;
+	}
+
 	u32 width(u32 k) const { return pl.wbase + ((_wbits[k >> 5] >> (k & 31)) & 1u); }
 	u64 *R(size_t r) { return _reg + r * (size_t)pl.n; }
 	const Tables &tables() const { return _t; }

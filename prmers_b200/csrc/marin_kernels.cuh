@@ -66,20 +66,25 @@ HD u64 boundary_tw(const Tables &t, u64 e, bool inv)
 
 // ------------------------------------------------------------------ views
 
-// Addressing of one FFT dimension.  kind 0: global/linear with element stride; kind 1: shared, padded
-// one pair per 16 (contiguous pass); kind 2: shared tile [row][8] with XOR-swizzled columns.
+// Addressing of one FFT dimension for ONE lane of the pairs (lane 0 = even digit, 1 = odd digit).
+// kind 0: global/linear with pair stride; kind 1: shared, padded one pair per 16 (contiguous pass);
+// kind 2: shared tile [row][8] with XOR-swizzled columns.  Adjacent threads take the two lanes of the
+// same pair, so a warp touches 16 consecutive pairs = 256 contiguous bytes.
 struct View
 {
-	pair_t *p; u32 kind; u32 stride; u32 col;
-	HD size_t idx(u32 i) const
+	u64 *p; u32 kind; u32 stride; u32 col; u32 lane;
+	HD size_t pidx(u32 i) const
 	{
 		if (kind == 0) return (size_t)i * stride;
 		if (kind == 1) return i + (i >> 4);
 		return (size_t)i * TILE_C + (col ^ (i & (TILE_C - 1)));
 	}
-	HD pair_t ld(u32 i) const { return p[idx(i)]; }
-	HD void st(u32 i, pair_t v) const { p[idx(i)] = v; }
+	HD u64 ld(u32 i) const { return p[2 * pidx(i) + lane]; }
+	HD void st(u32 i, u64 v) const { p[2 * pidx(i) + lane] = v; }
 };
+
+// whole pairs in the same layouts (pointwise stage, carry, tile store)
+HD size_t pair_index(u32 kind, u32 i, u32 col) { return (kind == 1) ? (size_t)(i + (i >> 4)) : (size_t)i * TILE_C + (col ^ (i & (TILE_C - 1))); }
 
 HD u32 smem_pairs_lin(u32 S) { return S + (S >> 4) + 1; }
 
@@ -178,49 +183,35 @@ template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
 template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 base, u32 s, u32 j, const Tw &tw,
 	const u64 *c5, const Boundary *bd)
 {
-	u64 a[R], b[R];
-	if (R == 16)
-	{
-		for (u32 q = 0; q < R; ++q)
-		{
-			const pair_t v = in.ld(base + s * q);
-			const u32 slot = INV ? sw16(q) : q;
-			a[slot] = v.x; b[slot] = v.y;
-		}
-	}
-	else for (u32 q = 0; q < R; ++q) { const pair_t v = in.ld(base + s * q); a[q] = v.x; b[q] = v.y; }
+	u64 a[R];
+	for (u32 q = 0; q < R; ++q) a[INV ? slot_of<R>(q) : q] = in.ld(base + s * q);
 
 	if (INV && bd)
 		for (u32 q = 0; q < R; ++q)
 		{
 			const u64 f = boundary_tw(*bd->t, (u64)bd->t->rowK[base + s * q] * bd->colscale, true);
-			const u32 sl = slot_of<R>(q); a[sl] = gl::mul(a[sl], f); b[sl] = gl::mul(b[sl], f);
+			const u32 sl = slot_of<R>(q); a[sl] = gl::mul(a[sl], f);
 		}
 
 	if (INV && j != 0 && tw.tab)
-		for (u32 k = 1; k < R; ++k) { const u64 t = tw_get(tw, j, k, true); const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], t); b[sl] = gl::mul(b[sl], t); }
+		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw_get(tw, j, k, true)); }
 
-	if (R == 16) { dft16<INV>(a); dft16<INV>(b); }
-	else if (R == 4) { dft4<INV>(a[0], a[1], a[2], a[3]); dft4<INV>(b[0], b[1], b[2], b[3]); }
-	else if (R == 2) { dft2<INV>(a[0], a[1]); dft2<INV>(b[0], b[1]); }
-	else if (R == 5) { dft5(a, c5); dft5(b, c5); }
+	if (R == 16) dft16<INV>(a);
+	else if (R == 4) dft4<INV>(a[0], a[1], a[2], a[3]);
+	else if (R == 2) dft2<INV>(a[0], a[1]);
+	else if (R == 5) dft5(a, c5);
 
 	if (!INV && j != 0 && tw.tab)
-		for (u32 k = 1; k < R; ++k) { const u64 t = tw_get(tw, j, k, false); const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], t); b[sl] = gl::mul(b[sl], t); }
+		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw_get(tw, j, k, false)); }
 
 	if (!INV && bd)
 		for (u32 k = 0; k < R; ++k)
 		{
 			const u64 f = boundary_tw(*bd->t, (u64)bd->t->rowK[base + s * k] * bd->colscale, false);
-			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f); b[sl] = gl::mul(b[sl], f);
+			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f);
 		}
 
-	for (u32 k = 0; k < R; ++k)
-	{
-		const u32 sl = INV ? k : slot_of<R>(k);
-		pair_t v; v.x = a[sl]; v.y = b[sl];
-		out.st(base + s * k, v);
-	}
+	for (u32 k = 0; k < R; ++k) out.st(base + s * k, a[INV ? k : slot_of<R>(k)]);
 }
 
 // ------------------------------------------------------------------ pointwise, modulo (t^2 - u)
@@ -240,38 +231,6 @@ HD pair_t mul22(pair_t v, pair_t y, u64 u)
 	r.x = gl::add(gl::mul(v.x, y.x), gl::mul(gl::mul(v.y, y.y), u));
 	r.y = gl::add(gl::mul(v.x, y.y), gl::mul(v.y, y.x));
 	return r;
-}
-
-// Last forward stage + pointwise + first inverse stage on one block of R consecutive positions
-// (s = 1, so no twiddles).  MODE_FWD stops after the forward butterfly (multiplicand form).
-template <int R> HD void bfly_mid(const View &in, const View &out, u32 base, int mode, const u64 *colroot /* at base */,
-	u64 rowroot, bool use_rowroot, const pair_t *ymul /* at base, or null */, const u64 *c5, const u64 *c5i)
-{
-	u64 a[R], b[R];
-	for (u32 q = 0; q < R; ++q) { const pair_t v = in.ld(base + q); a[q] = v.x; b[q] = v.y; }
-	if (R == 16) { dft16<false>(a); dft16<false>(b); }
-	else if (R == 4) { dft4<false>(a[0], a[1], a[2], a[3]); dft4<false>(b[0], b[1], b[2], b[3]); }
-	else if (R == 2) { dft2<false>(a[0], a[1]); dft2<false>(b[0], b[1]); }
-	else if (R == 5) { dft5(a, c5); dft5(b, c5); }
-	if (mode == MODE_FWD)
-	{
-		for (u32 k = 0; k < R; ++k) { const u32 sl = slot_of<R>(k); pair_t v; v.x = a[sl]; v.y = b[sl]; out.st(base + k, v); }
-		return;
-	}
-	// output k sits in slot_of(k); its position is base + k
-	for (u32 k = 0; k < R; ++k)
-	{
-		const u32 sl = slot_of<R>(k);
-		const u64 u = use_rowroot ? gl::mul(rowroot, colroot[k]) : colroot[k];
-		pair_t v; v.x = a[sl]; v.y = b[sl];
-		v = (mode == MODE_SQR) ? sqr22(v, u) : mul22(v, ymul[k], u);
-		a[sl] = v.x; b[sl] = v.y;
-	}
-	if (R == 16) { dft16<true>(a); dft16<true>(b); }
-	else if (R == 4) { dft4<true>(a[0], a[1], a[2], a[3]); dft4<true>(b[0], b[1], b[2], b[3]); }
-	else if (R == 2) { dft2<true>(a[0], a[1]); dft2<true>(b[0], b[1]); }
-	else if (R == 5) { dft5(a, c5i); dft5(b, c5i); }
-	for (u32 q = 0; q < R; ++q) { pair_t v; v.x = a[q]; v.y = b[q]; out.st(base + q, v); }
 }
 
 // ------------------------------------------------------------------ carry
@@ -357,82 +316,72 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 // tid's share of phase ph.  GPU: `for ph: phase(ph, threadIdx.x); __syncthreads();`  Emulator:
 // `for ph: for tid: phase(ph, tid)`.
 
-template <int R, bool INV> HD void run_stage_lin(const View &in, const View &out, const Stage &sg, const Tw &tw, u32 S, u32 tid, u32 nthr, const Tables &t)
+template <int R, bool INV> HD void run_stage_lin(View in, View out, const Stage &sg, const Tw &tw, u32 S, u32 tid, u32 nthr, const Tables &t)
 {
-	const u32 nb = S / R;
+	const u32 nb = 2 * (S / R); // butterflies x lanes
 	for (u32 b = tid; b < nb; b += nthr)
 	{
-		const u32 blk = b / sg.s, j = b % sg.s;
+		const u32 lane = b & 1, rb = b >> 1;
+		const u32 blk = rb / sg.s, j = rb % sg.s;
+		in.lane = lane; out.lane = lane;
 		bfly<R, INV>(in, out, blk * sg.L + j, sg.s, j, tw, INV ? t.w5i : t.w5, nullptr);
 	}
 }
 
+template <bool INV> HD void dispatch_stage_lin(const View &in, const View &out, const Stage &sg, const Tw &tw, u32 S, u32 tid, u32 nthr, const Tables &t)
+{
+	switch (sg.radix)
+	{
+	case 16: run_stage_lin<16, INV>(in, out, sg, tw, S, tid, nthr, t); break;
+	case 4: run_stage_lin<4, INV>(in, out, sg, tw, S, tid, nthr, t); break;
+	case 2: run_stage_lin<2, INV>(in, out, sg, tw, S, tid, nthr, t); break;
+	case 5: run_stage_lin<5, INV>(in, out, sg, tw, S, tid, nthr, t); break;
+	}
+}
+
 // ---- contiguous pass -------------------------------------------------------------------------
-// phases: 0 .. nst-2 forward stages, nst-1 middle, nst .. 2 nst - 2 inverse stages,
-// then for small engines: carry, absorb+store.
-HD u32 mid_num_phases(const MidArgs &A) { return (A.mode == MODE_FWD) ? A.nst : (2 * A.nst - 1 + (A.small ? 2 : 0)); }
+// phases: 0 .. nst-1 forward stages (the last has s = 1: no twiddles), nst pointwise on pairs,
+// nst+1 .. 2 nst inverse stages, then for single-CTA engines: carry, absorb + store.
+HD u32 mid_num_phases(const MidArgs &A) { return (A.mode == MODE_FWD) ? A.nst : (2 * A.nst + 1 + (A.small ? 2 : 0)); }
 
 HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc)
 {
 	const Tables &t = A.t;
 	const u32 S = A.S, nst = A.nst;
 	pair_t *xg = A.x + (size_t)blk * S;
-	View G{xg, 0, 1, 0}, Sv{sm, 1, 1, 0};
-	if (ph + 1 < nst)
+	const View G{(u64 *)xg, 0, 1, 0, 0}, Sv{(u64 *)sm, 1, 1, 0, 0};
+	if (ph < nst)
 	{
 		const Stage &sg = A.st[ph];
 		const Tw tw{t.twS, t.S, t.S / sg.L};
-		const View &in = (ph == 0) ? G : Sv;
-		switch (sg.radix)
-		{
-		case 16: run_stage_lin<16, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
-		case 4: run_stage_lin<4, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
-		case 2: run_stage_lin<2, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
-		case 5: run_stage_lin<5, false>(in, Sv, sg, tw, S, tid, nthr, t); break;
-		}
+		const View Gd{(u64 *)(A.dst + (size_t)blk * S), 0, 1, 0, 0};
+		dispatch_stage_lin<false>((ph == 0) ? G : Sv, (A.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
-	if (ph == nst - 1)
+	if (ph == nst)
 	{
-		const Stage &sg = A.st[nst - 1];
-		const View &in = (nst == 1) ? G : Sv;
-		View Gd{A.dst + (size_t)blk * S, 0, 1, 0};
-		const View &out = (A.mode == MODE_FWD) ? Gd : ((nst == 1 && !A.small) ? G : Sv);
-		const u32 R = sg.radix, nb = S / R;
+		// pointwise square / multiply of the pairs modulo (t^2 - u), u = w_m^freq(position)
 		const u64 rr = A.use_rowroot ? t.rowroot[blk] : 1;
-		for (u32 b = tid; b < nb; b += nthr)
+		for (u32 i = tid; i < S; i += nthr)
 		{
-			const u64 *cr = t.colroot + b * R;
-			const pair_t *ym = (A.mode == MODE_MUL) ? A.y + (size_t)blk * S + b * R : nullptr;
-			const bool ur = A.use_rowroot != 0;
-			switch (R)
-			{
-			case 16: bfly_mid<16>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
-			case 4: bfly_mid<4>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
-			case 2: bfly_mid<2>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
-			case 5: bfly_mid<5>(in, out, b * R, A.mode, cr, rr, ur, ym, t.w5, t.w5i); break;
-			}
+			const u64 cr = t.colroot[i];
+			const u64 u = A.use_rowroot ? gl::mul(rr, cr) : cr;
+			pair_t &v = sm[pair_index(1, i, 0)];
+			v = (A.mode == MODE_SQR) ? sqr22(v, u) : mul22(v, A.y[(size_t)blk * S + i], u);
 		}
 		return;
 	}
-	if (ph < 2 * nst - 1)
+	if (ph <= 2 * nst)
 	{
-		const u32 si = 2 * nst - 2 - ph; // nst-2 .. 0
+		const u32 si = 2 * nst - ph; // nst-1 .. 0
 		const Stage &sg = A.st[si];
 		const Tw tw{t.twS, t.S, t.S / sg.L};
-		const View &out = (si == 0 && !A.small) ? G : Sv;
-		switch (sg.radix)
-		{
-		case 16: run_stage_lin<16, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
-		case 4: run_stage_lin<4, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
-		case 2: run_stage_lin<2, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
-		case 5: run_stage_lin<5, true>(Sv, out, sg, tw, S, tid, nthr, t); break;
-		}
+		dispatch_stage_lin<true>(Sv, (si == 0 && !A.small) ? G : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
 	// ---- small engines only: whole register is in shared memory (natural order)
 	const u32 D = A.D, nruns = t.n / D;
-	if (ph == 2 * nst - 1)
+	if (ph == 2 * nst + 1)
 	{
 		for (u32 r = tid; r < nruns; r += nthr)
 		{
@@ -440,12 +389,12 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 			const u32 j0 = r * D;
 			for (u32 i = 0; i < D; i += 2)
 			{
-				const pair_t pv = Sv.ld((j0 + i) >> 1);
+				const pair_t pv = sm[pair_index(1, (j0 + i) >> 1, 0)];
 				v[i] = gl::mul(gl::mul(pv.x, t.winv_nat[j0 + i]), t.inv_m);
 				v[i + 1] = gl::mul(gl::mul(pv.y, t.winv_nat[j0 + i + 1]), t.inv_m);
 			}
 			smc[r] = carry_run(v, D, t.wbase, run_bits(t, j0, D), A.a, 0);
-			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; Sv.st((j0 + i) >> 1, pv); }
+			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; sm[pair_index(1, (j0 + i) >> 1, 0)] = pv; }
 		}
 		return;
 	}
@@ -453,7 +402,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 	{
 		u64 v[RUN];
 		const u32 j0 = r * D;
-		for (u32 i = 0; i < D; i += 2) { const pair_t pv = Sv.ld((j0 + i) >> 1); v[i] = pv.x; v[i + 1] = pv.y; }
+		for (u32 i = 0; i < D; i += 2) { const pair_t pv = sm[pair_index(1, (j0 + i) >> 1, 0)]; v[i] = pv.x; v[i + 1] = pv.y; }
 		carry_absorb(v, (D < 4) ? D : 4, t.wbase, run_bits(t, j0, D), smc[(r == 0) ? nruns - 1 : r - 1]);
 		for (u32 i = 0; i < D; i += 2)
 		{
@@ -471,30 +420,21 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 	pair_t *sm, u32 tid, u32 nthr, bool out_smem_always)
 {
 	const Tables &t = A.t;
-	const u32 nb = (A.R / R) * TILE_C;
+	const u32 nb = (A.R / R) * TILE_C * 2;
 	const Tw tw{t.twR, t.R, t.R / sg.L};
 	for (u32 b = tid; b < nb; b += nthr)
 	{
-		const u32 c = b & (TILE_C - 1), rb = b >> 3;
+		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b >> 4;
 		const u32 blk = rb / sg.s, j = rb % sg.s;
 		const u32 base = blk * sg.L + j;
-		View Gi{const_cast<pair_t *>(A.src) + blockbase + c0 + c, 0, A.stride, 0};
-		View Go{A.dst + blockbase + c0 + c, 0, A.stride, 0};
-		View Sv{sm, 2, 0, c};
+		const View Gi{(u64 *)(const_cast<pair_t *>(A.src) + blockbase + c0 + c), 0, A.stride, 0, lane};
+		const View Go{(u64 *)(A.dst + blockbase + c0 + c), 0, A.stride, 0, lane};
+		const View Sv{(u64 *)sm, 2, 0, c, lane};
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale};
 		if (!INV)
-		{
-			const View &in = first ? Gi : Sv;
-			const View &out = last ? Go : Sv;
-			bfly<R, false>(in, out, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
-		}
-		else
-		{
-			// inverse order: the stage that is `last` in forward order comes first and reads global
-			const View &in = last ? Gi : Sv;
-			const View &out = (first && !out_smem_always) ? Go : Sv;
-			bfly<R, true>(in, out, base, sg.s, j, tw, t.w5i, last ? &bd : nullptr);
-		}
+			bfly<R, false>(first ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
+		else // inverse order: the stage that is `last` in forward order comes first and reads global
+			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, last ? &bd : nullptr);
 	}
 }
 
@@ -526,11 +466,9 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
 			u64 v[RUN];
-			View Sv{sm, 2, 0, 0};
 			for (u32 c = 0; c < TILE_C; ++c)
 			{
-				Sv.col = c;
-				const pair_t pv = Sv.ld(row);
+				const pair_t pv = sm[pair_index(2, row, c)];
 				v[2 * c] = gl::mul(pv.x, t.winvs_perm[perm_index(A.R, g, 2 * c, row)]);
 				v[2 * c + 1] = gl::mul(pv.y, t.winvs_perm[perm_index(A.R, g, 2 * c + 1, row)]);
 			}
@@ -542,8 +480,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 				pair_t pv;
 				pv.x = gl::mul(v[2 * c], t.w_perm[perm_index(A.R, g, 2 * c, row)]);
 				pv.y = gl::mul(v[2 * c + 1], t.w_perm[perm_index(A.R, g, 2 * c + 1, row)]);
-				Sv.col = c;
-				Sv.st(row, pv);
+				sm[pair_index(2, row, c)] = pv;
 			}
 		}
 		return;
@@ -552,8 +489,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 	for (u32 e = tid; e < A.R * TILE_C; e += nthr)
 	{
 		const u32 row = e >> 3, c = e & 7;
-		View Sv{sm, 2, 0, c};
-		A.dst[blockbase + (size_t)row * A.stride + c0 + c] = Sv.ld(row);
+		A.dst[blockbase + (size_t)row * A.stride + c0 + c] = sm[pair_index(2, row, c)];
 	}
 }
 

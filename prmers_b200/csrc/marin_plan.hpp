@@ -73,7 +73,7 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0)
 		pl.small = true; pl.S = m; pl.R = 1;
 		pl.nstS = factor_stages(m, pl.stS, true);
 		pl.nstR = 0;
-		pl.thrMid = round_threads(m / 16, 512);
+		pl.thrMid = round_threads(m / 8, 512);
 	}
 	else
 	{
@@ -90,9 +90,9 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0)
 		}
 		pl.nstS = factor_stages(pl.S, pl.stS, true);
 		pl.nstR = factor_stages(pl.R, pl.stR, false);
-		pl.thrMid = round_threads(pl.S / 16, 512);
-		const u32 bf = pl.R * TILE_C / 16; // radix-16 butterflies per stage
-		pl.thrStr = (bf <= 512) ? round_threads(bf, 512) : round_threads(bf / 2, 512);
+		pl.thrMid = round_threads(pl.S / 8, 512);
+		const u32 bf = pl.R * TILE_C * 2 / 16; // radix-16 butterflies x lanes per stage
+		pl.thrStr = (bf <= 1024) ? round_threads(bf, 1024) : round_threads(bf / 2, 1024);
 	}
 	pl.D = (n % 16 == 0 && n >= 256) ? 16 : ((n % 8 == 0 && n >= 16) ? 8 : 4);
 	// a * conv < 2^(64 + w) keeps the carry out of a run below 2^64, and the carry left after three

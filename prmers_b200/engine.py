@@ -49,6 +49,8 @@ _SIGS = {
     "mb200_set_checkpoint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mb200_bench_square_mul": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "mb200_square_mul_repeat": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
+    "mb200_bench_pass": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_float)]),
+    "mb200_is_single_cta": (C.c_int, [C.c_void_p]),
     "mb200_launch_count": (C.c_uint64, [C.c_void_p]),
     "mb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "mb200_host_free": (None, [C.c_void_p]),
@@ -222,7 +224,7 @@ class Engine:
         self._ck(self._L.mb200_set_digits(self._h, dst, enc.ctypes.data, self.n))
 
     def widths(self):
-        return (self.get(0) >> np.uint64(32)).astype(np.uint8) if False else _widths(self.n, self.p)
+        return _widths(self.n, self.p)
 
     def get_mpz(self, src):
         """Value in [0, 2^p - 1): all-ones (= 2^p - 1) maps to 0 (engine.h:173-203)."""
@@ -286,6 +288,15 @@ class Engine:
         ms = C.c_float(0)
         self._ck(self._L.mb200_bench_square_mul(self._h, r, a, count, C.byref(ms)))
         return ms.value
+
+    def bench_pass(self, r, which, count):
+        """One kernel of square_mul alone (0 strided fwd, 1 middle, 2 strided inv + carry, 3 fix-up); ms."""
+        ms = C.c_float(0)
+        self._ck(self._L.mb200_bench_pass(self._h, r, which, count, C.byref(ms)))
+        return ms.value
+
+    def is_single_cta(self):
+        return bool(self._L.mb200_is_single_cta(self._h))
 
     def square_mul_repeat(self, r, count, a=1):
         self._ck(self._L.mb200_square_mul_repeat(self._h, r, a, count))
