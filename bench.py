@@ -34,7 +34,7 @@ OTHER_P = [139123459, 139246931, 139370393, 139493863, 139617329, 139740787, 139
 ITERS = 1000            # squarings per step
 METRIC = "PRP iterations/s, M136279841-class exponents (n = 2^23 IBDWT), whole job"
 PASS_NAMES = ["k_strided<0> (strided forward pass)", "k_mid (contiguous middle pass)",
-              "k_strided<1> (strided inverse pass + unweight/carry/reweight)", "k_fixup (carry fix-up)"]
+              "k_strided<1> (strided inverse pass + unweight/carry/reweight)"]
 
 
 def measured_peak():
@@ -229,7 +229,7 @@ def main():
         peak, peak_src = measured_peak()
         # per-kernel durations, live, with CUDA events on the launching stream
         passes = []
-        for which in range(4):
+        for which in range(3):
             cnt = 100
             passes.append(eng.bench_pass(1, which, cnt) / cnt)            # ms per launch
         dom = max(range(3), key=lambda i: passes[i])
@@ -238,7 +238,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"].get(["k_strided<0>", "k_mid", "k_strided<1>", "k_fixup"][dom])
+                traffic = json.load(f)["dram_bytes_per_launch"].get(["k_strided<0>", "k_mid", "k_strided<1>"][dom])
         except Exception:
             pass
         ms_iter = ms_max / (args.steps * iters)
@@ -260,7 +260,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": PASS_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": {PASS_NAMES[i]: passes[i] for i in range(4)},
+                         "kernel_ms": {PASS_NAMES[i]: passes[i] for i in range(3)},
                          "note": "integer-pipe bound, not HBM bound: see profiles/ and DESIGN.md"},
             "roofline_square_mul": {"achieved": 48 * n / (ms_iter * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": 48 * n / (ms_iter * 1e-3) / 1e9 / peak,

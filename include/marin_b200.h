@@ -75,7 +75,7 @@ int mb200_bench_square_mul(void *eng, size_t r, uint32_t a, uint32_t count, floa
 int mb200_square_mul_repeat(void *eng, size_t r, uint32_t a, uint32_t count);
 /* one kernel of square_mul alone, `count` launches timed with CUDA events (the register content is
    scrambled): which = 0 strided forward pass, 1 contiguous middle pass, 2 strided inverse pass with
-   unweight/carry/reweight, 3 carry fix-up.  Engines small enough for one CTA only have pass 1. */
+   unweight/carry/reweight (carry hand-off between tiles included).  Engines small enough for one CTA only have pass 1. */
 int mb200_bench_pass(void *eng, size_t r, int which, uint32_t count, float *ms);
 int mb200_is_single_cta(void *eng);
 /* kernel launches issued by this engine since creation (bench.py's gpu_launches) */

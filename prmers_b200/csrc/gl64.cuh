@@ -19,6 +19,12 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+#if defined(__CUDACC__)
+// 1 and -1 that ptxas cannot fold: multiplying by them turns an add into IMAD / IMAD.HI, i.e. moves it
+// from the ALU pipe (IADD3, the bottleneck of this engine) to the FMA pipe, which otherwise idles.
+__constant__ u32 GL_ONE = 1u, GL_MONE = 0xffffffffu;
+#endif
+
 namespace gl {
 
 static constexpr u64 P = 0xffffffff00000001ull;
@@ -48,12 +54,23 @@ HD u64 sub(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
 	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), d0, d1, m;
+#if defined(MARIN_SUB_IMAD)
+	// 3 ALU + 3 FMA-pipe instructions: the +P correction (d += 1 - 2^32 when borrowing) as IMADs
+	asm("sub.cc.u32 %0, %3, %5;\n\t"
+		"subc.cc.u32 %1, %4, %6;\n\t"
+		"subc.u32 %2, 0, 0;\n\t"             // m = borrow ? 0xffffffff : 0
+		"mad.lo.cc.s32 %0, %2, %8, %0;\n\t"   // d += borrow          (m * -1)
+		"madc.hi.s32 %1, %2, %8, %1;\n\t"
+		"mad.lo.u32 %1, %2, %7, %1;\n\t"      // d.hi -= borrow       (m * 1)
+		: "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(GL_ONE), "r"(GL_MONE));
+#else
 	asm("sub.cc.u32 %0, %3, %5;\n\t"
 		"subc.cc.u32 %1, %4, %6;\n\t"
 		"subc.u32 %2, 0, 0;\n\t"             // m = borrow ? 0xffffffff : 0
 		"sub.cc.u32 %0, %0, %2;\n\t"         // d -= borrow ? 2^32 - 1 : 0   (i.e. d += P)
 		"subc.u32 %1, %1, 0;\n\t"
 		: "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+#endif
 	return ((u64)d1 << 32) | d0;
 #else
 	const u64 d = a - b;
@@ -154,10 +171,12 @@ template <int K> HD u64 mul_pow2(u64 a)
 	else if constexpr (K < 64) return reduce128(a << K, a >> (64 - K));
 	else
 	{
-		// 64 <= K < 96: v = a 2^(K-64) = vh 2^64 + vl;  v 2^64 = vl 2^64 + vh 2^128, 2^128 = -2^32
+		// 64 <= K < 96, J = K - 64: a 2^J = v2 2^64 + v1 2^32 + v0, and 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32:
+		// a 2^K = v0 (2^32 - 1) - (v2 2^32 + v1)
 		constexpr int J = K - 64;
-		const u64 vl = a << J, vh = (J == 0) ? 0 : (a >> ((64 - J) & 63));
-		return sub(reduce128(0, vl), vh << 32); // vh < 2^32 so vh << 32 <= 2^64 - 2^32 < P
+		const u64 v0 = (u32)(a << J);
+		const u64 hi = (J == 0) ? (a >> 32) : (a >> ((32 - J) & 63));   // < 2^(32 + J) <= 2^63 < P
+		return sub((v0 << 32) - v0, hi);
 	}
 }
 

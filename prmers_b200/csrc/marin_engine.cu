@@ -18,7 +18,18 @@ using namespace marin;
 
 // ------------------------------------------------------------------ kernels
 
-__global__ void __launch_bounds__(512, 2) k_mid(const __grid_constant__ MidArgs A)
+#ifndef MARIN_MID_MAXT
+#define MARIN_MID_MAXT 256
+#define MARIN_MID_MINB 3
+#endif
+#ifndef MARIN_STR_MAXT
+#define MARIN_STR_MAXT 256
+#endif
+#ifndef MARIN_STR_MINB
+#define MARIN_STR_MINB 2
+#endif
+
+__global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __grid_constant__ MidArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
@@ -31,7 +42,7 @@ __global__ void __launch_bounds__(512, 2) k_mid(const __grid_constant__ MidArgs 
 	}
 }
 
-template <bool INV> __global__ void __launch_bounds__(1024, 1) k_strided(const __grid_constant__ StridedArgs A)
+template <bool INV> __global__ void __launch_bounds__(MARIN_STR_MAXT, MARIN_STR_MINB) k_strided(const __grid_constant__ StridedArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
@@ -43,11 +54,6 @@ template <bool INV> __global__ void __launch_bounds__(1024, 1) k_strided(const _
 	}
 }
 
-__global__ void k_fixup(const __grid_constant__ FixArgs A, u32 count)
-{
-	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count) fixup_thread(A, i);
-}
 __global__ void k_lin_p1(const __grid_constant__ LinArgs A, u32 count)
 {
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,10 +110,10 @@ struct CudaBackend
 	void sync() { use(); CK(cudaStreamSynchronize(st)); }
 	void post() { ++launches; CK(cudaGetLastError()); }
 
-	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_mid<<<grid, thr, smem, st>>>(A); post(); }
-	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<false><<<grid, thr, smem, st>>>(A); post(); }
-	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<true><<<grid, thr, smem, st>>>(A); post(); }
-	void fixup(const FixArgs &A, u32 count) { use(); k_fixup<<<(count + 255) / 256, 256, 0, st>>>(A, count); post(); }
+	static u32 cap(u32 thr, u32 maxt) { return thr > maxt ? maxt : thr; }
+	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_mid<<<grid, cap(thr, MARIN_MID_MAXT), smem, st>>>(A); post(); }
+	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<false><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
+	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<true><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
 	void lin_p1(const LinArgs &A, u32 count) { use(); k_lin_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void lin_p2(const LinArgs &A, u32 count) { use(); k_lin_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }

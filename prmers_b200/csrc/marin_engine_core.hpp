@@ -36,19 +36,26 @@ public:
 		t.p = pl.p; t.n = pl.n; t.m = pl.m; t.wbase = pl.wbase; t.inv_m = h.inv_m;
 		t.wbits = (const u32 *)upload(h.wbits.data(), h.wbits.size() * 4);
 		t.twS = (const u64 *)upload(h.twS.data(), h.twS.size() * 8); t.S = pl.S;
+		t.twSi = (const u64 *)upload(h.twSi.data(), h.twSi.size() * 8);
 		t.twR = (const u64 *)upload(h.twR.data(), h.twR.size() * 8); t.R = pl.R;
+		t.twRi = (const u64 *)upload(h.twRi.data(), h.twRi.size() * 8);
 		t.bl_lo = (const u64 *)upload(h.bl_lo.data(), h.bl_lo.size() * 8);
 		t.bl_hi = (const u64 *)upload(h.bl_hi.data(), h.bl_hi.size() * 8); t.bl_h = h.bl_h;
+		t.bl_loi = (const u64 *)upload(h.bl_loi.data(), h.bl_loi.size() * 8);
+		t.bl_hii = (const u64 *)upload(h.bl_hii.data(), h.bl_hii.size() * 8);
 		t.rowK = (const u32 *)upload(h.rowK.data(), h.rowK.size() * 4);
 		t.rowroot = (const u64 *)upload(h.rowroot.data(), h.rowroot.size() * 8);
 		t.colroot = (const u64 *)upload(h.colroot.data(), h.colroot.size() * 8);
 		for (int i = 0; i < 4; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
-		u64 *w_nat = (u64 *)be.alloc(n * 8), *winv_nat = (u64 *)be.alloc(n * 8), *w_perm = nullptr, *winvs_perm = nullptr;
-		_owned.push_back(w_nat); _owned.push_back(winv_nat);
-		if (!pl.small) { w_perm = (u64 *)be.alloc(n * 8); winvs_perm = (u64 *)be.alloc(n * 8); _owned.push_back(w_perm); _owned.push_back(winvs_perm); }
-		WeightArgs W{pl.p, pl.n, pl.m, pl.R, pl.S, pl.S / TILE_C, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, w_perm, winvs_perm, pl.small ? 0u : 1u};
+		u64 *w_nat = (u64 *)be.alloc(n * 8), *winv_nat = (u64 *)be.alloc(n * 8), *winvs_nat = (u64 *)be.alloc(n * 8);
+		_owned.push_back(w_nat); _owned.push_back(winv_nat); _owned.push_back(winvs_nat);
+		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat};
 		be.weights(W, pl.n);
-		t.w_nat = w_nat; t.winv_nat = winv_nat; t.w_perm = w_perm; t.winvs_perm = winvs_perm;
+		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat;
+		const size_t nflags = 2 * (size_t)(pl.S / TILE_C) + 1;
+		_flags = (u32 *)be.alloc(nflags * 4);
+		be.memset0(_flags, nflags * 4);
+		_nflags = nflags;
 		be.sync();
 	}
 
@@ -56,12 +63,21 @@ public:
 	{
 		be.sync();
 		for (void *p : _owned) be.free(p);
-		be.free(_reg); be.free(_carry); be.free(_scratch);
+		be.free(_reg); be.free(_carry); be.free(_scratch); be.free(_flags);
 	}
 
 	size_t size() const { return pl.n; }
 	size_t regs() const { return _regs; }
-	void sync() { be.sync(); }
+	void sync()
+	{
+		be.sync();
+		if (_flags)
+		{
+			u32 err = 0;
+			be.d2h(&err, _flags + (_nflags - 1), 4);
+			if (err) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
+		}
+	}
 
 	void set_u32(size_t dst, u32 a)
 	{
@@ -153,11 +169,11 @@ public:
 		std::memset(&A, 0, sizeof(A));
 		fill_strided_args(pl, A);
 		A.t = _t; A.src = (const pair_t *)R(r); A.dst = (pair_t *)R(r); A.a = 1; A.carry = _carry;
-		const size_t smem = (size_t)pl.R * TILE_C * 16;
+		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
 		if (which == 0) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return true; }
 		if (which == 1) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
-		if (which == 2) { A.with_carry = 1; be.strided_inv(A, A.tiles, pl.thrStr, smem); return true; }
-		if (which == 3) { FixArgs F{_t, R(r), _carry, pl.R, pl.S, A.tiles}; be.fixup(F, pl.R * A.tiles); return true; }
+		if (which == 2 || which >= 100) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.dbg = (which >= 100) ? (u32)(which - 100) : 0; be.strided_inv(A, A.tiles, pl.thrStr, smem); return true; }
+		if (which == 4) { A.with_carry = 0; be.strided_inv(A, A.tiles, pl.thrStr, smem); return true; } // plain inverse pass (timing aid)
 		return false;
 	}
 
@@ -168,6 +184,8 @@ public:
 private:
 	size_t _regs;
 	u64 *_reg = nullptr, *_carry = nullptr, *_scratch = nullptr;
+	u32 *_flags = nullptr, _epoch = 0;
+	size_t _nflags = 0;
 	Tables _t;
 	std::vector<u32> _wbits;
 	std::vector<void *> _owned;
@@ -223,11 +241,16 @@ private:
 		std::memset(&A, 0, sizeof(A));
 		fill_strided_args(pl, A);
 		A.t = _t; A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.carry = _carry; A.with_carry = inv ? 1 : 0;
-		const size_t smem = (size_t)pl.R * TILE_C * 16;
+		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
 		if (!inv) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return; }
+		A.flags = _flags; A.epoch = next_epoch();
 		be.strided_inv(A, A.tiles, pl.thrStr, smem);
-		FixArgs F{_t, dst, _carry, pl.R, pl.S, A.tiles};
-		be.fixup(F, pl.R * A.tiles);
+	}
+
+	u32 next_epoch()
+	{
+		if (++_epoch == 0) { be.memset0(_flags, _nflags * 4); _epoch = 1; } // wrapped: start over from clean flags
+		return _epoch;
 	}
 
 	void lin(int op, size_t dst, size_t src, u32 a, const u64 *digits)

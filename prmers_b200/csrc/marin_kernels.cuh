@@ -21,11 +21,30 @@ typedef ulonglong2 pair_t;
 struct alignas(16) pair_t { u64 x, y; };
 #endif
 
+// inter-CTA hand-off primitives (carry look-back in the strided inverse pass); the emulator runs the
+// CTAs one after the other in order, so plain accesses are enough there.
+#if defined(__CUDA_ARCH__)
+#define MARIN_FENCE() __threadfence()
+#define MARIN_LD_VOLATILE_U32(p) (*(volatile const unsigned int *)(p))
+#define MARIN_ST_VOLATILE_U32(p, v) (*(volatile unsigned int *)(p) = (v))
+#define MARIN_LD_CG_U64(p) __ldcg((const unsigned long long *)(p))
+#else
+#define MARIN_FENCE() ((void)0)
+#define MARIN_LD_VOLATILE_U32(p) (*(const unsigned int *)(p))
+#define MARIN_ST_VOLATILE_U32(p, v) (*(unsigned int *)(p) = (v))
+#define MARIN_LD_CG_U64(p) (*(const unsigned long long *)(p))
+#endif
+
 namespace marin {
 
 static constexpr int MAX_STAGES = 8;
-static constexpr int TILE_C = 8;          // pair columns per strided tile (8 * 16 B = one 128 B line)
-static constexpr int RUN = 16;            // digits per carry run in the strided inverse pass (= 2 * TILE_C)
+#ifndef MARIN_TILE_C
+#define MARIN_TILE_C 4
+#endif
+static constexpr int TILE_C = MARIN_TILE_C; // pair columns per strided tile: 4 * 16 B = two 32 B sectors per row; small
+                                            // enough (R * 5 * 16 B) for two CTAs per SM, which overlaps load/compute/store phases
+static constexpr int RUN = 2 * TILE_C;    // digits per carry run in the strided inverse pass
+static constexpr int MAXRUN = 16;         // largest run any kernel carries in one thread
 
 enum Mode : int { MODE_SQR = 0, MODE_MUL = 1, MODE_FWD = 2 };
 
@@ -38,12 +57,12 @@ struct Tables
 	u32 wbase;                   // floor(p / n); digit j has wbase + bit_j(wbits) bits
 	const u32 *wbits;            // n bits, natural order
 	const u64 *w_nat, *winv_nat; // weight, 1/weight (natural digit order)
-	const u64 *w_perm, *winvs_perm; // weight, 1/(weight m) in strided-inverse tile order (see perm_index)
+	const u64 *winvs_nat;        // 1/(weight m): unweighting fused with the 1/m of the inverse transform
 	u64 inv_m;                   // 1/m
 	// block transforms
-	const u64 *twS; u32 S;       // S powers of the S-th root (contiguous pass), S a power of two
-	const u64 *twR; u32 R;       // R powers of the R-th root (strided pass), R = 2^a or 5 2^a
-	const u64 *bl_lo, *bl_hi; u32 bl_h; // m-th root: w^e = bl_lo[e & (2^h - 1)] * bl_hi[e >> h]
+	const u64 *twS, *twSi; u32 S; // S powers of the S-th root and of its inverse (contiguous pass)
+	const u64 *twR, *twRi; u32 R; // R powers of the R-th root and of its inverse (strided pass), R = 2^a or 5 2^a
+	const u64 *bl_lo, *bl_hi, *bl_loi, *bl_hii; u32 bl_h; // m-th root: w^(+-e) = lo[e & (2^h - 1)] * hi[e >> h]
 	const u32 *rowK;             // frequency index of row rho after the strided pass
 	const u64 *rowroot;          // w_m^rowK[rho]
 	const u64 *colroot;          // w_S^freq(sigma), position order inside a contiguous block
@@ -55,36 +74,35 @@ struct Tables
 
 HD u32 digit_width(const Tables &t, u32 j) { return t.wbase + ((t.wbits[j >> 5] >> (j & 31)) & 1u); }
 
-// index of digit i (0..15) of run (row, g) in the permuted weight tables: coalesced over rows
-HD size_t perm_index(u32 R, u32 g, u32 i, u32 row) { return ((size_t)g * RUN + i) * R + row; }
-
 HD u64 boundary_tw(const Tables &t, u64 e, bool inv)
 {
-	if (inv) e = e ? (u64)t.m - e : 0;
-	return gl::mul(t.bl_lo[e & ((1u << t.bl_h) - 1)], t.bl_hi[e >> t.bl_h]);
+	const u32 lo = (u32)e & ((1u << t.bl_h) - 1), hi = (u32)(e >> t.bl_h);
+	return inv ? gl::mul(t.bl_loi[lo], t.bl_hii[hi]) : gl::mul(t.bl_lo[lo], t.bl_hi[hi]);
 }
 
 // ------------------------------------------------------------------ views
 
-// Addressing of one FFT dimension for ONE lane of the pairs (lane 0 = even digit, 1 = odd digit).
-// kind 0: global/linear with pair stride; kind 1: shared, padded one pair per 16 (contiguous pass);
-// kind 2: shared tile [row][8] with XOR-swizzled columns.  Adjacent threads take the two lanes of the
-// same pair, so a warp touches 16 consecutive pairs = 256 contiguous bytes.
+// Addressing of one FFT dimension for ONE lane of the pairs (lane 0 = even digit, 1 = odd digit):
+// element i lives at p[2 * (i * mul + ((i >> 4) & pad))]; p already includes column and lane.
+//   global / linear:           mul = pair stride, pad = 0
+//   shared, contiguous pass:   mul = 1, pad = ~0   (one pair of padding per 16: conflict-free radix-16 stages)
+//   shared, strided tile:      mul = TILE_PITCH (9 pairs per row of 8: conflict-free row-wise carry), pad = 0
+// Adjacent threads take the two lanes of the same pair, so a warp touches 16 consecutive pairs.
+static constexpr u32 TILE_PITCH = TILE_C + 1;
 struct View
 {
-	u64 *p; u32 kind; u32 stride; u32 col; u32 lane;
-	HD size_t pidx(u32 i) const
-	{
-		if (kind == 0) return (size_t)i * stride;
-		if (kind == 1) return i + (i >> 4);
-		return (size_t)i * TILE_C + (col ^ (i & (TILE_C - 1)));
-	}
-	HD u64 ld(u32 i) const { return p[2 * pidx(i) + lane]; }
-	HD void st(u32 i, u64 v) const { p[2 * pidx(i) + lane] = v; }
+	u64 *p; u32 mul; u32 pad;
+	HD size_t pidx(u32 i) const { return (size_t)i * mul + ((i >> 4) & pad); }
+	HD u64 ld(u32 i) const { return p[2 * pidx(i)]; }
+	HD void st(u32 i, u64 v) const { p[2 * pidx(i)] = v; }
 };
+HD View view_global(const void *base, size_t pair_off, u32 stride, u32 lane) { return View{(u64 *)base + 2 * pair_off + lane, stride, 0}; }
+HD View view_lin(void *sm, u32 lane) { return View{(u64 *)sm + lane, 1, 0xffffffffu}; }
+HD View view_tile(void *sm, u32 col, u32 lane) { return View{(u64 *)sm + 2 * col + lane, TILE_PITCH, 0}; }
 
-// whole pairs in the same layouts (pointwise stage, carry, tile store)
-HD size_t pair_index(u32 kind, u32 i, u32 col) { return (kind == 1) ? (size_t)(i + (i >> 4)) : (size_t)i * TILE_C + (col ^ (i & (TILE_C - 1))); }
+// whole pairs in the shared layouts (pointwise stage, carry, tile store)
+HD size_t lin_pair(u32 i) { return i + (i >> 4); }
+HD size_t tile_pair(u32 row, u32 col) { return (size_t)row * TILE_PITCH + col; }
 
 HD u32 smem_pairs_lin(u32 S) { return S + (S >> 4) + 1; }
 
@@ -98,49 +116,59 @@ HD void addsub(u64 &a, u64 &b) // (a, b) <- (a + b, a - b)
 	b = d;
 }
 
-// 4-point DFT, natural order in and out; the 4th root of unity is 2^48 (forward) / -2^48 (inverse)
-template <bool INV> HD void dft4(u64 &x0, u64 &x1, u64 &x2, u64 &x3)
+// 4-point DFT, natural order in and out; the 4th root of unity is 2^48 (forward) / -2^48 (inverse).
+// N1, N2, N3: input k holds the NEGATION of the true value (sign folded into the butterfly for free,
+// which is how the negative shift twiddles -2^k of the 16-point transform cost nothing).
+template <bool INV, bool N1 = false, bool N2 = false, bool N3 = false> HD void dft4(u64 &x0, u64 &x1, u64 &x2, u64 &x3)
 {
-	addsub(x0, x2);                  // x0 = t0, x2 = t1
-	addsub(x1, x3);                  // x1 = t2, x3 = b - d
-	x3 = gl::mul_pow2<48>(x3);       // t3 = i (b - d)
-	addsub(x0, x1);                  // x0 = y0, x1 = y2
-	addsub(x2, x3);                  // x2 = t1 + t3, x3 = t1 - t3
-	const u64 y2 = x1;
-	if (!INV) { x1 = x2; x2 = y2; }             // y1 = t1 + t3, y3 = t1 - t3
-	else { x1 = x3; x3 = x2; x2 = y2; }         // conjugate: y1 = t1 - t3, y3 = t1 + t3
+	addsub(x0, x2);                  // (x0 + x2, x0 - x2)
+	u64 t0 = N2 ? x2 : x0, t1 = N2 ? x0 : x2;
+	addsub(x1, x3);                  // (S, D) = (x1 + x3, x1 - x3)
+	u64 t2 = (N1 != N3) ? x3 : x1, t3 = (N1 != N3) ? x1 : x3; // |X1 + X3|, |X1 - X3|; both negated iff N1
+	t3 = gl::mul_pow2<48>(t3);
+	addsub(t0, t2);                  // t0 = y0 (or y2 if negated), t2 = y2 (or y0)
+	addsub(t1, t3);                  // t1 + t3, t1 - t3
+	x0 = N1 ? t2 : t0;
+	x2 = N1 ? t0 : t2;
+	const bool swap13 = (INV != N1);
+	x1 = swap13 ? t3 : t1;           // forward: y1 = t1 + t3, y3 = t1 - t3; inverse: conjugate
+	x3 = swap13 ? t1 : t3;
 }
 
 template <bool INV> HD void dft2(u64 &x0, u64 &x1) { addsub(x0, x1); }
 
-// twiddle 2^(12 e) (forward) or its inverse, e = q0 * k0 in {1,2,3,4,6,9}
-template <bool INV, int E> HD u64 tw16(u64 v)
-{
-	if (!INV) return gl::mul_pow2<(12 * E) % 192>(v);
-	else return gl::mul_pow2<(192 - 12 * E) % 192>(v);
-}
-
 // 16-point DFT.  Forward: natural slots in, output k in slot sw(k) = 4 (k & 3) + (k >> 2).
-// Inverse: input y[k] in slot sw(k), natural slots out.  Unnormalised.
+// Inverse: input y[k] in slot sw(k), natural slots out.  Unnormalised.  The 16th root of unity is 2^12,
+// so the inner twiddles 2^(12 q k) are shifts; exponents >= 96 are -2^(e - 96) with the sign folded.
 HD constexpr u32 sw16(u32 k) { return ((k & 3) << 2) | (k >> 2); }
 
 template <bool INV> HD void dft16(u64 *x)
 {
 	if (!INV)
 	{
+		#pragma unroll
 		for (int q = 0; q < 4; ++q) dft4<false>(x[q], x[q + 4], x[q + 8], x[q + 12]);
-		x[5] = tw16<false, 1>(x[5]); x[9] = tw16<false, 2>(x[9]); x[13] = tw16<false, 3>(x[13]);
-		x[6] = tw16<false, 2>(x[6]); x[10] = tw16<false, 4>(x[10]); x[14] = tw16<false, 6>(x[14]);
-		x[7] = tw16<false, 3>(x[7]); x[11] = tw16<false, 6>(x[11]); x[15] = tw16<false, 9>(x[15]);
-		for (int k = 0; k < 4; ++k) dft4<false>(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+		// x[q + 4 k] *= 2^(12 q k)
+		x[5] = gl::mul_pow2<12>(x[5]); x[9] = gl::mul_pow2<24>(x[9]); x[13] = gl::mul_pow2<36>(x[13]);
+		x[6] = gl::mul_pow2<24>(x[6]); x[10] = gl::mul_pow2<48>(x[10]); x[14] = gl::mul_pow2<72>(x[14]);
+		x[7] = gl::mul_pow2<36>(x[7]); x[11] = gl::mul_pow2<72>(x[11]); x[15] = gl::mul_pow2<12>(x[15]); // 2^108 = -2^12
+		dft4<false>(x[0], x[1], x[2], x[3]);
+		dft4<false>(x[4], x[5], x[6], x[7]);
+		dft4<false>(x[8], x[9], x[10], x[11]);
+		dft4<false, false, false, true>(x[12], x[13], x[14], x[15]);
 	}
 	else
 	{
+		#pragma unroll
 		for (int k = 0; k < 4; ++k) dft4<true>(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
-		x[5] = tw16<true, 1>(x[5]); x[9] = tw16<true, 2>(x[9]); x[13] = tw16<true, 3>(x[13]);
-		x[6] = tw16<true, 2>(x[6]); x[10] = tw16<true, 4>(x[10]); x[14] = tw16<true, 6>(x[14]);
-		x[7] = tw16<true, 3>(x[7]); x[11] = tw16<true, 6>(x[11]); x[15] = tw16<true, 9>(x[15]);
-		for (int q = 0; q < 4; ++q) dft4<true>(x[q], x[q + 4], x[q + 8], x[q + 12]);
+		// x[q + 4 k] *= 2^(-12 q k) = -2^(96 - 12 q k) (q k = 9: +2^84); signs folded below
+		x[5] = gl::mul_pow2<84>(x[5]); x[9] = gl::mul_pow2<72>(x[9]); x[13] = gl::mul_pow2<60>(x[13]);
+		x[6] = gl::mul_pow2<72>(x[6]); x[10] = gl::mul_pow2<48>(x[10]); x[14] = gl::mul_pow2<24>(x[14]);
+		x[7] = gl::mul_pow2<60>(x[7]); x[11] = gl::mul_pow2<24>(x[11]); x[15] = gl::mul_pow2<84>(x[15]);
+		dft4<true>(x[0], x[4], x[8], x[12]);
+		dft4<true, true, true, true>(x[1], x[5], x[9], x[13]);
+		dft4<true, true, true, true>(x[2], x[6], x[10], x[14]);
+		dft4<true, true, true, false>(x[3], x[7], x[11], x[15]);
 	}
 }
 
@@ -162,21 +190,17 @@ HD void dft5(u64 *x, const u64 *c)
 // ------------------------------------------------------------------ one butterfly of one stage
 
 // Twiddle source of a stage: table of X powers of the X-th root, exponent scale = X / L.
-struct Tw { const u64 *tab; u32 X; u32 scale; };
-
-HD u64 tw_get(const Tw &tw, u32 j, u32 k, bool inv)
-{
-	u32 e = j * k * tw.scale;
-	if (inv) e = e ? tw.X - e : 0;
-	return tw.tab[e];
-}
+// tab is the forward or the inverse table according to the direction; null when s = 1 (no twiddles).
+struct Tw { const u64 *tab; u32 scale; };
 
 // Forward (DIF): y_k = sum_q x_q w_R^(qk), then y_k *= w_L^(jk); element q/k lives at base + s q/k.
 // Inverse: the exact mirror (conjugate twiddle first, then conjugate DFT), unnormalised.
 // PRE/POST: optional per-element factor applied to loaded inputs / stored outputs (boundary twiddles).
 // Boundary: per-row factor w_m^(+-rowK[row] * colscale) applied to loaded inputs (inverse) or stored
 // outputs (forward) of the stage that touches global memory in a strided pass.
-struct Boundary { const Tables *t; u64 colscale; };
+// The stage that carries the boundary twiddle is the last forward stage (s = 1): its rows base + k have
+// frequency indices K0 + k * Kstep, K0 = rowK[base], Kstep = R / radix.
+struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; };
 
 template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
 
@@ -184,33 +208,44 @@ template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 bas
 	const u64 *c5, const Boundary *bd)
 {
 	u64 a[R];
+	#pragma unroll
 	for (u32 q = 0; q < R; ++q) a[INV ? slot_of<R>(q) : q] = in.ld(base + s * q);
 
-	if (INV && bd)
+	if (INV && bd && bd->twiddle)
+		#pragma unroll
 		for (u32 q = 0; q < R; ++q)
 		{
-			const u64 f = boundary_tw(*bd->t, (u64)bd->t->rowK[base + s * q] * bd->colscale, true);
+			const u64 f = boundary_tw(*bd->t, (u64)(bd->K0 + q * bd->Kstep) * bd->colscale, true);
 			const u32 sl = slot_of<R>(q); a[sl] = gl::mul(a[sl], f);
 		}
 
-	if (INV && j != 0 && tw.tab)
-		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw_get(tw, j, k, true)); }
+	const u32 je = j * tw.scale;
+	if (INV && tw.tab)
+		#pragma unroll
+		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw.tab[je * k]); }
 
 	if (R == 16) dft16<INV>(a);
 	else if (R == 4) dft4<INV>(a[0], a[1], a[2], a[3]);
 	else if (R == 2) dft2<INV>(a[0], a[1]);
 	else if (R == 5) dft5(a, c5);
 
-	if (!INV && j != 0 && tw.tab)
-		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw_get(tw, j, k, false)); }
+	if (!INV && tw.tab)
+		#pragma unroll
+		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw.tab[je * k]); }
 
-	if (!INV && bd)
+	if (!INV && bd && bd->twiddle)
+		#pragma unroll
 		for (u32 k = 0; k < R; ++k)
 		{
-			const u64 f = boundary_tw(*bd->t, (u64)bd->t->rowK[base + s * k] * bd->colscale, false);
+			const u64 f = boundary_tw(*bd->t, (u64)(bd->K0 + k * bd->Kstep) * bd->colscale, false);
 			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f);
 		}
 
+	if (INV && bd && bd->wpost) // unweight (and scale by 1/m) the outputs of the last inverse stage: natural order, coalesced
+		#pragma unroll
+		for (u32 q = 0; q < R; ++q) a[q] = gl::mul(a[q], bd->wpost[(size_t)(base + s * q) * bd->wstride]);
+
+	#pragma unroll
 	for (u32 k = 0; k < R; ++k) out.st(base + s * k, a[INV ? k : slot_of<R>(k)]);
 }
 
@@ -309,6 +344,9 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	u32 a;              // multiplier for the carry
 	u64 *carry;         // carry[g * R + row]
 	u32 with_carry;
+	u32 *flags;         // [2 * tiles + 1]: published[g], stored[g], error; hold the epoch of the last launch
+	u32 epoch;
+	u32 dbg;            // timing experiments only (results are wrong when set): see strided_phase
 };
 
 // ------------------------------------------------------------------ phase functions
@@ -323,8 +361,9 @@ template <int R, bool INV> HD void run_stage_lin(View in, View out, const Stage 
 	{
 		const u32 lane = b & 1, rb = b >> 1;
 		const u32 blk = rb / sg.s, j = rb % sg.s;
-		in.lane = lane; out.lane = lane;
-		bfly<R, INV>(in, out, blk * sg.L + j, sg.s, j, tw, INV ? t.w5i : t.w5, nullptr);
+		View vi = in, vo = out;
+		vi.p += lane; vo.p += lane;
+		bfly<R, INV>(vi, vo, blk * sg.L + j, sg.s, j, tw, INV ? t.w5i : t.w5, nullptr);
 	}
 }
 
@@ -349,12 +388,12 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 	const Tables &t = A.t;
 	const u32 S = A.S, nst = A.nst;
 	pair_t *xg = A.x + (size_t)blk * S;
-	const View G{(u64 *)xg, 0, 1, 0, 0}, Sv{(u64 *)sm, 1, 1, 0, 0};
+	const View G = view_global(xg, 0, 1, 0), Sv = view_lin(sm, 0);
 	if (ph < nst)
 	{
 		const Stage &sg = A.st[ph];
-		const Tw tw{t.twS, t.S, t.S / sg.L};
-		const View Gd{(u64 *)(A.dst + (size_t)blk * S), 0, 1, 0, 0};
+		const Tw tw{(sg.s > 1) ? t.twS : nullptr, t.S / sg.L};
+		const View Gd = view_global(A.dst + (size_t)blk * S, 0, 1, 0);
 		dispatch_stage_lin<false>((ph == 0) ? G : Sv, (A.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
@@ -366,7 +405,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 		{
 			const u64 cr = t.colroot[i];
 			const u64 u = A.use_rowroot ? gl::mul(rr, cr) : cr;
-			pair_t &v = sm[pair_index(1, i, 0)];
+			pair_t &v = sm[lin_pair(i)];
 			v = (A.mode == MODE_SQR) ? sqr22(v, u) : mul22(v, A.y[(size_t)blk * S + i], u);
 		}
 		return;
@@ -375,7 +414,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 	{
 		const u32 si = 2 * nst - ph; // nst-1 .. 0
 		const Stage &sg = A.st[si];
-		const Tw tw{t.twS, t.S, t.S / sg.L};
+		const Tw tw{(sg.s > 1) ? t.twSi : nullptr, t.S / sg.L};
 		dispatch_stage_lin<true>(Sv, (si == 0 && !A.small) ? G : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
@@ -385,24 +424,24 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 	{
 		for (u32 r = tid; r < nruns; r += nthr)
 		{
-			u64 v[RUN];
+			u64 v[MAXRUN];
 			const u32 j0 = r * D;
 			for (u32 i = 0; i < D; i += 2)
 			{
-				const pair_t pv = sm[pair_index(1, (j0 + i) >> 1, 0)];
-				v[i] = gl::mul(gl::mul(pv.x, t.winv_nat[j0 + i]), t.inv_m);
-				v[i + 1] = gl::mul(gl::mul(pv.y, t.winv_nat[j0 + i + 1]), t.inv_m);
+				const pair_t pv = sm[lin_pair((j0 + i) >> 1)];
+				v[i] = gl::mul(pv.x, t.winvs_nat[j0 + i]);
+				v[i + 1] = gl::mul(pv.y, t.winvs_nat[j0 + i + 1]);
 			}
 			smc[r] = carry_run(v, D, t.wbase, run_bits(t, j0, D), A.a, 0);
-			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; sm[pair_index(1, (j0 + i) >> 1, 0)] = pv; }
+			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; sm[lin_pair((j0 + i) >> 1)] = pv; }
 		}
 		return;
 	}
 	for (u32 r = tid; r < nruns; r += nthr)
 	{
-		u64 v[RUN];
+		u64 v[MAXRUN];
 		const u32 j0 = r * D;
-		for (u32 i = 0; i < D; i += 2) { const pair_t pv = sm[pair_index(1, (j0 + i) >> 1, 0)]; v[i] = pv.x; v[i + 1] = pv.y; }
+		for (u32 i = 0; i < D; i += 2) { const pair_t pv = sm[lin_pair((j0 + i) >> 1)]; v[i] = pv.x; v[i + 1] = pv.y; }
 		carry_absorb(v, (D < 4) ? D : 4, t.wbase, run_bits(t, j0, D), smc[(r == 0) ? nruns - 1 : r - 1]);
 		for (u32 i = 0; i < D; i += 2)
 		{
@@ -421,24 +460,44 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 {
 	const Tables &t = A.t;
 	const u32 nb = (A.R / R) * TILE_C * 2;
-	const Tw tw{t.twR, t.R, t.R / sg.L};
+	const Tw tw{(sg.s > 1) ? (INV ? t.twRi : t.twR) : nullptr, t.R / sg.L};
 	for (u32 b = tid; b < nb; b += nthr)
 	{
-		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b >> 4;
+		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b / (2 * TILE_C);
 		const u32 blk = rb / sg.s, j = rb % sg.s;
 		const u32 base = blk * sg.L + j;
-		const View Gi{(u64 *)(const_cast<pair_t *>(A.src) + blockbase + c0 + c), 0, A.stride, 0, lane};
-		const View Go{(u64 *)(A.dst + blockbase + c0 + c), 0, A.stride, 0, lane};
-		const View Sv{(u64 *)sm, 2, 0, c, lane};
-		const Boundary bd{&t, (u64)(c0 + c) * A.escale};
+		const View Gi = view_global(A.src, (size_t)blockbase + c0 + c, A.stride, lane);
+		const View Go = view_global(A.dst, (size_t)blockbase + c0 + c, A.stride, lane);
+		const View Sv = view_tile(sm, c, lane);
+		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
+		const bool wp = INV && first && out_smem_always;
+		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_nat + 2 * (size_t)(c0 + c) + lane : nullptr, 2 * (size_t)A.stride,
+			last ? t.rowK[base] : 0u, A.R / R};
 		if (!INV)
 			bfly<R, false>(first ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
-			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, last ? &bd : nullptr);
+			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, (last || wp) ? &bd : nullptr);
 	}
 }
 
-HD u32 strided_num_phases(const StridedArgs &A, bool inv) { return A.nst + ((inv && A.with_carry) ? 2 : 0); }
+// phases of the inverse pass with carry: nst stages (the last one unweights), then
+//   nst     carry each row's run of 16 digits, publish the carry out
+//   nst + 1 one thread: fence, raise published[g], wait for published[g - 1]          (look-back of one tile)
+//   nst + 2 absorb the carry of the run before (tile g - 1, same row) into the first digits
+//   nst + 3 reweight and store the tile, coalesced
+//   nst + 4 one thread: raise stored[g]; the LAST tile waits for stored[0]
+//   nst + 5 last tile only: end-around carry (2^p = 1) into tile 0's rows, in global memory
+HD u32 strided_num_phases(const StridedArgs &A, bool inv) { return A.nst + ((inv && A.with_carry) ? 6 : 0); }
+
+static constexpr u32 SPIN_LIMIT = 1u << 27; // bounded wait: a lost flag raises the error word instead of hanging the GPU
+
+HD void wait_flag(const StridedArgs &A, u32 idx)
+{
+	u32 spins = 0;
+	while (MARIN_LD_VOLATILE_U32(&A.flags[idx]) != A.epoch)
+		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[2 * A.tiles], 1u); break; }
+	MARIN_FENCE();
+}
 
 template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 ph, u32 tid, u32 nthr, pair_t *sm)
 {
@@ -460,57 +519,105 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 		return;
 	}
 	if (!INV) return;
-	if (ph == A.nst)
+	const u32 cph = ph - A.nst;
+	if (cph == 0)
 	{
-		// unweight (x 1/m), carry, reweight: one thread per row = one run of 16 consecutive digits
+		if (A.dbg & 4) return;
+		// the tile holds exact convolution values: carry each row's run of 16 consecutive digits
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
 			u64 v[RUN];
-			for (u32 c = 0; c < TILE_C; ++c)
-			{
-				const pair_t pv = sm[pair_index(2, row, c)];
-				v[2 * c] = gl::mul(pv.x, t.winvs_perm[perm_index(A.R, g, 2 * c, row)]);
-				v[2 * c + 1] = gl::mul(pv.y, t.winvs_perm[perm_index(A.R, g, 2 * c + 1, row)]);
-			}
+			#pragma unroll
+			for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
 			const u32 j0 = 2 * (row * A.stride + c0);
 			const u64 cout = carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
 			A.carry[(size_t)g * A.R + row] = cout;
-			for (u32 c = 0; c < TILE_C; ++c)
-			{
-				pair_t pv;
-				pv.x = gl::mul(v[2 * c], t.w_perm[perm_index(A.R, g, 2 * c, row)]);
-				pv.y = gl::mul(v[2 * c + 1], t.w_perm[perm_index(A.R, g, 2 * c + 1, row)]);
-				sm[pair_index(2, row, c)] = pv;
-			}
+			#pragma unroll
+			for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
+		}
+		if (!(A.dbg & 2)) MARIN_FENCE();
+		return;
+	}
+	if (cph == 1)
+	{
+		if (tid == 0)
+		{
+			MARIN_FENCE();
+			MARIN_ST_VOLATILE_U32(&A.flags[g], A.epoch);
+			if (g > 0 && !(A.dbg & 1)) wait_flag(A, g - 1);
 		}
 		return;
 	}
-	// coalesced store of the tile
-	for (u32 e = tid; e < A.R * TILE_C; e += nthr)
+	if (cph == 2)
 	{
-		const u32 row = e >> 3, c = e & 7;
-		A.dst[blockbase + (size_t)row * A.stride + c0 + c] = sm[pair_index(2, row, c)];
+		if (g == 0 || (A.dbg & 8)) return; // tile 0 gets its carries (from the last tile, one row up) at the very end
+		for (u32 row = tid; row < A.R; row += nthr)
+		{
+			const u64 c = MARIN_LD_CG_U64(&A.carry[(size_t)(g - 1) * A.R + row]);
+			if (c == 0) continue;
+			const pair_t p0 = sm[tile_pair(row, 0)], p1 = sm[tile_pair(row, 1)];
+			u64 d[4] = {p0.x, p0.y, p1.x, p1.y};
+			carry_absorb(d, 4, t.wbase, run_bits(t, 2 * (row * A.stride + c0), 4), c);
+			pair_t q0, q1; q0.x = d[0]; q0.y = d[1]; q1.x = d[2]; q1.y = d[3];
+			sm[tile_pair(row, 0)] = q0; sm[tile_pair(row, 1)] = q1;
+		}
+		return;
 	}
-}
-
-// ---- carry fix-up after the strided inverse pass: run (row, g) takes the carry of the run before it
-struct FixArgs { Tables t; u64 *x; const u64 *carry; u32 R, stride, tiles; };
-
-HD void fixup_thread(const FixArgs &A, u32 id)
-{
-	const Tables &t = A.t;
-	const u32 g = id / A.R, row = id % A.R; // rows fastest: coalesced carry / weight reads
-	if (g >= A.tiles) return;
-	u64 c;
-	if (g > 0) c = A.carry[(size_t)(g - 1) * A.R + row];
-	else c = A.carry[(size_t)(A.tiles - 1) * A.R + ((row == 0) ? A.R - 1 : row - 1)];
-	if (c == 0) return;
-	const size_t j0 = 2 * ((size_t)row * A.stride + (size_t)g * TILE_C);
-	const u64 mm = (u64)t.m;
-	u64 d[4];
-	for (u32 i = 0; i < 4; ++i) d[i] = gl::mul(gl::mul(A.x[j0 + i], t.winvs_perm[perm_index(A.R, g, i, row)]), mm);
-	carry_absorb(d, 4, t.wbase, run_bits(t, (u32)j0, 4), c);
-	for (u32 i = 0; i < 4; ++i) A.x[j0 + i] = gl::mul(d[i], t.w_perm[perm_index(A.R, g, i, row)]);
+	if (cph == 3)
+	{
+		// reweight and store, coalesced (TILE_C threads cover one row segment); four elements in flight
+		const u32 total = A.R * TILE_C;
+		for (u32 e0 = tid; e0 < total; e0 += 4 * nthr)
+		{
+			pair_t d[4], w[4]; size_t pi[4];
+			#pragma unroll
+			for (u32 u = 0; u < 4; ++u)
+			{
+				const u32 e = e0 + u * nthr;
+				if (e < total)
+				{
+					const u32 row = e / TILE_C, c = e % TILE_C;
+					pi[u] = (size_t)row * A.stride + c0 + c;
+					w[u] = reinterpret_cast<const pair_t *>(t.w_nat)[pi[u]];
+					d[u] = sm[tile_pair(row, c)];
+				}
+			}
+			#pragma unroll
+			for (u32 u = 0; u < 4; ++u)
+				if (e0 + u * nthr < total)
+				{
+					pair_t o; o.x = gl::mul(d[u].x, w[u].x); o.y = gl::mul(d[u].y, w[u].y);
+					if (A.dbg & 16) o = d[u];
+					A.dst[blockbase + pi[u]] = o;
+				}
+		}
+		if (!(A.dbg & 2)) MARIN_FENCE();
+		return;
+	}
+	if (cph == 4)
+	{
+		if (tid == 0)
+		{
+			MARIN_FENCE();
+			MARIN_ST_VOLATILE_U32(&A.flags[A.tiles + g], A.epoch);
+			if (g == A.tiles - 1 && !(A.dbg & 1)) wait_flag(A, A.tiles + 0);
+		}
+		return;
+	}
+	if (g != A.tiles - 1 || (A.dbg & 32)) return;
+	// end-around: the run after (row, last tile) is (row + 1, tile 0); after the very last run comes digit 0
+	u64 *x = reinterpret_cast<u64 *>(A.dst);
+	for (u32 row = tid; row < A.R; row += nthr)
+	{
+		const u64 c = A.carry[(size_t)g * A.R + row]; // written by this CTA in phase nst
+		if (c == 0) continue;
+		const u32 trow = (row + 1 == A.R) ? 0 : row + 1;
+		const size_t j0 = 2 * (size_t)trow * A.stride;
+		u64 d[4];
+		for (u32 i = 0; i < 4; ++i) d[i] = gl::mul(MARIN_LD_CG_U64(&x[j0 + i]), t.winv_nat[j0 + i]);
+		carry_absorb(d, 4, t.wbase, run_bits(t, (u32)j0, 4), c);
+		for (u32 i = 0; i < 4; ++i) x[j0 + i] = gl::mul(d[i], t.w_nat[j0 + i]);
+	}
 }
 
 // ---- linear operations on digits (natural order, runs of D digits) -----------------------------
@@ -541,7 +648,7 @@ HD void lin_p1_thread(const LinArgs &A, u32 r)
 	if (r >= nruns) return;
 	const u32 j0 = r * D;
 	const u32 bits = run_bits(t, j0, D);
-	u64 v[RUN];
+	u64 v[MAXRUN];
 	for (u32 i = 0; i < D; ++i)
 	{
 		const u32 j = j0 + i;
@@ -580,7 +687,7 @@ HD void lin_p2_thread(const LinArgs &A, u32 r)
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
 
 // weight tables: digit j has weight r^((n - p j mod n) mod n), r the n-th root of two (ibdwt.h:111-147)
-struct WeightArgs { u32 p, n, m, R, stride, tiles; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *w_perm, *winvs_perm; u32 have_perm; };
+struct WeightArgs { u32 p, n; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *winvs_nat; };
 
 HD void weight_thread(const WeightArgs &A, u32 j)
 {
@@ -588,13 +695,7 @@ HD void weight_thread(const WeightArgs &A, u32 j)
 	const u64 r = ((u64)A.p * j) % A.n;
 	const u64 e = r ? (u64)A.n - r : 0;
 	const u64 w = gl::pow(A.nr2, e), wi = gl::pow(A.nr2_inv, e);
-	A.w_nat[j] = w; A.winv_nat[j] = wi;
-	if (A.have_perm)
-	{
-		const u32 pairidx = j >> 1, row = pairidx / A.stride, c = pairidx % A.stride, g = c / TILE_C, i = 2 * (c % TILE_C) + (j & 1);
-		const size_t k = perm_index(A.R, g, i, row);
-		A.w_perm[k] = w; A.winvs_perm[k] = gl::mul(wi, A.inv_m);
-	}
+	A.w_nat[j] = w; A.winv_nat[j] = wi; A.winvs_nat[j] = gl::mul(wi, A.inv_m);
 }
 
 } // namespace marin

@@ -27,7 +27,7 @@ inline size_t transform_size(uint32_t exponent)
 
 static constexpr u32 SMALL_MAX_PAIRS = 8192;  // whole register in one CTA's shared memory (128 KiB + pad)
 static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
-static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 8 pairs * 16 B = 160 KiB
+static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 9 pairs * 16 B = 180 KiB
 
 struct Plan
 {
@@ -116,7 +116,7 @@ inline u32 freq_of_pos(const Stage *st, u32 nst, u32 pos)
 struct HostTables
 {
 	std::vector<u32> wbits, rowK;
-	std::vector<u64> twS, twR, bl_lo, bl_hi, rowroot, colroot;
+	std::vector<u64> twS, twSi, twR, twRi, bl_lo, bl_hi, bl_loi, bl_hii, rowroot, colroot;
 	u64 inv_m = 0, nr2 = 0, nr2_inv = 0, w5[4], w5i[4];
 	u32 bl_h = 0;
 };
@@ -146,11 +146,15 @@ inline void build_tables(const Plan &pl, HostTables &h)
 	h.nr2_inv = gl::inv(h.nr2);
 	h.inv_m = gl::inv((u64)m);
 	powers(h.twS, gl::root_of_unity(pl.S), pl.S);
+	powers(h.twSi, gl::inv(gl::root_of_unity(pl.S)), pl.S);
 	powers(h.twR, gl::root_of_unity(pl.R), pl.R);
+	powers(h.twRi, gl::inv(gl::root_of_unity(pl.R)), pl.R);
 	h.bl_h = 11;
-	const u64 rm = gl::root_of_unity(m);
+	const u64 rm = gl::root_of_unity(m), rmi = gl::inv(rm);
 	powers(h.bl_lo, rm, (size_t)1 << h.bl_h);
 	powers(h.bl_hi, gl::pow(rm, (u64)1 << h.bl_h), (m >> h.bl_h) + 1);
+	powers(h.bl_loi, rmi, (size_t)1 << h.bl_h);
+	powers(h.bl_hii, gl::pow(rmi, (u64)1 << h.bl_h), (m >> h.bl_h) + 1);
 	h.rowK.resize(pl.R); h.rowroot.resize(pl.R);
 	for (u32 r = 0; r < pl.R; ++r)
 	{

@@ -66,8 +66,8 @@ def load_library(build_if_needed=True):
     """dlopen libmarin_b200.so (building it first if stale); raises if it cannot be had."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if build_if_needed and _build.nvcc_path() is not None:
+        path = os.environ.get("MARIN_B200_LIB") or _build.LIB   # development aid: try another build of the library
+        if build_if_needed and _build.nvcc_path() is not None and path == _build.LIB:
             path = _build.build()
         if not os.path.exists(path):
             raise RuntimeError("libmarin_b200.so is missing: run `python -m prmers_b200.build` (needs nvcc); "

@@ -6,7 +6,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libmarin_emu.so")
+_EXTRA = os.environ.get("MARIN_EMU_CFLAGS", "").split()          # e.g. -DMARIN_TILE_C=4
+_SO = os.path.join(_HERE, "libmarin_emu" + ("_" + "_".join(f.strip("-").replace("=", "") for f in _EXTRA) if _EXTRA else "") + ".so")
 _SRC = os.path.join(_HERE, "emu_engine.cpp")
 _CSRC = os.path.join(_HERE, "..", "..", "prmers_b200", "csrc")
 
@@ -16,7 +17,7 @@ def build():
     if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [cxx, "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", _SO, _SRC]
+    cmd = [cxx, "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared"] + _EXTRA + ["-o", _SO, _SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         r = subprocess.run([c for c in cmd if c != "-fopenmp"], capture_output=True, text=True)

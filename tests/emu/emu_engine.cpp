@@ -47,7 +47,6 @@ struct CpuBackend
 			for (u32 ph = 0; ph < nph; ++ph)
 				for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, b, ph, t, thr, sm.data());
 	}
-	void fixup(const FixArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) fixup_thread(A, i); }
 	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
 	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { for (u32 j = 0; j < n; ++j) unweight_thread(t, x, out, j); }
