@@ -1,0 +1,169 @@
+"""Callers of the hot path: PRP, Lucas-Lehmer and P-1 stage 1 loops over the engine API.
+
+Host loops only -- every arithmetic step is an engine call (square_mul, mul, set_multiplicand, copy,
+sub), exactly as src/modes does it; nothing here touches digits except the final residue export.
+They take any object with the engine methods (the CUDA `Engine`, or the kernel emulator in the CPU
+tests).  Restated from: RunPrpOrLlMarin.cpp:213-462 (PRP type 1 base 3 with Gerbicz-Li checking and
+-erroriter injection; classic LL), AlgoUtils.hpp:165-224 (residue words, /9, res64 / res2048),
+RunPM1.cpp:7016-7135,7263-7299 (stage 1, E = 2 p prod q^floor(log_q B1), "fast3" squarings).
+"""
+import math
+
+import numpy as np
+
+from .engine import digits_to_int
+
+# register map of RunPrpOrLlMarin.cpp:213
+R0, R1, R2, R3, R4, R5, RBASE, RTMP = range(8)
+
+
+def _digits(eng, r):
+    return eng.get(r) if hasattr(eng, "get") else eng.get_digits(r)
+
+
+def _value(eng, r, p):
+    v = digits_to_int(_digits(eng, r))
+    return 0 if v == (1 << p) - 1 else v
+
+
+def pack_words(enc, p):
+    """pack_words_from_eng_digits (AlgoUtils.hpp:165-187): the residue as little-endian 32-bit words."""
+    v = digits_to_int(enc)
+    nwords = (p + 31) // 32
+    return np.frombuffer(v.to_bytes(nwords * 4 + 8, "little")[:nwords * 4], dtype=np.uint32).copy()
+
+
+def words_to_int(words):
+    return int.from_bytes(np.asarray(words, dtype=np.uint32).tobytes(), "little")
+
+
+def prp3_div9(p, r):
+    """prp3_div9 (AlgoUtils.hpp:195-206): residue / 9 modulo 2^p - 1 (two exact divisions by 3)."""
+    m = (1 << p) - 1
+    for _ in range(2):
+        r = (r + ((3 - r % 3) % 3) * m) // 3 if m % 3 else r
+    return r % m
+
+
+def format_res64(r):
+    return f"{r & 0xFFFFFFFFFFFFFFFF:016X}"
+
+
+def format_res2048(r):
+    return f"{r & ((1 << 2048) - 1):0512x}"
+
+
+def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4):
+    """PRP test of 2^p - 1 (type 1, base 3): p squarings from 3, prime iff the residue is 9.
+
+    Gerbicz-Li checking as the reference: every B = floor(sqrt(p)) iterations the accumulator
+    d <- d * x, and every `check_level` blocks (and at the end) d is checked against
+    (d_prev)^(2^B) * 3 recomputed from the previous accumulator; on mismatch the last good state is
+    restored (RunPrpOrLlMarin.cpp:338-412).  `error_iter` injects a fault (x -= 2) after that
+    iteration, like -erroriter (RunPrpOrLlMarin.cpp:326-336).
+    """
+    say = log or (lambda s: None)
+    total = p
+    B = max(int(math.isqrt(p)), 1)
+    level_auto = int(1000 * 600.0 / B) or max((total // B) // max(int(math.isqrt(B)), 1), 1)
+    level = check_level if check_level > 0 else max(level_auto, 1)
+    eng.set(R1, 1)
+    eng.set(R0, 3)
+    eng.copy(R4, R0); eng.copy(R5, R1)
+    eng.set(RBASE, 3)
+    eng.set_multiplicand(RTMP, RBASE)
+    itersave, jsave = 0, total - 1
+    checkpass, errors, restores, errordone = 0, 0, 0, False
+    it, j = 0, total - 1
+    while it < total:
+        eng.square_mul(R0)
+        if error_iter > 0 and it + 1 == error_iter and not errordone:
+            errordone = True
+            eng.sub(R0, 2)
+            say(f"Injected error at iteration {it + 1}")
+        if gerbicz and ((j != 0 and j % B == 0) or it == total - 1):
+            checkpass += 1
+            eng.copy(R3, R1)
+            eng.set_multiplicand(R2, R0)
+            eng.mul(R1, R2)
+            if checkpass == level or it == total - 1:
+                checkpass = 0
+                modB = B if p % B == 0 else p % B
+                for _ in range(B - modB - 1 if B > modB else 0):
+                    eng.square_mul(R3)
+                if p % B == 0:
+                    eng.mul(R3, RTMP)
+                else:
+                    eng.square_mul(R3, 3)
+                for _ in range(modB):
+                    eng.square_mul(R3)
+                if _value(eng, R3, p) != _value(eng, R1, p):
+                    say(f"[Gerbicz Li] Check FAILED! iter={it + 1}")
+                    say(f"[Gerbicz Li] Restore iter={itersave} (j={jsave})")
+                    errors += 1
+                    restores += 1
+                    if restores > max_restores:
+                        raise RuntimeError("Gerbicz-Li: too many restores")
+                    eng.copy(R0, R4); eng.copy(R1, R5)
+                    it, j, checkpass = itersave, jsave, 0
+                    if it == 0:
+                        continue            # restart from the very beginning (iter = -1 + 1)
+                    it += 1; j -= 1
+                    continue
+                say(f"[Gerbicz Li] Check passed! iter={it + 1}")
+                eng.copy(R4, R0); eng.copy(R5, R1)
+                itersave, jsave = it, j
+        it += 1; j -= 1
+    enc = _digits(eng, R0)
+    x = digits_to_int(enc)
+    m = (1 << p) - 1
+    x = 0 if x == m else x
+    r = prp3_div9(p, x)
+    return {"exponent": p, "worktype": "PRP-3", "is_prp": x == 9 % m, "res64": format_res64(r), "res2048": format_res2048(r),
+            "residue_type": 1, "errors_gerbicz": errors, "fft_length": eng.get_size(), "iterations": total}
+
+
+def run_ll(eng, p, error_iter=0):
+    """Classic Lucas-Lehmer (-llunsafe, RunPrpOrLlMarin.cpp:229,322-324): s <- s^2 - 2, p - 2 times from 4."""
+    eng.set(R0, 4)
+    for it in range(p - 2):
+        eng.square_mul(R0)
+        eng.sub(R0, 2)
+        if error_iter and it + 1 == error_iter:
+            eng.sub(R0, 2)
+    x = _value(eng, R0, p)
+    return {"exponent": p, "worktype": "LL", "is_prime": x == 0, "res64": format_res64(x), "fft_length": eng.get_size()}
+
+
+def primes_upto(n):
+    sieve = bytearray([1]) * (n + 1)
+    sieve[:2] = b"\0\0"
+    for i in range(2, int(n ** 0.5) + 1):
+        if sieve[i]:
+            sieve[i * i::i] = bytearray(len(sieve[i * i::i]))
+    return [i for i in range(n + 1) if sieve[i]]
+
+
+def pm1_exponent(p, b1):
+    """buildE (AlgoUtils.hpp:248-336): E = 2 p prod_{q <= B1} q^floor(log_q B1)."""
+    e = 2 * p
+    for q in primes_upto(b1):
+        qk = q
+        while qk * q <= b1:
+            qk *= q
+        e *= qk
+    return e
+
+
+def run_pm1_stage1(eng, p, b1, reg=0):
+    """P-1 stage 1, "fast3" (RunPM1.cpp:7127): X <- X^2 * (3 if bit else 1) over the bits of E, MSB first;
+    the factor is gcd(X - 1, 2^p - 1)."""
+    E = pm1_exponent(p, b1)
+    eng.set(reg, 1)
+    for bit in bin(E)[2:]:
+        eng.square_mul(reg, 3 if bit == "1" else 1)
+    x = _value(eng, reg, p)
+    m = (1 << p) - 1
+    g = math.gcd((x - 1) % m, m)
+    return {"exponent": p, "worktype": "PM1", "b1": b1, "factor": g if 1 < g < m else None, "bits": E.bit_length(),
+            "fft_length": eng.get_size(), "x": x}

@@ -83,6 +83,12 @@ class EmuEngine:
         self._ck(lib().emu_get_digits(self._h, s, out.ctypes.data))
         return out
 
+    def get(self, s):
+        return self.get_digits(s)
+
+    def get_size(self):
+        return self.n
+
     def set_digits(self, d, enc):
         enc = np.ascontiguousarray(enc, dtype=np.uint64)
         self._ck(lib().emu_set_digits(self._h, d, enc.ctypes.data))

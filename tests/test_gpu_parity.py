@@ -293,3 +293,20 @@ def test_long_chain_gerbicz_identity_full_size():
     e.set_multiplicand(2, 2); e.mul(0, 2)
     assert e.is_equal(0, 3)
     e.close()
+
+
+def test_cpp_adapter_conformance():
+    """include/marin_b200_engine.hpp: the C++ `engine` subclass over the C ABI, built with g++ and run
+    on the GPU (sequence of the reference's tests/test_aevum_reg_adapter.cpp)."""
+    import subprocess
+    import prmers_b200 as pb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pb.load_library()
+    exe = os.path.join(root, "tests", "cpp", "test_engine_adapter")
+    libdir = os.path.join(root, "prmers_b200")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "cpp", "test_engine_adapter.cpp"),
+                    "-L", libdir, "-l:libmarin_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "adapter test passed" in r.stdout, r.stdout + r.stderr

@@ -1,0 +1,82 @@
+"""The mode loops (prmers_b200/modes.py) on the kernel emulator (CPU tier) and, marked gpu, on the CUDA
+engine: known answers of the reference's unit_tests.sh."""
+import pytest
+
+from oracle import mersenne_ref as mr
+from prmers_b200 import modes
+from tests.emu.emu import EmuEngine
+
+
+def test_prp_small_primes_and_composites_emulated():
+    for p in (89, 107, 127, 521, 607):
+        r = modes.run_prp(EmuEngine(p, 8), p)
+        assert r["is_prp"] and r["res64"] == "0000000000000001" and r["errors_gerbicz"] == 0
+    for p in (91, 101, 257, 1001):
+        r = modes.run_prp(EmuEngine(p, 8), p, check_level=1)
+        is_prp, res = mr.prp_type1_res(p)
+        assert r["is_prp"] == is_prp and r["res64"] == mr.res64_hex(res) and r["errors_gerbicz"] == 0
+
+
+def test_gerbicz_detects_injected_error_and_recovers_emulated():
+    """unit_tests.sh:24-52: an error at iteration 55 must be caught at the final check and rolled back
+    to iteration 0; the rerun gives the right residue."""
+    p, log = 1279, []
+    r = modes.run_prp(EmuEngine(p, 8), p, error_iter=55, log=log.append)
+    assert "Injected error at iteration 55" in log
+    assert f"[Gerbicz Li] Check FAILED! iter={p}" in log
+    assert f"[Gerbicz Li] Restore iter=0 (j={p - 1})" in log
+    assert r["errors_gerbicz"] == 1 and r["is_prp"] and r["res64"] == "0000000000000001"
+    # with frequent checks the rollback goes to the last verified block instead
+    log = []
+    r = modes.run_prp(EmuEngine(p, 8), p, error_iter=700, check_level=1, log=log.append)
+    assert r["errors_gerbicz"] == 1 and r["is_prp"]
+    assert any(s.startswith("[Gerbicz Li] Restore iter=") and "iter=0 " not in s for s in log)
+
+
+def test_ll_and_pm1_emulated():
+    assert modes.run_ll(EmuEngine(127, 8), 127)["is_prime"]
+    assert not modes.run_ll(EmuEngine(91, 8), 91)["is_prime"]
+    for p, b1, f in [(269, 2141, 13822297), (269, 192, None), (541, 899, 4312790327), (263, 3527, 23671)]:
+        assert modes.run_pm1_stage1(EmuEngine(p, 2), p, b1)["factor"] == f       # unit_tests.sh:54-69,204-213
+
+
+def test_residue_formatting():
+    assert modes.prp3_div9(127, 9) == 1
+    p = 100003
+    x = 123456789123456789123456789 % mr.mp(p)
+    assert modes.prp3_div9(p, x) == x * pow(9, -1, mr.mp(p)) % mr.mp(p)
+    assert modes.format_res64(0x1CF45E9503C71FD6) == "1CF45E9503C71FD6"
+    assert len(modes.format_res2048(1)) == 512
+
+
+@pytest.mark.gpu
+def test_prp_9941_error_injection_gpu():
+    """unit_tests.sh:24-52 verbatim: ./prmers 9941 -erroriter 55 / 9940 -prp."""
+    import prmers_b200 as pb
+    for erriter in (55, 9940):
+        log = []
+        r = modes.run_prp(pb.Engine(9941, 8), 9941, error_iter=erriter, log=log.append)
+        assert f"Injected error at iteration {erriter}" in log
+        assert "[Gerbicz Li] Check FAILED! iter=9941" in log
+        assert "[Gerbicz Li] Restore iter=0 (j=9940)" in log
+        assert r["is_prp"] and r["errors_gerbicz"] == 1
+
+
+@pytest.mark.gpu
+def test_prp_known_primes_and_m100003_gpu():
+    import prmers_b200 as pb
+    for p in (9689, 11213, 19937, 21701, 23209, 44497, 86243):            # unit_tests.sh:5-10
+        r = modes.run_prp(pb.Engine(p, 8), p)
+        assert r["is_prp"] and r["res64"] == "0000000000000001", p
+    r = modes.run_prp(pb.Engine(100003, 8), 100003)
+    assert not r["is_prp"] and r["res64"] == "1CF45E9503C71FD6"             # unit_tests.sh:137-148
+    for p in (57, 91, 100, 200, 500, 1001, 4095):                          # unit_tests.sh:12-14 (-ll must fail)
+        assert not modes.run_ll(pb.Engine(p, 8), p)["is_prime"]
+
+
+@pytest.mark.gpu
+def test_pm1_stage1_gpu():
+    import prmers_b200 as pb
+    for p, b1, f in [(269, 2141, 13822297), (541, 899, 4312790327), (367, 11981, 646300400639),
+                     (2151, 256, 327405968242246366421788399), (544139, 3, 22853839), (44159, 23, None)]:
+        assert modes.run_pm1_stage1(pb.Engine(p, 11), p, b1)["factor"] == f
