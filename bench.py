@@ -33,8 +33,10 @@ HEADLINE_P = 136279841
 OTHER_P = [139123459, 139246931, 139370393, 139493863, 139617329, 139740787, 139864247]  # primes, all n = 2^23
 ITERS = 1000            # squarings per step
 METRIC = "PRP iterations/s, M136279841-class exponents (n = 2^23 IBDWT), whole job"
-PASS_NAMES = ["k_strided<0> (strided forward pass)", "k_mid (contiguous middle pass)",
-              "k_strided<1> (strided inverse pass + unweight/carry/reweight)"]
+# steady state of a squaring chain: two launches per square_mul (the inverse pass also runs the next
+# squaring's forward strided pass on the tile it holds); (name, bench_pass id, algorithmic bytes / n)
+PASSES = [("k_mid (contiguous pass: forward, pointwise square, inverse)", 1, 16),
+          ("k_strided<1> (strided inverse + unweight/carry/reweight + next strided forward)", 3, 32)]
 
 
 def measured_peak():
@@ -90,6 +92,7 @@ class ClockSampler:
 
 def cpu_baseline(sample_iters, p=HEADLINE_P):
     """The oracle port (exact restatement of the Marin IBDWT, OpenMP over the host cores)."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())      # torchrun pins it to 1; the baseline uses every core
     from oracle import marin_oracle as mo
     o = mo.OracleEngine(p, 1)
     o.set(0, 3)
@@ -110,6 +113,7 @@ def run_reference(args, rank):
     binary cannot be built here: no CL/cl.h, no gmp.h, no PoCL)."""
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())      # torchrun pins it to 1; the reference arm uses every core
     from oracle import marin_oracle as mo
     sample = 2
     o = mo.OracleEngine(HEADLINE_P, 1)
@@ -229,16 +233,16 @@ def main():
         peak, peak_src = measured_peak()
         # per-kernel durations, live, with CUDA events on the launching stream
         passes = []
-        for which in range(3):
+        for _, which, _ in PASSES:
             cnt = 100
             passes.append(eng.bench_pass(1, which, cnt) / cnt)            # ms per launch
-        dom = max(range(3), key=lambda i: passes[i])
-        alg_bytes = 16 * n                                                # 8n read + 8n write per pass
+        dom = max(range(len(PASSES)), key=lambda i: passes[i])
+        alg_bytes = PASSES[dom][2] * n                                    # 8n read + 8n write per pass of the 3-pass count
         achieved = alg_bytes / (passes[dom] * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"].get(["k_strided<0>", "k_mid", "k_strided<1>"][dom])
+                traffic = json.load(f)["dram_bytes_per_launch"].get(["k_mid", "k_strided<1>+fwd"][dom])
         except Exception:
             pass
         ms_iter = ms_max / (args.steps * iters)
@@ -257,10 +261,10 @@ def main():
                     "note": "set_digits from pinned host memory + iters x square_mul + get (canonical digits) per step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": PASS_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": PASSES[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": {PASS_NAMES[i]: passes[i] for i in range(3)},
+                         "kernel_ms": {PASSES[i][0]: passes[i] for i in range(len(PASSES))},
                          "note": "integer-pipe bound, not HBM bound: see profiles/ and DESIGN.md"},
             "roofline_square_mul": {"achieved": 48 * n / (ms_iter * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": 48 * n / (ms_iter * 1e-3) / 1e9 / peak,

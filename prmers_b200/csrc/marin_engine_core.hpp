@@ -31,6 +31,7 @@ public:
 		const size_t ncarry = std::max<size_t>(n / pl.D, n / RUN + 1);
 		_carry = (u64 *)be.alloc(ncarry * 8);
 		_scratch = (u64 *)be.alloc(n * 8);
+		if (!pl.small) _fwd = (u64 *)be.alloc(n * 8);
 		Tables &t = _t;
 		std::memset(&t, 0, sizeof(t));
 		t.p = pl.p; t.n = pl.n; t.m = pl.m; t.wbase = pl.wbase; t.inv_m = h.inv_m;
@@ -52,7 +53,7 @@ public:
 		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat};
 		be.weights(W, pl.n);
 		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat;
-		const size_t nflags = 2 * (size_t)(pl.S / TILE_C) + 1;
+		const size_t nflags = (size_t)(pl.S / TILE_C) + 1;
 		_flags = (u32 *)be.alloc(nflags * 4);
 		be.memset0(_flags, nflags * 4);
 		_nflags = nflags;
@@ -63,7 +64,7 @@ public:
 	{
 		be.sync();
 		for (void *p : _owned) be.free(p);
-		be.free(_reg); be.free(_carry); be.free(_scratch); be.free(_flags);
+		be.free(_reg); be.free(_carry); be.free(_scratch); be.free(_flags); if (_fwd) be.free(_fwd);
 	}
 
 	size_t size() const { return pl.n; }
@@ -86,22 +87,32 @@ public:
 		lin(LIN_SETSMALL, dst, dst, a, nullptr);
 	}
 
-	void copy(size_t dst, size_t src) { check(dst); check(src); if (dst != src) be.d2d(R(dst), R(src), pl.n * 8); }
+	void copy(size_t dst, size_t src) { check(dst); check(src); if (dst != src) { touch(dst); be.d2d(R(dst), R(src), pl.n * 8); } }
 
+	// r = r^2 * a.  In a chain of squarings of the same register (PRP, LL, P-1 stage 1) the inverse
+	// pass of one squaring also runs the forward strided pass of the next on the tile it still holds in
+	// shared memory and parks it in _fwd: two launches per squaring instead of three, and one 16n-byte
+	// round trip through HBM less.  The register itself always holds the finished digits, so any other
+	// operation simply ignores (and invalidates) the parked transform.
 	void square_mul(size_t r, u32 a)
 	{
 		check(r); check_a(a);
 		if (pl.small) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M); return; }
-		strided(false, R(r), R(r), 1);
-		MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M);
-		strided(true, R(r), R(r), a);
+		const bool chained = (_last_sq == r);            // second squaring in a row: start speculating
+		if (_fwd_reg != r) strided(false, R(r), _fwd, 1, nullptr);
+		_fwd_reg = (size_t)-1;
+		MidArgs M = mid_args(_fwd, nullptr, _fwd, MODE_SQR, a); launch_mid(M);
+		strided(true, _fwd, R(r), a, chained ? _fwd : nullptr);
+		if (chained) _fwd_reg = r;
+		_last_sq = r;
 	}
 
 	void set_multiplicand(size_t dst, size_t src)
 	{
 		check(dst); check(src);
 		if (pl.small) { MidArgs M = mid_args(R(src), nullptr, R(dst), MODE_FWD, 1); launch_mid(M); return; }
-		strided(false, R(src), R(dst), 1);
+		touch(dst);
+		strided(false, R(src), R(dst), 1, nullptr);
 		MidArgs M = mid_args(R(dst), nullptr, R(dst), MODE_FWD, 1); launch_mid(M);
 	}
 
@@ -110,9 +121,10 @@ public:
 		check(dst); check(src); check_a(a);
 		if (dst == src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
 		if (pl.small) { MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M); return; }
-		strided(false, R(dst), R(dst), 1);
-		MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M);
-		strided(true, R(dst), R(dst), a);
+		if (_fwd_reg != dst) strided(false, R(dst), _fwd, 1, nullptr);
+		touch(dst);
+		MidArgs M = mid_args(_fwd, R(src), _fwd, MODE_MUL, a); launch_mid(M);
+		strided(true, _fwd, R(dst), a, nullptr);
 	}
 
 	void sub_u32(size_t r, u32 a)
@@ -155,9 +167,9 @@ public:
 	}
 
 	void get_raw(size_t src, void *buf) { check(src); be.d2h(buf, R(src), (size_t)pl.n * 8); }
-	void set_raw(size_t dst, const void *buf) { check(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
+	void set_raw(size_t dst, const void *buf) { check(dst); touch(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
 	void get_all(void *buf) { be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
-	void set_all(const void *buf) { be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
+	void set_all(const void *buf) { _fwd_reg = _last_sq = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
 
 	// single passes of square_mul, for per-kernel timing (3-pass engines only): 0 strided forward,
 	// 1 contiguous middle, 2 strided inverse + carry, 3 carry fix-up
@@ -165,6 +177,7 @@ public:
 	{
 		check(r);
 		if (pl.small) { if (which != 1) return false; MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
+		touch(r);
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
 		fill_strided_args(pl, A);
@@ -172,7 +185,13 @@ public:
 		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
 		if (which == 0) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return true; }
 		if (which == 1) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
-		if (which == 2 || which >= 100) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.dbg = (which >= 100) ? (u32)(which - 100) : 0; be.strided_inv(A, A.tiles, pl.thrStr, smem); return true; }
+		if (which == 2 || which == 3)
+		{
+			// 2: inverse pass + carry; 3: the same with the next forward strided pass fused in (chained squarings)
+			A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (which == 3) ? (pair_t *)_fwd : nullptr;
+			_fwd_reg = (size_t)-1;
+			be.strided_inv(A, A.tiles, pl.thrStr, smem); return true;
+		}
 		if (which == 4) { A.with_carry = 0; be.strided_inv(A, A.tiles, pl.thrStr, smem); return true; } // plain inverse pass (timing aid)
 		return false;
 	}
@@ -185,6 +204,9 @@ private:
 	size_t _regs;
 	u64 *_reg = nullptr, *_carry = nullptr, *_scratch = nullptr;
 	u32 *_flags = nullptr, _epoch = 0;
+	// speculation for squaring chains: _fwd holds the forward strided pass of register _fwd_reg's current value
+	u64 *_fwd = nullptr;
+	size_t _fwd_reg = (size_t)-1, _last_sq = (size_t)-1;
 	size_t _nflags = 0;
 	Tables _t;
 	std::vector<u32> _wbits;
@@ -235,7 +257,10 @@ private:
 		be.mid(M, pl.m / pl.S, pl.thrMid, smem);
 	}
 
-	void strided(bool inv, const u64 *src, u64 *dst, u32 a)
+	// any write to a register other than by square_mul drops the parked forward transform of it
+	void touch(size_t r) { if (_fwd_reg == r) _fwd_reg = (size_t)-1; if (_last_sq == r) _last_sq = (size_t)-1; }
+
+	void strided(bool inv, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst)
 	{
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
@@ -243,7 +268,7 @@ private:
 		A.t = _t; A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.carry = _carry; A.with_carry = inv ? 1 : 0;
 		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
 		if (!inv) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return; }
-		A.flags = _flags; A.epoch = next_epoch();
+		A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst;
 		be.strided_inv(A, A.tiles, pl.thrStr, smem);
 	}
 
@@ -255,6 +280,7 @@ private:
 
 	void lin(int op, size_t dst, size_t src, u32 a, const u64 *digits)
 	{
+		touch(dst);
 		LinArgs L{_t, R(dst), R(src), digits, _carry, op, a, pl.D};
 		be.lin_p1(L, pl.n / pl.D);
 		be.lin_p2(L, pl.n / pl.D);

@@ -344,9 +344,9 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	u32 a;              // multiplier for the carry
 	u64 *carry;         // carry[g * R + row]
 	u32 with_carry;
-	u32 *flags;         // [2 * tiles + 1]: published[g], stored[g], error; hold the epoch of the last launch
+	u32 *flags;         // [tiles + 1]: published[g], error word; hold the epoch of the last launch
 	u32 epoch;
-	u32 dbg;            // timing experiments only (results are wrong when set): see strided_phase
+	pair_t *fwd_dst;    // inverse pass only: also run the next forward strided pass on each tile and write it here
 };
 
 // ------------------------------------------------------------------ phase functions
@@ -456,7 +456,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 // Tile = R rows x 8 pair columns; butterfly id b -> column c = b & 7 (fastest: 128 B rows), row-butterfly b >> 3.
 
 template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, u32 blockbase /*pairs*/, u32 c0,
-	pair_t *sm, u32 tid, u32 nthr, bool out_smem_always)
+	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)
 {
 	const Tables &t = A.t;
 	const u32 nb = (A.R / R) * TILE_C * 2;
@@ -466,28 +466,48 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b / (2 * TILE_C);
 		const u32 blk = rb / sg.s, j = rb % sg.s;
 		const u32 base = blk * sg.L + j;
-		const View Gi = view_global(A.src, (size_t)blockbase + c0 + c, A.stride, lane);
-		const View Go = view_global(A.dst, (size_t)blockbase + c0 + c, A.stride, lane);
+		const View Gi = view_global(gsrc, (size_t)blockbase + c0 + c, A.stride, lane);
+		const View Go = view_global(gdst, (size_t)blockbase + c0 + c, A.stride, lane);
 		const View Sv = view_tile(sm, c, lane);
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_nat + 2 * (size_t)(c0 + c) + lane : nullptr, 2 * (size_t)A.stride,
 			last ? t.rowK[base] : 0u, A.R / R};
 		if (!INV)
-			bfly<R, false>(first ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
+			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
 			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, (last || wp) ? &bd : nullptr);
 	}
 }
 
-// phases of the inverse pass with carry: nst stages (the last one unweights), then
-//   nst     carry each row's run of 16 digits, publish the carry out
-//   nst + 1 one thread: fence, raise published[g], wait for published[g - 1]          (look-back of one tile)
-//   nst + 2 absorb the carry of the run before (tile g - 1, same row) into the first digits
-//   nst + 3 reweight and store the tile, coalesced
-//   nst + 4 one thread: raise stored[g]; the LAST tile waits for stored[0]
-//   nst + 5 last tile only: end-around carry (2^p = 1) into tile 0's rows, in global memory
-HD u32 strided_num_phases(const StridedArgs &A, bool inv) { return A.nst + ((inv && A.with_carry) ? 6 : 0); }
+template <bool INV> HD void dispatch_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, u32 blockbase, u32 c0,
+	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)
+{
+	switch (sg.radix)
+	{
+	case 16: run_stage_tile<16, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, gsrc, gdst, in_smem_always, out_smem_always); break;
+	case 4: run_stage_tile<4, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, gsrc, gdst, in_smem_always, out_smem_always); break;
+	case 2: run_stage_tile<2, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, gsrc, gdst, in_smem_always, out_smem_always); break;
+	case 5: run_stage_tile<5, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, gsrc, gdst, in_smem_always, out_smem_always); break;
+	}
+}
+
+// Phases of the inverse pass with carry (nst = number of stages):
+//   0 .. nst-1   inverse stages; the last one unweights (x 1/(w m)) into shared memory
+//   nst          carry each row's run of 2*TILE_C digits; write the carries out
+//   nst + 1      one thread: fence, raise published[g]
+//   nst + 2      one thread: wait for published[g - 1]; tile 0 waits for the LAST tile (end-around, 2^p = 1)
+//   nst + 3      absorb the carry of the run before into the first digits
+//   nst + 4      reweight, store the digits to the register (coalesced); keep the tile if the forward pass follows
+//   nst + 5 ..   optional: forward stages of the NEXT squaring on the tile still in shared memory -> A.fwd_dst
+// One-hop look-back only: tile g never waits for anything tile g - 1 has not already published, and
+// tile 0 (launched first) parks on the last tile's flag, which costs one CTA slot out of 148 x 2.
+HD u32 strided_num_phases(const StridedArgs &A, bool inv)
+{
+	if (!inv || !A.with_carry) return A.nst;
+	return A.nst + 5 + (A.fwd_dst ? A.nst : 0);
+}
+HD u32 strided_publish_phase(const StridedArgs &A) { return A.nst + 1; }
 
 static constexpr u32 SPIN_LIMIT = 1u << 27; // bounded wait: a lost flag raises the error word instead of hanging the GPU
 
@@ -495,7 +515,7 @@ HD void wait_flag(const StridedArgs &A, u32 idx)
 {
 	u32 spins = 0;
 	while (MARIN_LD_VOLATILE_U32(&A.flags[idx]) != A.epoch)
-		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[2 * A.tiles], 1u); break; }
+		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[A.tiles], 1u); break; }
 	MARIN_FENCE();
 }
 
@@ -507,23 +527,14 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 	if (ph < A.nst)
 	{
 		const u32 si = INV ? (A.nst - 1 - ph) : ph;
-		const Stage &sg = A.st[si];
-		const bool first = (si == 0), last = (si == A.nst - 1);
-		switch (sg.radix)
-		{
-		case 16: run_stage_tile<16, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
-		case 4: run_stage_tile<4, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
-		case 2: run_stage_tile<2, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
-		case 5: run_stage_tile<5, INV>(A, sg, first, last, blockbase, c0, sm, tid, nthr, A.with_carry != 0); break;
-		}
+		dispatch_stage_tile<INV>(A, A.st[si], si == 0, si == A.nst - 1, blockbase, c0, sm, tid, nthr, A.src, A.dst, false, A.with_carry != 0);
 		return;
 	}
 	if (!INV) return;
 	const u32 cph = ph - A.nst;
 	if (cph == 0)
 	{
-		if (A.dbg & 4) return;
-		// the tile holds exact convolution values: carry each row's run of 16 consecutive digits
+		// the tile holds exact convolution values: carry each row's run of consecutive digits
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
 			u64 v[RUN];
@@ -535,25 +546,26 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 			#pragma unroll
 			for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
 		}
-		if (!(A.dbg & 2)) MARIN_FENCE();
+		MARIN_FENCE();
 		return;
 	}
 	if (cph == 1)
 	{
-		if (tid == 0)
-		{
-			MARIN_FENCE();
-			MARIN_ST_VOLATILE_U32(&A.flags[g], A.epoch);
-			if (g > 0 && !(A.dbg & 1)) wait_flag(A, g - 1);
-		}
+		if (tid == 0) { MARIN_FENCE(); MARIN_ST_VOLATILE_U32(&A.flags[g], A.epoch); }
 		return;
 	}
 	if (cph == 2)
 	{
-		if (g == 0 || (A.dbg & 8)) return; // tile 0 gets its carries (from the last tile, one row up) at the very end
+		if (tid == 0) wait_flag(A, (g == 0) ? A.tiles - 1 : g - 1);
+		return;
+	}
+	if (cph == 3)
+	{
+		// the run before (row, g) is (row, g - 1); before (row, 0) comes (row - 1, last tile); before (0, 0) the very last run
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
-			const u64 c = MARIN_LD_CG_U64(&A.carry[(size_t)(g - 1) * A.R + row]);
+			const size_t from = (g > 0) ? (size_t)(g - 1) * A.R + row : (size_t)(A.tiles - 1) * A.R + ((row == 0) ? A.R - 1 : row - 1);
+			const u64 c = MARIN_LD_CG_U64(&A.carry[from]);
 			if (c == 0) continue;
 			const pair_t p0 = sm[tile_pair(row, 0)], p1 = sm[tile_pair(row, 1)];
 			u64 d[4] = {p0.x, p0.y, p1.x, p1.y};
@@ -563,7 +575,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 		}
 		return;
 	}
-	if (cph == 3)
+	if (cph == 4)
 	{
 		// reweight and store, coalesced (TILE_C threads cover one row segment); four elements in flight
 		const u32 total = A.R * TILE_C;
@@ -584,40 +596,21 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 			}
 			#pragma unroll
 			for (u32 u = 0; u < 4; ++u)
-				if (e0 + u * nthr < total)
+			{
+				const u32 e = e0 + u * nthr;
+				if (e < total)
 				{
 					pair_t o; o.x = gl::mul(d[u].x, w[u].x); o.y = gl::mul(d[u].y, w[u].y);
-					if (A.dbg & 16) o = d[u];
 					A.dst[blockbase + pi[u]] = o;
+					if (A.fwd_dst) sm[tile_pair(e / TILE_C, e % TILE_C)] = o;
 				}
-		}
-		if (!(A.dbg & 2)) MARIN_FENCE();
-		return;
-	}
-	if (cph == 4)
-	{
-		if (tid == 0)
-		{
-			MARIN_FENCE();
-			MARIN_ST_VOLATILE_U32(&A.flags[A.tiles + g], A.epoch);
-			if (g == A.tiles - 1 && !(A.dbg & 1)) wait_flag(A, A.tiles + 0);
+			}
 		}
 		return;
 	}
-	if (g != A.tiles - 1 || (A.dbg & 32)) return;
-	// end-around: the run after (row, last tile) is (row + 1, tile 0); after the very last run comes digit 0
-	u64 *x = reinterpret_cast<u64 *>(A.dst);
-	for (u32 row = tid; row < A.R; row += nthr)
-	{
-		const u64 c = A.carry[(size_t)g * A.R + row]; // written by this CTA in phase nst
-		if (c == 0) continue;
-		const u32 trow = (row + 1 == A.R) ? 0 : row + 1;
-		const size_t j0 = 2 * (size_t)trow * A.stride;
-		u64 d[4];
-		for (u32 i = 0; i < 4; ++i) d[i] = gl::mul(MARIN_LD_CG_U64(&x[j0 + i]), t.winv_nat[j0 + i]);
-		carry_absorb(d, 4, t.wbase, run_bits(t, (u32)j0, 4), c);
-		for (u32 i = 0; i < 4; ++i) x[j0 + i] = gl::mul(d[i], t.w_nat[j0 + i]);
-	}
+	// forward strided pass of the next squaring, straight from the tile in shared memory
+	const u32 si = cph - 5;
+	dispatch_stage_tile<false>(A, A.st[si], si == 0, si == A.nst - 1, blockbase, c0, sm, tid, nthr, nullptr, A.fwd_dst, true, false);
 }
 
 // ---- linear operations on digits (natural order, runs of D digits) -----------------------------

@@ -41,11 +41,18 @@ struct CpuBackend
 	}
 	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
 	{
-		std::vector<pair_t> sm(smem / 16 + 1);
+		// Tile 0 waits for the last tile's flag (end-around carry), so on a sequential emulator its CTA runs up
+		// to the publish phase, parks (keeping its shared memory), and resumes after every other CTA is done.
+		std::vector<pair_t> sm(smem / 16 + 1), sm0(smem / 16 + 1);
 		const u32 nph = strided_num_phases(A, true);
-		for (u32 b = 0; b < grid; ++b)
+		const u32 park = A.with_carry ? strided_publish_phase(A) + 1 : nph;
+		for (u32 ph = 0; ph < park; ++ph)
+			for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, 0, ph, t, thr, sm0.data());
+		for (u32 b = 1; b < grid; ++b)
 			for (u32 ph = 0; ph < nph; ++ph)
 				for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, b, ph, t, thr, sm.data());
+		for (u32 ph = park; ph < nph; ++ph)
+			for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, 0, ph, t, thr, sm0.data());
 	}
 	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
 	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }

@@ -6,8 +6,6 @@ p = int(sys.argv[1]) if len(sys.argv) > 1 else 136279841
 e = pb.Engine(p, 4)
 e.set(0, 3); e.square_mul_repeat(0, 100); e.sync()
 ms = e.bench_square_mul(0, 1000) / 1000
-ps = [e.bench_pass(1, w, 200) / 200 for w in (0, 1, 2, 4)]
-print(f"p={p} n={e.get_size()} total {ms*1000:.1f} us  fwd {ps[0]*1000:.1f}  mid {ps[1]*1000:.1f}  inv {ps[2]*1000:.1f}  inv-plain {ps[3]*1000:.1f}", flush=True)
+ps = [e.bench_pass(1, w, 200) / 200 for w in (0, 1, 2, 4, 3)]
+print(f"p={p} n={e.get_size()} total {ms*1000:.1f} us  fwd {ps[0]*1000:.1f}  mid {ps[1]*1000:.1f}  inv {ps[2]*1000:.1f}  inv-plain {ps[3]*1000:.1f}  inv+carry+fwd {ps[4]*1000:.1f}", flush=True)
 
-for dbg in (1, 2, 3, 4, 8, 16, 32, 63):
-    print(f"  inv dbg={dbg:2d}: {e.bench_pass(1, 100 + dbg, 200) / 200 * 1000:.1f} us", flush=True)
