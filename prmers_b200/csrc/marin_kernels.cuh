@@ -95,6 +95,11 @@ struct View
 	HD size_t pidx(u32 i) const { return (size_t)i * mul + ((i >> 4) & pad); }
 	HD u64 ld(u32 i) const { return p[2 * pidx(i)]; }
 	HD void st(u32 i, u64 v) const { p[2 * pidx(i)] = v; }
+	// elements base + s q, q < R, sit at constant distance when there is no padding, when s is a multiple
+	// of 16, or when the whole butterfly lies inside one aligned group of 16 (s R <= 16, a power of two):
+	// true for every hot stage, and it replaces a multiply-shift-mask-add per element by one add
+	HD bool linear(u32 s, u32 R) const { const u32 L = s * R; return pad == 0 || (s & 15) == 0 || (L <= 16 && (L & (L - 1)) == 0); }
+	HD size_t step(u32 s) const { return 2 * ((size_t)s * mul + ((s >> 4) & pad)); }
 };
 HD View view_global(const void *base, size_t pair_off, u32 stride, u32 lane) { return View{(u64 *)base + 2 * pair_off + lane, stride, 0}; }
 HD View view_lin(void *sm, u32 lane) { return View{(u64 *)sm + lane, 1, 0xffffffffu}; }
@@ -208,8 +213,18 @@ template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 bas
 	const u64 *c5, const Boundary *bd)
 {
 	u64 a[R];
-	#pragma unroll
-	for (u32 q = 0; q < R; ++q) a[INV ? slot_of<R>(q) : q] = in.ld(base + s * q);
+	if (in.linear(s, R))
+	{
+		const u64 *pi = in.p + 2 * in.pidx(base);
+		const size_t di = in.step(s);
+		#pragma unroll
+		for (u32 q = 0; q < R; ++q) a[INV ? slot_of<R>(q) : q] = pi[q * di];
+	}
+	else
+	{
+		#pragma unroll
+		for (u32 q = 0; q < R; ++q) a[INV ? slot_of<R>(q) : q] = in.ld(base + s * q);
+	}
 
 	if (INV && bd && bd->twiddle)
 		#pragma unroll
@@ -245,8 +260,18 @@ template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 bas
 		#pragma unroll
 		for (u32 q = 0; q < R; ++q) a[q] = gl::mul(a[q], bd->wpost[(size_t)(base + s * q) * bd->wstride]);
 
-	#pragma unroll
-	for (u32 k = 0; k < R; ++k) out.st(base + s * k, a[INV ? k : slot_of<R>(k)]);
+	if (out.linear(s, R))
+	{
+		u64 *po = out.p + 2 * out.pidx(base);
+		const size_t dstep = out.step(s);
+		#pragma unroll
+		for (u32 k = 0; k < R; ++k) po[k * dstep] = a[INV ? k : slot_of<R>(k)];
+	}
+	else
+	{
+		#pragma unroll
+		for (u32 k = 0; k < R; ++k) out.st(base + s * k, a[INV ? k : slot_of<R>(k)]);
+	}
 }
 
 // ------------------------------------------------------------------ pointwise, modulo (t^2 - u)
