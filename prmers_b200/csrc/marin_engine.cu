@@ -64,6 +64,28 @@ __global__ void k_lin_p2(const __grid_constant__ LinArgs A, u32 count)
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < count) lin_p2_thread(A, i);
 }
+// carry into the first pair of every block, taken from the ORIGINAL register content (runs before k_lin_pairs)
+__global__ void k_lin_boundary(const __grid_constant__ LinArgs A, u32 nblocks)
+{
+	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nblocks) return;
+	const u32 npairs = A.t.n / 2;
+	const u32 first = b * LIN_BLOCK;
+	A.carry[b] = lin_pair_carry(A, (first == 0) ? npairs - 1 : first - 1);
+}
+
+__global__ void __launch_bounds__(LIN_BLOCK) k_lin_pairs(const __grid_constant__ LinArgs A)
+{
+	__shared__ u64 cs[LIN_BLOCK];
+	const u32 npairs = A.t.n / 2;
+	const u32 i = blockIdx.x * LIN_BLOCK + threadIdx.x;
+	u64 u0 = 0, u1 = 0; u32 w0 = 1, w1 = 1;
+	if (i < npairs) { lin_pair_compute(A, i, u0, u1, w0, w1); cs[threadIdx.x] = u1 >> w1; }
+	__syncthreads();
+	// a register that fits one block wraps its own end-around carry (no boundary kernel needed)
+	if (i < npairs) lin_pair_finish(A, i, u0, u1, w0, w1, threadIdx.x ? cs[threadIdx.x - 1] : ((gridDim.x == 1) ? cs[npairs - 1] : A.carry[blockIdx.x]));
+}
+
 __global__ void k_unweight(const __grid_constant__ Tables t, const u64 *x, u64 *out, u32 n)
 {
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,6 +136,13 @@ struct CudaBackend
 	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_mid<<<grid, cap(thr, MARIN_MID_MAXT), smem, st>>>(A); post(); }
 	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<false><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
 	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<true><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
+	void lin_pairs(const LinArgs &A)
+	{
+		use();
+		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
+		if (nblocks > 1) { k_lin_boundary<<<(nblocks + 127) / 128, 128, 0, st>>>(A, nblocks); post(); }
+		k_lin_pairs<<<nblocks, LIN_BLOCK, 0, st>>>(A); post();
+	}
 	void lin_p1(const LinArgs &A, u32 count) { use(); k_lin_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void lin_p2(const LinArgs &A, u32 count) { use(); k_lin_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }

@@ -282,6 +282,7 @@ private:
 	{
 		touch(dst);
 		LinArgs L{_t, R(dst), R(src), digits, _carry, op, a, pl.D};
+		if (op == LIN_ADD || op == LIN_SUBREG || op == LIN_SUBSMALL) { be.lin_pairs(L); return; }
 		be.lin_p1(L, pl.n / pl.D);
 		be.lin_p2(L, pl.n / pl.D);
 	}

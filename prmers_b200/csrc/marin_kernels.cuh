@@ -701,6 +701,53 @@ HD void lin_p2_thread(const LinArgs &A, u32 r)
 	for (u32 i = 0; i < cnt; ++i) A.dst[j0 + i] = gl::mul(d[i], t.w_nat[j0 + i]);
 }
 
+// ---- fast path for add / sub_reg / sub(small): one thread per PAIR, fully coalesced, single-hop carry.
+// The sums are tiny (a few units above 2^w), so each digit takes the carry of the digit before it and
+// stops there; what is left keeps digits within a few units of their width, which is the same
+// semi-carried state the reference leaves (adc4 / addc4, marin.cl:203-212,268-279).
+HD void lin_pair_compute(const LinArgs &A, u32 i, u64 &u0, u64 &u1, u32 &w0, u32 &w1)
+{
+	const Tables &t = A.t;
+	const u32 j = 2 * i;
+	w0 = digit_width(t, j); w1 = digit_width(t, j + 1);
+	const pair_t x = reinterpret_cast<const pair_t *>(A.dst)[i], wi = reinterpret_cast<const pair_t *>(t.winv_nat)[i];
+	const u64 m0 = ((u64)1 << w0) - 1, m1 = ((u64)1 << w1) - 1;
+	if (A.op == LIN_ADD)
+	{
+		const pair_t y = reinterpret_cast<const pair_t *>(A.src)[i];
+		u0 = gl::mul(gl::add(x.x, y.x), wi.x); u1 = gl::mul(gl::add(x.y, y.y), wi.y);
+	}
+	else if (A.op == LIN_SUBREG)
+	{
+		const pair_t y = reinterpret_cast<const pair_t *>(A.src)[i];
+		u0 = gl::add(gl::mul(gl::sub(x.x, y.x), wi.x), 2 * m0); u1 = gl::add(gl::mul(gl::sub(x.y, y.y), wi.y), 2 * m1);
+	}
+	else // LIN_SUBSMALL
+	{
+		u0 = gl::mul(x.x, wi.x) + (m0 - ((j < 64) ? small_digit(t, j, A.a) : 0));
+		u1 = gl::mul(x.y, wi.y) + (m1 - ((j + 1 < 64) ? small_digit(t, j + 1, A.a) : 0));
+	}
+}
+
+HD void lin_pair_finish(const LinArgs &A, u32 i, u64 u0, u64 u1, u32 w0, u32 w1, u64 cin)
+{
+	const pair_t w = reinterpret_cast<const pair_t *>(A.t.w_nat)[i];
+	const u64 v0 = (u0 & (((u64)1 << w0) - 1)) + cin;
+	const u64 v1 = (u1 & (((u64)1 << w1) - 1)) + (u0 >> w0);
+	pair_t o; o.x = gl::mul(v0, w.x); o.y = gl::mul(v1, w.y);
+	reinterpret_cast<pair_t *>(A.dst)[i] = o;
+}
+
+// carry out of pair i (what the first digit of pair i + 1 receives)
+HD u64 lin_pair_carry(const LinArgs &A, u32 i)
+{
+	u64 u0, u1; u32 w0, w1;
+	lin_pair_compute(A, i, u0, u1, w0, w1);
+	return u1 >> w1;
+}
+
+static constexpr u32 LIN_BLOCK = 256; // pairs per CTA of the fast linear kernel
+
 // unweighted digit values (not carried) for the host-side canonical export (engine_gpu.h:1534-1561)
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
 

@@ -3,6 +3,7 @@
 // emulated thread after the other with a barrier between phases, so that indexing, twiddles and
 // carry logic can be checked against the oracle in the CPU-only test tier.  It is never built into
 // or loaded by the product library; the product has no CPU path.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -53,6 +54,23 @@ struct CpuBackend
 				for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, b, ph, t, thr, sm.data());
 		for (u32 ph = park; ph < nph; ++ph)
 			for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, 0, ph, t, thr, sm0.data());
+	}
+	void lin_pairs(const LinArgs &A)
+	{
+		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
+		for (u32 b = 0; b < nblocks; ++b) { const u32 first = b * LIN_BLOCK; A.carry[b] = lin_pair_carry(A, first == 0 ? npairs - 1 : first - 1); }
+		std::vector<u64> cs(LIN_BLOCK);
+		for (u32 b = 0; b < nblocks; ++b)
+		{
+			const u32 cnt = std::min<u32>(LIN_BLOCK, npairs - b * LIN_BLOCK);
+			for (u32 t = 0; t < cnt; ++t) cs[t] = lin_pair_carry(A, b * LIN_BLOCK + t);
+			for (u32 t = 0; t < cnt; ++t)
+			{
+				u64 u0, u1; u32 w0, w1;
+				lin_pair_compute(A, b * LIN_BLOCK + t, u0, u1, w0, w1);
+				lin_pair_finish(A, b * LIN_BLOCK + t, u0, u1, w0, w1, t ? cs[t - 1] : A.carry[b]);
+			}
+		}
 	}
 	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
 	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
