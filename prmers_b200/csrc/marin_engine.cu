@@ -170,11 +170,13 @@ void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose)
 	{
 		g_err.clear();
 		u32 force_S = 0;
-		if (const char *s = getenv("MARIN_B200_FORCE_S")) force_S = (u32)atoi(s); // test hook: force the 3-pass path
-		Eng *e = new Eng(p, reg_count, (int)device, force_S);
+		u32 force_R2 = 0;
+		if (const char *s = getenv("MARIN_B200_FORCE_S")) force_S = (u32)atoi(s);   // test hooks: force the 3-pass path
+		if (const char *s = getenv("MARIN_B200_FORCE_R2")) force_R2 = (u32)atoi(s); // ... and the second strided pass
+		Eng *e = new Eng(p, reg_count, (int)device, force_S, force_R2);
 		if (verbose)
-			fprintf(stderr, "marin_b200: p = %u, n = %u, %s, R = %u, S = %u, %zu registers, device %u\n", p, e->pl.n,
-				e->pl.small ? "single-CTA path" : "3-pass path", e->pl.R, e->pl.S, reg_count, device);
+			fprintf(stderr, "marin_b200: p = %u, n = %u, %s, R = %u x %u, S = %u, %zu registers, device %u\n", p, e->pl.n,
+				e->pl.small ? "single-CTA path" : (e->pl.R2 > 1 ? "5-pass path" : "3-pass path"), e->pl.R, e->pl.R2, e->pl.S, reg_count, device);
 		return e;
 	}
 	catch (const std::exception &ex) { g_err = ex.what(); return nullptr; }

@@ -17,11 +17,11 @@ public:
 	Plan pl;
 	Backend be;
 
-	EngineCore(u32 p, size_t regs, int device, u32 force_S = 0) : be(device), _regs(regs)
+	EngineCore(u32 p, size_t regs, int device, u32 force_S = 0, u32 force_R2 = 0) : be(device), _regs(regs)
 	{
 		std::string err;
 		if (regs == 0) throw std::runtime_error("marin_b200: register count must be >= 1");
-		if (!make_plan(p, pl, err, force_S)) throw std::runtime_error("marin_b200: " + err);
+		if (!make_plan(p, pl, err, force_S, force_R2)) throw std::runtime_error("marin_b200: " + err);
 		HostTables h;
 		build_tables(pl, h);
 		_wbits = h.wbits;
@@ -38,13 +38,16 @@ public:
 		t.wbits = (const u32 *)upload(h.wbits.data(), h.wbits.size() * 4);
 		t.twS = (const u64 *)upload(h.twS.data(), h.twS.size() * 8); t.S = pl.S;
 		t.twSi = (const u64 *)upload(h.twSi.data(), h.twSi.size() * 8);
-		t.twR = (const u64 *)upload(h.twR.data(), h.twR.size() * 8); t.R = pl.R;
-		t.twRi = (const u64 *)upload(h.twRi.data(), h.twRi.size() * 8);
+		_twR = (const u64 *)upload(h.twR.data(), h.twR.size() * 8);
+		_twRi = (const u64 *)upload(h.twRi.data(), h.twRi.size() * 8);
+		_twR2 = (const u64 *)upload(h.twR2.data(), h.twR2.size() * 8);
+		_twR2i = (const u64 *)upload(h.twR2i.data(), h.twR2i.size() * 8);
+		_rowK2 = (const u32 *)upload(h.rowK2.data(), h.rowK2.size() * 4);
 		t.bl_lo = (const u64 *)upload(h.bl_lo.data(), h.bl_lo.size() * 8);
 		t.bl_hi = (const u64 *)upload(h.bl_hi.data(), h.bl_hi.size() * 8); t.bl_h = h.bl_h;
 		t.bl_loi = (const u64 *)upload(h.bl_loi.data(), h.bl_loi.size() * 8);
 		t.bl_hii = (const u64 *)upload(h.bl_hii.data(), h.bl_hii.size() * 8);
-		t.rowK = (const u32 *)upload(h.rowK.data(), h.rowK.size() * 4);
+		_rowK = (const u32 *)upload(h.rowK.data(), h.rowK.size() * 4);
 		t.rowroot = (const u64 *)upload(h.rowroot.data(), h.rowroot.size() * 8);
 		t.colroot = (const u64 *)upload(h.colroot.data(), h.colroot.size() * 8);
 		for (int i = 0; i < 4; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
@@ -53,7 +56,7 @@ public:
 		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat};
 		be.weights(W, pl.n);
 		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat;
-		const size_t nflags = (size_t)(pl.S / TILE_C) + 1;
+		const size_t nflags = (size_t)(pl.R2 * pl.S / TILE_C) + 1;
 		_flags = (u32 *)be.alloc(nflags * 4);
 		be.memset0(_flags, nflags * 4);
 		_nflags = nflags;
@@ -99,10 +102,12 @@ public:
 		check(r); check_a(a);
 		if (pl.small) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M); return; }
 		const bool chained = (_last_sq == r);            // second squaring in a row: start speculating
-		if (_fwd_reg != r) strided(false, R(r), _fwd, 1, nullptr);
+		if (_fwd_reg != r) strided(false, 0, R(r), _fwd, 1, nullptr);
 		_fwd_reg = (size_t)-1;
+		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
 		MidArgs M = mid_args(_fwd, nullptr, _fwd, MODE_SQR, a); launch_mid(M);
-		strided(true, _fwd, R(r), a, chained ? _fwd : nullptr);
+		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
+		strided(true, 0, _fwd, R(r), a, chained ? _fwd : nullptr);
 		if (chained) _fwd_reg = r;
 		_last_sq = r;
 	}
@@ -112,7 +117,8 @@ public:
 		check(dst); check(src);
 		if (pl.small) { MidArgs M = mid_args(R(src), nullptr, R(dst), MODE_FWD, 1); launch_mid(M); return; }
 		touch(dst);
-		strided(false, R(src), R(dst), 1, nullptr);
+		strided(false, 0, R(src), R(dst), 1, nullptr);
+		if (pl.R2 > 1) strided(false, 1, R(dst), R(dst), 1, nullptr);
 		MidArgs M = mid_args(R(dst), nullptr, R(dst), MODE_FWD, 1); launch_mid(M);
 	}
 
@@ -121,10 +127,12 @@ public:
 		check(dst); check(src); check_a(a);
 		if (dst == src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
 		if (pl.small) { MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M); return; }
-		if (_fwd_reg != dst) strided(false, R(dst), _fwd, 1, nullptr);
+		if (_fwd_reg != dst) strided(false, 0, R(dst), _fwd, 1, nullptr);
 		touch(dst);
+		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
 		MidArgs M = mid_args(_fwd, R(src), _fwd, MODE_MUL, a); launch_mid(M);
-		strided(true, _fwd, R(dst), a, nullptr);
+		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
+		strided(true, 0, _fwd, R(dst), a, nullptr);
 	}
 
 	void sub_u32(size_t r, u32 a)
@@ -180,8 +188,9 @@ public:
 		touch(r);
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
-		fill_strided_args(pl, A);
-		A.t = _t; A.src = (const pair_t *)R(r); A.dst = (pair_t *)R(r); A.a = 1; A.carry = _carry;
+		fill_strided_args(pl, A, 0);
+		set_pass_tables(A, 0);
+		A.src = (const pair_t *)R(r); A.dst = (pair_t *)R(r); A.a = 1; A.carry = _carry;
 		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
 		if (which == 0) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return true; }
 		if (which == 1) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
@@ -209,6 +218,8 @@ private:
 	size_t _fwd_reg = (size_t)-1, _last_sq = (size_t)-1;
 	size_t _nflags = 0;
 	Tables _t;
+	const u64 *_twR = nullptr, *_twRi = nullptr, *_twR2 = nullptr, *_twR2i = nullptr;
+	const u32 *_rowK = nullptr, *_rowK2 = nullptr;
 	std::vector<u32> _wbits;
 	std::vector<void *> _owned;
 
@@ -260,16 +271,26 @@ private:
 	// any write to a register other than by square_mul drops the parked forward transform of it
 	void touch(size_t r) { if (_fwd_reg == r) _fwd_reg = (size_t)-1; if (_last_sq == r) _last_sq = (size_t)-1; }
 
-	void strided(bool inv, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst)
+	void set_pass_tables(StridedArgs &A, int level)
+	{
+		A.t = _t;
+		A.tw = level ? _twR2 : _twR; A.twi = level ? _twR2i : _twRi; A.rowK = level ? _rowK2 : _rowK;
+	}
+
+	// level 0 = strided pass over the whole register (the inverse one carries), level 1 = second strided
+	// pass inside each of the R blocks (only for transforms with more rows than one tile can hold)
+	void strided(bool inv, int level, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst)
 	{
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
-		fill_strided_args(pl, A);
-		A.t = _t; A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.carry = _carry; A.with_carry = inv ? 1 : 0;
-		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
-		if (!inv) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return; }
-		A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst;
-		be.strided_inv(A, A.tiles, pl.thrStr, smem);
+		fill_strided_args(pl, A, level);
+		set_pass_tables(A, level);
+		A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.carry = _carry;
+		const size_t smem = (size_t)A.R * TILE_PITCH * 16;
+		const u32 grid = A.tiles * (level ? pl.R : 1), thr = level ? pl.thrStr2 : pl.thrStr;
+		if (!inv) { be.strided_fwd(A, grid, thr, smem); return; }
+		if (level == 0) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst; }
+		be.strided_inv(A, grid, thr, smem);
 	}
 
 	u32 next_epoch()

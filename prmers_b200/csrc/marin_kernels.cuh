@@ -61,10 +61,8 @@ struct Tables
 	u64 inv_m;                   // 1/m
 	// block transforms
 	const u64 *twS, *twSi; u32 S; // S powers of the S-th root and of its inverse (contiguous pass)
-	const u64 *twR, *twRi; u32 R; // R powers of the R-th root and of its inverse (strided pass), R = 2^a or 5 2^a
 	const u64 *bl_lo, *bl_hi, *bl_loi, *bl_hii; u32 bl_h; // m-th root: w^(+-e) = lo[e & (2^h - 1)] * hi[e >> h]
-	const u32 *rowK;             // frequency index of row rho after the strided pass
-	const u64 *rowroot;          // w_m^rowK[rho]
+	const u64 *rowroot;          // w_m^(frequency index of the contiguous block) after the strided pass(es)
 	const u64 *colroot;          // w_S^freq(sigma), position order inside a contiguous block
 	u64 w5[4];                   // radix-5 constants (c1, c2, s1, s2), see dft5
 	u64 w5i[4];
@@ -362,6 +360,8 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	const pair_t *src; pair_t *dst; // src == dst for in-place
 	u32 R, nst;
 	Stage st[MAX_STAGES];
+	const u64 *tw, *twi; // R powers of the R-th root of unity and of its inverse (R = 2^a or 5 2^a)
+	const u32 *rowK;    // frequency index of row rho after this pass's stages
 	u32 Lb;             // block length in pairs (= R * stride)
 	u32 stride;         // pairs between rows
 	u32 escale;         // m / Lb
@@ -480,24 +480,24 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 // ---- strided passes ----------------------------------------------------------------------------
 // Tile = R rows x 8 pair columns; butterfly id b -> column c = b & 7 (fastest: 128 B rows), row-butterfly b >> 3.
 
-template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, u32 blockbase /*pairs*/, u32 c0,
+template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, size_t blockbase /*pairs*/, u32 c0,
 	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)
 {
 	const Tables &t = A.t;
 	const u32 nb = (A.R / R) * TILE_C * 2;
-	const Tw tw{(sg.s > 1) ? (INV ? t.twRi : t.twR) : nullptr, t.R / sg.L};
+	const Tw tw{(sg.s > 1) ? (INV ? A.twi : A.tw) : nullptr, A.R / sg.L};
 	for (u32 b = tid; b < nb; b += nthr)
 	{
 		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b / (2 * TILE_C);
 		const u32 blk = rb / sg.s, j = rb % sg.s;
 		const u32 base = blk * sg.L + j;
-		const View Gi = view_global(gsrc, (size_t)blockbase + c0 + c, A.stride, lane);
-		const View Go = view_global(gdst, (size_t)blockbase + c0 + c, A.stride, lane);
+		const View Gi = view_global(gsrc, blockbase + c0 + c, A.stride, lane);
+		const View Go = view_global(gdst, blockbase + c0 + c, A.stride, lane);
 		const View Sv = view_tile(sm, c, lane);
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_nat + 2 * (size_t)(c0 + c) + lane : nullptr, 2 * (size_t)A.stride,
-			last ? t.rowK[base] : 0u, A.R / R};
+			last ? A.rowK[base] : 0u, A.R / R};
 		if (!INV)
 			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
@@ -505,7 +505,7 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 	}
 }
 
-template <bool INV> HD void dispatch_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, u32 blockbase, u32 c0,
+template <bool INV> HD void dispatch_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, size_t blockbase, u32 c0,
 	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)
 {
 	switch (sg.radix)
@@ -548,7 +548,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 {
 	const Tables &t = A.t;
 	const u32 ob = blkid / A.tiles, g = blkid % A.tiles; // outer block, tile
-	const u32 blockbase = ob * A.Lb, c0 = g * TILE_C;
+	const size_t blockbase = (size_t)ob * A.Lb; const u32 c0 = g * TILE_C;
 	if (ph < A.nst)
 	{
 		const u32 si = INV ? (A.nst - 1 - ph) : ph;

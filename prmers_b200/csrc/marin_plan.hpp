@@ -33,10 +33,11 @@ struct Plan
 {
 	u32 p = 0, n = 0, m = 0;
 	bool small = false;
-	u32 S = 0, R = 1;            // m = R * S
-	u32 nstS = 0, nstR = 0;
-	Stage stS[MAX_STAGES], stR[MAX_STAGES];
-	u32 thrMid = 0, thrStr = 0;  // threads per CTA
+	u32 S = 0, R = 1;            // m = R * R2 * S (R2 = 1 unless a second strided pass is needed)
+	u32 R2 = 1;
+	u32 nstS = 0, nstR = 0, nstR2 = 0;
+	Stage stS[MAX_STAGES], stR[MAX_STAGES], stR2[MAX_STAGES];
+	u32 thrMid = 0, thrStr = 0, thrStr2 = 0;  // threads per CTA
 	u32 D = 0;                   // digits per carry run of the linear / small kernels
 	u32 wbase = 0;
 	u32 a_max = 1;               // largest multiplier `a` the carry chain supports without overflow
@@ -61,7 +62,7 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
 
 inline u32 round_threads(u32 t, u32 cap) { t = (t + 31) / 32 * 32; if (t < 32) t = 32; return t > cap ? cap : t; }
 
-inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0)
+inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 force_R2 = 0)
 {
 	if (p < 3) { err = "exponent must be >= 3"; return false; }
 	const size_t n = transform_size(p);
@@ -83,16 +84,28 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0)
 		else if (m / five >= ((five == 5) ? 16u : 64u) * MID_S) { pl.S = MID_S; pl.R = m / MID_S; }
 		else { pl.R = (five == 5) ? 80 : 64; pl.S = m / pl.R; }
 		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || (pl.S & (pl.S - 1)) != 0 || pl.R < 2) { err = "bad forced split"; return false; }
-		if (pl.R > MAX_R || pl.S > MID_S)
+		// more rows than one tile can hold: split them over two strided passes, R = RA * RB, the radix-5
+		// factor (if any) staying in the first
+		if (pl.R > MAX_R || force_R2)
 		{
-			err = "transform size n = " + std::to_string(n) + " needs a second strided pass (not built yet; n <= 2^23 and 5*2^21 are)";
-			return false;
+			const u32 Rall = pl.R, ramin = (five == 5) ? 80u : 64u;
+			u32 rb = force_R2 ? force_R2 : 128;
+			if (!force_R2) while (rb > 2 && Rall / rb < ramin) rb /= 2;
+			if (rb < 2 || Rall % rb != 0 || (rb & (rb - 1)) != 0 || Rall / rb < 2) { err = "bad second-level split"; return false; }
+			pl.R2 = rb; pl.R = Rall / rb;
 		}
+		if (pl.R > MAX_R || pl.S > MID_S) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
 		pl.nstS = factor_stages(pl.S, pl.stS, true);
 		pl.nstR = factor_stages(pl.R, pl.stR, false);
 		pl.thrMid = round_threads(pl.S / 8, 512);
 		const u32 bf = pl.R * TILE_C * 2 / 16; // radix-16 butterflies x lanes per stage
 		pl.thrStr = (bf <= 1024) ? round_threads(bf, 1024) : round_threads(bf / 2, 1024);
+		if (pl.R2 > 1)
+		{
+			pl.nstR2 = factor_stages(pl.R2, pl.stR2, false);
+			const u32 bf2 = pl.R2 * TILE_C * 2 / 16;
+			pl.thrStr2 = round_threads(bf2 ? bf2 : 1, 1024);
+		}
 	}
 	pl.D = (n % 16 == 0 && n >= 256) ? 16 : ((n % 8 == 0 && n >= 16) ? 8 : 4);
 	// a * conv < 2^(64 + w) keeps the carry out of a run below 2^64, and the carry left after three
@@ -115,8 +128,8 @@ inline u32 freq_of_pos(const Stage *st, u32 nst, u32 pos)
 
 struct HostTables
 {
-	std::vector<u32> wbits, rowK;
-	std::vector<u64> twS, twSi, twR, twRi, bl_lo, bl_hi, bl_loi, bl_hii, rowroot, colroot;
+	std::vector<u32> wbits, rowK, rowK2;
+	std::vector<u64> twS, twSi, twR, twRi, twR2, twR2i, bl_lo, bl_hi, bl_loi, bl_hii, rowroot, colroot;
 	u64 inv_m = 0, nr2 = 0, nr2_inv = 0, w5[4], w5i[4];
 	u32 bl_h = 0;
 };
@@ -155,11 +168,17 @@ inline void build_tables(const Plan &pl, HostTables &h)
 	powers(h.bl_hi, gl::pow(rm, (u64)1 << h.bl_h), (m >> h.bl_h) + 1);
 	powers(h.bl_loi, rmi, (size_t)1 << h.bl_h);
 	powers(h.bl_hii, gl::pow(rmi, (u64)1 << h.bl_h), (m >> h.bl_h) + 1);
-	h.rowK.resize(pl.R); h.rowroot.resize(pl.R);
-	for (u32 r = 0; r < pl.R; ++r)
+	// frequency index of each row after the strided pass(es): block rA * R2 + rB holds K_A(rA) + R * K_B(rB)
+	h.rowK.resize(pl.R); h.rowK2.resize(pl.R2); h.rowroot.resize((size_t)pl.R * pl.R2);
+	for (u32 r = 0; r < pl.R; ++r) h.rowK[r] = pl.nstR ? freq_of_pos(pl.stR, pl.nstR, r) : 0;
+	for (u32 r = 0; r < pl.R2; ++r) h.rowK2[r] = pl.nstR2 ? freq_of_pos(pl.stR2, pl.nstR2, r) : 0;
+	for (u32 ra = 0; ra < pl.R; ++ra)
+		for (u32 rb = 0; rb < pl.R2; ++rb)
+			h.rowroot[(size_t)ra * pl.R2 + rb] = gl::pow(rm, (u64)h.rowK[ra] + (u64)pl.R * h.rowK2[rb]);
+	if (pl.R2 > 1)
 	{
-		h.rowK[r] = pl.nstR ? freq_of_pos(pl.stR, pl.nstR, r) : 0;
-		h.rowroot[r] = gl::pow(rm, h.rowK[r]);
+		powers(h.twR2, gl::root_of_unity(pl.R2), pl.R2);
+		powers(h.twR2i, gl::inv(gl::root_of_unity(pl.R2)), pl.R2);
 	}
 	h.colroot.resize(pl.S);
 	const u64 rS = gl::root_of_unity(pl.S);
@@ -180,11 +199,23 @@ inline void fill_mid_args(const Plan &pl, MidArgs &A)
 	A.D = pl.D; A.a = 1;
 }
 
-inline void fill_strided_args(const Plan &pl, StridedArgs &A)
+// level 0: the (first) strided pass over the whole register; level 1: the second strided pass, run
+// independently on each of the R blocks of R2 * S pairs the first one leaves
+inline void fill_strided_args(const Plan &pl, StridedArgs &A, int level = 0)
 {
-	A.R = pl.R; A.nst = pl.nstR;
-	for (u32 i = 0; i < pl.nstR; ++i) A.st[i] = pl.stR[i];
-	A.Lb = pl.m; A.stride = pl.S; A.escale = 1; A.tiles = pl.S / TILE_C; A.a = 1; A.with_carry = 0;
+	if (level == 0)
+	{
+		A.R = pl.R; A.nst = pl.nstR;
+		for (u32 i = 0; i < pl.nstR; ++i) A.st[i] = pl.stR[i];
+		A.Lb = pl.m; A.stride = pl.R2 * pl.S; A.escale = 1;
+	}
+	else
+	{
+		A.R = pl.R2; A.nst = pl.nstR2;
+		for (u32 i = 0; i < pl.nstR2; ++i) A.st[i] = pl.stR2[i];
+		A.Lb = pl.R2 * pl.S; A.stride = pl.S; A.escale = pl.R;
+	}
+	A.tiles = A.stride / TILE_C; A.a = 1; A.with_carry = 0;
 }
 
 } // namespace marin

@@ -35,10 +35,10 @@ def lib():
         L = C.CDLL(_SO)
         vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
         L.emu_last_error.restype = C.c_char_p
-        L.emu_create.restype = vp; L.emu_create.argtypes = [u32, sz, u32]
+        L.emu_create.restype = vp; L.emu_create.argtypes = [u32, sz, u32, u32]
         L.emu_destroy.argtypes = [vp]
         L.emu_size.restype = sz; L.emu_size.argtypes = [vp]
-        for f in ("emu_is_small", "emu_plan_R", "emu_plan_S", "emu_a_max"):
+        for f in ("emu_is_small", "emu_plan_R", "emu_plan_S", "emu_plan_R2", "emu_a_max"):
             getattr(L, f).argtypes = [vp]; getattr(L, f).restype = u32
         for f, a in (("emu_set_u32", [vp, sz, u32]), ("emu_copy", [vp, sz, sz]), ("emu_square_mul", [vp, sz, u32]),
                      ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_sub_u32", [vp, sz, u32]),
@@ -51,14 +51,14 @@ def lib():
 
 
 class EmuEngine:
-    def __init__(self, p, regs, force_S=0):
+    def __init__(self, p, regs, force_S=0, force_R2=0):
         L = lib()
-        self._h = L.emu_create(p, regs, force_S)
+        self._h = L.emu_create(p, regs, force_S, force_R2)
         if not self._h:
             raise ValueError(L.emu_last_error().decode())
         self.p, self.n = p, L.emu_size(self._h)
         self.small = bool(L.emu_is_small(self._h))
-        self.R, self.S = L.emu_plan_R(self._h), L.emu_plan_S(self._h)
+        self.R, self.S, self.R2 = L.emu_plan_R(self._h), L.emu_plan_S(self._h), L.emu_plan_R2(self._h)
         self.a_max = L.emu_a_max(self._h)
 
     def __del__(self):

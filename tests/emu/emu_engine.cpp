@@ -89,15 +89,16 @@ static thread_local std::string g_err;
 
 extern "C" {
 const char *emu_last_error() { return g_err.c_str(); }
-void *emu_create(uint32_t p, size_t regs, uint32_t force_S)
+void *emu_create(uint32_t p, size_t regs, uint32_t force_S, uint32_t force_R2)
 {
-	try { return new Emu(p, regs, 0, force_S); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+	try { return new Emu(p, regs, 0, force_S, force_R2); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 void emu_destroy(void *h) { delete (Emu *)h; }
 size_t emu_size(void *h) { return ((Emu *)h)->size(); }
 int emu_is_small(void *h) { return ((Emu *)h)->pl.small ? 1 : 0; }
 uint32_t emu_plan_R(void *h) { return ((Emu *)h)->pl.R; }
 uint32_t emu_plan_S(void *h) { return ((Emu *)h)->pl.S; }
+uint32_t emu_plan_R2(void *h) { return ((Emu *)h)->pl.R2; }
 uint32_t emu_a_max(void *h) { return ((Emu *)h)->pl.a_max; }
 int emu_set_u32(void *h, size_t d, uint32_t a) { GUARD(((Emu *)h)->set_u32(d, a)) }
 int emu_copy(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->copy(d, s)) }

@@ -129,3 +129,23 @@ def test_planner_and_limits():
         e.copy(0, 9)
     with pytest.raises(ValueError):
         EmuEngine(2, 1)
+
+
+@pytest.mark.parametrize("p,force_S,force_R2", [(9941, 4, 2), (86243, 8, 16), (86243, 16, 4), (216091, 16, 8), (1362763, 64, 8)])
+def test_two_level_strided_passes(p, force_S, force_R2):
+    """Transforms with more rows than one tile holds run two strided passes each way (5 kernels per
+    squaring); forced here on small sizes so the emulator covers the indexing and twiddles."""
+    e = EmuEngine(p, 4, force_S, force_R2)
+    assert e.R2 == force_R2
+    wd = mo.widths(e.n, p)
+    m = mr.mp(p)
+    rng = random.Random(p + force_R2)
+    x, y = rng.randrange(m), rng.randrange(m)
+    put(e, 0, x, wd); put(e, 1, y, wd)
+    for a in (1, 3, 1, 1):                       # a chain: the fused inverse+forward path kicks in from the 2nd
+        e.square_mul(0, a); x = x * x * a % m
+        assert val(e, 0) == x
+    e.set_multiplicand(2, 1); e.mul(0, 2); x = x * y % m
+    assert val(e, 0) == x
+    e.sub(0, 2); e.square_mul(0); x = (x - 2) ** 2 % m
+    assert val(e, 0) == x

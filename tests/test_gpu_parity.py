@@ -13,14 +13,17 @@ from oracle import mersenne_ref as mr
 pytestmark = pytest.mark.gpu
 
 
-def _engine(p, regs, force_S=0):
+def _engine(p, regs, force_S=0, force_R2=0):
     import prmers_b200 as pb
     if force_S:
         os.environ["MARIN_B200_FORCE_S"] = str(force_S)
+    if force_R2:
+        os.environ["MARIN_B200_FORCE_R2"] = str(force_R2)
     try:
         return pb.Engine(p, regs)
     finally:
         os.environ.pop("MARIN_B200_FORCE_S", None)
+        os.environ.pop("MARIN_B200_FORCE_R2", None)
 
 
 def val(e, r):
@@ -292,6 +295,57 @@ def test_long_chain_gerbicz_identity_full_size():
     e.set(2, 0); e.set_data(2, ck); e.square_mul(2)            # b^2
     e.set_multiplicand(2, 2); e.mul(0, 2)
     assert e.is_equal(0, 3)
+    e.close()
+
+
+@pytest.mark.parametrize("p,force_S,force_R2", [(9941, 4, 2), (86243, 8, 16), (216091, 16, 8), (1362763, 64, 8), (20000003, 4096, 4)])
+def test_two_level_strided_passes_forced(p, force_S, force_R2):
+    e = _engine(p, 4, force_S, force_R2)
+    m = mr.mp(p)
+    rng = random.Random(p + force_R2)
+    x, y = rng.randrange(m), rng.randrange(m)
+    M = lambda u, v: mr.mulmod(u, v, p)
+    e.set_mpz(0, x); e.set_mpz(1, y)
+    for a in (1, 3, 1, 1):
+        e.square_mul(0, a); x = M(M(x, x), a)
+        assert val(e, 0) == x
+    e.set_multiplicand(2, 1); e.mul(0, 2); x = M(x, y)
+    assert val(e, 0) == x
+    e.sub(0, 2); e.square_mul(0); x = M((x - 2) % m, (x - 2) % m)
+    assert val(e, 0) == x
+    e.close()
+
+
+@pytest.mark.parametrize("p", [300000007, 400000009, 1100000011, 2200000007])
+def test_large_transforms_two_level(p):
+    """n = 2^24 (p = 3.0e8), 2^25 (4.0e8), 2^26 (1.1e9) and 5 * 2^25 (2.2e9): beyond one tile of rows, five kernels per
+    squaring.  Exact small powers (3^(2^k) fits a few digits), then size-independent identities on a
+    dense pseudo-random residue, and one squaring against GMP."""
+    e = _engine(p, 5)
+    n = e.get_size()
+    assert n == mo.transform_size(p) and n > (1 << 23)
+    e.set(0, 3)
+    for k in range(1, 7):
+        e.square_mul(0)
+        assert val(e, 0) == 3 ** (2 ** k)
+    rng = np.random.default_rng(p)
+    wd = mo.widths(n, p).astype(np.uint64)
+    x = (rng.integers(0, 1 << 32, size=n, dtype=np.uint64) & ((np.uint64(1) << wd) - np.uint64(1))) | (wd << np.uint64(32))
+    e.set_digits(0, x)
+    assert np.array_equal(e.get(0), x)
+    xv = val(e, 0)
+    e.copy(1, 0); e.copy(2, 0)
+    e.square_mul(0, 3)
+    if p < 500000000:
+        assert val(e, 0) == mr.mulmod(mr.mulmod(xv, xv, p), 3, p)
+    e.set_multiplicand(3, 1); e.mul(2, 3, 3)
+    assert e.is_equal(2, 0)                                      # x*x via mul == square_mul
+    e.add(1, 1); e.square_mul(1, 3)                              # 3 (2x)^2 = 4 * (3 x^2)
+    e.copy(4, 0); e.add(4, 4); e.add(4, 4)
+    assert e.is_equal(1, 4)
+    e.square_mul(0); e.square_mul(0); e.square_mul(4); e.square_mul(4)   # chained path: (4 y)^4 = 256 y^4
+    e.set(3, 256); e.set_multiplicand(3, 3); e.mul(0, 3)
+    assert e.is_equal(0, 4)
     e.close()
 
 
