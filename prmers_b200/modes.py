@@ -1,4 +1,5 @@
-"""Callers of the hot path: PRP, Lucas-Lehmer and P-1 stage 1 loops over the engine API.
+"""Callers of the hot path: PRP, Lucas-Lehmer (classic and LL-safe) and P-1 (stage 1, V-trace
+stage 2) loops over the engine API.
 
 Host loops only -- every arithmetic step is an engine call (square_mul, mul, set_multiplicand, copy,
 sub), exactly as src/modes does it; nothing here touches digits except the final residue export.
@@ -290,3 +291,90 @@ def split_k_range(b1, b2, D, world):
     total = k_last + 1 - k_first
     cuts = [k_first + total * r // world for r in range(world + 1)]
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+# ---- LL-safe: Lucas-Lehmer in Z[sqrt 3] with pair Gerbicz-Li (`prmers p -ll`, RunLlSafeMarin.cpp:479-694) ----
+(LS_RES_A, LS_RES_B, LS_ACC_A, LS_ACC_B, LS_CHK_A, LS_CHK_B, LS_SAVE_R_A, LS_SAVE_R_B, LS_SAVE_F_A, LS_SAVE_F_B,
+ LS_BASE_A, LS_BASE_B, LS_TA, LS_TB, LS_M0, LS_M1, LS_PREV_A, LS_PREV_B) = range(18)
+
+
+def _pair_square(eng, A, B):
+    """(A, B) <- (A^2 + 3 B^2, 2 A B), i.e. (A + B sqrt 3)^2 (RunLlSafeMarin.cpp:481-490)."""
+    eng.copy(LS_TA, A); eng.copy(LS_TB, B)
+    eng.square_mul(A); eng.square_mul(B, 3); eng.add(A, B)
+    eng.copy(B, LS_TA); eng.set_multiplicand(LS_M0, LS_TB); eng.mul(B, LS_M0, 2)
+
+
+def _pair_mul_by(eng, A, B, Cc, Dd):
+    """(A, B) <- (A C + 3 B D, A D + B C) (RunLlSafeMarin.cpp:492-507)."""
+    eng.set_multiplicand(LS_M0, Cc); eng.set_multiplicand(LS_M1, Dd)
+    eng.copy(LS_TA, A); eng.copy(LS_TB, B)
+    eng.copy(A, LS_TA); eng.mul(A, LS_M0)
+    eng.copy(B, LS_TA); eng.mul(B, LS_M1)
+    eng.copy(LS_TA, LS_TB); eng.mul(LS_TA, LS_M1, 3); eng.add(A, LS_TA)
+    eng.copy(LS_TA, LS_TB); eng.mul(LS_TA, LS_M0); eng.add(B, LS_TA)
+
+
+def run_ll_safe(eng, p, check_level=0, error_iter=0, log=None, max_restores=4):
+    """`prmers p -ll`: (2 + sqrt 3)^(2^(p-1)) in Z[sqrt 3] mod 2^p - 1 is (-1, 0) iff 2^p - 1 is prime; the
+    running product of the block-end pairs is checked Gerbicz-Li style and a mismatch restores the last
+    verified pair (RunLlSafeMarin.cpp:539-694).  Needs 18 registers."""
+    say = log or (lambda s: None)
+    m = (1 << p) - 1
+    total = p - 1
+    B = max(min(int(math.isqrt(p)), total), 1)
+    level_auto = int(1000 * 600.0 / B) or 1
+    level = check_level if check_level > 0 else max(level_auto, 1)
+    eng.set(LS_RES_A, 2); eng.set(LS_RES_B, 1)
+    eng.set(LS_ACC_A, 1); eng.set(LS_ACC_B, 0)
+    for d, s in ((LS_SAVE_R_A, LS_RES_A), (LS_SAVE_R_B, LS_RES_B), (LS_SAVE_F_A, LS_ACC_A), (LS_SAVE_F_B, LS_ACC_B)):
+        eng.copy(d, s)
+    eng.set(LS_BASE_A, 2); eng.set(LS_BASE_B, 1)
+    itersave, jsave, checkpass, errors, restores, errordone = 0, total - 1, 0, 0, 0, False
+    it, j = 0, total - 1
+    while it < total:
+        if error_iter > 0 and it + 1 == error_iter and not errordone:
+            errordone = True
+            eng.sub(LS_RES_A, 2)
+            say(f"Injected error at iteration {it + 1}")
+        if it + 1 == total:
+            eng.copy(LS_PREV_A, LS_RES_A); eng.copy(LS_PREV_B, LS_RES_B)
+        _pair_square(eng, LS_RES_A, LS_RES_B)
+        if (j != 0 and j % B == 0) or it == total - 1:
+            checkpass += 1
+            eng.copy(LS_CHK_A, LS_ACC_A); eng.copy(LS_CHK_B, LS_ACC_B)
+            _pair_mul_by(eng, LS_ACC_A, LS_ACC_B, LS_RES_A, LS_RES_B)
+            if checkpass >= level or it == total - 1:
+                modB = B if total % B == 0 else total % B
+                for _ in range(B - modB - 1 if B > modB else 0):
+                    _pair_square(eng, LS_CHK_A, LS_CHK_B)
+                if modB != B:
+                    _pair_square(eng, LS_CHK_A, LS_CHK_B)
+                _pair_mul_by(eng, LS_CHK_A, LS_CHK_B, LS_BASE_A, LS_BASE_B)
+                for _ in range(modB):
+                    _pair_square(eng, LS_CHK_A, LS_CHK_B)
+                same = (_value(eng, LS_CHK_A, p) == _value(eng, LS_ACC_A, p) and _value(eng, LS_CHK_B, p) == _value(eng, LS_ACC_B, p))
+                checkpass = 0
+                if not same:
+                    say(f"[Gerbicz Li] Check FAILED! iter={it + 1}")
+                    errors += 1; restores += 1
+                    if restores > max_restores:
+                        raise RuntimeError("Gerbicz-Li: too many restores")
+                    for d, s in ((LS_RES_A, LS_SAVE_R_A), (LS_RES_B, LS_SAVE_R_B), (LS_ACC_A, LS_SAVE_F_A), (LS_ACC_B, LS_SAVE_F_B)):
+                        eng.copy(d, s)
+                    if itersave == 0:
+                        it, j = 0, total - 1
+                    else:
+                        it, j = itersave + 1, jsave - 1
+                    continue
+                say(f"[Gerbicz Li] Check passed! iter={it + 1}")
+                for d, s in ((LS_SAVE_R_A, LS_RES_A), (LS_SAVE_R_B, LS_RES_B), (LS_SAVE_F_A, LS_ACC_A), (LS_SAVE_F_B, LS_ACC_B)):
+                    eng.copy(d, s)
+                itersave, jsave = it, j
+        it += 1; j -= 1
+    a, b = _value(eng, LS_RES_A, p), _value(eng, LS_RES_B, p)
+    # the classical LL residue s_{p-2} is twice the A component of the previous pair (RunLlSafeMarin.cpp:688-693)
+    eng.add(LS_PREV_A, LS_PREV_A)
+    ll = _value(eng, LS_PREV_A, p)
+    return {"exponent": p, "worktype": "LL", "is_prime": a == m - 1 and b == 0, "res64": format_res64(ll),
+            "res2048": format_res2048(ll), "errors_gerbicz": errors, "fft_length": eng.get_size()}

@@ -122,3 +122,31 @@ def test_pm1_stage2_vtrace_gpu(p, b1, b2, factor):
     assert _stage2(lambda q, r: pb.Engine(q, r), p, b1, b2) == factor
     if b2 > 100:
         assert _stage2(lambda q, r: pb.Engine(q, r), p, b1, b2, world=4) == factor
+
+
+def test_ll_safe_emulated():
+    """`prmers 127 -ll` (BASELINE config 1): LL-safe in Z[sqrt 3], 18 registers, pair Gerbicz-Li."""
+    r = modes.run_ll_safe(EmuEngine(127, 18), 127, check_level=1)
+    assert r["is_prime"] and r["errors_gerbicz"] == 0 and r["res64"] == "0000000000000000"
+    r = modes.run_ll_safe(EmuEngine(89, 18), 89)
+    assert r["is_prime"]
+    for p in (91, 101, 263):
+        r = modes.run_ll_safe(EmuEngine(p, 18), p, check_level=2)
+        assert not r["is_prime"] and r["errors_gerbicz"] == 0
+        assert r["res64"] == mr.res64_hex(mr.ll_residue(p))                 # the classical LL residue s_{p-2}
+    log = []
+    r = modes.run_ll_safe(EmuEngine(521, 18), 521, error_iter=100, log=log.append)
+    assert r["errors_gerbicz"] == 1 and r["is_prime"] and any("Check FAILED" in s for s in log)
+
+
+@pytest.mark.gpu
+def test_ll_safe_gpu():
+    import prmers_b200 as pb
+    for p in (127, 2203, 9689):                                              # `prmers p -ll` on known primes
+        assert modes.run_ll_safe(pb.Engine(p, 18), p)["is_prime"]
+    for p in (57, 91, 1001, 8191 + 2):                                       # unit_tests.sh:122-132 style composites
+        r = modes.run_ll_safe(pb.Engine(p, 18), p)
+        assert not r["is_prime"] and r["res64"] == mr.res64_hex(mr.ll_residue(p))
+    log = []
+    r = modes.run_ll_safe(pb.Engine(2203, 18), 2203, error_iter=700, check_level=3, log=log.append)
+    assert r["is_prime"] and r["errors_gerbicz"] == 1
