@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include "marin_engine_core.hpp"
@@ -130,6 +131,29 @@ struct CudaBackend
 	void d2h(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
 	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
 	void sync() { use(); CK(cudaStreamSynchronize(st)); }
+
+	// Keep a buffer (the parked transform a squaring chain ping-pongs through) resident in L2: B200's 126 MB
+	// L2 holds a 64 MiB register, but the weight tables streaming through would evict it between kernels.
+	void persist(void *p, size_t bytes)
+	{
+		use();
+		if (getenv("MARIN_B200_NO_L2_PERSIST")) return;
+		int maxPersist = 0, maxWindow = 0;
+		cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+		if (maxPersist <= 0 || maxWindow <= 0) return;
+		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxPersist) != cudaSuccess) { cudaGetLastError(); return; }
+		cudaStreamAttrValue attr;
+		memset(&attr, 0, sizeof(attr));
+		const size_t win = bytes < (size_t)maxWindow ? bytes : (size_t)maxWindow;
+		attr.accessPolicyWindow.base_ptr = p;
+		attr.accessPolicyWindow.num_bytes = win;
+		attr.accessPolicyWindow.hitRatio = (win <= (size_t)maxPersist) ? 1.0f : (float)((double)maxPersist / (double)win);
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+		if (getenv("MARIN_B200_VERBOSE")) fprintf(stderr, "marin_b200: L2 persistence window %zu bytes (max persisting %d, max window %d)\n", win, maxPersist, maxWindow);
+	}
 	void post() { ++launches; CK(cudaGetLastError()); }
 
 	static u32 cap(u32 thr, u32 maxt) { return thr > maxt ? maxt : thr; }

@@ -31,7 +31,7 @@ public:
 		const size_t ncarry = std::max<size_t>(n / pl.D, n / RUN + 1);
 		_carry = (u64 *)be.alloc(ncarry * 8);
 		_scratch = (u64 *)be.alloc(n * 8);
-		if (!pl.small) _fwd = (u64 *)be.alloc(n * 8);
+		if (!pl.small) { _fwd = (u64 *)be.alloc(n * 8); be.persist(_fwd, n * 8); }
 		Tables &t = _t;
 		std::memset(&t, 0, sizeof(t));
 		t.p = pl.p; t.n = pl.n; t.m = pl.m; t.wbase = pl.wbase; t.inv_m = h.inv_m;

@@ -22,6 +22,7 @@ struct CpuBackend
 	void d2h(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 	void d2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 	void sync() {}
+	void persist(void *, size_t) {}
 
 	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem)
 	{
