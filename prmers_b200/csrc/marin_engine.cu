@@ -47,10 +47,19 @@ template <bool INV> __global__ void __launch_bounds__(MARIN_STR_MAXT, MARIN_STR_
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	__shared__ u32 s_tile;
+	u32 blk = blockIdx.x;
+	if (INV && A.ticket)
+	{
+		// decoupled look-back needs "the tile I wait for has started": take tile numbers from an atomic ticket
+		if (threadIdx.x == 0) s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
+		__syncthreads();
+		blk = s_tile;
+	}
 	const u32 nph = strided_num_phases(A, INV);
 	for (u32 ph = 0; ph < nph; ++ph)
 	{
-		strided_phase<INV>(A, blockIdx.x, ph, threadIdx.x, blockDim.x, sm);
+		strided_phase<INV>(A, blk, ph, threadIdx.x, blockDim.x, sm);
 		__syncthreads();
 	}
 }
@@ -116,7 +125,7 @@ struct CudaBackend
 		CK(cudaGetDeviceProperties(&pr, dev));
 		if (pr.major < 10) throw std::runtime_error("marin_b200: built for sm_100a (Blackwell B200) only");
 		CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-		const int maxsm = (int)pr.sharedMemPerBlockOptin;
+		const int maxsm = (int)pr.sharedMemPerBlockOptin - 1024; // room for the kernels' few static shared words
 		CK(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));

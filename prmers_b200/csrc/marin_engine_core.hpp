@@ -56,7 +56,7 @@ public:
 		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat};
 		be.weights(W, pl.n);
 		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat;
-		const size_t nflags = (size_t)(pl.R2 * pl.S / TILE_C) + 1;
+		const size_t nflags = (size_t)(pl.R2 * pl.S / TILE_C) + 4; // published[tiles], error word, then the 8-byte aligned 64-bit tile ticket
 		_flags = (u32 *)be.alloc(nflags * 4);
 		be.memset0(_flags, nflags * 4);
 		_nflags = nflags;
@@ -78,7 +78,7 @@ public:
 		if (_flags)
 		{
 			u32 err = 0;
-			be.d2h(&err, _flags + (_nflags - 1), 4);
+			be.d2h(&err, _flags + (size_t)(pl.R2 * pl.S / TILE_C), 4);
 			if (err) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
 		}
 	}
@@ -197,7 +197,7 @@ public:
 		if (which == 2 || which == 3)
 		{
 			// 2: inverse pass + carry; 3: the same with the next forward strided pass fused in (chained squarings)
-			A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (which == 3) ? (pair_t *)_fwd : nullptr;
+			A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (which == 3) ? (pair_t *)_fwd : nullptr; set_ticket(A);
 			_fwd_reg = (size_t)-1;
 			be.strided_inv(A, A.tiles, pl.thrStr, smem); return true;
 		}
@@ -217,6 +217,7 @@ private:
 	u64 *_fwd = nullptr;
 	size_t _fwd_reg = (size_t)-1, _last_sq = (size_t)-1;
 	size_t _nflags = 0;
+	unsigned long long _ticket_next = 0;
 	Tables _t;
 	const u64 *_twR = nullptr, *_twRi = nullptr, *_twR2 = nullptr, *_twR2i = nullptr;
 	const u32 *_rowK = nullptr, *_rowK2 = nullptr;
@@ -289,13 +290,23 @@ private:
 		const size_t smem = (size_t)A.R * TILE_PITCH * 16;
 		const u32 grid = A.tiles * (level ? pl.R : 1), thr = level ? pl.thrStr2 : pl.thrStr;
 		if (!inv) { be.strided_fwd(A, grid, thr, smem); return; }
-		if (level == 0) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst; }
+		if (level == 0) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst; set_ticket(A); }
 		be.strided_inv(A, grid, thr, smem);
+	}
+
+	// tile numbers of a carry pass come from a 64-bit counter that only grows: launch k hands out
+	// [k * tiles, (k + 1) * tiles)
+	void set_ticket(StridedArgs &A)
+	{
+		const size_t off = ((size_t)(pl.R2 * pl.S / TILE_C) + 2) & ~(size_t)1; // 8-byte aligned slot after the error word
+		A.ticket = (unsigned long long *)(_flags + off);
+		A.ticket_base = _ticket_next;
+		_ticket_next += A.tiles;
 	}
 
 	u32 next_epoch()
 	{
-		if (++_epoch == 0) { be.memset0(_flags, _nflags * 4); _epoch = 1; } // wrapped: start over from clean flags
+		if (++_epoch == 0) { be.memset0(_flags, ((size_t)(pl.R2 * pl.S / TILE_C) + 1) * 4); _epoch = 1; } // wrapped: start over from clean flags
 		return _epoch;
 	}
 

@@ -372,6 +372,8 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	u32 *flags;         // [tiles + 1]: published[g], error word; hold the epoch of the last launch
 	u32 epoch;
 	pair_t *fwd_dst;    // inverse pass only: also run the next forward strided pass on each tile and write it here
+	unsigned long long *ticket; // carry pass: tiles are handed out in START order (atomic counter, never reset), so the
+	unsigned long long ticket_base; // tile a CTA waits for has always started before it, whatever the block scheduler does
 };
 
 // ------------------------------------------------------------------ phase functions
