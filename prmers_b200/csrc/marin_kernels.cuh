@@ -5,11 +5,15 @@
 //   * a register is n weighted IBDWT digits (u64, natural order), viewed as m = n/2 pairs; the
 //     transform is a length-m NTT applied lane-wise to pairs, the last radix-2 level being replaced
 //     by the 2-term product modulo (t^2 - u)  (same algebra as marin.cl:378-392);
-//   * one squaring is THREE out-of-core passes (strided forward / contiguous middle / strided
-//     inverse + unweight + carry + reweight) instead of the reference's six, each pass a chain of
-//     radix-16 butterflies on 128-bit pairs held in registers with shared-memory exchanges between;
+//   * m = R * S: one squaring is a strided forward pass (tiles of R rows x 4 pair columns), a
+//     contiguous middle pass (one CTA per block of S = 4096 pairs: forward, pointwise, inverse) and a
+//     strided inverse pass that also unweights, carries, hands carries from tile to tile, reweights and
+//     (in a chain of squarings) already runs the next forward strided pass -- two or three launches
+//     where the reference needs seven; transforms too long for one tile of rows get a second strided pass;
+//   * each pass is a chain of radix-16 butterflies held in registers, one lane of the pairs per
+//     thread, with shared-memory exchanges between stages;
 //   * twiddles inside a radix-16 butterfly are shifts (2^12 is a 16th root of unity for our
-//     generator), the ones between stages come from small L1-resident tables.
+//     generator), the ones between stages come from small tables.
 // Everything here is __host__ __device__ and free of threadIdx/blockIdx so that tests/emu can run the
 // very same phase functions on a CPU, thread by thread (test infrastructure; never a product path).
 #pragma once
