@@ -239,10 +239,12 @@ def main():
         dom = max(range(len(PASSES)), key=lambda i: passes[i])
         alg_bytes = PASSES[dom][2] * n                                    # 8n read + 8n write per pass of the 3-pass count
         achieved = alg_bytes / (passes[dom] * 1e-3) / 1e9
-        traffic = None
+        traffic, alu_instr = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"].get(["k_mid", "k_strided<1>+fwd"][dom])
+                summ = json.load(f)
+            traffic = summ["dram_bytes_per_launch"].get(["k_mid", "k_strided<1>+fwd"][dom])
+            alu_instr = sum(summ["alu_pipe_warp_instructions_per_launch"].values())
         except Exception:
             pass
         ms_iter = ms_max / (args.steps * iters)
@@ -270,6 +272,16 @@ def main():
                                     "frac": 48 * n / (ms_iter * 1e-3) / 1e9 / peak,
                                     "algorithmic_bytes_per_iter": 48 * n},
         }
+        if alu_instr and n == (1 << 23):
+            # the unit that actually bounds this path on B200: the integer ALU pipe (one warp instruction per
+            # 2 clocks per SM sub-partition); instruction count from the committed ncu capture, time measured here
+            sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            peak_alu = sms * 4 * 0.5 * sm_hz
+            line["roofline_int_alu_pipe"] = {"achieved": alu_instr / (ms_iter * 1e-3), "peak": peak_alu, "unit": "warp-inst/s",
+                                             "frac": alu_instr / (ms_iter * 1e-3) / peak_alu,
+                                             "alu_warp_instructions_per_square_mul": alu_instr,
+                                             "source": "profiles/ncu_summary.json (ncu capture r1f) + live timing"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = cpu_baseline(8)
