@@ -54,14 +54,16 @@ def format_res2048(r):
     return f"{r & ((1 << 2048) - 1):0512x}"
 
 
-def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4):
+def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4, stop_after_checks=0):
     """PRP test of 2^p - 1 (type 1, base 3): p squarings from 3, prime iff the residue is 9.
 
     Gerbicz-Li checking as the reference: every B = floor(sqrt(p)) iterations the accumulator
     d <- d * x, and every `check_level` blocks (and at the end) d is checked against
     (d_prev)^(2^B) * 3 recomputed from the previous accumulator; on mismatch the last good state is
     restored (RunPrpOrLlMarin.cpp:338-412).  `error_iter` injects a fault (x -= 2) after that
-    iteration, like -erroriter (RunPrpOrLlMarin.cpp:326-336).
+    iteration, like -erroriter (RunPrpOrLlMarin.cpp:326-336).  `stop_after_checks` ends the run after that
+    many passed checks (the reference's size-ladder smoke test stops at the first "Check passed",
+    unit_test_all.sh:54-79); the result then carries `stopped_at` instead of a verdict.
     """
     say = log or (lambda s: None)
     total = p
@@ -74,7 +76,7 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
     eng.set(RBASE, 3)
     eng.set_multiplicand(RTMP, RBASE)
     itersave, jsave = 0, total - 1
-    checkpass, errors, restores, errordone = 0, 0, 0, False
+    checkpass, errors, restores, errordone, passed = 0, 0, 0, False, 0
     it, j = 0, total - 1
     while it < total:
         eng.square_mul(R0)
@@ -114,6 +116,10 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
                 say(f"[Gerbicz Li] Check passed! iter={it + 1}")
                 eng.copy(R4, R0); eng.copy(R5, R1)
                 itersave, jsave = it, j
+                passed += 1
+                if stop_after_checks and passed >= stop_after_checks:
+                    return {"exponent": p, "worktype": "PRP-3", "stopped_at": it + 1, "checks_passed": passed,
+                            "errors_gerbicz": errors, "fft_length": eng.get_size()}
         it += 1; j -= 1
     enc = _digits(eng, R0)
     x = digits_to_int(enc)

@@ -150,3 +150,35 @@ def test_ll_safe_gpu():
     log = []
     r = modes.run_ll_safe(pb.Engine(2203, 18), 2203, error_iter=700, check_level=3, log=log.append)
     assert r["is_prime"] and r["errors_gerbicz"] == 1
+
+
+def test_gerbicz_smoke_stop_at_first_check_emulated():
+    r = modes.run_prp(EmuEngine(9941, 8), 9941, check_level=1, stop_after_checks=1)
+    assert r["checks_passed"] == 1 and r["errors_gerbicz"] == 0 and r["stopped_at"] < 400
+
+
+# unit_test_all.sh:12-40: every transform-size family, -checklevel 1, stop at the first "Check passed"
+LADDER = [127, 1279, 2203, 9941, 44497, 756839, 3021377, 37156667, 57885161, 77232917, 82589933, 136279841,
+          146410013, 161051017, 177156127, 180000017, 200000033, 220000013, 250000013, 300000007, 400000009]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p", LADDER)
+def test_gerbicz_smoke_over_the_size_ladder_gpu(p):
+    import prmers_b200 as pb
+    e = pb.Engine(p, 8)
+    r = modes.run_prp(e, p, check_level=1, stop_after_checks=1)
+    assert r["checks_passed"] == 1 and r["errors_gerbicz"] == 0
+    e.close()
+
+
+@pytest.mark.gpu
+def test_gerbicz_catches_injected_error_at_full_size_gpu():
+    """M136279841 (BASELINE config 2): a fault injected in the first block is caught by the first check and the
+    run restarts from the last good state."""
+    import prmers_b200 as pb
+    p, log = 136279841, []
+    e = pb.Engine(p, 8)
+    r = modes.run_prp(e, p, check_level=1, error_iter=5000, stop_after_checks=1, log=log.append)
+    assert any("Check FAILED" in s for s in log) and r["errors_gerbicz"] == 1 and r["checks_passed"] == 1
+    e.close()
