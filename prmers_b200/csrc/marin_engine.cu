@@ -10,6 +10,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include "marin_engine_core.hpp"
 #include "../../include/marin_b200.h"
 
@@ -130,16 +131,60 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 	}
-	~CudaBackend() { if (st) { cudaSetDevice(dev); cudaStreamDestroy(st); } }
+	~CudaBackend()
+	{
+		cudaSetDevice(dev);
+		for (cudaGraphExec_t g : graphs) cudaGraphExecDestroy(g);
+		if (st) cudaStreamDestroy(st);
+	}
+
+	// ---- CUDA-graph replay of fixed op sequences (ECM point operations at n = 32 are pure launch latency:
+	// the reference pays one enqueue per engine op, include/marin/engine_gpu.h:886-1248)
+	std::vector<cudaGraphExec_t> graphs;
+	std::vector<uint64_t> graph_nodes;
+	bool capturing = false;
+	uint64_t launches_at_begin = 0;
+	void no_capture(const char *what) const { if (capturing) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
+	void graph_begin()
+	{
+		use(); no_capture("graph_begin");
+		cudaFuncAttributes fa; // make sure every kernel a recorded op may launch is loaded before the capture starts
+		CK(cudaFuncGetAttributes(&fa, k_mid)); CK(cudaFuncGetAttributes(&fa, k_lin_pairs)); CK(cudaFuncGetAttributes(&fa, k_lin_boundary));
+		CK(cudaFuncGetAttributes(&fa, k_lin_p1)); CK(cudaFuncGetAttributes(&fa, k_lin_p2));
+		CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+		capturing = true; launches_at_begin = launches;
+	}
+	int graph_end()
+	{
+		if (!capturing) throw std::runtime_error("marin_b200: graph_end without graph_begin");
+		capturing = false;
+		cudaGraph_t g = nullptr;
+		CK(cudaStreamEndCapture(st, &g));
+		cudaGraphExec_t ex = nullptr;
+		const cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+		cudaGraphDestroy(g);
+		CK(e);
+		graphs.push_back(ex); graph_nodes.push_back(launches - launches_at_begin);
+		launches = launches_at_begin;
+		return (int)graphs.size() - 1;
+	}
+	void graph_abort() { if (capturing) { capturing = false; cudaGraph_t g = nullptr; cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); launches = launches_at_begin; } }
+	void graph_launch(int id)
+	{
+		use(); no_capture("graph_launch");
+		if (id < 0 || (size_t)id >= graphs.size()) throw std::runtime_error("marin_b200: unknown graph id");
+		CK(cudaGraphLaunch(graphs[(size_t)id], st));
+		launches += graph_nodes[(size_t)id];
+	}
 
 	void use() { CK(cudaSetDevice(dev)); }
 	void *alloc(size_t b) { use(); void *p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); return p; }
 	void free(void *p) { cudaSetDevice(dev); cudaFree(p); }
 	void memset0(void *p, size_t b) { use(); CK(cudaMemsetAsync(p, 0, b, st)); }
-	void h2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
-	void d2h(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+	void h2d(void *d, const void *s, size_t b) { use(); no_capture("a host transfer"); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+	void d2h(void *d, const void *s, size_t b) { use(); no_capture("a host transfer"); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
 	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
-	void sync() { use(); CK(cudaStreamSynchronize(st)); }
+	void sync() { use(); no_capture("sync"); CK(cudaStreamSynchronize(st)); }
 
 	// Keep a buffer (the parked transform a squaring chain ping-pongs through) resident in L2: B200's 126 MB
 	// L2 holds a 64 MiB register, but the weight tables streaming through would evict it between kernels.
@@ -294,6 +339,15 @@ static void bench_pass(Eng *e, size_t r, int which, uint32_t count, float *ms)
 
 int mb200_bench_pass(void *eng, size_t r, int which, uint32_t count, float *ms) { GUARD(bench_pass(E(eng), r, which, count, ms)); }
 int mb200_is_single_cta(void *eng) { return (eng && E(eng)->pl.small) ? 1 : 0; }
+
+int mb200_graph_begin(void *eng) { GUARD(E(eng)->graph_begin()); }
+int mb200_graph_end(void *eng, int *id)
+{
+	if (!eng) { g_err = "null engine"; return 0; }
+	try { g_err.clear(); *id = E(eng)->graph_end(); return 1; }
+	catch (const std::exception &ex) { g_err = ex.what(); return 0; }
+}
+int mb200_graph_launch(void *eng, int id) { GUARD(E(eng)->graph_launch(id)); }
 
 uint64_t mb200_launch_count(void *eng) { return eng ? E(eng)->be.launches : 0; }
 

@@ -74,6 +74,7 @@ public:
 	size_t regs() const { return _regs; }
 	void sync()
 	{
+		blocking("sync");
 		be.sync();
 		if (_flags)
 		{
@@ -82,6 +83,24 @@ public:
 			if (err) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
 		}
 	}
+
+	// Record the engine calls that follow into a CUDA graph instead of running them (graph_end returns its id,
+	// graph_launch replays it).  Only engines whose every op is one self-contained launch can be recorded: the
+	// multi-pass transforms carry per-launch epochs and tickets in their kernel arguments.
+	void graph_begin()
+	{
+		if (!pl.small) throw std::runtime_error("marin_b200: graph recording is for single-CTA engines (n <= 16384) only");
+		blocking("graph_begin");
+		be.graph_begin();
+		_recording = true;
+	}
+	int graph_end()
+	{
+		if (!_recording) throw std::runtime_error("marin_b200: graph_end without graph_begin");
+		_recording = false;
+		try { return be.graph_end(); } catch (...) { be.graph_abort(); throw; }
+	}
+	void graph_launch(int id) { blocking("graph_launch"); be.graph_launch(id); }
 
 	void set_u32(size_t dst, u32 a)
 	{
@@ -148,7 +167,7 @@ public:
 	// engine_gpu_flat::get does (engine_gpu.h:1534-1561)
 	void get_digits(size_t src, u64 *enc)
 	{
-		check(src);
+		check(src); blocking("get");
 		const u32 n = pl.n;
 		be.unweight(_t, R(src), _scratch, n);
 		be.d2h(enc, _scratch, (size_t)n * 8);
@@ -161,7 +180,7 @@ public:
 
 	void set_digits(size_t dst, const u64 *enc)
 	{
-		check(dst);
+		check(dst); blocking("set");
 		be.h2d(_scratch, enc, (size_t)pl.n * 8);
 		lin(LIN_SETDIGITS, dst, dst, 0, _scratch);
 	}
@@ -174,10 +193,10 @@ public:
 		return a == b;
 	}
 
-	void get_raw(size_t src, void *buf) { check(src); be.d2h(buf, R(src), (size_t)pl.n * 8); }
-	void set_raw(size_t dst, const void *buf) { check(dst); touch(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
-	void get_all(void *buf) { be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
-	void set_all(const void *buf) { _fwd_reg = _last_sq = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
+	void get_raw(size_t src, void *buf) { check(src); blocking("get_data"); be.d2h(buf, R(src), (size_t)pl.n * 8); }
+	void set_raw(size_t dst, const void *buf) { check(dst); blocking("set_data"); touch(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
+	void get_all(void *buf) { blocking("get_checkpoint"); be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
+	void set_all(const void *buf) { blocking("set_checkpoint"); _fwd_reg = _last_sq = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
 
 	// single passes of square_mul, for per-kernel timing (3-pass engines only): 0 strided forward,
 	// 1 contiguous middle, 2 strided inverse + carry, 3 carry fix-up
@@ -232,6 +251,8 @@ private:
 		return d;
 	}
 
+	bool _recording = false;
+	void blocking(const char *what) const { if (_recording) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
 	void check(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }
 	void check_a(u32 a) const
 	{

@@ -1,0 +1,535 @@
+"""ECM on twisted Edwards curves over the engine API (BASELINE config 5).
+
+Host loop only: every field operation is an engine call on the register map of the reference
+(RunEcmTwistedEdwards.cpp:2702-2705,3055-3090: point (X,Y,Z,T) = R3,R4,R1,R5; affine base (X2,Y2,T2) = R6,R7,R9
+and its negative R47,R48,R49; constants a = R16, 2d = R17, d = R29, 2 = R8; persistent multiplicands R43 (a),
+R44 (2), R45 (d), R46 (T2), R50 (-T2); scratch multiplicand R11; temporaries R20-R42; 51 registers).
+Restated from src/modes/RunEcmTwistedEdwards.cpp of the reference:
+  :859-886    splitmix64 / mix64 / rnd_mpz_bits (curve_seed_c = mix64(base_seed, c))
+  :1399-1431  prime lists, :1455-1465 + :1500-1512 stage-1 exponent K = prod q^floor(log_q B1)
+  :2436-2598  default ("no torsion") curve: Suyama sigma -> Montgomery (A, B) -> twisted Edwards (a, d, X0, Y0)
+  :2717-2909  eADD_RP / eADD_RP_2 (mixed addition of +-P) and eDBL_XYTZ (doubling, general a)
+  :3126-3153,3264-3283  NAF of the scalar, double-and-add from the top digit
+  :2626-2652  curve-equation invariant a X^2 + Y^2 = Z^2 + d T^2
+  :3372-3440  stage-1 gcd(T, N), :3542-3566 stage-2 base = affine(Q), :3569-3606,3775-3794 stage-2 chunks
+Not restated (out of the hot path's scope): checkpoint files, Prime95 hand-off, GUI, torsion-16 and family-IV
+curve generators (the a = 1 point operations those use are below for completeness).
+"""
+import math
+
+from .modes import _set_int, _value
+
+M64 = (1 << 64) - 1
+REGS = 51
+
+
+# ---- seeds (RunEcmTwistedEdwards.cpp:859-886) --------------------------------------------------------
+def splitmix64_step(x):
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    z = x
+    z ^= z >> 30; z = (z * 0xBF58476D1CE4E5B9) & M64
+    z ^= z >> 27; z = (z * 0x94D049BB133111EB) & M64
+    z ^= z >> 31
+    return x, z
+
+
+def mix64(seed, idx):
+    x = (seed ^ 0x9E3779B97F4A7C15) & M64
+    x ^= ((idx + 1) * 0xBF58476D1CE4E5B9) & M64
+    x ^= ((idx + 0x100) * 0x94D049BB133111EB) & M64
+    return splitmix64_step(x)[1]
+
+
+def rnd_mpz_bits(N, seed0, bits):
+    z, s = 0, seed0 & M64
+    for _ in range(0, bits, 64):
+        s, w = splitmix64_step(s)
+        z = (z << 64) + w
+    z %= N
+    return z + 3 if z <= 2 else z
+
+
+# ---- scalars ----------------------------------------------------------------------------------------
+def _primes_upto(n):
+    if n < 2:
+        return []
+    sieve = bytearray([1]) * (n + 1)
+    sieve[:2] = b"\0\0"
+    for i in range(2, int(n ** 0.5) + 1):
+        if sieve[i]:
+            sieve[i * i::i] = bytearray(len(sieve[i * i::i]))
+    return [i for i in range(n + 1) if sieve[i]]
+
+
+def ecm_primes(b1, b2):
+    """(primes <= B1, primes in (B1, B2]) -- :1399-1431."""
+    ps = _primes_upto(max(b1, b2))
+    return [q for q in ps if q <= b1], [q for q in ps if b1 < q <= b2]
+
+
+def stage1_exponent(b1):
+    """K = prod_{q <= B1} q^floor(log_q B1) (:1459-1463)."""
+    k = 1
+    for q in _primes_upto(b1):
+        mm = q
+        while mm <= b1 // q:
+            mm *= q
+        k *= mm
+    return k
+
+
+def naf(e):
+    """Non-adjacent form, least significant digit first, top zeros trimmed (:3129-3141,3174)."""
+    out = []
+    while e:
+        d = 0
+        if e & 1:
+            d = 1 if (e & 3) == 1 else -1
+            e -= d
+        out.append(d)
+        e >>= 1
+    while out and out[-1] == 0:
+        out.pop()
+    return out
+
+
+def s2_chunk_bits(n):
+    """compute_s2_chunk_bits (:138-144)."""
+    for lim, bits in ((256, 1048576), (1024, 524288), (4096, 262144), (16384, 131072)):
+        if n <= lim:
+            return bits
+    return 65536
+
+
+def s2_chunks(primes_s2, max_bits):
+    """Stage-2 scalars: products of consecutive primes, closed when they reach max_bits (:3694-3699)."""
+    out, i = [], 0
+    while i < len(primes_s2):
+        e, j = 1, i
+        while j < len(primes_s2):
+            e *= primes_s2[j]; j += 1
+            if e.bit_length() >= max_bits:
+                break
+        out.append((i, j, e))
+        i = j
+    return out
+
+
+# ---- curve from a seed (:2436-2598) --------------------------------------------------------------------
+class FactorFound(Exception):
+    """A modular inversion hit a proper divisor of N (invm returning 1, :2108-2119)."""
+    def __init__(self, g):
+        super().__init__(str(g)); self.g = g
+
+
+def _inv(a, N):
+    """invm: None when a = 0 or gcd(a, N) = N, FactorFound on a proper divisor."""
+    a %= N
+    if a == 0:
+        return None
+    g = math.gcd(a, N)
+    if g == 1:
+        return pow(a, -1, N)
+    if 1 < g < N:
+        raise FactorFound(g)
+    return None
+
+
+def curve_from_sigma(N, sigma):
+    """Suyama parametrisation -> Montgomery (A + 2, B) -> twisted Edwards a = (A+2)/B, d = (A-2)/B and the point
+    (X0, Y0); None when the sigma is singular for this modulus (the reference then tries the next one)."""
+    sigma %= N
+    if sigma == 0:
+        sigma = 1
+    s2 = sigma * sigma % N
+    su = (s2 - 5) % N
+    sv = 4 * sigma % N
+    inv_sv = _inv(sv, N)
+    if inv_sv is None:
+        return None
+    den_a = 4 * (su * su % N * su % N) * sv % N
+    inv_den_a = _inv(den_a, N)
+    if inv_den_a is None:
+        return None
+    d = (sv - su) % N
+    tnum = d * d % N * d % N
+    aplus2 = tnum * ((3 * su + sv) % N) % N * inv_den_a % N
+    bmont = su * inv_sv % N
+    inv_b = _inv(bmont, N)
+    if inv_b is None:
+        return None
+    aE = aplus2 * inv_b % N
+    dE = (aplus2 - 4) % N * inv_b % N
+    sp = (s2 + 5) % N
+    den_x = (su - sv) % N * ((su + sv) % N) % N * sp % N
+    inv_den_x = _inv(den_x, N)
+    if inv_den_x is None:
+        return None
+    X0 = su * su % N * sv % N * inv_den_x % N
+    su3, sv3 = su * su % N * su % N, sv * sv % N * sv % N
+    inv_den_y = _inv((su3 + sv3) % N, N)
+    if inv_den_y is None:
+        return None
+    Y0 = (su3 - sv3) % N * inv_den_y % N
+    if X0 == 0 or Y0 == 0:
+        return None
+    x2, y2 = X0 * X0 % N, Y0 * Y0 % N
+    if (aE * x2 + y2 - 1 - dE * x2 % N * y2) % N != 0:
+        return None
+    return {"a": aE, "d": dE, "X0": X0, "Y0": Y0, "sigma": sigma}
+
+
+def curve_from_seed(N, curve_seed):
+    """Default curve family of the reference: up to 256 sigmas derived from the curve seed (:2436-2461)."""
+    for tries in range(256):
+        sigma_seed = curve_seed if tries == 0 else mix64(curve_seed, 0x5EED5EED + tries)
+        cv = curve_from_sigma(N, rnd_mpz_bits(N, sigma_seed, 63))
+        if cv is not None:
+            cv["tries"] = tries
+            return cv
+    return None
+
+
+# ---- point operations on engine registers ------------------------------------------------------------
+class EdwardsOps:
+    """The reference's op schedules, register for register.  `eng` needs the engine.h methods; the fused helpers
+    (addsub, addsub_copy, mul_copy) fall back to their default compositions (engine.h:65-131) when absent."""
+
+    def __init__(self, eng, notwist=False, graphs=None):
+        self.e = eng
+        self.ops = 0
+        self.notwist = notwist
+        # B200: a point operation is 17-27 engine calls of a few microseconds each at ECM sizes, so record the three
+        # schedules once as CUDA graphs and replay them (one host call per point operation instead of one per op)
+        if graphs is None:
+            graphs = hasattr(eng, "graph_begin") and bool(getattr(eng, "is_single_cta", lambda: False)())
+        self._g = None
+        if graphs:
+            self._g = {}
+            for key, fn in (("dbl", lambda: self._dbl()), ("add+", lambda: self._add(False)), ("add-", lambda: self._add(True))):
+                eng.graph_begin()
+                try:
+                    fn()
+                finally:
+                    self._g[key] = eng.graph_end()
+
+    def dbl(self):
+        self.ops += 1
+        if self._g:
+            self.e.graph_launch(self._g["dbl"])
+        else:
+            self._dbl()
+
+    def add(self, negative=False):
+        self.ops += 1
+        if self._g:
+            self.e.graph_launch(self._g["add-" if negative else "add+"])
+        else:
+            self._add(negative)
+
+    def _dbl(self):
+        (self.dbl_notwist if self.notwist else self.dbl_twisted)(3, 4, 1, 5)
+
+    def _add(self, negative):
+        (self.add_notwist if self.notwist else self.add_twisted)(negative)
+
+    def _addsub(self, s, d, a, b):
+        e = self.e
+        if hasattr(e, "addsub"):
+            e.addsub(s, d, a, b)
+        else:
+            e.copy(s, a); e.copy(d, a); e.add(s, b); e.sub_reg(d, b)
+
+    def _addsub_copy(self, s, d, sc, dc, a, b):
+        e = self.e
+        if hasattr(e, "addsub_copy"):
+            e.addsub_copy(s, d, sc, dc, a, b)
+        else:
+            self._addsub(s, d, a, b); e.copy(sc, s); e.copy(dc, d)
+
+    def _mul_copy(self, dst, src, cp):
+        e = self.e
+        if hasattr(e, "mul_copy"):
+            e.mul_copy(dst, src, cp)
+        else:
+            e.mul(dst, src); e.copy(cp, dst)
+
+    def dbl_twisted(self, RX=3, RY=4, RZ=1, RT=5):
+        """eDBL_XYTZ (:2867-2909): A = X^2, B = Y^2, C = 2 Z^2, D = a A, E = 2 T Z, G = D + B, H = D - B, F = G - C;
+        X3 = E F, Y3 = G H, T3 = E H, Z3 = F G."""
+        e = self.e
+        e.set_multiplicand(11, RZ); e.mul(RT, 11); e.add(RT, RT)
+        e.square_mul(RZ); e.add(RZ, RZ)
+        e.square_mul(RX); e.square_mul(RY)
+        e.mul(RX, 43)
+        self._addsub(23, 25, RX, RY)
+        e.copy(24, 23); e.sub_reg(24, RZ)
+        e.set_multiplicand(11, 24)
+        e.copy(RX, RT); e.mul(RX, 11)
+        e.copy(RZ, 23); e.mul(RZ, 11)
+        e.set_multiplicand(11, 25)
+        e.copy(RY, 23); e.mul(RY, 11)
+        e.mul(RT, 11)
+
+    def dbl_notwist(self, RX=3, RY=4, RZ=1, RT=5):
+        """eDBL_XYTZ_notwist (:2911-2945), a = 1."""
+        e = self.e
+        e.set_multiplicand(11, RZ); e.mul(RT, 11); e.add(RT, RT)
+        e.square_mul(RZ); e.add(RZ, RZ)
+        e.square_mul(RX); e.square_mul(RY)
+        self._addsub_copy(23, 25, 24, 22, RX, RY)
+        e.sub_reg(24, RZ)
+        e.set_multiplicand(11, 24)
+        e.copy(RX, RT); e.mul(RX, 11)
+        e.copy(RZ, 23); e.mul(RZ, 11)
+        e.set_multiplicand(11, 25)
+        e.copy(RY, 23); e.mul(RY, 11)
+        e.mul(RT, 11)
+
+    def add_twisted(self, negative=False):
+        """eADD_RP / eADD_RP_2 (:2717-2772,2794-2848): mixed addition of the affine base (Z2 = 1) or of its negative.
+        E = X1 Y2 + Y1 X2, H = Y1 Y2 - a X1 X2, C = d T1 T2, D = Z1; X3 = E (D - C), Y3 = H (D + C), T3 = E H,
+        Z3 = (D - C)(D + C)."""
+        e = self.e
+        X2, Y2, MT2 = (47, 48, 50) if negative else (6, 7, 46)
+        self._addsub(34, 35, 4, 3)
+        self._addsub(36, 37, Y2, X2)
+        e.copy(30, 3); e.set_multiplicand(11, X2); self._mul_copy(30, 11, 39)
+        e.copy(31, 4); e.set_multiplicand(11, Y2); e.mul(31, 11)
+        e.copy(32, 5); e.mul(32, MT2); e.mul(32, 45)
+        self._addsub(42, 41, 1, 32)
+        e.copy(38, 34); e.set_multiplicand(11, 36); e.mul(38, 11)
+        e.sub_reg(38, 30); e.sub_reg(38, 31)
+        e.mul(39, 43)
+        e.copy(40, 31); e.sub_reg(40, 39)
+        e.copy(3, 38); e.set_multiplicand(11, 41); e.mul(3, 11)
+        e.copy(1, 42); e.mul(1, 11)
+        e.set_multiplicand(11, 40)
+        e.copy(4, 42); e.mul(4, 11)
+        e.copy(5, 38); e.mul(5, 11)
+
+    def add_notwist(self, negative=False):
+        """eADD_RP_notwist / _2 (:2957-3067), a = 1."""
+        e = self.e
+        X2, Y2, MT2 = (47, 48, 50) if negative else (6, 7, 46)
+        self._addsub(34, 35, 4, 3)
+        self._addsub(36, 37, Y2, X2)
+        e.copy(30, 3); e.set_multiplicand(11, X2); e.mul(30, 11)
+        e.copy(31, 4); e.set_multiplicand(11, Y2); e.mul(31, 11)
+        self._addsub(20, 40, 31, 30)
+        e.copy(32, 5); e.mul(32, MT2); e.mul(32, 45)
+        self._addsub(42, 41, 1, 32)
+        e.copy(38, 34); e.set_multiplicand(11, 36); e.mul(38, 11)
+        e.sub_reg(38, 20)
+        e.set_multiplicand(11, 40)
+        e.copy(4, 42); e.mul(4, 11)
+        e.copy(5, 38); e.mul(5, 11)
+        e.set_multiplicand(11, 41)
+        e.copy(3, 38); e.mul(3, 11)
+        e.copy(1, 42); e.mul(1, 11)
+
+
+def _load_base(eng, p, N, X, Y):
+    """Base point +-P in R6,R7,R9 / R47,R48,R49 and the persistent multiplicands (:3180-3201, :1851-1864)."""
+    T = X * Y % N
+    for r, v in ((6, X), (7, Y), (9, T), (47, (N - X) % N), (48, Y), (49, (N - T) % N)):
+        _set_int(eng, r, v, p)
+    eng.set_multiplicand(43, 16); eng.set_multiplicand(44, 8); eng.set_multiplicand(45, 29)
+    eng.set_multiplicand(46, 9); eng.set_multiplicand(50, 49)
+
+
+def _scalar_mul(eng, ops, digits, on_step=None):
+    """Q <- k P over the NAF digits (top digit first); the point registers already hold +-P for the top digit."""
+    for step, i in enumerate(range(len(digits) - 2, -1, -1)):
+        ops.dbl()
+        d = digits[i]
+        if d:
+            ops.add(negative=d < 0)
+        if on_step:
+            on_step(step + 1)
+
+
+def check_invariant(eng, p, aE, dE):
+    """a X^2 + Y^2 == Z^2 + d T^2 on the current point (:2626-2652)."""
+    N = (1 << p) - 1
+    X, Y, Z, T = (_value(eng, r, p) for r in (3, 4, 1, 5))
+    return (aE * X * X + Y * Y - Z * Z - dE * T * T) % N == 0
+
+
+def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None):
+    """One curve of RunEcmTwistedEdwards.cpp:1737-3859 on a 51-register engine.  Returns a dict with `status` in
+    {"found", "NF", "singular", "nocurve", "invariant"}, `factor`, `stage` (0 = curve generation, 1, 2) and the final
+    extended coordinates (for parity checks against a big-integer restatement of the same formulas)."""
+    say = log or (lambda s: None)
+    N = (1 << p) - 1
+    res = {"curve_seed": curve_seed, "status": "NF", "factor": None, "stage": None, "n": eng.get_size()}
+    try:
+        cv = curve if curve is not None else curve_from_seed(N, curve_seed)
+    except FactorFound as f:
+        res.update(status="found", factor=f.g, stage=0)
+        return res
+    if cv is None:
+        res["status"] = "nocurve"
+        return res
+    aE, dE, X0, Y0 = cv["a"], cv["d"], cv["X0"], cv["Y0"]
+    res["sigma"] = cv.get("sigma")
+    say(f"[ECM] curve_seed={curve_seed} | twisted_edwards | torsion=none")
+
+    # constants and the starting point (:3069-3090)
+    _set_int(eng, 16, aE, p); _set_int(eng, 17, 2 * dE % N, p); _set_int(eng, 29, dE, p)
+    eng.set(0, 0); eng.set(1, 1); eng.set(8, 2)
+    if K is None:
+        K = stage1_exponent(b1)
+    digits = naf(K)
+    _load_base(eng, p, N, X0, Y0)
+    neg = bool(digits) and digits[-1] < 0
+    T0 = X0 * Y0 % N
+    for r, v in ((3, (N - X0) % N if neg else X0), (4, Y0), (5, (N - T0) % N if neg else T0)):
+        _set_int(eng, r, v, p)
+
+    ops = EdwardsOps(eng, graphs=graphs)
+    def inject(step):
+        # -erroriter (:3285-3288): corrupt Z after that many steps; the invariant must catch it
+        if step == error_iter:
+            eng.sub(1, 2)
+            say(f"Injected error at iteration {step}")
+    _scalar_mul(eng, ops, digits, on_step=inject if error_iter else None)
+    if not check_invariant(eng, p, aE, dE):
+        say("[ECM] invariant FAIL")
+        res.update(status="invariant", stage=1, point_ops=ops.ops)
+        return res
+    say("[ECM] check invariant OK")
+
+    # stage-1 gcd on T (:3372-3374)
+    T = _value(eng, 5, p)
+    g = math.gcd(T, N)
+    res["stage1_T"] = T
+    res["point_ops"] = ops.ops
+    if g == N:
+        res.update(status="singular", stage=1)
+        return res
+    if 1 < g < N:
+        res.update(status="found", factor=g, stage=1)
+        return res
+    # g == 1: the Montgomery resume values need 1/(Z - Y) and 1/(a - d); either inversion may split N (:3396-3413)
+    Zv, Yv = _value(eng, 1, p), _value(eng, 4, p)
+    try:
+        if _inv((Zv - Yv) % N, N) is not None:
+            _inv((aE - dE) % N, N)
+    except FactorFound as f:
+        res.update(status="found", factor=f.g, stage=1)
+        return res
+
+    if b2 > b1:
+        if primes_s2 is None:
+            primes_s2 = ecm_primes(b1, b2)[1]
+        for (i0, i1, echunk) in s2_chunks(primes_s2, s2_chunk_bits(eng.get_size())):
+            # setup_te_stage2_base (:3542-3566): the current point, made affine, becomes the base
+            Xv, Yv, Zv = (_value(eng, r, p) for r in (3, 4, 1))
+            try:
+                iz = _inv(Zv, N)
+            except FactorFound as f:
+                res.update(status="found", factor=f.g, stage=2)
+                return res
+            if iz is None:
+                res.update(status="singular", stage=2)
+                return res
+            Xa, Ya = Xv * iz % N, Yv * iz % N
+            _load_base(eng, p, N, Xa, Ya)
+            d2 = naf(echunk)
+            if d2:
+                eng.set(1, 1)
+                for dst, src in (((3, 47), (4, 48), (5, 49)) if d2[-1] < 0 else ((3, 6), (4, 7), (5, 9))):
+                    eng.copy(dst, src)
+                _scalar_mul(eng, ops, d2)
+            T = _value(eng, 5, p)
+            g = math.gcd(T, N)
+            res["stage2_T"] = T
+            res["point_ops"] = ops.ops
+            say(f"[ECM] Stage2 chunk end | next_prime_idx={i1} | gcd(T,N)={g}")
+            if g == N:
+                res.update(status="singular", stage=2)
+                return res
+            if g > 1:
+                res.update(status="found", factor=g, stage=2)
+                return res
+    return res
+
+
+def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), continue_after_factor=False,
+            curve_indices=None, log=None, graphs=None):
+    """The curve loop (:1737-1830, 3415-3455): curve c uses curve_seed = mix64(seed, c) on its own engine
+    (`engine_factory(p, 51)`), stops at the first new factor unless told to continue.  `curve_indices` restricts
+    the loop to a subset (multi-GPU: curve c -> rank c mod world)."""
+    say = log or (lambda s: None)
+    K = stage1_exponent(b1)
+    primes_s2 = ecm_primes(b1, b2)[1] if b2 > b1 else []
+    known = {int(f) for f in known_factors}
+    out = {"exponent": p, "worktype": "ECM", "b1": b1, "b2": b2, "seed": seed, "status": "NF", "factor": None,
+           "curves": [], "k_bits": K.bit_length()}
+    for c in (range(curves) if curve_indices is None else curve_indices):
+        eng = engine_factory(p, REGS)
+        try:
+            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs)
+        finally:
+            if hasattr(eng, "close"):
+                eng.close()
+        r["curve"] = c
+        out["curves"].append(r)
+        out["fft_length"] = r["n"]
+        if r["status"] == "found":
+            if r["factor"] in known:
+                say(f"[ECM] Curve {c + 1}/{curves} | known factor={r['factor']}")
+                continue
+            say(f"[ECM] Curve {c + 1}/{curves} | factor={r['factor']}")
+            if out["factor"] is None:
+                out.update(status="found", factor=r["factor"], curves_tested_for_found=c + 1)
+            if not continue_after_factor:
+                break
+            known.add(r["factor"])
+    return out
+
+
+def run_ecm_sharded(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), log=None, graphs=None):
+    """Config 5 across the GPUs of one box: curve c runs on rank c mod world with its own engine, every
+    rank runs ALL of its curves (no cross-GPU stop flag: a curve at these sizes is seconds), the per-curve results are
+    gathered and merged in curve order, so the answer -- first new factor by curve index -- is the one a single
+    process running the curves in sequence reports."""
+    from . import multi
+    rank, world = multi.rank_world()
+    mine = multi.assign(list(range(curves)), rank, world)
+    local = run_ecm(engine_factory, p, b1, b2, curves=curves, seed=seed, known_factors=known_factors,
+                    continue_after_factor=True, curve_indices=mine, log=log, graphs=graphs)
+    for c in local["curves"]:
+        c["rank"] = rank
+    allc = sorted(multi.gather(local["curves"]), key=lambda c: c["curve"])
+    out = {k: local[k] for k in ("exponent", "worktype", "b1", "b2", "seed", "k_bits")}
+    out.update(status="NF", factor=None, curves=allc, world=world)
+    known = {int(f) for f in known_factors}
+    for c in allc:
+        if c["status"] == "found" and c["factor"] not in known:
+            out.update(status="found", factor=c["factor"], curves_tested_for_found=c["curve"] + 1)
+            break
+    return out
+
+
+# ---- big-integer restatement of the same formulas (used by tests as the arithmetic reference) --------
+def reference_scalar_mul(N, aE, dE, X2, Y2, digits):
+    """(X, Y, Z, T) after the same double-and-add in Python integers: the engine must reproduce these residues."""
+    T2 = X2 * Y2 % N
+    sgn = -1 if digits[-1] < 0 else 1
+    X, Y, Z, T = sgn * X2 % N, Y2, 1, sgn * T2 % N
+    for i in range(len(digits) - 2, -1, -1):
+        A, B, C = X * X % N, Y * Y % N, 2 * Z * Z % N
+        D, E = aE * A % N, 2 * T * Z % N
+        G, H = (D + B) % N, (D - B) % N
+        F = (G - C) % N
+        X, Y, T, Z = E * F % N, G * H % N, E * H % N, F * G % N
+        d = digits[i]
+        if d:
+            x2, t2 = d * X2 % N, d * T2 % N
+            E = (X * Y2 + Y * x2) % N
+            H = (Y * Y2 - aE * X * x2) % N
+            C = dE * T % N * t2 % N
+            X, Y, T, Z = E * (Z - C) % N, H * (Z + C) % N, E * H % N, (Z - C) * (Z + C) % N
+    return X, Y, Z, T

@@ -51,6 +51,9 @@ _SIGS = {
     "mb200_square_mul_repeat": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
     "mb200_bench_pass": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_float)]),
     "mb200_is_single_cta": (C.c_int, [C.c_void_p]),
+    "mb200_graph_begin": (C.c_int, [C.c_void_p]),
+    "mb200_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mb200_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),
     "mb200_launch_count": (C.c_uint64, [C.c_void_p]),
     "mb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "mb200_host_free": (None, [C.c_void_p]),
@@ -297,6 +300,18 @@ class Engine:
 
     def is_single_cta(self):
         return bool(self._L.mb200_is_single_cta(self._h))
+
+    # -- CUDA-graph replay of fixed op sequences (single-CTA engines; see include/marin_b200.h) ---
+    def graph_begin(self):
+        self._ck(self._L.mb200_graph_begin(self._h))
+
+    def graph_end(self):
+        gid = C.c_int(-1)
+        self._ck(self._L.mb200_graph_end(self._h, C.byref(gid)))
+        return gid.value
+
+    def graph_launch(self, gid):
+        self._ck(self._L.mb200_graph_launch(self._h, gid))
 
     def square_mul_repeat(self, r, count, a=1):
         self._ck(self._L.mb200_square_mul_repeat(self._h, r, a, count))

@@ -1,0 +1,190 @@
+"""ECM twisted-Edwards driver (prmers_b200/ecm.py, SURVEY 8 f4 / BASELINE config 5).
+
+CPU tier: seed mixing, scalars, curve generation, and the register schedules run on the kernel emulator against
+the big-integer engine (oracle/int_engine.py) and the closed formulas.  GPU tier: the same on the CUDA engine,
+against tests/golden/ecm_*.json (tools/make_golden_ecm.py)."""
+import hashlib
+import json
+import os
+
+import pytest
+
+from oracle.int_engine import IntEngine
+from prmers_b200 import ecm
+from tests.emu.emu import EmuEngine
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(x):
+    return None if x is None else hashlib.sha256(hex(x).encode()).hexdigest()[:32]
+
+
+def test_splitmix64_known_answers():
+    # published splitmix64 test vector (seed 0)
+    s, z0 = ecm.splitmix64_step(0)
+    s, z1 = ecm.splitmix64_step(s)
+    assert (z0, z1) == (0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4)
+    assert ecm.mix64(123456789, 0) == 2600022760115733002 and ecm.mix64(123456789, 0) != ecm.mix64(123456789, 1)
+    N = (1 << 701) - 1
+    assert 2 < ecm.rnd_mpz_bits(N, 5, 63) < 1 << 64 and ecm.rnd_mpz_bits(N, 5, 256).bit_length() > 200
+
+
+def test_scalars():
+    assert ecm.stage1_exponent(10) == 2520 and ecm.stage1_exponent(1) == 1
+    assert ecm.ecm_primes(10, 30) == ([2, 3, 5, 7], [11, 13, 17, 19, 23, 29])
+    for e in (1, 2, 3, 7, 11, 2520, 3 ** 40 + 12345, ecm.stage1_exponent(300)):
+        d = ecm.naf(e)
+        assert sum(di << i for i, di in enumerate(d)) == e and d[-1] != 0
+        assert all(not (d[i] and d[i + 1]) for i in range(len(d) - 1))
+    assert [ecm.s2_chunk_bits(n) for n in (32, 256, 1024, 4096, 16384, 1 << 23)] == [1048576, 1048576, 524288, 262144, 131072, 65536]
+    ps = ecm.ecm_primes(100, 2000)[1]
+    ch = ecm.s2_chunks(ps, 64)
+    assert ch[0][0] == 0 and ch[-1][1] == len(ps) and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+    assert all(e.bit_length() >= 64 for _, _, e in ch[:-1])
+
+
+def test_curve_from_seed_is_on_curve():
+    for p in (101, 701, 1277):
+        N = (1 << p) - 1
+        cv = ecm.curve_from_seed(N, ecm.mix64(123456789, 0))
+        a, d, x, y = cv["a"], cv["d"], cv["X0"], cv["Y0"]
+        assert (a * x * x + y * y - 1 - d * x * x * y * y) % N == 0 and a != d and d % N not in (0, 1)
+    # a sigma that shares a factor with N gives the factor straight away (invm returning 1)
+    with pytest.raises(ecm.FactorFound) as f:
+        ecm.curve_from_sigma((1 << 101) - 1, 7432339208719)
+    assert f.value.g == 7432339208719
+
+
+@pytest.mark.parametrize("p,seed", [(127, 7), (101, 123456789), (521, 3)])
+def test_point_schedules_match_big_integers_emulated(p, seed):
+    """Every register schedule (doubling, +P, -P) on the emulated kernels reproduces the closed formulas."""
+    N = (1 << p) - 1
+    cv = ecm.curve_from_seed(N, seed)
+    K = ecm.stage1_exponent(40)
+    digits = ecm.naf(K)
+    assert -1 in digits and 1 in digits
+    want = ecm.reference_scalar_mul(N, cv["a"], cv["d"], cv["X0"], cv["Y0"], digits)
+    for eng in (EmuEngine(p, ecm.REGS), IntEngine(p, ecm.REGS)):
+        r = ecm.run_curve(eng, p, 40, 0, seed, curve=cv, K=K)
+        got = tuple(ecm._value(eng, reg, p) for reg in (3, 4, 1, 5))
+        if r["status"] == "NF":                       # no factor: the point registers still hold k P
+            assert got == tuple(v % N for v in want)
+        assert r["stage1_T"] == want[3] % N
+
+
+def test_notwist_schedules_emulated():
+    """The a = 1 schedules (torsion-16 curves of the reference) against the same formulas with a = 1."""
+    p = 127; N = (1 << p) - 1
+    x, y = 1234567, 7654321
+    inv = pow(x * x * y * y, -1, N)
+    d = (x * x + y * y - 1) * inv % N                 # force_on_curve (:2173-2186) with a = 1
+    digits = ecm.naf(ecm.stage1_exponent(30))
+    want = ecm.reference_scalar_mul(N, 1, d, x, y, digits)
+    eng = EmuEngine(p, ecm.REGS)
+    ecm._set_int(eng, 16, 1, p); ecm._set_int(eng, 29, d, p); eng.set(8, 2); eng.set(1, 1)
+    ecm._load_base(eng, p, N, x, y)
+    sgn = -1 if digits[-1] < 0 else 1
+    for r, v in ((3, sgn * x % N), (4, y), (5, sgn * x * y % N)):
+        ecm._set_int(eng, r, v, p)
+    ecm._scalar_mul(eng, ecm.EdwardsOps(eng, notwist=True), digits)
+    assert tuple(ecm._value(eng, r, p) for r in (3, 4, 1, 5)) == tuple(v % N for v in want)
+
+
+def test_run_ecm_m101_emulated_matches_golden():
+    gold = json.load(open(os.path.join(GOLD, "ecm_m101.json")))
+    log = []
+    r = ecm.run_ecm(lambda p, regs: EmuEngine(p, regs), 101, 300, 2000, curves=3, seed=123456789, log=log.append)
+    assert r["status"] == "found" and str(r["factor"]) == gold["factor"] == "7432339208719"
+    assert r["curves_tested_for_found"] == 1 and len(r["curves"]) == 1      # stops at the first new factor
+    c, g = r["curves"][0], gold["per_curve"][0]
+    assert (str(c["curve_seed"]), c["stage"], sha(c["stage1_T"]), sha(c["stage2_T"])) == (g["curve_seed"], g["stage"], g["stage1_T_sha"], g["stage2_T_sha"])
+    assert "[ECM] check invariant OK" in log
+    # a known factor is reported and skipped, the loop goes on (is_known, :953-962)
+    r = ecm.run_ecm(lambda p, regs: EmuEngine(p, regs), 101, 300, 2000, curves=2, seed=123456789, known_factors=[7432339208719])
+    assert r["status"] == "NF" and len(r["curves"]) == 2
+
+
+def test_invariant_catches_injected_error_emulated():
+    """-erroriter (:3285-3288): Z -= 2 after some step must break a X^2 + Y^2 = Z^2 + d T^2."""
+    log = []
+    r = ecm.run_curve(EmuEngine(127, ecm.REGS), 127, 60, 0, 99, error_iter=17, log=log.append)
+    assert r["status"] == "invariant" and "Injected error at iteration 17" in log and "[ECM] invariant FAIL" in log
+
+
+def test_curve_sharding_covers_all_curves():
+    from prmers_b200 import multi
+    for world in (1, 2, 3, 8):
+        got = sorted(c for r in range(world) for c in multi.assign(list(range(8)), r, world))
+        assert got == list(range(8))
+
+
+def _check_against_golden(name, engine_factory, graphs):
+    gold = json.load(open(os.path.join(GOLD, name + ".json")))
+    r = ecm.run_ecm(engine_factory, gold["p"], gold["b1"], gold["b2"], curves=gold["curves"], seed=gold["seed"],
+                    continue_after_factor=True, graphs=graphs)
+    assert r["status"] == gold["status"] and (None if r["factor"] is None else str(r["factor"])) == gold["factor"]
+    assert len(r["curves"]) == len(gold["per_curve"])
+    for c, g in zip(r["curves"], gold["per_curve"]):
+        assert str(c["curve_seed"]) == g["curve_seed"] and c["status"] == g["status"] and c["stage"] == g["stage"]
+        assert (None if c["factor"] is None else str(c["factor"])) == g["factor"]
+        assert sha(c.get("stage1_T")) == g["stage1_T_sha"] and sha(c.get("stage2_T")) == g["stage2_T_sha"]
+        assert c.get("point_ops") == g["point_ops"]
+    return r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graphs", [True, False])
+def test_ecm_m701_config5_gpu(graphs):
+    """BASELINE config 5: M701, B1 = 6000, B2 = 33333, 8 curves, fixed seed -- every curve's residue and factor."""
+    import prmers_b200 as pb
+    r = _check_against_golden("ecm_m701", lambda p, regs: pb.Engine(p, regs), graphs)
+    assert r["fft_length"] == 32
+
+
+@pytest.mark.gpu
+def test_ecm_stage2_gpu():
+    """Curves that run stage 2 to the end (M1277 has no small factor; M101 finds its factor in stage 2)."""
+    import prmers_b200 as pb
+    _check_against_golden("ecm_m1277", lambda p, regs: pb.Engine(p, regs), True)
+    _check_against_golden("ecm_m101", lambda p, regs: pb.Engine(p, regs), True)
+
+
+@pytest.mark.gpu
+def test_ecm_point_ops_on_the_multi_pass_path_gpu():
+    """addsub / mul_copy / sub_reg on a 3-pass engine (n = 65536): the Edwards schedules against big integers."""
+    import prmers_b200 as pb
+    p = 1362763; N = (1 << p) - 1
+    cv = ecm.curve_from_seed(N, 2024)
+    K = ecm.stage1_exponent(30)
+    want = ecm.reference_scalar_mul(N, cv["a"], cv["d"], cv["X0"], cv["Y0"], ecm.naf(K))
+    eng = pb.Engine(p, ecm.REGS)
+    assert not eng.is_single_cta()
+    r = ecm.run_curve(eng, p, 30, 0, 2024, curve=cv, K=K)
+    assert r["status"] == "NF" and r["stage1_T"] == want[3] % N
+    assert tuple(eng.get_mpz(reg) for reg in (3, 4, 1)) == tuple(v % N for v in want[:3])
+
+
+@pytest.mark.gpu
+def test_graph_replay_equals_direct_calls_gpu():
+    import numpy as np
+    import prmers_b200 as pb
+    e = pb.Engine(701, 8)
+    with pytest.raises(RuntimeError):
+        e.graph_end()
+    e.set(0, 3); e.set(1, 5)
+    e.graph_begin()
+    e.square_mul(0, 3); e.set_multiplicand(2, 1); e.mul(0, 2); e.add(0, 1); e.sub_reg(0, 1); e.copy(3, 0)
+    with pytest.raises(RuntimeError):
+        e.get(0)                                     # blocking calls are refused while recording
+    g = e.graph_end()
+    x, N = 3, (1 << 701) - 1
+    assert e.get_mpz(0) == 3                          # recording did not run anything
+    for _ in range(50):
+        e.graph_launch(g)
+        x = x * x * 3 * 5 % N
+    assert e.get_mpz(0) == x and e.get_mpz(3) == x
+    big = pb.Engine(1362763, 2)
+    with pytest.raises(RuntimeError):
+        big.graph_begin()                             # multi-pass engines carry per-launch epochs
+    assert np.array_equal(e.get(0), e.get(3))
