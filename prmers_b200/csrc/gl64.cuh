@@ -20,9 +20,9 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 
 #if defined(__CUDACC__)
-// 1 and -1 that ptxas cannot fold: multiplying by them turns an add into IMAD / IMAD.HI, i.e. moves it
-// from the ALU pipe (IADD3, the bottleneck of this engine) to the FMA pipe, which otherwise idles.
-__constant__ u32 GL_ONE = 1u, GL_MONE = 0xffffffffu;
+// 0, 1 and -1 that ptxas cannot fold: a madc with them stays an IMAD / IMAD.X, i.e. the add moves from the ALU
+// pipe (IADD3, the bottleneck of this engine) to the FMA pipe, which otherwise idles.
+__constant__ u32 GL_ONE = 1u, GL_MONE = 0xffffffffu, GL_ZERO = 0u;
 #endif
 
 namespace gl {
@@ -30,22 +30,20 @@ namespace gl {
 static constexpr u64 P = 0xffffffff00000001ull;
 static constexpr u32 EPS = 0xffffffffu; // 2^64 mod P
 
-// ---- a + b, canonical inputs, canonical output
-HD u64 add(u64 a, u64 b)
+HD u64 neg(u64 a) { return a ? P - a : 0; }
+
+// ---- P - b for b <= P (result in [0, P]); used as the subtrahend that turns a subtraction into an addition
+HD u64 pminus(u64 b)
 {
 #if defined(__CUDA_ARCH__)
-	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), s0, s1, u0, u1, c;
-	asm("add.cc.u32 %0, %5, %7;\n\t"
-		"addc.cc.u32 %1, %6, %8;\n\t"
-		"addc.u32 %4, 0, 0;\n\t"
-		"add.cc.u32 %2, %0, 0xffffffff;\n\t" // u = s - P (mod 2^64)
-		"addc.cc.u32 %3, %1, 0;\n\t"
-		"addc.u32 %4, %4, 0;\n\t"            // at most one of the two carries is set
-		: "=&r"(s0), "=&r"(s1), "=&r"(u0), "=&r"(u1), "=&r"(c) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-	return c ? (((u64)u1 << 32) | u0) : (((u64)s1 << 32) | s0);
+	// one ALU + one FMA-pipe instruction
+	u32 b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1;
+	asm("sub.cc.u32 %0, 1, %2;\n\t"
+		"madc.lo.u32 %1, %3, %4, 0xfffffffe;\n\t"  // 2^32 - 1 - b1 - borrow
+		: "=&r"(r0), "=&r"(r1) : "r"(b0), "r"(b1), "r"(GL_MONE));
+	return ((u64)r1 << 32) | r0;
 #else
-	const u64 s = a + b;
-	return (s < a || s >= P) ? s + EPS : s;
+	return P - b;
 #endif
 }
 
@@ -54,27 +52,31 @@ HD u64 sub(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
 	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), d0, d1, m;
-#if defined(MARIN_SUB_IMAD)
-	// 3 ALU + 3 FMA-pipe instructions: the +P correction (d += 1 - 2^32 when borrowing) as IMADs
+	// 3 ALU + 2 FMA-pipe instructions: the two carry consumers that produce no carry themselves are written as
+	// madc, which ptxas keeps on the FMA pipe as IMAD.X (the integer ALU pipe is what bounds this engine; measured
+	// with tools/micro/bfly_bench.cu: 35 -> 51 G butterflies/s with this, pminus and reduce128 below).  After a
+	// sub.cc chain the flag that madc reads is the hardware carry (1 = no borrow), hence the 2^32 - 1 addends.
 	asm("sub.cc.u32 %0, %3, %5;\n\t"
 		"subc.cc.u32 %1, %4, %6;\n\t"
-		"subc.u32 %2, 0, 0;\n\t"             // m = borrow ? 0xffffffff : 0
-		"mad.lo.cc.s32 %0, %2, %8, %0;\n\t"   // d += borrow          (m * -1)
-		"madc.hi.s32 %1, %2, %8, %1;\n\t"
-		"mad.lo.u32 %1, %2, %7, %1;\n\t"      // d.hi -= borrow       (m * 1)
-		: "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(GL_ONE), "r"(GL_MONE));
-#else
-	asm("sub.cc.u32 %0, %3, %5;\n\t"
-		"subc.cc.u32 %1, %4, %6;\n\t"
-		"subc.u32 %2, 0, 0;\n\t"             // m = borrow ? 0xffffffff : 0
-		"sub.cc.u32 %0, %0, %2;\n\t"         // d -= borrow ? 2^32 - 1 : 0   (i.e. d += P)
-		"subc.u32 %1, %1, 0;\n\t"
-		: "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-#endif
+		"madc.lo.u32 %2, %7, %7, 0xffffffff;\n\t" // m = borrow ? 2^32 - 1 : 0
+		"sub.cc.u32 %0, %0, %2;\n\t"              // d -= borrow ? 2^32 - 1 : 0   (i.e. d += P)
+		"madc.lo.u32 %1, %1, %8, 0xffffffff;\n\t"
+		: "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(GL_ZERO), "r"(GL_ONE));
 	return ((u64)d1 << 32) | d0;
 #else
 	const u64 d = a - b;
 	return (a < b) ? d - EPS : d;
+#endif
+}
+
+// ---- a + b, canonical inputs, canonical output: a - (P - b), 4 ALU + 3 FMA-pipe instructions
+HD u64 add(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+	return sub(a, pminus(b));
+#else
+	const u64 s = a + b;
+	return (s < a || s >= P) ? s + EPS : s;
 #endif
 }
 
@@ -98,8 +100,6 @@ HD u64 add_lazy(u64 a, u64 b)
 #endif
 }
 
-HD u64 neg(u64 a) { return a ? P - a : 0; }
-
 // ---- (hi, lo) mod P for ANY 128-bit value; canonical output.
 // X = lo + h0 (2^32 - 1) - h1; add 2^32 - 1 first so that the sum never goes negative
 // (Craig-Wood's trick, the one marin.cl:115-142 also relies on), then take it off again.
@@ -107,21 +107,22 @@ HD u64 reduce128(u64 lo, u64 hi)
 {
 #if defined(__CUDA_ARCH__)
 	u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32), r0, r1;
+	// the five instructions that consume a carry without producing one go to the FMA pipe (IMAD / IMAD.X)
 	asm("{\n\t"
 		".reg .u32 d, s0, s1, nc, c;\n\t"
-		"sub.u32 d, 0xffffffff, %5;\n\t"     // d = 2^32 - 1 - h1
-		"sub.cc.u32 s0, d, %4;\n\t"          // s = (h0 : d) - h0 = h0 (2^32 - 1) + d   < P
-		"subc.u32 s1, %4, 0;\n\t"
-		"add.cc.u32 %0, s0, %2;\n\t"         // r = s + lo
+		"mad.lo.u32 d, %5, %7, 0xffffffff;\n\t"    // d = 2^32 - 1 - h1
+		"sub.cc.u32 s0, d, %4;\n\t"
+		"madc.lo.u32 s1, %4, %8, 0xffffffff;\n\t"  // s1 = h0 - borrow
+		"add.cc.u32 %0, s0, %2;\n\t"
 		"addc.cc.u32 %1, s1, %3;\n\t"
-		"addc.u32 nc, 0xffffffff, 0;\n\t"    // nc = carry ? 0 : 2^32 - 1
-		"sub.cc.u32 %0, %0, nc;\n\t"         // no carry: r -= 2^32 - 1
+		"madc.lo.u32 nc, %6, %6, 0xffffffff;\n\t"  // nc = carry ? 0 : 2^32 - 1
+		"sub.cc.u32 %0, %0, nc;\n\t"
 		"subc.cc.u32 %1, %1, 0;\n\t"
-		"subc.u32 c, 0, 0;\n\t"              // borrow: r += P  (== r -= 2^32 - 1 mod 2^64)
+		"madc.lo.u32 c, %6, %6, 0xffffffff;\n\t"   // c = borrow ? 2^32 - 1 : 0
 		"sub.cc.u32 %0, %0, c;\n\t"
-		"subc.u32 %1, %1, 0;\n\t"
+		"madc.lo.u32 %1, %1, %8, 0xffffffff;\n\t"
 		"}"
-		: "=&r"(r0), "=&r"(r1) : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
+		: "=&r"(r0), "=&r"(r1) : "r"(l0), "r"(l1), "r"(h0), "r"(h1), "r"(GL_ZERO), "r"(GL_MONE), "r"(GL_ONE));
 	return ((u64)r1 << 32) | r0;
 #else
 	const u32 h0 = (u32)hi, h1 = (u32)(hi >> 32);

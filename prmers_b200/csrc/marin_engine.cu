@@ -211,7 +211,15 @@ struct CudaBackend
 	void post() { ++launches; CK(cudaGetLastError()); }
 
 	static u32 cap(u32 thr, u32 maxt) { return thr > maxt ? maxt : thr; }
-	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_mid<<<grid, cap(thr, MARIN_MID_MAXT), smem, st>>>(A); post(); }
+	static u32 env_u32(const char *name) { const char *s = getenv(name); return s ? (u32)atoi(s) : 0u; }
+	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem)
+	{
+		// timing probes only (results are wrong with a truncated grid): MARIN_B200_MID_GRID / MARIN_B200_MID_THREADS
+		static const u32 fg = env_u32("MARIN_B200_MID_GRID"), ft = env_u32("MARIN_B200_MID_THREADS");
+		if (fg && fg < grid) grid = fg;
+		if (ft) thr = ft;
+		use(); k_mid<<<grid, cap(thr, MARIN_MID_MAXT), smem, st>>>(A); post();
+	}
 	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<false><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
 	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<true><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
 	void lin_pairs(const LinArgs &A)

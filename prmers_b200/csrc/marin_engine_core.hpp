@@ -4,6 +4,7 @@
 // and launches: the CUDA backend in marin_engine.cu is the product; tests/emu instantiates the same
 // template with a CPU emulator of the kernels to check the host logic without a GPU.
 #pragma once
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -31,6 +32,9 @@ public:
 		const size_t ncarry = std::max<size_t>(n / pl.D, n / RUN + 1);
 		_carry = (u64 *)be.alloc(ncarry * 8);
 		_scratch = (u64 *)be.alloc(n * 8);
+		_nslots = n / RUN + 1;
+		_slots = (pair_t *)be.alloc(_nslots * 16);   // {carry, epoch} hand-off slots of the inverse strided pass
+		be.memset0(_slots, _nslots * 16);
 		if (!pl.small) { _fwd = (u64 *)be.alloc(n * 8); be.persist(_fwd, n * 8); }
 		Tables &t = _t;
 		std::memset(&t, 0, sizeof(t));
@@ -67,7 +71,7 @@ public:
 	{
 		be.sync();
 		for (void *p : _owned) be.free(p);
-		be.free(_reg); be.free(_carry); be.free(_scratch); be.free(_flags); if (_fwd) be.free(_fwd);
+		be.free(_reg); be.free(_carry); be.free(_scratch); be.free(_slots); be.free(_flags); if (_fwd) be.free(_fwd);
 	}
 
 	size_t size() const { return pl.n; }
@@ -209,7 +213,10 @@ public:
 		std::memset(&A, 0, sizeof(A));
 		fill_strided_args(pl, A, 0);
 		set_pass_tables(A, 0);
-		A.src = (const pair_t *)R(r); A.dst = (pair_t *)R(r); A.a = 1; A.carry = _carry;
+		A.src = (const pair_t *)R(r); A.dst = (pair_t *)R(r); A.a = 1; A.slots = _slots;
+#if defined(MARIN_DEBUG_SKIP)
+		if (const char *s = getenv("MARIN_B200_DBG")) A.dbg = (u32)atoi(s);
+#endif
 		const size_t smem = (size_t)pl.R * TILE_PITCH * 16;
 		if (which == 0) { be.strided_fwd(A, A.tiles, pl.thrStr, smem); return true; }
 		if (which == 1) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
@@ -231,6 +238,7 @@ public:
 private:
 	size_t _regs;
 	u64 *_reg = nullptr, *_carry = nullptr, *_scratch = nullptr;
+	pair_t *_slots = nullptr; size_t _nslots = 0;
 	u32 *_flags = nullptr, _epoch = 0;
 	// speculation for squaring chains: _fwd holds the forward strided pass of register _fwd_reg's current value
 	u64 *_fwd = nullptr;
@@ -307,7 +315,10 @@ private:
 		std::memset(&A, 0, sizeof(A));
 		fill_strided_args(pl, A, level);
 		set_pass_tables(A, level);
-		A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.carry = _carry;
+		A.src = (const pair_t *)src; A.dst = (pair_t *)dst; A.a = a; A.slots = _slots;
+#if defined(MARIN_DEBUG_SKIP)
+		if (const char *s = getenv("MARIN_B200_DBG")) A.dbg = (u32)atoi(s);
+#endif
 		const size_t smem = (size_t)A.R * TILE_PITCH * 16;
 		const u32 grid = A.tiles * (level ? pl.R : 1), thr = level ? pl.thrStr2 : pl.thrStr;
 		if (!inv) { be.strided_fwd(A, grid, thr, smem); return; }
@@ -327,7 +338,7 @@ private:
 
 	u32 next_epoch()
 	{
-		if (++_epoch == 0) { be.memset0(_flags, ((size_t)(pl.R2 * pl.S / TILE_C) + 1) * 4); _epoch = 1; } // wrapped: start over from clean flags
+		if (++_epoch == 0) { be.memset0(_slots, _nslots * 16); _epoch = 1; } // wrapped: start over from clean slots
 		return _epoch;
 	}
 

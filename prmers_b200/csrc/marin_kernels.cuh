@@ -32,11 +32,24 @@ struct alignas(16) pair_t { u64 x, y; };
 #define MARIN_LD_VOLATILE_U32(p) (*(volatile const unsigned int *)(p))
 #define MARIN_ST_VOLATILE_U32(p, v) (*(volatile unsigned int *)(p) = (v))
 #define MARIN_LD_CG_U64(p) __ldcg((const unsigned long long *)(p))
+#define MARIN_NANOSLEEP(ns) __nanosleep(ns)
+// 16-byte {carry, epoch} slots: one vector store publishes value and tag together (the single-word
+// status+value of a decoupled look-back), one vector load reads both
+static __device__ __forceinline__ void marin_st_slot(ulonglong2 *p, unsigned long long v, unsigned long long tag)
+{ asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(v), "l"(tag) : "memory"); }
+static __device__ __forceinline__ ulonglong2 marin_ld_slot(const ulonglong2 *p)
+{ ulonglong2 r; asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory"); return r; }
 #else
 #define MARIN_FENCE() ((void)0)
 #define MARIN_LD_VOLATILE_U32(p) (*(const unsigned int *)(p))
 #define MARIN_ST_VOLATILE_U32(p, v) (*(unsigned int *)(p) = (v))
 #define MARIN_LD_CG_U64(p) (*(const unsigned long long *)(p))
+#define MARIN_NANOSLEEP(ns) ((void)0)
+#endif
+
+#if !defined(__CUDA_ARCH__)
+static inline void marin_st_slot(pair_t *p, unsigned long long v, unsigned long long tag) { p->x = v; p->y = tag; }
+static inline pair_t marin_ld_slot(const pair_t *p) { return *p; }
 #endif
 
 namespace marin {
@@ -117,7 +130,7 @@ HD u32 smem_pairs_lin(u32 S) { return S + (S >> 4) + 1; }
 
 HD void addsub(u64 &a, u64 &b) // (a, b) <- (a + b, a - b)
 {
-	const u64 nb = gl::P - b; // in (0, P]; P itself is a valid subtrahend for gl::sub
+	const u64 nb = gl::pminus(b); // in (0, P]; P itself is a valid subtrahend for gl::sub
 	const u64 d = gl::sub(a, b);
 	a = gl::sub(a, nb);
 	b = d;
@@ -207,7 +220,7 @@ struct Tw { const u64 *tab; u32 scale; };
 // outputs (forward) of the stage that touches global memory in a strided pass.
 // The stage that carries the boundary twiddle is the last forward stage (s = 1): its rows base + k have
 // frequency indices K0 + k * Kstep, K0 = rowK[base], Kstep = R / radix.
-struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; };
+struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost; };
 
 template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
 
@@ -258,7 +271,7 @@ template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 bas
 			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f);
 		}
 
-	if (INV && bd && bd->wpost) // unweight (and scale by 1/m) the outputs of the last inverse stage: natural order, coalesced
+	if (INV && bd && bd->wpost && !bd->skip_wpost) // unweight (and scale by 1/m) the outputs of the last inverse stage: natural order, coalesced
 		#pragma unroll
 		for (u32 q = 0; q < R; ++q) a[q] = gl::mul(a[q], bd->wpost[(size_t)(base + s * q) * bd->wstride]);
 
@@ -371,14 +384,20 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	u32 escale;         // m / Lb
 	u32 tiles;          // stride / 8 tiles per block
 	u32 a;              // multiplier for the carry
-	u64 *carry;         // carry[g * R + row]
+	pair_t *slots;      // slots[g * R + row] = {carry out of that run, epoch of the launch that wrote it}
 	u32 with_carry;
-	u32 *flags;         // [tiles + 1]: published[g], error word; hold the epoch of the last launch
+	u32 *flags;         // flags[tiles]: error word (a hand-off that timed out)
 	u32 epoch;
 	pair_t *fwd_dst;    // inverse pass only: also run the next forward strided pass on each tile and write it here
 	unsigned long long *ticket; // carry pass: tiles are handed out in START order (atomic counter, never reset), so the
 	unsigned long long ticket_base; // tile a CTA waits for has always started before it, whatever the block scheduler does
+	u32 dbg;            // timing experiments only (builds with -DMARIN_DEBUG_SKIP): bit mask of steps to leave out
 };
+#if defined(MARIN_DEBUG_SKIP)
+#define MARIN_DBG(A, bit) (((A).dbg >> (bit)) & 1u)
+#else
+#define MARIN_DBG(A, bit) 0
+#endif
 
 // ------------------------------------------------------------------ phase functions
 // A kernel is a sequence of phases separated by block-wide barriers.  phase(ph, tid) does thread
@@ -503,7 +522,7 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_nat + 2 * (size_t)(c0 + c) + lane : nullptr, 2 * (size_t)A.stride,
-			last ? A.rowK[base] : 0u, A.R / R};
+			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0};
 		if (!INV)
 			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
@@ -525,29 +544,41 @@ template <bool INV> HD void dispatch_stage_tile(const StridedArgs &A, const Stag
 
 // Phases of the inverse pass with carry (nst = number of stages):
 //   0 .. nst-1   inverse stages; the last one unweights (x 1/(w m)) into shared memory
-//   nst          carry each row's run of 2*TILE_C digits; write the carries out
-//   nst + 1      one thread: fence, raise published[g]
-//   nst + 2      one thread: wait for published[g - 1]; tile 0 waits for the LAST tile (end-around, 2^p = 1)
-//   nst + 3      absorb the carry of the run before into the first digits
-//   nst + 4      reweight, store the digits to the register (coalesced); keep the tile if the forward pass follows
-//   nst + 5 ..   optional: forward stages of the NEXT squaring on the tile still in shared memory -> A.fwd_dst
-// One-hop look-back only: tile g never waits for anything tile g - 1 has not already published, and
-// tile 0 (launched first) parks on the last tile's flag, which costs one CTA slot out of 148 x 2.
+//   nst          carry each row's run of 2*TILE_C digits and publish the carry out as a {carry, epoch} slot (one
+//                16-byte store: value and tag arrive together, no fence, no separate flag); thread 0 then waits for
+//                the first slot it will need, so that a tile whose predecessor is far behind (tile 0 needs the LAST
+//                tile: end-around, 2^p = 1) parks one thread instead of 256
+//   nst + 1      absorb the carry of the run before into the first digits (each thread checks its own slot's tag)
+//   nst + 2      reweight, store the digits to the register (coalesced); keep the tile if the forward pass follows
+//   nst + 3 ..   optional: forward stages of the NEXT squaring on the tile still in shared memory -> A.fwd_dst
+// One-hop look-back only: a tile publishes before it waits, and tile numbers are handed out in start order, so the
+// tile it waits for is already running.  Tile 0 parks on the last tile, which costs one CTA slot out of 148 x 2.
 HD u32 strided_num_phases(const StridedArgs &A, bool inv)
 {
 	if (!inv || !A.with_carry) return A.nst;
-	return A.nst + 5 + (A.fwd_dst ? A.nst : 0);
+	return A.nst + 3 + (A.fwd_dst ? A.nst : 0);
 }
-HD u32 strided_publish_phase(const StridedArgs &A) { return A.nst + 1; }
+HD u32 strided_publish_phase(const StridedArgs &A) { return A.nst; } // every slot of the tile is published when this phase ends
 
 static constexpr u32 SPIN_LIMIT = 1u << 27; // bounded wait: a lost flag raises the error word instead of hanging the GPU
 
-HD void wait_flag(const StridedArgs &A, u32 idx)
+// carry published in slot idx by this launch; bounded wait (an error word instead of a hung GPU)
+HD u64 wait_slot(const StridedArgs &A, size_t idx, bool backoff)
 {
 	u32 spins = 0;
-	while (MARIN_LD_VOLATILE_U32(&A.flags[idx]) != A.epoch)
-		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[A.tiles], 1u); break; }
-	MARIN_FENCE();
+	for (;;)
+	{
+		const pair_t v = marin_ld_slot(&A.slots[idx]);
+		if (v.y == (u64)A.epoch) return v.x;
+		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[A.tiles], 1u); return 0; }
+		if (backoff) MARIN_NANOSLEEP(200);
+	}
+}
+
+// the run before (row, g) is (row, g - 1); before (row, 0) comes (row - 1, last tile); before (0, 0) the very last run
+HD size_t slot_before(const StridedArgs &A, u32 g, u32 row)
+{
+	return (g > 0) ? (size_t)(g - 1) * A.R + row : (size_t)(A.tiles - 1) * A.R + ((row == 0) ? A.R - 1 : row - 1);
 }
 
 template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 ph, u32 tid, u32 nthr, pair_t *sm)
@@ -572,31 +603,21 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 			#pragma unroll
 			for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
 			const u32 j0 = 2 * (row * A.stride + c0);
-			const u64 cout = carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
-			A.carry[(size_t)g * A.R + row] = cout;
+			const u64 cout = MARIN_DBG(A, 4) ? 0 : carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
+			marin_st_slot(&A.slots[(size_t)g * A.R + row], cout, A.epoch);
 			#pragma unroll
 			for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
 		}
-		MARIN_FENCE();
+#if defined(__CUDA_ARCH__)
+		if (tid == 0 && !MARIN_DBG(A, 1)) wait_slot(A, slot_before(A, g, 0), true); // a gate for performance only
+#endif
 		return;
 	}
 	if (cph == 1)
 	{
-		if (tid == 0) { MARIN_FENCE(); MARIN_ST_VOLATILE_U32(&A.flags[g], A.epoch); }
-		return;
-	}
-	if (cph == 2)
-	{
-		if (tid == 0) wait_flag(A, (g == 0) ? A.tiles - 1 : g - 1);
-		return;
-	}
-	if (cph == 3)
-	{
-		// the run before (row, g) is (row, g - 1); before (row, 0) comes (row - 1, last tile); before (0, 0) the very last run
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
-			const size_t from = (g > 0) ? (size_t)(g - 1) * A.R + row : (size_t)(A.tiles - 1) * A.R + ((row == 0) ? A.R - 1 : row - 1);
-			const u64 c = MARIN_LD_CG_U64(&A.carry[from]);
+			const u64 c = wait_slot(A, slot_before(A, g, row), false);
 			if (c == 0) continue;
 			const pair_t p0 = sm[tile_pair(row, 0)], p1 = sm[tile_pair(row, 1)];
 			u64 d[4] = {p0.x, p0.y, p1.x, p1.y};
@@ -606,15 +627,17 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 		}
 		return;
 	}
-	if (cph == 4)
+	if (cph == 2)
 	{
-		// reweight and store, coalesced (TILE_C threads cover one row segment); four elements in flight
+		// reweight and store, coalesced (TILE_C threads cover one row segment); eight elements in flight per thread so
+		// that the weight loads (a stream no cache holds) overlap instead of costing one memory latency each
+		constexpr u32 B = 8;
 		const u32 total = A.R * TILE_C;
-		for (u32 e0 = tid; e0 < total; e0 += 4 * nthr)
+		for (u32 e0 = tid; e0 < total; e0 += B * nthr)
 		{
-			pair_t d[4], w[4]; size_t pi[4];
+			pair_t d[B], w[B]; size_t pi[B];
 			#pragma unroll
-			for (u32 u = 0; u < 4; ++u)
+			for (u32 u = 0; u < B; ++u)
 			{
 				const u32 e = e0 + u * nthr;
 				if (e < total)
@@ -622,16 +645,22 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 					const u32 row = e / TILE_C, c = e % TILE_C;
 					pi[u] = (size_t)row * A.stride + c0 + c;
 					w[u] = reinterpret_cast<const pair_t *>(t.w_nat)[pi[u]];
-					d[u] = sm[tile_pair(row, c)];
 				}
 			}
 			#pragma unroll
-			for (u32 u = 0; u < 4; ++u)
+			for (u32 u = 0; u < B; ++u)
+			{
+				const u32 e = e0 + u * nthr;
+				if (e < total) d[u] = sm[tile_pair(e / TILE_C, e % TILE_C)];
+			}
+			#pragma unroll
+			for (u32 u = 0; u < B; ++u)
 			{
 				const u32 e = e0 + u * nthr;
 				if (e < total)
 				{
 					pair_t o; o.x = gl::mul(d[u].x, w[u].x); o.y = gl::mul(d[u].y, w[u].y);
+					if (MARIN_DBG(A, 2)) o = d[u];
 					A.dst[blockbase + pi[u]] = o;
 					if (A.fwd_dst) sm[tile_pair(e / TILE_C, e % TILE_C)] = o;
 				}
@@ -640,7 +669,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 		return;
 	}
 	// forward strided pass of the next squaring, straight from the tile in shared memory
-	const u32 si = cph - 5;
+	const u32 si = cph - 3;
 	dispatch_stage_tile<false>(A, A.st[si], si == 0, si == A.nst - 1, blockbase, c0, sm, tid, nthr, nullptr, A.fwd_dst, true, false);
 }
 

@@ -516,20 +516,32 @@ def run_ecm_sharded(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors
 # ---- big-integer restatement of the same formulas (used by tests as the arithmetic reference) --------
 def reference_scalar_mul(N, aE, dE, X2, Y2, digits):
     """(X, Y, Z, T) after the same double-and-add in Python integers: the engine must reproduce these residues."""
-    T2 = X2 * Y2 % N
+    p = N.bit_length()
+
+    def M(x):                                         # x mod 2^p - 1 by folding (Python's % is quadratic)
+        neg = x < 0
+        if neg:
+            x = -x
+        while x >> p:
+            x = (x & N) + (x >> p)
+        if x == N:
+            x = 0
+        return (N - x) % N if neg and x else x
+
+    T2 = M(X2 * Y2)
     sgn = -1 if digits[-1] < 0 else 1
-    X, Y, Z, T = sgn * X2 % N, Y2, 1, sgn * T2 % N
+    X, Y, Z, T = M(sgn * X2), Y2, 1, M(sgn * T2)
     for i in range(len(digits) - 2, -1, -1):
-        A, B, C = X * X % N, Y * Y % N, 2 * Z * Z % N
-        D, E = aE * A % N, 2 * T * Z % N
-        G, H = (D + B) % N, (D - B) % N
-        F = (G - C) % N
-        X, Y, T, Z = E * F % N, G * H % N, E * H % N, F * G % N
+        A, B, C = M(X * X), M(Y * Y), M(2 * Z * Z)
+        D, E = M(aE * A), M(2 * T * Z)
+        G, H = M(D + B), M(D - B)
+        F = M(G - C)
+        X, Y, T, Z = M(E * F), M(G * H), M(E * H), M(F * G)
         d = digits[i]
         if d:
-            x2, t2 = d * X2 % N, d * T2 % N
-            E = (X * Y2 + Y * x2) % N
-            H = (Y * Y2 - aE * X * x2) % N
-            C = dE * T % N * t2 % N
-            X, Y, T, Z = E * (Z - C) % N, H * (Z + C) % N, E * H % N, (Z - C) * (Z + C) % N
+            x2, t2 = M(d * X2), M(d * T2)
+            E = M(X * Y2 + Y * x2)
+            H = M(Y * Y2 - M(aE * X) * x2)
+            C = M(M(dE * T) * t2)
+            X, Y, T, Z = M(E * (Z - C)), M(H * (Z + C)), M(E * H), M((Z - C) * (Z + C))
     return X, Y, Z, T

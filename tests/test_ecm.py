@@ -151,16 +151,19 @@ def test_ecm_stage2_gpu():
 
 
 @pytest.mark.gpu
-def test_ecm_point_ops_on_the_multi_pass_path_gpu():
-    """addsub / mul_copy / sub_reg on a 3-pass engine (n = 65536): the Edwards schedules against big integers."""
+@pytest.mark.parametrize("p,force_s", [(86243, 64), (216091, 64)])
+def test_ecm_point_ops_on_the_multi_pass_path_gpu(p, force_s, monkeypatch):
+    """addsub / mul_copy / sub_reg on 3-pass engines (n = 4096 forced off the single-CTA path, and n = 10240 = 5 * 2^11):
+    the Edwards schedules against big integers."""
     import prmers_b200 as pb
-    p = 1362763; N = (1 << p) - 1
+    N = (1 << p) - 1
     cv = ecm.curve_from_seed(N, 2024)
-    K = ecm.stage1_exponent(30)
+    K = ecm.stage1_exponent(60)
     want = ecm.reference_scalar_mul(N, cv["a"], cv["d"], cv["X0"], cv["Y0"], ecm.naf(K))
+    monkeypatch.setenv("MARIN_B200_FORCE_S", str(force_s))
     eng = pb.Engine(p, ecm.REGS)
     assert not eng.is_single_cta()
-    r = ecm.run_curve(eng, p, 30, 0, 2024, curve=cv, K=K)
+    r = ecm.run_curve(eng, p, 60, 0, 2024, curve=cv, K=K)
     assert r["status"] == "NF" and r["stage1_T"] == want[3] % N
     assert tuple(eng.get_mpz(reg) for reg in (3, 4, 1)) == tuple(v % N for v in want[:3])
 
