@@ -55,11 +55,15 @@ public:
 		t.rowroot = (const u64 *)upload(h.rowroot.data(), h.rowroot.size() * 8);
 		t.colroot = (const u64 *)upload(h.colroot.data(), h.colroot.size() * 8);
 		for (int i = 0; i < 4; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
-		u64 *w_nat = (u64 *)be.alloc(n * 8), *winv_nat = (u64 *)be.alloc(n * 8), *winvs_nat = (u64 *)be.alloc(n * 8);
-		_owned.push_back(w_nat); _owned.push_back(winv_nat); _owned.push_back(winvs_nat);
-		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat};
+		// natural-order tables for the linear and single-CTA kernels; multi-pass engines unweight / reweight from
+		// the tile-ordered copies instead
+		u64 *w_nat = (u64 *)be.alloc(n * 8), *winv_nat = (u64 *)be.alloc(n * 8);
+		u64 *winvs_nat = pl.small ? (u64 *)be.alloc(n * 8) : nullptr;
+		u64 *w_tile = pl.small ? nullptr : (u64 *)be.alloc(n * 8), *winvs_tile = pl.small ? nullptr : (u64 *)be.alloc(n * 8);
+		for (u64 *q : {w_nat, winv_nat, winvs_nat, w_tile, winvs_tile}) if (q) _owned.push_back(q);
+		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat, w_tile, winvs_tile, pl.R, pl.small ? 1u : pl.R2 * pl.S};
 		be.weights(W, pl.n);
-		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat;
+		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat; t.w_tile = w_tile; t.winvs_tile = winvs_tile;
 		const size_t nflags = (size_t)(pl.R2 * pl.S / TILE_C) + 4; // published[tiles], error word, then the 8-byte aligned 64-bit tile ticket
 		_flags = (u32 *)be.alloc(nflags * 4);
 		be.memset0(_flags, nflags * 4);

@@ -55,6 +55,9 @@ static inline pair_t marin_ld_slot(const pair_t *p) { return *p; }
 namespace marin {
 
 static constexpr int MAX_STAGES = 8;
+#ifndef MARIN_RW_BATCH
+#define MARIN_RW_BATCH 4 // weight loads in flight per thread in the reweight/store phase
+#endif
 #ifndef MARIN_TILE_C
 #define MARIN_TILE_C 4
 #endif
@@ -75,6 +78,10 @@ struct Tables
 	const u32 *wbits;            // n bits, natural order
 	const u64 *w_nat, *winv_nat; // weight, 1/weight (natural digit order)
 	const u64 *winvs_nat;        // 1/(weight m): unweighting fused with the 1/m of the inverse transform
+	// the same two tables in the order the strided inverse pass walks them (multi-pass engines): pair (row, column)
+	// of tile g at pair index (g R + row) TILE_C + column % TILE_C, so that a tile's weights are one contiguous
+	// 16 R TILE_C byte stream instead of R segments of 16 TILE_C bytes one row stride apart
+	const u64 *w_tile, *winvs_tile;
 	u64 inv_m;                   // 1/m
 	// block transforms
 	const u64 *twS, *twSi; u32 S; // S powers of the S-th root and of its inverse (contiguous pass)
@@ -521,7 +528,7 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 		const View Sv = view_tile(sm, c, lane);
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
-		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_nat + 2 * (size_t)(c0 + c) + lane : nullptr, 2 * (size_t)A.stride,
+		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_tile + 2 * ((size_t)(c0 / TILE_C) * A.R * TILE_C + c) + lane : nullptr, 2 * (size_t)TILE_C,
 			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0};
 		if (!INV)
 			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
@@ -597,6 +604,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 	if (cph == 0)
 	{
 		// the tile holds exact convolution values: carry each row's run of consecutive digits
+		if (MARIN_DBG(A, 6)) return;
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
 			u64 v[RUN];
@@ -604,7 +612,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 			for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
 			const u32 j0 = 2 * (row * A.stride + c0);
 			const u64 cout = MARIN_DBG(A, 4) ? 0 : carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
-			marin_st_slot(&A.slots[(size_t)g * A.R + row], cout, A.epoch);
+			if (!MARIN_DBG(A, 7)) marin_st_slot(&A.slots[(size_t)g * A.R + row], cout, A.epoch);
 			#pragma unroll
 			for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
 		}
@@ -615,6 +623,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 	}
 	if (cph == 1)
 	{
+		if (MARIN_DBG(A, 8)) return;
 		for (u32 row = tid; row < A.R; row += nthr)
 		{
 			const u64 c = wait_slot(A, slot_before(A, g, row), false);
@@ -631,11 +640,18 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 	{
 		// reweight and store, coalesced (TILE_C threads cover one row segment); eight elements in flight per thread so
 		// that the weight loads (a stream no cache holds) overlap instead of costing one memory latency each
-		constexpr u32 B = 8;
+		constexpr u32 B = MARIN_RW_BATCH;
 		const u32 total = A.R * TILE_C;
+		if (MARIN_DBG(A, 5)) return;
 		for (u32 e0 = tid; e0 < total; e0 += B * nthr)
 		{
-			pair_t d[B], w[B]; size_t pi[B];
+			pair_t w[B];
+			#pragma unroll
+			for (u32 u = 0; u < B; ++u)
+			{
+				const u32 e = e0 + u * nthr;
+				if (e < total) w[u] = reinterpret_cast<const pair_t *>(t.w_tile)[(size_t)g * total + e];
+			}
 			#pragma unroll
 			for (u32 u = 0; u < B; ++u)
 			{
@@ -643,26 +659,11 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 				if (e < total)
 				{
 					const u32 row = e / TILE_C, c = e % TILE_C;
-					pi[u] = (size_t)row * A.stride + c0 + c;
-					w[u] = reinterpret_cast<const pair_t *>(t.w_nat)[pi[u]];
-				}
-			}
-			#pragma unroll
-			for (u32 u = 0; u < B; ++u)
-			{
-				const u32 e = e0 + u * nthr;
-				if (e < total) d[u] = sm[tile_pair(e / TILE_C, e % TILE_C)];
-			}
-			#pragma unroll
-			for (u32 u = 0; u < B; ++u)
-			{
-				const u32 e = e0 + u * nthr;
-				if (e < total)
-				{
-					pair_t o; o.x = gl::mul(d[u].x, w[u].x); o.y = gl::mul(d[u].y, w[u].y);
-					if (MARIN_DBG(A, 2)) o = d[u];
-					A.dst[blockbase + pi[u]] = o;
-					if (A.fwd_dst) sm[tile_pair(e / TILE_C, e % TILE_C)] = o;
+					const pair_t d = sm[tile_pair(row, c)];
+					pair_t o; o.x = gl::mul(d.x, w[u].x); o.y = gl::mul(d.y, w[u].y);
+					if (MARIN_DBG(A, 2)) o = d;
+					A.dst[blockbase + (size_t)row * A.stride + c0 + c] = o;
+					if (A.fwd_dst) sm[tile_pair(row, c)] = o;
 				}
 			}
 		}
@@ -787,7 +788,7 @@ static constexpr u32 LIN_BLOCK = 256; // pairs per CTA of the fast linear kernel
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
 
 // weight tables: digit j has weight r^((n - p j mod n) mod n), r the n-th root of two (ibdwt.h:111-147)
-struct WeightArgs { u32 p, n; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *winvs_nat; };
+struct WeightArgs { u32 p, n; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *winvs_nat; u64 *w_tile, *winvs_tile; u32 R, stride; };
 
 HD void weight_thread(const WeightArgs &A, u32 j)
 {
@@ -795,7 +796,15 @@ HD void weight_thread(const WeightArgs &A, u32 j)
 	const u64 r = ((u64)A.p * j) % A.n;
 	const u64 e = r ? (u64)A.n - r : 0;
 	const u64 w = gl::pow(A.nr2, e), wi = gl::pow(A.nr2_inv, e);
-	A.w_nat[j] = w; A.winv_nat[j] = wi; A.winvs_nat[j] = gl::mul(wi, A.inv_m);
+	const u64 wis = gl::mul(wi, A.inv_m);
+	A.w_nat[j] = w; A.winv_nat[j] = wi;
+	if (A.winvs_nat) A.winvs_nat[j] = wis;
+	if (A.w_tile)
+	{
+		const u32 i = j >> 1, row = i / A.stride, col = i % A.stride;
+		const size_t k = 2 * (((size_t)(col / TILE_C) * A.R + row) * TILE_C + col % TILE_C) + (j & 1);
+		A.w_tile[k] = w; A.winvs_tile[k] = wis;
+	}
 }
 
 } // namespace marin
