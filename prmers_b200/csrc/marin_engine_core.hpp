@@ -35,7 +35,7 @@ public:
 		_nslots = n / RUN + 1;
 		_slots = (pair_t *)be.alloc(_nslots * 16);   // {carry, epoch} hand-off slots of the inverse strided pass
 		be.memset0(_slots, _nslots * 16);
-		if (!pl.small) { _fwd = (u64 *)be.alloc(n * 8); be.persist(_fwd, n * 8); }
+		if (!pl.small) { _fwd = (u64 *)be.alloc(n * 8); be.persist(_fwd, n * 8); _inv_R = gl::inv(pl.R); }
 		Tables &t = _t;
 		std::memset(&t, 0, sizeof(t));
 		t.p = pl.p; t.n = pl.n; t.m = pl.m; t.wbase = pl.wbase; t.inv_m = h.inv_m;
@@ -126,17 +126,32 @@ public:
 	// operation simply ignores (and invalidates) the parked transform.
 	void square_mul(size_t r, u32 a)
 	{
-		check(r); check_a(a);
+		check_range(r); check_a(a);
 		if (pl.small) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M); return; }
+		if (_lazy != r) materialize();                   // another register's state lives in _fwd: write it out first
 		const bool chained = (_last_sq == r);            // second squaring in a row: start speculating
 		if (_fwd_reg != r) strided(false, 0, R(r), _fwd, 1, nullptr);
 		_fwd_reg = (size_t)-1;
 		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
 		MidArgs M = mid_args(_fwd, nullptr, _fwd, MODE_SQR, a); launch_mid(M);
 		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
-		strided(true, 0, _fwd, R(r), a, chained ? _fwd : nullptr);
-		if (chained) _fwd_reg = r;
+		// In a chain the finished digits are not even written back: the parked transform of them IS the register's
+		// state (8n bytes of HBM writes less per squaring); materialize() recovers the digits, exactly, the first
+		// time anything else looks at the register.
+		strided(true, 0, _fwd, R(r), a, chained ? _fwd : nullptr, chained);
+		if (chained) { _fwd_reg = r; _lazy = r; } else _lazy = (size_t)-1;
 		_last_sq = r;
+	}
+
+	// Register _lazy's memory is stale; _fwd holds the forward strided pass of its digits.  The plain inverse
+	// strided pass times 1/R is the exact inverse (field arithmetic), so this writes the very digits the carry pass
+	// would have stored.  _fwd is left intact: the chain may go on.
+	void materialize()
+	{
+		if (_lazy == (size_t)-1) return;
+		const size_t r = _lazy;
+		_lazy = (size_t)-1;
+		strided(true, 0, _fwd, R(r), 1, nullptr, false, true);
 	}
 
 	void set_multiplicand(size_t dst, size_t src)
@@ -154,8 +169,10 @@ public:
 		check(dst); check(src); check_a(a);
 		if (dst == src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
 		if (pl.small) { MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M); return; }
+		materialize();
 		if (_fwd_reg != dst) strided(false, 0, R(dst), _fwd, 1, nullptr);
 		touch(dst);
+		_fwd_reg = (size_t)-1;                           // _fwd is the scratch buffer of this product: whatever was parked there is gone
 		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
 		MidArgs M = mid_args(_fwd, R(src), _fwd, MODE_MUL, a); launch_mid(M);
 		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
@@ -203,8 +220,8 @@ public:
 
 	void get_raw(size_t src, void *buf) { check(src); blocking("get_data"); be.d2h(buf, R(src), (size_t)pl.n * 8); }
 	void set_raw(size_t dst, const void *buf) { check(dst); blocking("set_data"); touch(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
-	void get_all(void *buf) { blocking("get_checkpoint"); be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
-	void set_all(const void *buf) { blocking("set_checkpoint"); _fwd_reg = _last_sq = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
+	void get_all(void *buf) { blocking("get_checkpoint"); materialize(); be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
+	void set_all(const void *buf) { blocking("set_checkpoint"); _fwd_reg = _last_sq = _lazy = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
 
 	// single passes of square_mul, for per-kernel timing (3-pass engines only): 0 strided forward,
 	// 1 contiguous middle, 2 strided inverse + carry, 3 carry fix-up
@@ -212,6 +229,7 @@ public:
 	{
 		check(r);
 		if (pl.small) { if (which != 1) return false; MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, 1); launch_mid(M); return true; }
+		materialize();
 		touch(r);
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
@@ -227,7 +245,7 @@ public:
 		if (which == 2 || which == 3)
 		{
 			// 2: inverse pass + carry; 3: the same with the next forward strided pass fused in (chained squarings)
-			A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (which == 3) ? (pair_t *)_fwd : nullptr; set_ticket(A);
+			A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (which == 3) ? (pair_t *)_fwd : nullptr; A.skip_dst = (which == 3); set_ticket(A);
 			_fwd_reg = (size_t)-1;
 			be.strided_inv(A, A.tiles, pl.thrStr, smem); return true;
 		}
@@ -247,6 +265,8 @@ private:
 	// speculation for squaring chains: _fwd holds the forward strided pass of register _fwd_reg's current value
 	u64 *_fwd = nullptr;
 	size_t _fwd_reg = (size_t)-1, _last_sq = (size_t)-1;
+	size_t _lazy = (size_t)-1;   // register whose digits exist only as the parked transform in _fwd (see square_mul)
+	u64 _inv_R = 0;
 	size_t _nflags = 0;
 	unsigned long long _ticket_next = 0;
 	Tables _t;
@@ -265,7 +285,8 @@ private:
 
 	bool _recording = false;
 	void blocking(const char *what) const { if (_recording) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
-	void check(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }
+	void check_range(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }
+	void check(size_t r) { check_range(r); if (r == _lazy) materialize(); }
 	void check_a(u32 a) const
 	{
 		if (a == 0 || a > pl.a_max)
@@ -313,7 +334,7 @@ private:
 
 	// level 0 = strided pass over the whole register (the inverse one carries), level 1 = second strided
 	// pass inside each of the R blocks (only for transforms with more rows than one tile can hold)
-	void strided(bool inv, int level, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst)
+	void strided(bool inv, int level, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst, bool skip_dst = false, bool exact_inverse = false)
 	{
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
@@ -326,6 +347,8 @@ private:
 		const size_t smem = (size_t)A.R * TILE_PITCH * 16;
 		const u32 grid = A.tiles * (level ? pl.R : 1), thr = level ? pl.thrStr2 : pl.thrStr;
 		if (!inv) { be.strided_fwd(A, grid, thr, smem); return; }
+		if (exact_inverse) { A.scale = _inv_R; be.strided_inv(A, grid, thr, smem); return; }
+		A.skip_dst = skip_dst ? 1u : 0u;
 		if (level == 0) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst; set_ticket(A); }
 		be.strided_inv(A, grid, thr, smem);
 	}

@@ -227,14 +227,12 @@ struct Tw { const u64 *tab; u32 scale; };
 // outputs (forward) of the stage that touches global memory in a strided pass.
 // The stage that carries the boundary twiddle is the last forward stage (s = 1): its rows base + k have
 // frequency indices K0 + k * Kstep, K0 = rowK[base], Kstep = R / radix.
-struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost; };
+struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost; u64 scale; };
 
 template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
 
-template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 base, u32 s, u32 j, const Tw &tw,
-	const u64 *c5, const Boundary *bd)
+template <int R, bool INV> HD void bfly_load(u64 *a, const View &in, u32 base, u32 s)
 {
-	u64 a[R];
 	if (in.linear(s, R))
 	{
 		const u64 *pi = in.p + 2 * in.pidx(base);
@@ -247,7 +245,20 @@ template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 bas
 		#pragma unroll
 		for (u32 q = 0; q < R; ++q) a[INV ? slot_of<R>(q) : q] = in.ld(base + s * q);
 	}
+}
 
+template <int R, bool INV> HD void bfly_core(u64 *a, const View &out, u32 base, u32 s, u32 j, const Tw &tw, const u64 *c5, const Boundary *bd);
+
+template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 base, u32 s, u32 j, const Tw &tw,
+	const u64 *c5, const Boundary *bd)
+{
+	u64 a[R];
+	bfly_load<R, INV>(a, in, base, s);
+	bfly_core<R, INV>(a, out, base, s, j, tw, c5, bd);
+}
+
+template <int R, bool INV> HD void bfly_core(u64 *a, const View &out, u32 base, u32 s, u32 j, const Tw &tw, const u64 *c5, const Boundary *bd)
+{
 	if (INV && bd && bd->twiddle)
 		#pragma unroll
 		for (u32 q = 0; q < R; ++q)
@@ -277,6 +288,10 @@ template <int R, bool INV> HD void bfly(const View &in, const View &out, u32 bas
 			const u64 f = boundary_tw(*bd->t, (u64)(bd->K0 + k * bd->Kstep) * bd->colscale, false);
 			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f);
 		}
+
+	if (INV && bd && bd->scale) // plain inverse pass that must return the exact input of the forward pass: x 1/R
+		#pragma unroll
+		for (u32 q = 0; q < R; ++q) a[q] = gl::mul(a[q], bd->scale);
 
 	if (INV && bd && bd->wpost && !bd->skip_wpost) // unweight (and scale by 1/m) the outputs of the last inverse stage: natural order, coalesced
 		#pragma unroll
@@ -398,6 +413,8 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	pair_t *fwd_dst;    // inverse pass only: also run the next forward strided pass on each tile and write it here
 	unsigned long long *ticket; // carry pass: tiles are handed out in START order (atomic counter, never reset), so the
 	unsigned long long ticket_base; // tile a CTA waits for has always started before it, whatever the block scheduler does
+	u32 skip_dst;       // carry pass of a squaring chain: leave the register alone, the parked transform in fwd_dst is the state
+	u64 scale;          // plain inverse pass (no carry): multiply the outputs by this (1/R turns it into the exact inverse)
 	u32 dbg;            // timing experiments only (builds with -DMARIN_DEBUG_SKIP): bit mask of steps to leave out
 };
 #if defined(MARIN_DEBUG_SKIP)
@@ -529,11 +546,11 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_tile + 2 * ((size_t)(c0 / TILE_C) * A.R * TILE_C + c) + lane : nullptr, 2 * (size_t)TILE_C,
-			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0};
+			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0, (INV && first && !out_smem_always) ? A.scale : 0};
 		if (!INV)
 			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
-			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, (last || wp) ? &bd : nullptr);
+			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, (last || wp || (first && A.scale)) ? &bd : nullptr);
 	}
 }
 
@@ -662,7 +679,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 					const pair_t d = sm[tile_pair(row, c)];
 					pair_t o; o.x = gl::mul(d.x, w[u].x); o.y = gl::mul(d.y, w[u].y);
 					if (MARIN_DBG(A, 2)) o = d;
-					A.dst[blockbase + (size_t)row * A.stride + c0 + c] = o;
+					if (!A.skip_dst) A.dst[blockbase + (size_t)row * A.stride + c0 + c] = o;
 					if (A.fwd_dst) sm[tile_pair(row, c)] = o;
 				}
 			}

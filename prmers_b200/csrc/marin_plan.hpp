@@ -43,6 +43,10 @@ struct Plan
 	u32 a_max = 1;               // largest multiplier `a` the carry chain supports without overflow
 };
 
+#ifndef MARIN_R_SMALL_FIRST
+#define MARIN_R_SMALL_FIRST 0
+#endif
+
 inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
 {
 	// radices: optional 5 first, then 2, 4 and 16s (or 16s first) with product len
@@ -96,7 +100,7 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 		}
 		if (pl.R > MAX_R || pl.S > MID_S) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
 		pl.nstS = factor_stages(pl.S, pl.stS, true);
-		pl.nstR = factor_stages(pl.R, pl.stR, false);
+		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0);
 		pl.thrMid = round_threads(pl.S / 8, 512);
 		const u32 bf = pl.R * TILE_C * 2 / 16; // radix-16 butterflies x lanes per stage
 		pl.thrStr = (bf <= 1024) ? round_threads(bf, 1024) : round_threads(bf / 2, 1024);

@@ -66,6 +66,54 @@ def test_register_ops_match_bigint(p, force_S):
     assert val(e, 0) == x
 
 
+def chain_state_script(e, p, put, val):
+    """Squaring chains leave the register's digits parked in transform form (no write-back); every other way of
+    looking at or changing the register must see the finished digits.  Shared by the emulated and the GPU tier."""
+    m = (1 << p) - 1
+    wd = mo.widths(e.get_size(), p)
+    rng = random.Random(p)
+    x, y, z = rng.randrange(m), rng.randrange(m), rng.randrange(m)
+    put(e, 0, x, wd); put(e, 1, y, wd); put(e, 4, z, wd)
+    for _ in range(4):
+        e.square_mul(0); x = x * x % m
+    assert val(e, 0) == x                                     # get after a chain
+    for _ in range(3):
+        e.square_mul(0); x = x * x % m                        # the chain goes on after the read
+    e.copy(2, 0)                                              # copy out of a parked register
+    assert val(e, 2) == x
+    for _ in range(3):
+        e.square_mul(0); x = x * x % m
+    for _ in range(3):
+        e.square_mul(1); y = y * y % m                        # another register squared while 0 is parked
+    assert val(e, 0) == x and val(e, 1) == y
+    for _ in range(3):
+        e.square_mul(0); x = x * x % m
+    e.set_multiplicand(3, 4); e.mul(4, 3); z = z * z % m      # mul borrows the parking buffer
+    assert val(e, 4) == z
+    for _ in range(3):
+        e.square_mul(0); x = x * x % m
+    e.add(0, 1); x = (x + y) % m                              # linear op on a parked register
+    for _ in range(3):
+        e.square_mul(0); x = x * x % m
+    e.set_multiplicand(3, 0)                                  # parked register as the source of a multiplicand
+    e.square_mul(0); x2 = x * x % m
+    e.mul(1, 3); y = y * x % m
+    assert val(e, 0) == x2 and val(e, 1) == y
+    for _ in range(3):
+        e.square_mul(0); x2 = x2 * x2 % m
+    e.set(0, 7)                                               # overwritten while parked
+    e.square_mul(0)
+    assert val(e, 0) == 49 % m
+    return True
+
+
+@pytest.mark.parametrize("p,force_S,force_R2", [(86243, 64, 0), (216091, 64, 0), (86243, 8, 16), (216091, 128, 0)])
+def test_chain_state_is_materialised_on_demand(p, force_S, force_R2):
+    e = EmuEngine(p, 6, force_S, force_R2)
+    assert not e.small
+    assert chain_state_script(e, p, put, val)
+
+
 @pytest.mark.parametrize("p,force_S", [(127, 0), (9941, 0), (9941, 16), (86243, 64), (216091, 64)])
 def test_digits_bit_exact_vs_oracle(p, force_S):
     """Canonical digits (value | width << 32) equal the oracle's digit for digit."""

@@ -272,6 +272,33 @@ def test_full_size_squarings_match_oracle_and_identities(p, n):
     e.close()
 
 
+def test_interim_res64_golden_full_size():
+    """tests/golden/prp_interim_res64.json (GMP big integers, tools/make_golden_prp.py): the type-1 PRP state after i
+    squarings of 3 at the BASELINE.json sizes, read back in the middle of the chain (the digits are parked in
+    transform form between squarings and materialised for each read)."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "prp_interim_res64.json")))["res64"]
+    for p, marks in gold.items():
+        e = _engine(int(p), 2)
+        e.set(0, 3)
+        done = 0
+        for it in sorted(int(k) for k in marks):
+            e.square_mul_repeat(0, it - done); done = it
+            assert e.digit(0).res64() == int(marks[str(it)], 16), (p, it)
+        e.close()
+
+
+@pytest.mark.parametrize("p,force_S,force_R2", [(86243, 64, 0), (216091, 64, 0), (86243, 8, 16), (216091, 128, 0)])
+def test_chain_state_is_materialised_on_demand(p, force_S, force_R2):
+    """A chain, then a product on another register, then the chain again (the parked transform must not survive the
+    product: regression), reads, copies, linear ops and overwrites of a parked register."""
+    from tests.test_emu_kernels import chain_state_script
+    e = _engine(p, 6, force_S, force_R2)
+    assert not e.is_single_cta()
+    assert chain_state_script(e, p, lambda eng, r, x, wd: eng.set_mpz(r, x), val)
+    e.close()
+
+
 def test_long_chain_gerbicz_identity_full_size():
     """Gerbicz-Li style check (RunPrpOrLlMarin.cpp:338-369) at n = 2^23: with d_k the product of the
     residues at block ends, d_{k+1} == d_k^(2^B) * 3 ... here in its simplest size-independent
