@@ -68,7 +68,7 @@ static constexpr int MAXRUN = 16;         // largest run any kernel carries in o
 
 enum Mode : int { MODE_SQR = 0, MODE_MUL = 1, MODE_FWD = 2 };
 
-struct Stage { u32 radix, L, s; };        // block length L = radix * s
+struct Stage { u32 radix, L, s, toff; };  // block length L = radix * s; toff: where this stage's twiddles start in the table
 
 // Constant tables of one engine (device pointers).
 struct Tables
@@ -84,7 +84,7 @@ struct Tables
 	const u64 *w_tile, *winvs_tile;
 	u64 inv_m;                   // 1/m
 	// block transforms
-	const u64 *twS, *twSi; u32 S; // S powers of the S-th root and of its inverse (contiguous pass)
+	const u64 *twS, *twSi; u32 S; // stage twiddles of the contiguous pass (see Tw), forward and inverse
 	const u64 *bl_lo, *bl_hi, *bl_loi, *bl_hii; u32 bl_h; // m-th root: w^(+-e) = lo[e & (2^h - 1)] * hi[e >> h]
 	const u64 *rowroot;          // w_m^(frequency index of the contiguous block) after the strided pass(es)
 	const u64 *colroot;          // w_S^freq(sigma), position order inside a contiguous block
@@ -216,9 +216,11 @@ HD void dft5(u64 *x, const u64 *c)
 
 // ------------------------------------------------------------------ one butterfly of one stage
 
-// Twiddle source of a stage: table of X powers of the X-th root, exponent scale = X / L.
-// tab is the forward or the inverse table according to the direction; null when s = 1 (no twiddles).
-struct Tw { const u64 *tab; u32 scale; };
+// Twiddles of a stage with block length L = R s: tab[(k - 1) s + j] = w_L^(+-j k), 1 <= k < R, j < s -- one row per
+// output index k, so that the threads of a warp (consecutive j) read consecutive words (coalesced; a flat table of
+// powers indexed by j k made every load touch up to 30 sectors).  tab is the forward or the inverse table according
+// to the direction; null when s = 1 (no twiddles).
+struct Tw { const u64 *tab; u32 s; };
 
 // Forward (DIF): y_k = sum_q x_q w_R^(qk), then y_k *= w_L^(jk); element q/k lives at base + s q/k.
 // Inverse: the exact mirror (conjugate twiddle first, then conjugate DFT), unnormalised.
@@ -267,10 +269,9 @@ template <int R, bool INV> HD void bfly_core(u64 *a, const View &out, u32 base, 
 			const u32 sl = slot_of<R>(q); a[sl] = gl::mul(a[sl], f);
 		}
 
-	const u32 je = j * tw.scale;
 	if (INV && tw.tab)
 		#pragma unroll
-		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw.tab[je * k]); }
+		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw.tab[(k - 1) * tw.s + j]); }
 
 	if (R == 16) dft16<INV>(a);
 	else if (R == 4) dft4<INV>(a[0], a[1], a[2], a[3]);
@@ -279,7 +280,7 @@ template <int R, bool INV> HD void bfly_core(u64 *a, const View &out, u32 base, 
 
 	if (!INV && tw.tab)
 		#pragma unroll
-		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw.tab[je * k]); }
+		for (u32 k = 1; k < R; ++k) { const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], tw.tab[(k - 1) * tw.s + j]); }
 
 	if (!INV && bd && bd->twiddle)
 		#pragma unroll
@@ -399,7 +400,7 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	const pair_t *src; pair_t *dst; // src == dst for in-place
 	u32 R, nst;
 	Stage st[MAX_STAGES];
-	const u64 *tw, *twi; // R powers of the R-th root of unity and of its inverse (R = 2^a or 5 2^a)
+	const u64 *tw, *twi; // stage twiddles of this pass (see Tw), forward and inverse
 	const u32 *rowK;    // frequency index of row rho after this pass's stages
 	u32 Lb;             // block length in pairs (= R * stride)
 	u32 stride;         // pairs between rows
@@ -466,7 +467,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 	if (ph < nst)
 	{
 		const Stage &sg = A.st[ph];
-		const Tw tw{(sg.s > 1) ? t.twS : nullptr, t.S / sg.L};
+		const Tw tw{(sg.s > 1) ? t.twS + sg.toff : nullptr, sg.s};
 		const View Gd = view_global(A.dst + (size_t)blk * S, 0, 1, 0);
 		dispatch_stage_lin<false>((ph == 0) ? G : Sv, (A.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
 		return;
@@ -488,7 +489,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 	{
 		const u32 si = 2 * nst - ph; // nst-1 .. 0
 		const Stage &sg = A.st[si];
-		const Tw tw{(sg.s > 1) ? t.twSi : nullptr, t.S / sg.L};
+		const Tw tw{(sg.s > 1) ? t.twSi + sg.toff : nullptr, sg.s};
 		dispatch_stage_lin<true>(Sv, (si == 0 && !A.small) ? G : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
@@ -534,7 +535,7 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 {
 	const Tables &t = A.t;
 	const u32 nb = (A.R / R) * TILE_C * 2;
-	const Tw tw{(sg.s > 1) ? (INV ? A.twi : A.tw) : nullptr, A.R / sg.L};
+	const Tw tw{(sg.s > 1) ? (INV ? A.twi : A.tw) + sg.toff : nullptr, sg.s};
 	for (u32 b = tid; b < nb; b += nthr)
 	{
 		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b / (2 * TILE_C);

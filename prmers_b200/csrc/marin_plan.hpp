@@ -60,7 +60,13 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
 	if (sixteen_last) { for (u32 i = 0; i < ns; ++i) r[k++] = small_r[i]; for (u32 i = 0; i < n16; ++i) r[k++] = 16; }
 	else { for (u32 i = 0; i < n16; ++i) r[k++] = 16; for (u32 i = ns; i > 0; --i) r[k++] = small_r[i - 1]; }
 	u32 L = len;
-	for (u32 i = 0; i < k; ++i) { st[i].radix = r[i]; st[i].L = L; st[i].s = L / r[i]; L /= r[i]; }
+	u32 off = 0;
+	for (u32 i = 0; i < k; ++i)
+	{
+		st[i].radix = r[i]; st[i].L = L; st[i].s = L / r[i]; st[i].toff = off;
+		if (st[i].s > 1) off += (r[i] - 1) * st[i].s;
+		L /= r[i];
+	}
 	return k;
 }
 
@@ -145,6 +151,23 @@ inline void powers(std::vector<u64> &v, u64 root, size_t cnt)
 	for (size_t i = 0; i < cnt; ++i) { v[i] = x; x = gl::mul(x, root); }
 }
 
+// stage twiddles of a transform of length len, one block per stage with s > 1: block[(k - 1) s + j] = root^((len / L) j k)
+inline void stage_twiddles(std::vector<u64> &v, const Stage *st, u32 nst, u32 len, u64 root)
+{
+	std::vector<u64> pw;
+	powers(pw, root, len);
+	v.clear();
+	for (u32 i = 0; i < nst; ++i)
+	{
+		if (st[i].s <= 1) continue;
+		if (v.size() != st[i].toff) v.resize(st[i].toff);
+		const u64 scale = len / st[i].L;
+		for (u32 k = 1; k < st[i].radix; ++k)
+			for (u32 j = 0; j < st[i].s; ++j) v.push_back(pw[(size_t)((scale * j * k) % len)]);
+	}
+	if (v.empty()) v.push_back(1);
+}
+
 inline void build_tables(const Plan &pl, HostTables &h)
 {
 	const u32 n = pl.n, m = pl.m, p = pl.p;
@@ -162,10 +185,10 @@ inline void build_tables(const Plan &pl, HostTables &h)
 	h.nr2 = gl::pow(554, (gl::P - 1) / 192 / n);
 	h.nr2_inv = gl::inv(h.nr2);
 	h.inv_m = gl::inv((u64)m);
-	powers(h.twS, gl::root_of_unity(pl.S), pl.S);
-	powers(h.twSi, gl::inv(gl::root_of_unity(pl.S)), pl.S);
-	powers(h.twR, gl::root_of_unity(pl.R), pl.R);
-	powers(h.twRi, gl::inv(gl::root_of_unity(pl.R)), pl.R);
+	stage_twiddles(h.twS, pl.stS, pl.nstS, pl.S, gl::root_of_unity(pl.S));
+	stage_twiddles(h.twSi, pl.stS, pl.nstS, pl.S, gl::inv(gl::root_of_unity(pl.S)));
+	stage_twiddles(h.twR, pl.stR, pl.nstR, pl.R, gl::root_of_unity(pl.R));
+	stage_twiddles(h.twRi, pl.stR, pl.nstR, pl.R, gl::inv(gl::root_of_unity(pl.R)));
 	h.bl_h = 11;
 	const u64 rm = gl::root_of_unity(m), rmi = gl::inv(rm);
 	powers(h.bl_lo, rm, (size_t)1 << h.bl_h);
@@ -181,8 +204,8 @@ inline void build_tables(const Plan &pl, HostTables &h)
 			h.rowroot[(size_t)ra * pl.R2 + rb] = gl::pow(rm, (u64)h.rowK[ra] + (u64)pl.R * h.rowK2[rb]);
 	if (pl.R2 > 1)
 	{
-		powers(h.twR2, gl::root_of_unity(pl.R2), pl.R2);
-		powers(h.twR2i, gl::inv(gl::root_of_unity(pl.R2)), pl.R2);
+		stage_twiddles(h.twR2, pl.stR2, pl.nstR2, pl.R2, gl::root_of_unity(pl.R2));
+		stage_twiddles(h.twR2i, pl.stR2, pl.nstR2, pl.R2, gl::inv(gl::root_of_unity(pl.R2)));
 	}
 	h.colroot.resize(pl.S);
 	const u64 rS = gl::root_of_unity(pl.S);
