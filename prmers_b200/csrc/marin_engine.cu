@@ -102,6 +102,10 @@ __global__ void k_unweight(const __grid_constant__ Tables t, const u64 *x, u64 *
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j < n) unweight_thread(t, x, out, j);
 }
+__global__ void k_scale(u64 *x, u64 f, u32 n)
+{
+	scale_thread(x, f, blockIdx.x * blockDim.x + threadIdx.x, n);
+}
 __global__ void k_weights(const __grid_constant__ WeightArgs A, u32 n)
 {
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,6 +236,7 @@ struct CudaBackend
 	void lin_p1(const LinArgs &A, u32 count) { use(); k_lin_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void lin_p2(const LinArgs &A, u32 count) { use(); k_lin_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }
+	void scale(u64 *x, u64 f, u32 n) { use(); k_scale<<<(n + 255) / 256, 256, 0, st>>>(x, f, n); post(); }
 	void weights(const WeightArgs &A, u32 n) { use(); k_weights<<<(n + 255) / 256, 256, 0, st>>>(A, n); post(); }
 };
 

@@ -152,6 +152,7 @@ public:
 		const size_t r = _lazy;
 		_lazy = (size_t)-1;
 		strided(true, 0, _fwd, R(r), 1, nullptr, false, true);
+		be.scale(R(r), _inv_R, pl.n);
 	}
 
 	void set_multiplicand(size_t dst, size_t src)
@@ -347,7 +348,7 @@ private:
 		const size_t smem = (size_t)A.R * TILE_PITCH * 16;
 		const u32 grid = A.tiles * (level ? pl.R : 1), thr = level ? pl.thrStr2 : pl.thrStr;
 		if (!inv) { be.strided_fwd(A, grid, thr, smem); return; }
-		if (exact_inverse) { A.scale = _inv_R; be.strided_inv(A, grid, thr, smem); return; }
+		if (exact_inverse) { be.strided_inv(A, grid, thr, smem); return; } // plain, unnormalised: the caller scales by 1/R
 		A.skip_dst = skip_dst ? 1u : 0u;
 		if (level == 0) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst; set_ticket(A); }
 		be.strided_inv(A, grid, thr, smem);

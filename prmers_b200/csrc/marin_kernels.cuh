@@ -229,7 +229,7 @@ struct Tw { const u64 *tab; u32 s; };
 // outputs (forward) of the stage that touches global memory in a strided pass.
 // The stage that carries the boundary twiddle is the last forward stage (s = 1): its rows base + k have
 // frequency indices K0 + k * Kstep, K0 = rowK[base], Kstep = R / radix.
-struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost; u64 scale; };
+struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost; };
 
 template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
 
@@ -289,10 +289,6 @@ template <int R, bool INV> HD void bfly_core(u64 *a, const View &out, u32 base, 
 			const u64 f = boundary_tw(*bd->t, (u64)(bd->K0 + k * bd->Kstep) * bd->colscale, false);
 			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f);
 		}
-
-	if (INV && bd && bd->scale) // plain inverse pass that must return the exact input of the forward pass: x 1/R
-		#pragma unroll
-		for (u32 q = 0; q < R; ++q) a[q] = gl::mul(a[q], bd->scale);
 
 	if (INV && bd && bd->wpost && !bd->skip_wpost) // unweight (and scale by 1/m) the outputs of the last inverse stage: natural order, coalesced
 		#pragma unroll
@@ -415,7 +411,6 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	unsigned long long *ticket; // carry pass: tiles are handed out in START order (atomic counter, never reset), so the
 	unsigned long long ticket_base; // tile a CTA waits for has always started before it, whatever the block scheduler does
 	u32 skip_dst;       // carry pass of a squaring chain: leave the register alone, the parked transform in fwd_dst is the state
-	u64 scale;          // plain inverse pass (no carry): multiply the outputs by this (1/R turns it into the exact inverse)
 	u32 dbg;            // timing experiments only (builds with -DMARIN_DEBUG_SKIP): bit mask of steps to leave out
 };
 #if defined(MARIN_DEBUG_SKIP)
@@ -547,11 +542,11 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_tile + 2 * ((size_t)(c0 / TILE_C) * A.R * TILE_C + c) + lane : nullptr, 2 * (size_t)TILE_C,
-			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0, (INV && first && !out_smem_always) ? A.scale : 0};
+			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0};
 		if (!INV)
 			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
-			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, (last || wp || (first && A.scale)) ? &bd : nullptr);
+			bfly<R, true>(last ? Gi : Sv, (first && !out_smem_always) ? Go : Sv, base, sg.s, j, tw, t.w5i, (last || wp) ? &bd : nullptr);
 	}
 }
 
@@ -801,6 +796,9 @@ HD u64 lin_pair_carry(const LinArgs &A, u32 i)
 }
 
 static constexpr u32 LIN_BLOCK = 256; // pairs per CTA of the fast linear kernel
+
+// x <- x * f, elementwise (the plain inverse strided pass is unnormalised: times 1/R it is the exact inverse)
+HD void scale_thread(u64 *x, u64 f, u32 j, u32 n) { if (j < n) x[j] = gl::mul(x[j], f); }
 
 // unweighted digit values (not carried) for the host-side canonical export (engine_gpu.h:1534-1561)
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }

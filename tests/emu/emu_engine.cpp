@@ -76,6 +76,7 @@ struct CpuBackend
 	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
 	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { for (u32 j = 0; j < n; ++j) unweight_thread(t, x, out, j); }
+	void scale(u64 *x, u64 f, u32 n) { for (u32 j = 0; j < n; ++j) scale_thread(x, f, j, n); }
 	void weights(const WeightArgs &A, u32 n)
 	{
 		#pragma omp parallel for schedule(static)
