@@ -138,6 +138,7 @@ struct CudaBackend
 	~CudaBackend()
 	{
 		cudaSetDevice(dev);
+		persist_off();
 		for (cudaGraphExec_t g : graphs) cudaGraphExecDestroy(g);
 		if (st) cudaStreamDestroy(st);
 	}
@@ -190,8 +191,11 @@ struct CudaBackend
 	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
 	void sync() { use(); no_capture("sync"); CK(cudaStreamSynchronize(st)); }
 
-	// Keep a buffer (the parked transform a squaring chain ping-pongs through) resident in L2: B200's 126 MB
-	// L2 holds a 64 MiB register, but the weight tables streaming through would evict it between kernels.
+	// Keep a buffer (the parked transform a squaring chain ping-pongs through) resident in L2: B200's 126 MB L2 holds
+	// a 64 MiB register, but the weight tables streaming through would evict it between kernels.  The persisting
+	// set-aside is taken from every other kernel's L2 (measured at n = 2^23: add 58 -> 85 us, copy 25 -> 52 us), so
+	// it is switched on only while a long squaring chain runs (persist_on / persist_off, driven by the engine core)
+	// and it buys that chain 1.8 %.
 	void persist(void *p, size_t bytes)
 	{
 		use();
@@ -200,17 +204,49 @@ struct CudaBackend
 		cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
 		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
 		if (maxPersist <= 0 || maxWindow <= 0) return;
-		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxPersist) != cudaSuccess) { cudaGetLastError(); return; }
-		cudaStreamAttrValue attr;
-		memset(&attr, 0, sizeof(attr));
-		const size_t win = bytes < (size_t)maxWindow ? bytes : (size_t)maxWindow;
-		attr.accessPolicyWindow.base_ptr = p;
-		attr.accessPolicyWindow.num_bytes = win;
-		attr.accessPolicyWindow.hitRatio = (win <= (size_t)maxPersist) ? 1.0f : (float)((double)maxPersist / (double)win);
-		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-		if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-		if (getenv("MARIN_B200_VERBOSE")) fprintf(stderr, "marin_b200: L2 persistence window %zu bytes (max persisting %d, max window %d)\n", win, maxPersist, maxWindow);
+		persist_bytes = (size_t)maxPersist;
+		if (const char *e = getenv("MARIN_B200_L2_PERSIST_MB")) { const size_t mb = (size_t)atoi(e) << 20; if (mb < persist_bytes) persist_bytes = mb; }
+		if (persist_bytes == 0) return;
+		const size_t winb = bytes < (size_t)maxWindow ? bytes : (size_t)maxWindow;
+		memset(&win, 0, sizeof(win));
+		win.base_ptr = p;
+		win.num_bytes = winb;
+		win.hitRatio = (winb <= persist_bytes) ? 1.0f : (float)((double)persist_bytes / (double)winb);
+		win.hitProp = cudaAccessPropertyPersisting;
+		win.missProp = cudaAccessPropertyStreaming;
+		if (getenv("MARIN_B200_VERBOSE")) fprintf(stderr, "marin_b200: L2 persistence window %zu bytes (set-aside %zu, max window %d)\n", winb, persist_bytes, maxWindow);
+	}
+	size_t persist_bytes = 0;
+	void persist_on()
+	{
+		if (has_win || persist_bytes == 0) return;
+		use();
+		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_bytes) != cudaSuccess) { cudaGetLastError(); persist_bytes = 0; return; }
+		has_win = true;
+	}
+	void persist_off()
+	{
+		if (!has_win) return;
+		use();
+		has_win = false;
+		cudaCtxResetPersistingL2Cache();
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+		cudaGetLastError();
+	}
+	// The window is a LAUNCH attribute of the transform kernels only: as a stream attribute it also made every other
+	// kernel's accesses (copies, linear ops) "streaming" misses and slowed them down by up to 2x.
+	cudaAccessPolicyWindow win;
+	bool has_win = false;
+	template <class K, class A> void launch_windowed(K kernel, const A &args, u32 grid, u32 thr, size_t smem)
+	{
+		cudaLaunchConfig_t cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+		at[0].val.accessPolicyWindow = win;
+		cfg.attrs = at; cfg.numAttrs = has_win ? 1 : 0;
+		CK(cudaLaunchKernelEx(&cfg, kernel, args));
 	}
 	void post() { ++launches; CK(cudaGetLastError()); }
 
@@ -222,10 +258,10 @@ struct CudaBackend
 		static const u32 fg = env_u32("MARIN_B200_MID_GRID"), ft = env_u32("MARIN_B200_MID_THREADS");
 		if (fg && fg < grid) grid = fg;
 		if (ft) thr = ft;
-		use(); k_mid<<<grid, cap(thr, MARIN_MID_MAXT), smem, st>>>(A); post();
+		use(); launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem); post();
 	}
-	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<false><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
-	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); k_strided<true><<<grid, cap(thr, MARIN_STR_MAXT), smem, st>>>(A); post(); }
+	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); launch_windowed(k_strided<false>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post(); }
+	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); launch_windowed(k_strided<true>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post(); }
 	void lin_pairs(const LinArgs &A)
 	{
 		use();

@@ -141,6 +141,7 @@ public:
 		strided(true, 0, _fwd, R(r), a, chained ? _fwd : nullptr, chained);
 		if (chained) { _fwd_reg = r; _lazy = r; } else _lazy = (size_t)-1;
 		_last_sq = r;
+		if (chained) { if (++_chain_len == CHAIN_PERSIST) be.persist_on(); } else calm();
 	}
 
 	// Register _lazy's memory is stale; _fwd holds the forward strided pass of its digits.  The plain inverse
@@ -266,6 +267,8 @@ private:
 	// speculation for squaring chains: _fwd holds the forward strided pass of register _fwd_reg's current value
 	u64 *_fwd = nullptr;
 	size_t _fwd_reg = (size_t)-1, _last_sq = (size_t)-1;
+	static constexpr u32 CHAIN_PERSIST = 64; // chained squarings after which the parked transform is pinned in L2
+	u32 _chain_len = 0;
 	size_t _lazy = (size_t)-1;   // register whose digits exist only as the parked transform in _fwd (see square_mul)
 	u64 _inv_R = 0;
 	size_t _nflags = 0;
@@ -287,7 +290,9 @@ private:
 	bool _recording = false;
 	void blocking(const char *what) const { if (_recording) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
 	void check_range(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }
-	void check(size_t r) { check_range(r); if (r == _lazy) materialize(); }
+	void check(size_t r) { check_range(r); calm(); if (r == _lazy) materialize(); }
+	// any operation other than the next squaring of a chain: the chain is broken, give the L2 set-aside back to everybody else
+	void calm() { if (_chain_len) { _chain_len = 0; be.persist_off(); } }
 	void check_a(u32 a) const
 	{
 		if (a == 0 || a > pl.a_max)

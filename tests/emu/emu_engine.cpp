@@ -23,6 +23,8 @@ struct CpuBackend
 	void d2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 	void sync() {}
 	void persist(void *, size_t) {}
+	void persist_on() {}
+	void persist_off() {}
 
 	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem)
 	{

@@ -11,7 +11,10 @@ def t(e, f, count):
     e.sync()
     return (time.perf_counter() - t0) / count * 1e6
 
-for p, regs in [(205271257, 14), (136279841, 8), (1362763, 8), (86243, 8), (701, 51), (127, 18)]:
+CASES = [(205271257, 14), (136279841, 8), (1362763, 8), (86243, 8), (701, 51), (127, 18)]
+if len(sys.argv) > 1:
+    CASES = [(int(a), 8) for a in sys.argv[1:]]
+for p, regs in CASES:
     e = pb.Engine(p, regs)
     e.set(0, 3); e.set(1, 5); e.set(3, 7)
     e.square_mul_repeat(0, 20); e.copy(1, 0); e.copy(3, 0); e.set_multiplicand(2, 1)
