@@ -79,11 +79,12 @@ int mb200_square_mul_repeat(void *eng, size_t r, uint32_t a, uint32_t count);
 int mb200_bench_pass(void *eng, size_t r, int which, uint32_t count, float *ms);
 int mb200_is_single_cta(void *eng);
 
-/* CUDA-graph replay of a fixed sequence of engine calls (no reference counterpart: the reference pays one
-   clEnqueueNDRangeKernel per op, include/marin/engine_gpu.h:886-1248, which is all an ECM curve at n = 32
-   costs, src/modes/RunEcmTwistedEdwards.cpp:2717-2945).  Between graph_begin and graph_end the asynchronous
-   ops (set_u32, copy, square_mul, set_multiplicand, mul, add, sub_reg, sub_u32 and their fused forms) are
-   recorded, not run; blocking calls fail.  Single-CTA engines (mb200_is_single_cta) only. */
+/* Replay of a fixed sequence of engine calls as ONE kernel launch (no reference counterpart: the reference pays one
+   clEnqueueNDRangeKernel per op, include/marin/engine_gpu.h:886-1248, which is all an ECM curve at n = 32 costs,
+   src/modes/RunEcmTwistedEdwards.cpp:2717-2945).  Between graph_begin and graph_end the asynchronous ops (set_u32,
+   copy, square_mul, set_multiplicand, mul, add, sub_reg, sub_u32 and their fused forms) are recorded, not run;
+   blocking calls fail.  graph_launch runs the recorded list inside one CTA (k_program).  Single-CTA engines
+   (mb200_is_single_cta, n <= 16384) only. */
 int mb200_graph_begin(void *eng);
 int mb200_graph_end(void *eng, int *graph_id);
 int mb200_graph_launch(void *eng, int graph_id);

@@ -97,6 +97,76 @@ __global__ void __launch_bounds__(LIN_BLOCK) k_lin_pairs(const __grid_constant__
 	if (i < npairs) lin_pair_finish(A, i, u0, u1, w0, w1, threadIdx.x ? cs[threadIdx.x - 1] : ((gridDim.x == 1) ? cs[npairs - 1] : A.carry[blockIdx.x]));
 }
 
+// A recorded sequence of engine ops on a single-CTA engine, run by ONE launch: the CTA walks the list, every op is the
+// same phase functions the stand-alone kernels run, separated by block barriers (registers live in global memory; a
+// barrier orders one op's stores before the next op's loads within the CTA).  At these sizes an op is a few
+// microseconds of launch latency, which is what an ECM point operation (17-27 ops) otherwise consists of.  (Staging
+// registers and tables in shared memory was tried and is no faster: what remains is the serial instruction latency
+// of the tiny transforms, not memory latency.)
+__global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ ProgArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	u64 *smc = reinterpret_cast<u64 *>(sm + smem_pairs_lin(A.M.S));
+	__shared__ MidArgs sM;
+	__shared__ LinArgs sL;
+	const u32 tid = threadIdx.x, nthr = blockDim.x, n = A.M.t.n, npairs = n / 2;
+	if (tid == 0) { sM = A.M; sL.t = A.M.t; sL.carry = A.carry; sL.D = A.D; sL.digits = nullptr; }
+	__syncthreads();
+	for (u32 k = 0; k < A.nops; ++k)
+	{
+		const ProgOp op = A.ops[k];
+		u64 *dst = A.reg + (size_t)op.dst * n;
+		const u64 *src = A.reg + (size_t)op.src * n;
+		switch (op.code)
+		{
+		case PO_COPY:
+			for (u32 i = tid; i < npairs; i += nthr) reinterpret_cast<pair_t *>(dst)[i] = reinterpret_cast<const pair_t *>(src)[i];
+			break;
+		case PO_SQR: case PO_MUL: case PO_SETMUL:
+		{
+			if (tid == 0)
+			{
+				sM.x = (pair_t *)((op.code == PO_SETMUL) ? const_cast<u64 *>(src) : dst);
+				sM.y = (op.code == PO_MUL) ? (const pair_t *)src : nullptr;
+				sM.dst = (pair_t *)dst;
+				sM.mode = (op.code == PO_SQR) ? MODE_SQR : ((op.code == PO_MUL) ? MODE_MUL : MODE_FWD);
+				sM.a = op.a;
+			}
+			__syncthreads();
+			const u32 nph = mid_num_phases(sM);
+			for (u32 ph = 0; ph < nph; ++ph) { mid_phase(sM, 0, ph, tid, nthr, sm, smc); __syncthreads(); }
+			break;
+		}
+		case PO_ADD: case PO_SUBREG: case PO_SUBSMALL:
+		{
+			if (tid == 0) { sL.dst = dst; sL.src = src; sL.a = op.a; sL.op = (op.code == PO_ADD) ? LIN_ADD : ((op.code == PO_SUBREG) ? LIN_SUBREG : LIN_SUBSMALL); }
+			__syncthreads();
+			for (u32 i = tid; i < npairs; i += nthr) A.carry[i] = lin_pair_carry(sL, i);      // from the ORIGINAL content
+			__syncthreads();
+			for (u32 i = tid; i < npairs; i += nthr)
+			{
+				u64 u0, u1; u32 w0, w1;
+				lin_pair_compute(sL, i, u0, u1, w0, w1);
+				lin_pair_finish(sL, i, u0, u1, w0, w1, A.carry[i ? i - 1 : npairs - 1]);
+			}
+			break;
+		}
+		default: // PO_SETSMALL
+		{
+			if (tid == 0) { sL.dst = dst; sL.src = dst; sL.a = op.a; sL.op = LIN_SETSMALL; }
+			__syncthreads();
+			const u32 runs = n / A.D;
+			for (u32 r = tid; r < runs; r += nthr) lin_p1_thread(sL, r);
+			__syncthreads();
+			for (u32 r = tid; r < runs; r += nthr) lin_p2_thread(sL, r);
+			break;
+		}
+		}
+		__syncthreads();
+	}
+}
+
 __global__ void k_unweight(const __grid_constant__ Tables t, const u64 *x, u64 *out, u32 n)
 {
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,6 +202,7 @@ struct CudaBackend
 		CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 		const int maxsm = (int)pr.sharedMemPerBlockOptin - 1024; // room for the kernels' few static shared words
 		CK(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 2048)); // it also keeps its argument blocks in static shared memory
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 	}
@@ -139,57 +210,39 @@ struct CudaBackend
 	{
 		cudaSetDevice(dev);
 		persist_off();
-		for (cudaGraphExec_t g : graphs) cudaGraphExecDestroy(g);
+		for (ProgOp *d : progs) cudaFree(d);
 		if (st) cudaStreamDestroy(st);
 	}
 
-	// ---- CUDA-graph replay of fixed op sequences (ECM point operations at n = 32 are pure launch latency:
-	// the reference pays one enqueue per engine op, include/marin/engine_gpu.h:886-1248)
-	std::vector<cudaGraphExec_t> graphs;
-	std::vector<uint64_t> graph_nodes;
-	bool capturing = false;
-	uint64_t launches_at_begin = 0;
-	void no_capture(const char *what) const { if (capturing) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
-	void graph_begin()
+	// ---- recorded op sequences ("programs") of single-CTA engines: uploaded once, run by one k_program launch each
+	// (the reference pays one enqueue per engine op, include/marin/engine_gpu.h:886-1248)
+	std::vector<ProgOp *> progs;
+	std::vector<u32> prog_len;
+	int prog_upload(const std::vector<ProgOp> &ops)
 	{
-		use(); no_capture("graph_begin");
-		cudaFuncAttributes fa; // make sure every kernel a recorded op may launch is loaded before the capture starts
-		CK(cudaFuncGetAttributes(&fa, k_mid)); CK(cudaFuncGetAttributes(&fa, k_lin_pairs)); CK(cudaFuncGetAttributes(&fa, k_lin_boundary));
-		CK(cudaFuncGetAttributes(&fa, k_lin_p1)); CK(cudaFuncGetAttributes(&fa, k_lin_p2));
-		CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-		capturing = true; launches_at_begin = launches;
+		use();
+		ProgOp *d = nullptr;
+		CK(cudaMalloc(&d, (ops.size() ? ops.size() : 1) * sizeof(ProgOp)));
+		if (!ops.empty()) CK(cudaMemcpy(d, ops.data(), ops.size() * sizeof(ProgOp), cudaMemcpyHostToDevice));
+		progs.push_back(d); prog_len.push_back((u32)ops.size());
+		return (int)progs.size() - 1;
 	}
-	int graph_end()
+	void prog_launch(int id, ProgArgs A, u32 thr, size_t smem)
 	{
-		if (!capturing) throw std::runtime_error("marin_b200: graph_end without graph_begin");
-		capturing = false;
-		cudaGraph_t g = nullptr;
-		CK(cudaStreamEndCapture(st, &g));
-		cudaGraphExec_t ex = nullptr;
-		const cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
-		cudaGraphDestroy(g);
-		CK(e);
-		graphs.push_back(ex); graph_nodes.push_back(launches - launches_at_begin);
-		launches = launches_at_begin;
-		return (int)graphs.size() - 1;
-	}
-	void graph_abort() { if (capturing) { capturing = false; cudaGraph_t g = nullptr; cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); launches = launches_at_begin; } }
-	void graph_launch(int id)
-	{
-		use(); no_capture("graph_launch");
-		if (id < 0 || (size_t)id >= graphs.size()) throw std::runtime_error("marin_b200: unknown graph id");
-		CK(cudaGraphLaunch(graphs[(size_t)id], st));
-		launches += graph_nodes[(size_t)id];
+		if (id < 0 || (size_t)id >= progs.size()) throw std::runtime_error("marin_b200: unknown graph id");
+		use();
+		A.ops = progs[(size_t)id]; A.nops = prog_len[(size_t)id];
+		k_program<<<1, thr, smem, st>>>(A); post();
 	}
 
 	void use() { CK(cudaSetDevice(dev)); }
 	void *alloc(size_t b) { use(); void *p = nullptr; CK(cudaMalloc(&p, b ? b : 8)); return p; }
 	void free(void *p) { cudaSetDevice(dev); cudaFree(p); }
 	void memset0(void *p, size_t b) { use(); CK(cudaMemsetAsync(p, 0, b, st)); }
-	void h2d(void *d, const void *s, size_t b) { use(); no_capture("a host transfer"); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
-	void d2h(void *d, const void *s, size_t b) { use(); no_capture("a host transfer"); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+	void h2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+	void d2h(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
 	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
-	void sync() { use(); no_capture("sync"); CK(cudaStreamSynchronize(st)); }
+	void sync() { use(); CK(cudaStreamSynchronize(st)); }
 
 	// Keep a buffer (the parked transform a squaring chain ping-pongs through) resident in L2: B200's 126 MB L2 holds
 	// a 64 MiB register, but the weight tables streaming through would evict it between kernels.  The persisting
@@ -395,6 +448,7 @@ int mb200_graph_end(void *eng, int *id)
 	if (!eng) { g_err = "null engine"; return 0; }
 	try { g_err.clear(); *id = E(eng)->graph_end(); return 1; }
 	catch (const std::exception &ex) { g_err = ex.what(); return 0; }
+	catch (...) { g_err = "unknown error"; return 0; }
 }
 int mb200_graph_launch(void *eng, int id) { GUARD(E(eng)->graph_launch(id)); }
 

@@ -29,7 +29,7 @@ public:
 		const size_t n = pl.n;
 		_reg = (u64 *)be.alloc(regs * n * 8);
 		be.memset0(_reg, regs * n * 8);
-		const size_t ncarry = std::max<size_t>(n / pl.D, n / RUN + 1);
+		const size_t ncarry = std::max<size_t>(std::max<size_t>(n / pl.D, n / RUN + 1), pl.small ? n / 2 : 0); // recorded linear ops keep one word per pair
 		_carry = (u64 *)be.alloc(ncarry * 8);
 		_scratch = (u64 *)be.alloc(n * 8);
 		_nslots = n / RUN + 1;
@@ -92,32 +92,41 @@ public:
 		}
 	}
 
-	// Record the engine calls that follow into a CUDA graph instead of running them (graph_end returns its id,
-	// graph_launch replays it).  Only engines whose every op is one self-contained launch can be recorded: the
-	// multi-pass transforms carry per-launch epochs and tickets in their kernel arguments.
+	// Record the engine calls that follow instead of running them (graph_end returns the id of the recorded sequence,
+	// graph_launch replays it as ONE kernel launch, k_program).  Only engines whose every op fits one CTA can be
+	// recorded: the multi-pass transforms need grid-wide passes.
 	void graph_begin()
 	{
-		if (!pl.small) throw std::runtime_error("marin_b200: graph recording is for single-CTA engines (n <= 16384) only");
+		if (!pl.small) throw std::runtime_error("marin_b200: recording is for single-CTA engines (n <= 16384) only");
 		blocking("graph_begin");
-		be.graph_begin();
+		_rec.clear();
 		_recording = true;
 	}
 	int graph_end()
 	{
 		if (!_recording) throw std::runtime_error("marin_b200: graph_end without graph_begin");
 		_recording = false;
-		try { return be.graph_end(); } catch (...) { be.graph_abort(); throw; }
+		return be.prog_upload(_rec);
 	}
-	void graph_launch(int id) { blocking("graph_launch"); be.graph_launch(id); }
+	void graph_launch(int id)
+	{
+		blocking("graph_launch");
+		ProgArgs A;
+		std::memset(&A, 0, sizeof(A));
+		A.M = mid_args(nullptr, nullptr, nullptr, MODE_SQR, 1);
+		A.reg = _reg; A.D = pl.D; A.carry = _carry;
+		be.prog_launch(id, A, pl.thrMid < 64 ? 64 : pl.thrMid, mid_smem());
+	}
 
 	void set_u32(size_t dst, u32 a)
 	{
 		check(dst);
 		if (pl.p < 32) a = (u32)((u64)a % (((u64)1 << pl.p) - 1));
+		if (rec(PO_SETSMALL, dst, dst, a)) return;
 		lin(LIN_SETSMALL, dst, dst, a, nullptr);
 	}
 
-	void copy(size_t dst, size_t src) { check(dst); check(src); if (dst != src) { touch(dst); be.d2d(R(dst), R(src), pl.n * 8); } }
+	void copy(size_t dst, size_t src) { check(dst); check(src); if (dst != src && !rec(PO_COPY, dst, src, 0)) { touch(dst); be.d2d(R(dst), R(src), pl.n * 8); } }
 
 	// r = r^2 * a.  In a chain of squarings of the same register (PRP, LL, P-1 stage 1) the inverse
 	// pass of one squaring also runs the forward strided pass of the next on the tile it still holds in
@@ -127,6 +136,7 @@ public:
 	void square_mul(size_t r, u32 a)
 	{
 		check_range(r); check_a(a);
+		if (rec(PO_SQR, r, r, a)) return;
 		if (pl.small) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); launch_mid(M); return; }
 		if (_lazy != r) materialize();                   // another register's state lives in _fwd: write it out first
 		const bool chained = (_last_sq == r);            // second squaring in a row: start speculating
@@ -159,6 +169,7 @@ public:
 	void set_multiplicand(size_t dst, size_t src)
 	{
 		check(dst); check(src);
+		if (rec(PO_SETMUL, dst, src, 1)) return;
 		if (pl.small) { MidArgs M = mid_args(R(src), nullptr, R(dst), MODE_FWD, 1); launch_mid(M); return; }
 		touch(dst);
 		strided(false, 0, R(src), R(dst), 1, nullptr);
@@ -170,6 +181,7 @@ public:
 	{
 		check(dst); check(src); check_a(a);
 		if (dst == src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
+		if (rec(PO_MUL, dst, src, a)) return;
 		if (pl.small) { MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); launch_mid(M); return; }
 		materialize();
 		if (_fwd_reg != dst) strided(false, 0, R(dst), _fwd, 1, nullptr);
@@ -185,10 +197,11 @@ public:
 	{
 		check(r);
 		if (pl.p < 32) a = (u32)((u64)a % (((u64)1 << pl.p) - 1));
+		if (rec(PO_SUBSMALL, r, r, a)) return;
 		lin(LIN_SUBSMALL, r, r, a, nullptr);
 	}
-	void add(size_t dst, size_t src) { check(dst); check(src); lin(LIN_ADD, dst, src, 0, nullptr); }
-	void sub_reg(size_t dst, size_t src) { check(dst); check(src); lin(LIN_SUBREG, dst, src, 0, nullptr); }
+	void add(size_t dst, size_t src) { check(dst); check(src); if (!rec(PO_ADD, dst, src, 0)) lin(LIN_ADD, dst, src, 0, nullptr); }
+	void sub_reg(size_t dst, size_t src) { check(dst); check(src); if (!rec(PO_SUBREG, dst, src, 0)) lin(LIN_SUBREG, dst, src, 0, nullptr); }
 
 	// canonical digits, value | width << 32: unweight on the device, strong carry on the host exactly as
 	// engine_gpu_flat::get does (engine_gpu.h:1534-1561)
@@ -288,6 +301,9 @@ private:
 	}
 
 	bool _recording = false;
+	std::vector<ProgOp> _rec;
+	bool rec(u32 code, size_t dst, size_t src, u32 a) { if (!_recording) return false; _rec.push_back(ProgOp{code, (u32)dst, (u32)src, a}); return true; }
+	size_t mid_smem() const { return (size_t)smem_pairs_lin(pl.S) * 16 + (pl.small ? ((size_t)pl.n / pl.D) * 8 : 0); }
 	void blocking(const char *what) const { if (_recording) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
 	void check_range(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }
 	void check(size_t r) { check_range(r); calm(); if (r == _lazy) materialize(); }
@@ -325,8 +341,7 @@ private:
 
 	void launch_mid(const MidArgs &M)
 	{
-		const size_t smem = (size_t)smem_pairs_lin(pl.S) * 16 + (pl.small ? ((size_t)pl.n / pl.D) * 8 : 0);
-		be.mid(M, pl.m / pl.S, pl.thrMid, smem);
+		be.mid(M, pl.m / pl.S, pl.thrMid, mid_smem());
 	}
 
 	// any write to a register other than by square_mul drops the parked forward transform of it

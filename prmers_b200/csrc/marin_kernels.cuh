@@ -803,6 +803,18 @@ HD void scale_thread(u64 *x, u64 f, u32 j, u32 n) { if (j < n) x[j] = gl::mul(x[
 // unweighted digit values (not carried) for the host-side canonical export (engine_gpu.h:1534-1561)
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
 
+// ---- recorded op sequences for single-CTA engines ("programs"): one kernel launch runs the whole list ------------
+enum ProgCode : u32 { PO_COPY = 0, PO_SQR, PO_SETMUL, PO_MUL, PO_ADD, PO_SUBREG, PO_SUBSMALL, PO_SETSMALL };
+struct ProgOp { u32 code, dst, src, a; };
+struct ProgArgs
+{
+	MidArgs M;          // tables and stages of the engine; x / y / dst / mode / a are set per op
+	u64 *reg;           // register slab
+	const ProgOp *ops; u32 nops;
+	u32 D;              // digits per run of the set-small path
+	u64 *carry;         // one word per run (set-small), one per pair (linear ops)
+};
+
 // weight tables: digit j has weight r^((n - p j mod n) mod n), r the n-th root of two (ibdwt.h:111-147)
 struct WeightArgs { u32 p, n; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *winvs_nat; u64 *w_tile, *winvs_tile; u32 R, stride; };
 

@@ -199,8 +199,8 @@ class EdwardsOps:
         self.e = eng
         self.ops = 0
         self.notwist = notwist
-        # B200: a point operation is 17-27 engine calls of a few microseconds each at ECM sizes, so record the three
-        # schedules once as CUDA graphs and replay them (one host call per point operation instead of one per op)
+        # B200: a point operation is 17-27 engine calls of a few microseconds of launch latency each at ECM sizes, so
+        # record the three schedules once and replay them (one kernel launch per point operation instead of one per op)
         if graphs is None:
             graphs = hasattr(eng, "graph_begin") and bool(getattr(eng, "is_single_cta", lambda: False)())
         self._g = None

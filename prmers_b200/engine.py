@@ -301,7 +301,7 @@ class Engine:
     def is_single_cta(self):
         return bool(self._L.mb200_is_single_cta(self._h))
 
-    # -- CUDA-graph replay of fixed op sequences (single-CTA engines; see include/marin_b200.h) ---
+    # -- record a fixed op sequence, replay it as one kernel launch (single-CTA engines; include/marin_b200.h) ---
     def graph_begin(self):
         self._ck(self._L.mb200_graph_begin(self._h))
 

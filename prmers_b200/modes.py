@@ -162,7 +162,7 @@ def pm1_exponent(p, b1):
     return e
 
 
-def run_pm1_stage1(eng, p, b1, reg=0):
+def run_pm1_stage1(eng, p, b1, reg=0, gcd=True):
     """P-1 stage 1, "fast3" (RunPM1.cpp:7127): X <- X^2 * (3 if bit else 1) over the bits of E, MSB first;
     the factor is gcd(X - 1, 2^p - 1)."""
     E = pm1_exponent(p, b1)
@@ -171,7 +171,7 @@ def run_pm1_stage1(eng, p, b1, reg=0):
         eng.square_mul(reg, 3 if bit == "1" else 1)
     x = _value(eng, reg, p)
     m = (1 << p) - 1
-    g = math.gcd((x - 1) % m, m)
+    g = math.gcd((x - 1) % m, m) if gcd else 1          # (Python's gcd is quadratic: skip it for 10^8-bit smoke runs)
     return {"exponent": p, "worktype": "PM1", "b1": b1, "factor": g if 1 < g < m else None, "bits": E.bit_length(),
             "fft_length": eng.get_size(), "x": x}
 

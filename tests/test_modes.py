@@ -140,6 +140,21 @@ def test_ll_safe_emulated():
 
 
 @pytest.mark.gpu
+def test_pm1_stage1_full_size_golden_gpu():
+    """BASELINE config 4's exponent (n = 5 * 2^21) and the headline exponent at a reduced B1: the stage-1 state 3^E against
+    tests/golden/pm1_stage1_res64.json (GMP, tools/make_golden_pm1.py)."""
+    import json, os
+    import prmers_b200 as pb
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pm1_stage1_res64.json")))["cases"]
+    for g in gold:
+        eng = pb.Engine(g["p"], 2)
+        r = modes.run_pm1_stage1(eng, g["p"], g["b1"], gcd=False)
+        assert r["bits"] == g["bits"]
+        assert f"{r['x'] & 0xFFFFFFFFFFFFFFFF:016X}" == g["res64"] and f"{r['x'] & ((1 << 256) - 1):064x}" == g["res2048_low"]
+        eng.close()
+
+
+@pytest.mark.gpu
 def test_ll_safe_gpu():
     import prmers_b200 as pb
     for p in (127, 2203, 9689):                                              # `prmers p -ll` on known primes
