@@ -25,7 +25,8 @@ inline size_t transform_size(uint32_t exponent)
 	return n2 < n5 ? n2 : n5;
 }
 
-static constexpr u32 SMALL_MAX_PAIRS = 8192;  // whole register in one CTA's shared memory (128 KiB + pad)
+static constexpr u32 SMALL_MAX_PAIRS = 1024;  // one CTA does the whole operation up to here; beyond, the grid-wide passes win
+                                              // (B200, us per squaring: n = 4096 one CTA 36 / three passes 26, n = 10240 79 / 31, n = 16384 119 / 33)
 static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
 static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 9 pairs * 16 B = 180 KiB
 
@@ -43,6 +44,9 @@ struct Plan
 	u32 a_max = 1;               // largest multiplier `a` the carry chain supports without overflow
 };
 
+#ifndef MARIN_SMALL_R4
+#define MARIN_SMALL_R4 1024 // pairs: measured on B200, n = 512: 18.4 -> 14.3 us, n = 1024: 26.6 -> 17.4, n = 2048: 24.6 -> 22.6, n = 4096: 36.9 -> 41.8 (not used there)
+#endif
 #ifndef MARIN_R_SMALL_FIRST
 #define MARIN_R_SMALL_FIRST 0
 #endif
@@ -54,9 +58,12 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
 	if (rest % 5 == 0) { r[k++] = 5; rest /= 5; }
 	u32 l2 = 0; while ((1u << l2) < rest) ++l2;
 	u32 n16 = l2 / 4, rem = l2 % 4;
-	u32 small_r[2], ns = 0;
+	// tiny transforms are pure instruction latency: a radix-16 butterfly is ~900 dependent-ish instructions in a
+	// handful of threads, radix-4 stages are shorter chains on four times the threads
+	if (len <= MARIN_SMALL_R4) { n16 = 0; rem = l2; }
+	u32 small_r[MAX_STAGES], ns = 0;
 	if (rem & 1) small_r[ns++] = 2;
-	if (rem & 2) small_r[ns++] = 4;
+	for (u32 i = 0; i < rem / 2; ++i) small_r[ns++] = 4;
 	if (sixteen_last) { for (u32 i = 0; i < ns; ++i) r[k++] = small_r[i]; for (u32 i = 0; i < n16; ++i) r[k++] = 16; }
 	else { for (u32 i = 0; i < n16; ++i) r[k++] = 16; for (u32 i = ns; i > 0; --i) r[k++] = small_r[i - 1]; }
 	u32 L = len;
@@ -84,7 +91,7 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 		pl.small = true; pl.S = m; pl.R = 1;
 		pl.nstS = factor_stages(m, pl.stS, true);
 		pl.nstR = 0;
-		pl.thrMid = round_threads(m / 8, 512);
+		pl.thrMid = round_threads((m <= MARIN_SMALL_R4) ? m / 2 : m / 8, 512); // one butterfly per thread and lane in the widest stage
 	}
 	else
 	{
@@ -92,7 +99,8 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 		const u32 five = (m % 5 == 0) ? 5 : 1;
 		if (force_S) { pl.S = force_S; pl.R = m / force_S; }
 		else if (m / five >= ((five == 5) ? 16u : 64u) * MID_S) { pl.S = MID_S; pl.R = m / MID_S; }
-		else { pl.R = (five == 5) ? 80 : 64; pl.S = m / pl.R; }
+		else if (five == 5) { pl.R = 80; pl.S = m / pl.R; }
+		else { pl.R = (m > 8192) ? 64 : ((m == 8192) ? 8 : 16); pl.S = m / pl.R; } // measured: m = 2048 R = 16, m = 8192 R = 8 (few short rows: latency, not throughput)
 		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || (pl.S & (pl.S - 1)) != 0 || pl.R < 2) { err = "bad forced split"; return false; }
 		// more rows than one tile can hold: split them over two strided passes, R = RA * RB, the radix-5
 		// factor (if any) staying in the first
