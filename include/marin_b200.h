@@ -84,7 +84,7 @@ int mb200_is_single_cta(void *eng);
    src/modes/RunEcmTwistedEdwards.cpp:2717-2945).  Between graph_begin and graph_end the asynchronous ops (set_u32,
    copy, square_mul, set_multiplicand, mul, add, sub_reg, sub_u32 and their fused forms) are recorded, not run;
    blocking calls fail.  graph_launch runs the recorded list inside one CTA (k_program).  Single-CTA engines
-   (mb200_is_single_cta, n <= 16384) only. */
+   (mb200_is_single_cta, n <= 2048: the ECM sizes) only. */
 int mb200_graph_begin(void *eng);
 int mb200_graph_end(void *eng, int *graph_id);
 int mb200_graph_launch(void *eng, int graph_id);

@@ -97,7 +97,7 @@ public:
 	// recorded: the multi-pass transforms need grid-wide passes.
 	void graph_begin()
 	{
-		if (!pl.small) throw std::runtime_error("marin_b200: recording is for single-CTA engines (n <= 16384) only");
+		if (!pl.small) throw std::runtime_error("marin_b200: recording is for single-CTA engines (n <= 2048) only");
 		blocking("graph_begin");
 		_rec.clear();
 		_recording = true;

@@ -26,7 +26,7 @@ inline size_t transform_size(uint32_t exponent)
 }
 
 static constexpr u32 SMALL_MAX_PAIRS = 1024;  // one CTA does the whole operation up to here; beyond, the grid-wide passes win
-                                              // (B200, us per squaring: n = 4096 one CTA 36 / three passes 26, n = 10240 79 / 31, n = 16384 119 / 33)
+                                              // (B200, us per squaring: n = 4096 one CTA 36 / three passes 24, n = 10240 79 / 33, n = 16384 119 / 30)
 static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
 static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 9 pairs * 16 B = 180 KiB
 
@@ -51,7 +51,7 @@ struct Plan
 #define MARIN_R_SMALL_FIRST 0
 #endif
 
-inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
+inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta = false)
 {
 	// radices: optional 5 first, then 2, 4 and 16s (or 16s first) with product len
 	u32 r[MAX_STAGES], k = 0, rest = len;
@@ -60,7 +60,7 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last)
 	u32 n16 = l2 / 4, rem = l2 % 4;
 	// tiny transforms are pure instruction latency: a radix-16 butterfly is ~900 dependent-ish instructions in a
 	// handful of threads, radix-4 stages are shorter chains on four times the threads
-	if (len <= MARIN_SMALL_R4) { n16 = 0; rem = l2; }
+	if (single_cta && len <= MARIN_SMALL_R4) { n16 = 0; rem = l2; }
 	u32 small_r[MAX_STAGES], ns = 0;
 	if (rem & 1) small_r[ns++] = 2;
 	for (u32 i = 0; i < rem / 2; ++i) small_r[ns++] = 4;
@@ -89,7 +89,7 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 	if (m <= SMALL_MAX_PAIRS && !force_S)
 	{
 		pl.small = true; pl.S = m; pl.R = 1;
-		pl.nstS = factor_stages(m, pl.stS, true);
+		pl.nstS = factor_stages(m, pl.stS, true, true);
 		pl.nstR = 0;
 		pl.thrMid = round_threads((m <= MARIN_SMALL_R4) ? m / 2 : m / 8, 512); // one butterfly per thread and lane in the widest stage
 	}
@@ -100,7 +100,7 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 		if (force_S) { pl.S = force_S; pl.R = m / force_S; }
 		else if (m / five >= ((five == 5) ? 16u : 64u) * MID_S) { pl.S = MID_S; pl.R = m / MID_S; }
 		else if (five == 5) { pl.R = 80; pl.S = m / pl.R; }
-		else { pl.R = (m > 8192) ? 64 : ((m == 8192) ? 8 : 16); pl.S = m / pl.R; } // measured: m = 2048 R = 16, m = 8192 R = 8 (few short rows: latency, not throughput)
+		else { pl.R = (m > 8192) ? 64 : 8; pl.S = m / pl.R; } // measured at n = 4096 and n = 16384: few long rows win (latency, not throughput)
 		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || (pl.S & (pl.S - 1)) != 0 || pl.R < 2) { err = "bad forced split"; return false; }
 		// more rows than one tile can hold: split them over two strided passes, R = RA * RB, the radix-5
 		// factor (if any) staying in the first
