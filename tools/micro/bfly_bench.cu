@@ -1,31 +1,11 @@
 // Microbenchmark (development aid): throughput of the register-resident radix-16 butterfly core of the engine
-// (dft16 forward + inverse, optionally with 15 table-free twiddle multiplies) for alternative formulations of
-// the Goldilocks add/sub.  Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a [-DVARIANT=n] -o bfly_bench bfly_bench.cu
+// (dft16 forward + inverse, optionally with 15 table-free twiddle multiplies), with a check of the device arithmetic
+// against the host formulation.  It is how the Goldilocks add / sub / reduce formulations in gl64.cuh were chosen
+// (profiles/bench_r1j/micro2.log: all-ALU carry chains 35.0 G butterflies/s, carry consumers as IMAD.X 51.1).
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -diag-suppress 550 -o bfly_bench bfly_bench.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
-#ifndef VARIANT
-#define VARIANT 0
-#endif
-#if VARIANT == 1
-#define MARIN_SUB_IMAD 1
-#endif
-#if VARIANT == 2
-#define MARIN_SUB_IMAD2 1
-#endif
-#if VARIANT == 3
-#define MARIN_SUB_IMAD2 1
-#define MARIN_NEG_IMAD 1
-#endif
-#if VARIANT >= 4
-#define MARIN_SUB_V4 1
-#endif
-#if VARIANT >= 5
-#define MARIN_NEG_V5 1
-#endif
-#if VARIANT >= 6
-#define MARIN_REDUCE_V6 1
-#endif
 #include "../../prmers_b200/csrc/marin_kernels.cuh"
 
 using namespace marin;
@@ -75,7 +55,7 @@ int main(int argc, char **argv)
 	cudaMemcpy(hout, out, sizeof(hout), cudaMemcpyDeviceToHost);
 	int bad = 0;
 	for (u32 g = 0; g < 1024; ++g) if (hout[g] != host_ref(hin, g, 2)) ++bad;
-	printf("variant %d: %s\n", VARIANT, bad ? "MISMATCH" : "matches host");
+	printf("device arithmetic %s\n", bad ? "MISMATCHES the host formulation" : "matches the host formulation");
 	cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
 	for (int mode = 0; mode < 2; ++mode)
 		for (int cps = 1; cps <= 4; ++cps) // CTAs (of 8 warps) per SM
