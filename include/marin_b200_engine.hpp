@@ -129,6 +129,10 @@ public:
 	void addsub_copy(const Reg s, const Reg d, const Reg sc, const Reg dc, const Reg a, const Reg b) const override { ck(mb200_addsub_copy(_h, s, d, sc, dc, a, b)); }
 	void square_mul_copy(const Reg src, const Reg c, const uint32 a = 1) const override { ck(mb200_square_mul_copy(_h, src, c, a)); }
 	void mul_copy(const Reg dst, const Reg src, const Reg c, const uint32 a = 1) const override { ck(mb200_mul_copy(_h, dst, src, c, a)); }
+	// extension, no reference counterpart: record a fixed op sequence on a single-CTA engine, replay it as one kernel launch
+	void graph_begin() const { ck(mb200_graph_begin(_h)); }
+	int graph_end() const { int id = -1; ck(mb200_graph_end(_h, &id)); return id; }
+	void graph_launch(const int id) const { ck(mb200_graph_launch(_h, id)); }
 	bool is_equal(const Reg lhs, const Reg rhs) const override { int out = 0; ck(mb200_equal(_h, lhs, rhs, &out)); return out != 0; }
 
 	size_t get_register_data_size() const override { return mb200_register_data_size(_h); }

@@ -68,7 +68,7 @@ static constexpr int MAXRUN = 16;         // largest run any kernel carries in o
 
 enum Mode : int { MODE_SQR = 0, MODE_MUL = 1, MODE_FWD = 2 };
 
-struct Stage { u32 radix, L, s, toff; };  // block length L = radix * s; toff: where this stage's twiddles start in the table
+struct Stage { u32 radix, L, s, toff, ls; }; // block length L = radix * s, s = 2^ls; toff: where this stage's twiddles start in the table
 
 // Constant tables of one engine (device pointers).
 struct Tables
@@ -430,7 +430,7 @@ template <int R, bool INV> HD void run_stage_lin(View in, View out, const Stage 
 	for (u32 b = tid; b < nb; b += nthr)
 	{
 		const u32 lane = b & 1, rb = b >> 1;
-		const u32 blk = rb / sg.s, j = rb % sg.s;
+		const u32 blk = rb >> sg.ls, j = rb & (sg.s - 1); // s is a power of two in every stage
 		View vi = in, vo = out;
 		vi.p += lane; vo.p += lane;
 		bfly<R, INV>(vi, vo, blk * sg.L + j, sg.s, j, tw, INV ? t.w5i : t.w5, nullptr);
@@ -534,7 +534,7 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 	for (u32 b = tid; b < nb; b += nthr)
 	{
 		const u32 lane = b & 1, c = (b >> 1) & (TILE_C - 1), rb = b / (2 * TILE_C);
-		const u32 blk = rb / sg.s, j = rb % sg.s;
+		const u32 blk = rb >> sg.ls, j = rb & (sg.s - 1); // s is a power of two in every stage
 		const u32 base = blk * sg.L + j;
 		const View Gi = view_global(gsrc, blockbase + c0 + c, A.stride, lane);
 		const View Go = view_global(gdst, blockbase + c0 + c, A.stride, lane);

@@ -71,6 +71,7 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta 
 	for (u32 i = 0; i < k; ++i)
 	{
 		st[i].radix = r[i]; st[i].L = L; st[i].s = L / r[i]; st[i].toff = off;
+		st[i].ls = 0; while ((1u << st[i].ls) < st[i].s) ++st[i].ls; // the radix-5 stage, if any, comes first: s is always a power of two
 		if (st[i].s > 1) off += (r[i] - 1) * st[i].s;
 		L /= r[i];
 	}
