@@ -55,6 +55,9 @@ static inline pair_t marin_ld_slot(const pair_t *p) { return *p; }
 namespace marin {
 
 static constexpr int MAX_STAGES = 8;
+#ifndef MARIN_PAIR_BOUNDARY
+#define MARIN_PAIR_BOUNDARY 1
+#endif
 #ifndef MARIN_RW_BATCH
 #define MARIN_RW_BATCH 4 // weight loads in flight per thread in the reweight/store phase
 #endif
@@ -529,6 +532,51 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)
 {
 	const Tables &t = A.t;
+	// The radix-4 stage next to global memory (s = 1, boundary twiddles, no stage twiddles): one thread takes BOTH lanes of
+	// its four pairs, so the boundary twiddle (a product of two table entries) is formed once per pair instead of once
+	// per lane, and global memory is touched 16 bytes at a time.
+	if (R == 4 && MARIN_PAIR_BOUNDARY && last && !first && sg.s == 1)
+	{
+		const u32 npb = (A.R / 4) * TILE_C, Kstep = A.R / 4;
+		for (u32 b = tid; b < npb; b += nthr)
+		{
+			const u32 c = b & (TILE_C - 1), base = (b / TILE_C) * 4;
+			const size_t gcol = blockbase + c0 + c;
+			const u64 colscale = (u64)(c0 + c) * A.escale;
+			const u32 K0 = A.rowK[base];
+			pair_t v[4];
+			if (INV)
+			{
+				#pragma unroll
+				for (u32 q = 0; q < 4; ++q) v[q] = gsrc[gcol + (size_t)(base + q) * A.stride];
+				#pragma unroll
+				for (u32 q = 0; q < 4; ++q)
+				{
+					const u64 f = boundary_tw(t, (u64)(K0 + q * Kstep) * colscale, true);
+					v[q].x = gl::mul(v[q].x, f); v[q].y = gl::mul(v[q].y, f);
+				}
+				dft4<true>(v[0].x, v[1].x, v[2].x, v[3].x);
+				dft4<true>(v[0].y, v[1].y, v[2].y, v[3].y);
+				#pragma unroll
+				for (u32 q = 0; q < 4; ++q) sm[tile_pair(base + q, c)] = v[q];
+			}
+			else
+			{
+				#pragma unroll
+				for (u32 q = 0; q < 4; ++q) v[q] = sm[tile_pair(base + q, c)];
+				dft4<false>(v[0].x, v[1].x, v[2].x, v[3].x);
+				dft4<false>(v[0].y, v[1].y, v[2].y, v[3].y);
+				#pragma unroll
+				for (u32 k = 0; k < 4; ++k)
+				{
+					const u64 f = boundary_tw(t, (u64)(K0 + k * Kstep) * colscale, false);
+					v[k].x = gl::mul(v[k].x, f); v[k].y = gl::mul(v[k].y, f);
+					gdst[gcol + (size_t)(base + k) * A.stride] = v[k];
+				}
+			}
+		}
+		return;
+	}
 	const u32 nb = (A.R / R) * TILE_C * 2;
 	const Tw tw{(sg.s > 1) ? (INV ? A.twi : A.tw) + sg.toff : nullptr, sg.s};
 	for (u32 b = tid; b < nb; b += nthr)
