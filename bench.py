@@ -281,7 +281,7 @@ def main():
             line["roofline_int_alu_pipe"] = {"achieved": alu_instr / (ms_iter * 1e-3), "peak": peak_alu, "unit": "warp-inst/s",
                                              "frac": alu_instr / (ms_iter * 1e-3) / peak_alu,
                                              "alu_warp_instructions_per_square_mul": alu_instr,
-                                             "source": "profiles/ncu_summary.json (ncu capture r1j) + live timing"}
+                                             "source": "profiles/ncu_summary.json (ncu capture r1n) + live timing"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = cpu_baseline(64)

@@ -532,46 +532,48 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)
 {
 	const Tables &t = A.t;
-	// The radix-4 stage next to global memory (s = 1, boundary twiddles, no stage twiddles): one thread takes BOTH lanes of
-	// its four pairs, so the boundary twiddle (a product of two table entries) is formed once per pair instead of once
-	// per lane, and global memory is touched 16 bytes at a time.
+	// The radix-4 stage next to global memory (s = 1: boundary twiddles, no stage twiddles): one thread takes BOTH lanes
+	// of its four pairs, so the boundary twiddle (a product of two table entries) is formed once per pair instead of
+	// once per lane, and global memory is touched 16 bytes at a time (405 -> 386 us per squaring at n = 2^23).  The
+	// same on a radix-16 stage needs 64 registers of data alone and spills: 579 -> 701 us at n = 5 * 2^21, not done.
 	if (R == 4 && MARIN_PAIR_BOUNDARY && last && !first && sg.s == 1)
 	{
-		const u32 npb = (A.R / 4) * TILE_C, Kstep = A.R / 4;
+		const u32 npb = (A.R / R) * TILE_C, Kstep = A.R / R;
 		for (u32 b = tid; b < npb; b += nthr)
 		{
-			const u32 c = b & (TILE_C - 1), base = (b / TILE_C) * 4;
+			const u32 c = b & (TILE_C - 1), base = (b / TILE_C) * R;
 			const size_t gcol = blockbase + c0 + c;
 			const u64 colscale = (u64)(c0 + c) * A.escale;
 			const u32 K0 = A.rowK[base];
-			pair_t v[4];
+			u64 ax[R], ay[R];
 			if (INV)
 			{
+				pair_t v[R];
 				#pragma unroll
-				for (u32 q = 0; q < 4; ++q) v[q] = gsrc[gcol + (size_t)(base + q) * A.stride];
+				for (u32 q = 0; q < R; ++q) v[q] = gsrc[gcol + (size_t)(base + q) * A.stride];
 				#pragma unroll
-				for (u32 q = 0; q < 4; ++q)
+				for (u32 q = 0; q < R; ++q)
 				{
 					const u64 f = boundary_tw(t, (u64)(K0 + q * Kstep) * colscale, true);
-					v[q].x = gl::mul(v[q].x, f); v[q].y = gl::mul(v[q].y, f);
+					const u32 sl = slot_of<R>(q);
+					ax[sl] = gl::mul(v[q].x, f); ay[sl] = gl::mul(v[q].y, f);
 				}
-				dft4<true>(v[0].x, v[1].x, v[2].x, v[3].x);
-				dft4<true>(v[0].y, v[1].y, v[2].y, v[3].y);
+				dft4<true>(ax[0], ax[1], ax[2], ax[3]); dft4<true>(ay[0], ay[1], ay[2], ay[3]);
 				#pragma unroll
-				for (u32 q = 0; q < 4; ++q) sm[tile_pair(base + q, c)] = v[q];
+				for (u32 q = 0; q < R; ++q) { pair_t o; o.x = ax[q]; o.y = ay[q]; sm[tile_pair(base + q, c)] = o; }
 			}
 			else
 			{
 				#pragma unroll
-				for (u32 q = 0; q < 4; ++q) v[q] = sm[tile_pair(base + q, c)];
-				dft4<false>(v[0].x, v[1].x, v[2].x, v[3].x);
-				dft4<false>(v[0].y, v[1].y, v[2].y, v[3].y);
+				for (u32 q = 0; q < R; ++q) { const pair_t v = sm[tile_pair(base + q, c)]; ax[q] = v.x; ay[q] = v.y; }
+				dft4<false>(ax[0], ax[1], ax[2], ax[3]); dft4<false>(ay[0], ay[1], ay[2], ay[3]);
 				#pragma unroll
-				for (u32 k = 0; k < 4; ++k)
+				for (u32 k = 0; k < R; ++k)
 				{
 					const u64 f = boundary_tw(t, (u64)(K0 + k * Kstep) * colscale, false);
-					v[k].x = gl::mul(v[k].x, f); v[k].y = gl::mul(v[k].y, f);
-					gdst[gcol + (size_t)(base + k) * A.stride] = v[k];
+					const u32 sl = slot_of<R>(k);
+					pair_t o; o.x = gl::mul(ax[sl], f); o.y = gl::mul(ay[sl], f);
+					gdst[gcol + (size_t)(base + k) * A.stride] = o;
 				}
 			}
 		}
