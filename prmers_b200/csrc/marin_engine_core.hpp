@@ -211,11 +211,12 @@ public:
 		const u32 n = pl.n;
 		be.unweight(_t, R(src), _scratch, n);
 		be.d2h(enc, _scratch, (size_t)n * 8);
+		// one pass carries and encodes (value | width << 32); the end-around carry (2^p = 1) then ripples from digit 0
+		// through digits that are already canonical, for a handful of digits at most
 		u64 c = 0;
-		for (u32 k = 0; k < n; ++k) enc[k] = adc(enc[k], width(k), c);
+		for (u32 k = 0; k < n; ++k) { const u32 w = width(k); enc[k] = (u64)adc(enc[k], w, c) | ((u64)w << 32); }
 		while (c != 0)
-			for (u32 k = 0; k < n; ++k) { enc[k] = adc(enc[k], width(k), c); if (c == 0) break; }
-		for (u32 k = 0; k < n; ++k) enc[k] = (u32)enc[k] | ((u64)width(k) << 32);
+			for (u32 k = 0; k < n; ++k) { const u32 w = width(k); enc[k] = (u64)adc((u32)enc[k], w, c) | ((u64)w << 32); if (c == 0) break; }
 	}
 
 	void set_digits(size_t dst, const u64 *enc)
