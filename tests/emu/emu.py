@@ -43,7 +43,8 @@ def lib():
         for f, a in (("emu_set_u32", [vp, sz, u32]), ("emu_copy", [vp, sz, sz]), ("emu_square_mul", [vp, sz, u32]),
                      ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_sub_u32", [vp, sz, u32]),
                      ("emu_add", [vp, sz, sz]), ("emu_sub_reg", [vp, sz, sz]), ("emu_get_digits", [vp, sz, vp]),
-                     ("emu_set_digits", [vp, sz, vp]), ("emu_equal", [vp, sz, sz, vp])):
+                     ("emu_set_digits", [vp, sz, vp]), ("emu_equal", [vp, sz, sz, vp]), ("emu_graph_begin", [vp]),
+                     ("emu_graph_end", [vp, vp]), ("emu_graph_launch", [vp, C.c_int])):
             getattr(L, f).argtypes = a; getattr(L, f).restype = C.c_int
         L.emu_transform_size.restype = sz; L.emu_transform_size.argtypes = [u32]
         _lib = L
@@ -77,6 +78,17 @@ class EmuEngine:
     def sub(self, r, a): self._ck(lib().emu_sub_u32(self._h, r, a))
     def add(self, d, s): self._ck(lib().emu_add(self._h, d, s))
     def sub_reg(self, d, s): self._ck(lib().emu_sub_reg(self._h, d, s))
+
+    # recorded op sequences (the emulated k_program)
+    def is_single_cta(self): return self.small
+    def graph_begin(self): self._ck(lib().emu_graph_begin(self._h))
+
+    def graph_end(self):
+        gid = C.c_int(-1)
+        self._ck(lib().emu_graph_end(self._h, C.byref(gid)))
+        return gid.value
+
+    def graph_launch(self, gid): self._ck(lib().emu_graph_launch(self._h, gid))
 
     def get_digits(self, s):
         out = np.zeros(self.n, dtype=np.uint64)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include "../../prmers_b200/csrc/marin_engine_core.hpp"
@@ -78,6 +79,51 @@ struct CpuBackend
 	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
 	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { for (u32 j = 0; j < n; ++j) unweight_thread(t, x, out, j); }
+	// recorded op sequences: the emulated k_program -- the same op order, each op through the same phase functions
+	std::vector<std::vector<ProgOp>> progs;
+	int prog_upload(const std::vector<ProgOp> &ops) { progs.push_back(ops); return (int)progs.size() - 1; }
+	void prog_launch(int id, ProgArgs A, u32 thr, size_t smem)
+	{
+		if (id < 0 || (size_t)id >= progs.size()) throw std::runtime_error("marin_b200: unknown graph id");
+		const u32 n = A.M.t.n, npairs = n / 2;
+		for (const ProgOp &op : progs[(size_t)id])
+		{
+			u64 *dst = A.reg + (size_t)op.dst * n;
+			const u64 *src = A.reg + (size_t)op.src * n;
+			LinArgs L{A.M.t, dst, src, nullptr, A.carry, 0, op.a, A.D};
+			switch (op.code)
+			{
+			case PO_COPY: std::memcpy(dst, src, (size_t)n * 8); break;
+			case PO_SQR: case PO_MUL: case PO_SETMUL:
+			{
+				MidArgs M = A.M;
+				M.x = (pair_t *)((op.code == PO_SETMUL) ? const_cast<u64 *>(src) : dst);
+				M.y = (op.code == PO_MUL) ? (const pair_t *)src : nullptr;
+				M.dst = (pair_t *)dst;
+				M.mode = (op.code == PO_SQR) ? MODE_SQR : ((op.code == PO_MUL) ? MODE_MUL : MODE_FWD);
+				M.a = op.a;
+				mid(M, 1, thr, smem);
+				break;
+			}
+			case PO_ADD: case PO_SUBREG: case PO_SUBSMALL:
+			{
+				L.op = (op.code == PO_ADD) ? LIN_ADD : ((op.code == PO_SUBREG) ? LIN_SUBREG : LIN_SUBSMALL);
+				for (u32 i = 0; i < npairs; ++i) A.carry[i] = lin_pair_carry(L, i);
+				for (u32 i = 0; i < npairs; ++i)
+				{
+					u64 u0, u1; u32 w0, w1;
+					lin_pair_compute(L, i, u0, u1, w0, w1);
+					lin_pair_finish(L, i, u0, u1, w0, w1, A.carry[i ? i - 1 : npairs - 1]);
+				}
+				break;
+			}
+			default:
+				L.src = dst; L.op = LIN_SETSMALL;
+				lin_p1(L, n / A.D); lin_p2(L, n / A.D);
+				break;
+			}
+		}
+	}
 	void scale(u64 *x, u64 f, u32 n) { for (u32 j = 0; j < n; ++j) scale_thread(x, f, j, n); }
 	void weights(const WeightArgs &A, u32 n)
 	{
@@ -114,6 +160,9 @@ int emu_add(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->add(d, s)) }
 int emu_sub_reg(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->sub_reg(d, s)) }
 int emu_get_digits(void *h, size_t s, uint64_t *enc) { GUARD(((Emu *)h)->get_digits(s, (u64 *)enc)) }
 int emu_set_digits(void *h, size_t d, const uint64_t *enc) { GUARD(((Emu *)h)->set_digits(d, (const u64 *)enc)) }
+int emu_graph_begin(void *h) { GUARD(((Emu *)h)->graph_begin()) }
+int emu_graph_end(void *h, int *id) { GUARD(*id = ((Emu *)h)->graph_end()) }
+int emu_graph_launch(void *h, int id) { GUARD(((Emu *)h)->graph_launch(id)) }
 int emu_equal(void *h, size_t l, size_t r, int *out) { GUARD(*out = ((Emu *)h)->equal(l, r) ? 1 : 0) }
 size_t emu_transform_size(uint32_t p) { return transform_size(p); }
 }

@@ -105,6 +105,41 @@ def test_run_ecm_m101_emulated_matches_golden():
     assert r["status"] == "NF" and len(r["curves"]) == 2
 
 
+def test_recorded_point_operations_equal_direct_calls_emulated():
+    """The three point operations recorded once and replayed (k_program on the GPU, its emulation here) give the same
+    residues in every register as the same schedules issued op by op."""
+    p, seed = 701, 5
+    K = ecm.stage1_exponent(120)
+    a, b = EmuEngine(p, ecm.REGS), EmuEngine(p, ecm.REGS)
+    ra = ecm.run_curve(a, p, 120, 400, seed, K=K, graphs=True)
+    rb = ecm.run_curve(b, p, 120, 400, seed, K=K, graphs=False)
+    assert {k: ra[k] for k in ("status", "stage", "factor", "stage1_T", "point_ops")} == {k: rb[k] for k in ("status", "stage", "factor", "stage1_T", "point_ops")}
+    for r in range(ecm.REGS):
+        if r not in (11, 43, 44, 45, 46, 50):           # multiplicand registers hold transform-domain data: compare raw digits only where digits exist
+            assert (a.get_digits(r) == b.get_digits(r)).all(), r
+
+
+def test_recording_rules_emulated():
+    e = EmuEngine(701, 8)
+    with pytest.raises(RuntimeError):
+        e.graph_end()                                    # nothing being recorded
+    e.set(0, 3); e.set(1, 5)
+    e.graph_begin()
+    e.square_mul(0, 3); e.set_multiplicand(2, 1); e.mul(0, 2); e.add(0, 1); e.sub_reg(0, 1); e.copy(3, 0); e.sub(3, 2); e.set(4, 9)
+    with pytest.raises(RuntimeError):
+        e.get_digits(0)                                  # blocking calls are refused while recording
+    g = e.graph_end()
+    N = (1 << 701) - 1
+    val = lambda r: ecm._value(e, r, 701)
+    assert val(0) == 3                                    # recording ran nothing
+    x = 3
+    for _ in range(10):
+        e.graph_launch(g); x = x * x * 3 * 5 % N
+    assert val(0) == x and val(3) == (x - 2) % N and val(4) == 9
+    with pytest.raises(RuntimeError):
+        EmuEngine(86243, 2).graph_begin()                 # multi-pass engines cannot be recorded
+
+
 def test_invariant_catches_injected_error_emulated():
     """-erroriter (:3285-3288): Z -= 2 after some step must break a X^2 + Y^2 = Z^2 + d T^2."""
     log = []
