@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarin_b200.so")
 SOURCES = ["marin_engine.cu"]
-HEADERS = ["gl64.cuh", "marin_kernels.cuh", "marin_plan.hpp", "marin_engine_core.hpp"]
+HEADERS = ["gl64.cuh", "marin_kernels.cuh", "marin_fast.cuh", "marin_plan.hpp", "marin_engine_core.hpp"]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-diag-suppress", "550", "-Xcompiler", "-fPIC", "-shared"]

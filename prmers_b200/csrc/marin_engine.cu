@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "marin_engine_core.hpp"
+#include "marin_fast.cuh"
 #include "../../include/marin_b200.h"
 
 using namespace marin;
@@ -205,6 +206,24 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 2048)); // it also keeps its argument blocks in static shared memory
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
+		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
+		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
+		use_fast = getenv("MARIN_B200_NO_FAST") == nullptr;
+	}
+	bool use_fast = true; // the specialised kernels of marin_fast.cuh (same results; MARIN_B200_NO_FAST=1 runs the generic ones: tests, A/B timing)
+
+	static bool fast_mid_shape(const MidArgs &A)
+	{
+		return !A.small && A.S == fast::MID_S && A.nst == 3 && A.st[0].radix == 16 && A.st[1].radix == 16 && A.st[2].radix == 16;
+	}
+	static bool fast_str_shape(const StridedArgs &A)
+	{
+		return TILE_C == 4 && A.R == 1024 && A.nst == 3 && A.st[0].radix == 16 && A.st[1].radix == 16 && A.st[2].radix == 4
+			&& A.escale == 1 && (size_t)A.Lb == (size_t)A.R * A.stride && A.tiles == A.stride / TILE_C;
 	}
 	~CudaBackend()
 	{
@@ -311,10 +330,33 @@ struct CudaBackend
 		static const u32 fg = env_u32("MARIN_B200_MID_GRID"), ft = env_u32("MARIN_B200_MID_THREADS");
 		if (fg && fg < grid) grid = fg;
 		if (ft) thr = ft;
-		use(); launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem); post();
+		use();
+		if (use_fast && !ft && fast_mid_shape(A))
+		{
+			if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			else launch_windowed(fast::k_mid_fast<MODE_FWD>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			post(); return;
+		}
+		launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem); post();
 	}
-	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); launch_windowed(k_strided<false>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post(); }
-	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem) { use(); launch_windowed(k_strided<true>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post(); }
+	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
+	{
+		use();
+		if (use_fast && fast_str_shape(A) && grid == A.tiles) { launch_windowed(fast::k_fwd_fast_T4, A, grid, fast::STR_THREADS, fast::SC<4>::SMEM); post(); return; }
+		launch_windowed(k_strided<false>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post();
+	}
+	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
+	{
+		use();
+		if (use_fast && A.with_carry && A.ticket && fast_str_shape(A) && grid == A.tiles)
+		{
+			if (A.fwd_dst) launch_windowed(fast::k_inv_fast_T4<true>, A, grid, fast::STR_THREADS, fast::SC<4>::SMEM);
+			else launch_windowed(fast::k_inv_fast_T4<false>, A, grid, fast::STR_THREADS, fast::SC<4>::SMEM);
+			post(); return;
+		}
+		launch_windowed(k_strided<true>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post();
+	}
 	void lin_pairs(const LinArgs &A)
 	{
 		use();

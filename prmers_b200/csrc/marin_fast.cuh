@@ -1,0 +1,416 @@
+// marin_fast.cuh -- specialised kernels of the three-pass squaring / multiplication for sm_100a.
+//
+// Same mathematics, same tables and the same register images as the generic phase functions of
+// marin_kernels.cuh (every value is canonical, so any exact evaluation order gives identical bits);
+// what changes is how the work is laid out on the SM:
+//   * every stride is a compile-time constant: shared memory is addressed with LDS / STS and immediate
+//     offsets (the generic path pays a 64-bit generic-pointer add per element: 17 % of its instructions);
+//   * phases that only exchange data inside a block of 512 lane elements are WARP-LOCAL: the warp that
+//     wrote the block reads it back after a __syncwarp(), so a contiguous pass has two block-wide
+//     barriers instead of seven and a strided inverse+carry+forward pass three instead of nine; warps
+//     drift apart and mix their ALU-heavy and multiply-heavy stretches instead of hitting them together;
+//   * the carry of a tile row, its publication, the wait for the row before it in the previous tile, the
+//     absorption and the write-back are ONE thread's job (no block barrier around the hand-off: a late
+//     neighbour stalls one warp, not the CTA);
+//   * digits are re-weighted with a 32 x 64-bit product (a digit is < 2^32), 11 instead of 18 instructions.
+// Replaces, by function, kernels/marin.cl:960-1107 (mid-stage forward/backward passes), :1245-1625 (last
+// stage forward + pointwise + backward) and :1693-1728 + :2196-2216 (unweight, carry, reweight, fix-up).
+//
+// Covered shapes: contiguous pass S = 4096 = 16^3; strided pass R = 256 T, T in {1, 2, 4}, four pair columns
+// per tile.  Everything else (5 * 2^k, second-level strided passes, small transforms) runs the generic kernels.
+#pragma once
+#include "marin_kernels.cuh"
+
+#if defined(__CUDACC__)
+namespace marin { namespace fast {
+
+// ------------------------------------------------------------------ arithmetic helpers
+
+// d * w mod P for a 32-bit d and canonical w; canonical result, identical to gl::mul(d, w).
+// d w = t2 2^64 + T, T = (t1:t0); T + t2 (2^32 - 1) = T - Nb with Nb = P - t2 (2^32 - 1) in (2^32, P]:
+// T + (t2 + 1)(2^32 - 1) carries out exactly when T >= Nb, and the canonical result is that sum when it
+// carries, that sum minus (2^32 - 1) (i.e. plus P) when it does not.
+__device__ __forceinline__ u64 mul_small(u32 d, u64 w)
+{
+	u32 w0 = (u32)w, w1 = (u32)(w >> 32), t0, t1, t2, r0, r1;
+	asm("{\n\t.reg .u32 u, m;\n\t"
+		"mul.lo.u32 %0, %5, %6;\n\t"
+		"mul.hi.u32 %1, %5, %6;\n\t"
+		"mad.lo.cc.u32 %1, %5, %7, %1;\n\t"
+		"madc.hi.u32 %2, %5, %7, 0;\n\t"
+		"add.u32 u, %2, 1;\n\t"
+		"mad.lo.cc.u32 %3, u, 0xffffffff, %0;\n\t"
+		"madc.hi.cc.u32 %4, u, 0xffffffff, %1;\n\t"
+		"madc.lo.u32 m, %8, %8, 0xffffffff;\n\t"  // m = carry ? 0 : 2^32 - 1
+		"sub.cc.u32 %3, %3, m;\n\t"
+		"subc.u32 %4, %4, 0;\n\t"
+		"}" : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(r0), "=&r"(r1) : "r"(d), "r"(w0), "r"(w1), "r"(GL_ZERO));
+	return ((u64)r1 << 32) | r0;
+}
+
+// ------------------------------------------------------------------ radix-16 stages with compile-time strides
+// Forward (DIF): inputs natural, output k in slot sw16(k), then times the stage twiddle tw[(k - 1) TWS] (k >= 1).
+// Inverse: input q (times the inverse stage twiddle) in slot sw16(q), outputs natural.  Unnormalised.
+
+template <int STW> __device__ __forceinline__ void ld16_nat(u64 *a, const u64 *p)
+{
+	#pragma unroll
+	for (int q = 0; q < 16; ++q) a[q] = p[q * STW];
+}
+template <int STW> __device__ __forceinline__ void ld16_sw(u64 *a, const u64 *p)
+{
+	#pragma unroll
+	for (int q = 0; q < 16; ++q) a[sw16(q)] = p[q * STW];
+}
+template <int STW> __device__ __forceinline__ void st16_nat(u64 *p, const u64 *a)
+{
+	#pragma unroll
+	for (int k = 0; k < 16; ++k) p[k * STW] = a[k];
+}
+template <int STW> __device__ __forceinline__ void st16_sw(u64 *p, const u64 *a)
+{
+	#pragma unroll
+	for (int k = 0; k < 16; ++k) p[k * STW] = a[sw16(k)];
+}
+template <int TWS> __device__ __forceinline__ void tw16(u64 *a, const u64 *tw)
+{
+	#pragma unroll
+	for (int k = 1; k < 16; ++k) a[sw16(k)] = gl::mul(a[sw16(k)], tw[(k - 1) * TWS]);
+}
+
+// ================================================================== contiguous pass, S = 4096 = 16 x 16 x 16
+// Shared layout: pair i at pair slot i + (i >> 4) (one pair of padding per 16), a thread works on ONE lane of the
+// pairs (even or odd digit): adjacent threads take the two lanes of the same pairs.
+//   F0  s = 256  global -> shared          (block-wide barrier after it)
+//   per 256-pair block, owned by one warp: F1 (s = 16), F2 (s = 1), pointwise, I2, I1   (__syncwarp between)
+//   I0  s = 256  shared -> global          (block-wide barrier before it)
+
+static constexpr u32 MID_S = 4096, MID_THREADS = 256;
+static constexpr u32 MID_SMEM = (MID_S + MID_S / 16 + 1) * 16;
+
+template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast(const __grid_constant__ MidArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	const Tables &t = A.t;
+	const u32 tid = threadIdx.x, lane = tid & 1, h = tid >> 1, wl = tid & 31, warp = tid >> 5;
+	const size_t rowbase = (size_t)blockIdx.x * MID_S;
+	u64 *smw = reinterpret_cast<u64 *>(sm) + lane;
+	const u64 *tw0 = t.twS + A.st[0].toff, *tw1 = t.twS + A.st[1].toff;
+	const u64 *twi0 = t.twSi + A.st[0].toff, *twi1 = t.twSi + A.st[1].toff;
+
+	// ---- F0: elements j + 256 q of the row, straight from global memory
+	{
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 it = 0; it < 2; ++it)
+		{
+			const u32 j = h + 128 * it;
+			u64 a[16];
+			ld16_nat<512>(a, g + 2 * j);
+			dft16<false>(a);
+			tw16<256>(a, tw0 + j);
+			st16_sw<544>(smw + 2 * (j + (j >> 4)), a);
+		}
+	}
+	__syncthreads();
+
+	// ---- warp-local part: blocks of 256 pairs
+	const u32 jl = wl >> 1; // butterfly of this thread inside a block (F1: column j, F2: group of 16)
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it)
+	{
+		const u32 Bk = warp + 8 * it;
+		u64 *blk = smw + 2 * (272 * Bk);
+		{	// F1: s = 16
+			u64 a[16];
+			ld16_nat<34>(a, blk + 2 * jl);
+			dft16<false>(a);
+			tw16<16>(a, tw1 + jl);
+			st16_sw<34>(blk + 2 * jl, a);
+		}
+		__syncwarp();
+		{	// F2: s = 1, no twiddles
+			u64 a[16];
+			ld16_nat<2>(a, blk + 2 * (17 * jl));
+			dft16<false>(a);
+			st16_sw<2>(blk + 2 * (17 * jl), a);
+		}
+		__syncwarp();
+		if (MODE == MODE_FWD)
+		{
+			// multiplicand: the forward transform in position order, copied out 16 bytes per thread
+			pair_t *dst = A.dst + rowbase + 256 * Bk;
+			#pragma unroll
+			for (u32 u = 0; u < 8; ++u) { const u32 i = wl + 32 * u; dst[i] = sm[272 * Bk + i + (i >> 4)]; }
+			continue;
+		}
+		{	// pointwise square / multiply modulo (t^2 - u), u = w_m^freq(position): one pair per thread
+			const u64 rr = t.rowroot[blockIdx.x];
+			#pragma unroll 2
+			for (u32 u = 0; u < 8; ++u)
+			{
+				const u32 i = wl + 32 * u, ig = 256 * Bk + i;
+				const u64 uu = gl::mul(rr, t.colroot[ig]);
+				pair_t &v = sm[272 * Bk + i + (i >> 4)];
+				v = (MODE == MODE_SQR) ? sqr22(v, uu) : mul22(v, A.y[rowbase + ig], uu);
+			}
+		}
+		__syncwarp();
+		{	// I2: s = 1
+			u64 a[16];
+			ld16_sw<2>(a, blk + 2 * (17 * jl));
+			dft16<true>(a);
+			st16_nat<2>(blk + 2 * (17 * jl), a);
+		}
+		__syncwarp();
+		{	// I1: s = 16
+			u64 a[16];
+			ld16_sw<34>(a, blk + 2 * jl);
+			tw16<16>(a, twi1 + jl);
+			dft16<true>(a);
+			st16_nat<34>(blk + 2 * jl, a);
+		}
+	}
+	if (MODE == MODE_FWD) return;
+	__syncthreads();
+
+	// ---- I0: s = 256, back to global memory (in place)
+	{
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 it = 0; it < 2; ++it)
+		{
+			const u32 j = h + 128 * it;
+			u64 a[16];
+			ld16_sw<544>(a, smw + 2 * (j + (j >> 4)));
+			tw16<256>(a, twi0 + j);
+			dft16<true>(a);
+			st16_nat<512>(g + 2 * j, a);
+		}
+	}
+}
+
+// ================================================================== strided passes, R = 256 T rows, 4 pair columns
+// Forward stage list (marin_plan.hpp, factor_stages): [16 (s = 16 T), 16 (s = T), T (s = 1)]; the last one is next to
+// global memory and carries the boundary twiddle w_m^(K(row) column).  Tile = R rows x 4 pairs in shared memory with a
+// pitch of 5 pairs.  Blocks of 16 T rows (512 lane elements for T = 4) are warp-local for the two small stages.
+
+static constexpr u32 STR_THREADS = 256, PITCH_W = 2 * TILE_PITCH; // words per tile row
+
+template <int T> struct SC
+{
+	static constexpr u32 R = 256 * T;
+	static constexpr u32 S0 = 16 * T;          // stride (rows) of the first radix-16 stage
+	static constexpr u32 NB = 16;              // blocks of 16 T rows per tile
+	static constexpr u32 SMEM = R * TILE_PITCH * 16;
+};
+
+__device__ __forceinline__ u64 wait_slot_fast(const StridedArgs &A, size_t idx)
+{
+	u32 spins = 0;
+	for (;;)
+	{
+		const pair_t v = marin_ld_slot(&A.slots[idx]);
+		if (v.y == (u64)A.epoch) return v.x;
+		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[A.tiles], 1u); return ~0ull; } // poisoned: the error word makes every later read-back fail
+		if (spins > 64) MARIN_NANOSLEEP(100);
+	}
+}
+
+// ---- the small stages of one block of 16 T rows (warp-local), T = 4: radix 16 with s = 4, then radix 4 on whole pairs
+
+// inverse direction: global -> radix-4 (boundary twiddle first) -> shared -> radix-16 (s = 4)
+__device__ __forceinline__ void inv_small_T4(const StridedArgs &A, pair_t *sm, u32 Bk, u32 c0, u32 wl)
+{
+	const Tables &t = A.t;
+	constexpr u32 Kstep = 256;
+	#pragma unroll 1
+	for (u32 i = 0; i < 2; ++i)
+	{
+		const u32 pb = wl + 32 * i, c = pb & 3, base = 64 * Bk + 4 * (pb >> 2);
+		const size_t gcol = (size_t)c0 + c;
+		const u64 colscale = (u64)(c0 + c) * A.escale;
+		const u32 K0 = A.rowK[base];
+		pair_t v[4];
+		#pragma unroll
+		for (u32 q = 0; q < 4; ++q) v[q] = A.src[gcol + (size_t)(base + q) * A.stride];
+		u64 ax[4], ay[4];
+		#pragma unroll
+		for (u32 q = 0; q < 4; ++q)
+		{
+			const u64 f = boundary_tw(t, (u64)(K0 + q * Kstep) * colscale, true);
+			ax[q] = gl::mul(v[q].x, f); ay[q] = gl::mul(v[q].y, f);
+		}
+		dft4<true>(ax[0], ax[1], ax[2], ax[3]); dft4<true>(ay[0], ay[1], ay[2], ay[3]);
+		#pragma unroll
+		for (u32 q = 0; q < 4; ++q) { pair_t o; o.x = ax[q]; o.y = ay[q]; sm[tile_pair(base + q, c)] = o; }
+	}
+	__syncwarp();
+	{
+		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = wl >> 3;
+		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * c + lane;
+		u64 a[16];
+		ld16_sw<4 * PITCH_W>(a, p);
+		tw16<4>(a, A.twi + A.st[1].toff + j);
+		dft16<true>(a);
+		st16_nat<4 * PITCH_W>(p, a);
+	}
+}
+
+// forward direction: shared -> radix-16 (s = 4) -> shared -> radix-4 on pairs, boundary twiddle -> global
+__device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, pair_t *gdst, u32 Bk, u32 c0, u32 wl)
+{
+	const Tables &t = A.t;
+	constexpr u32 Kstep = 256;
+	{
+		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = wl >> 3;
+		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * c + lane;
+		u64 a[16];
+		ld16_nat<4 * PITCH_W>(a, p);
+		dft16<false>(a);
+		tw16<4>(a, A.tw + A.st[1].toff + j);
+		st16_sw<4 * PITCH_W>(p, a);
+	}
+	__syncwarp();
+	#pragma unroll 1
+	for (u32 i = 0; i < 2; ++i)
+	{
+		const u32 pb = wl + 32 * i, c = pb & 3, base = 64 * Bk + 4 * (pb >> 2);
+		const size_t gcol = (size_t)c0 + c;
+		const u64 colscale = (u64)(c0 + c) * A.escale;
+		const u32 K0 = A.rowK[base];
+		u64 ax[4], ay[4];
+		#pragma unroll
+		for (u32 q = 0; q < 4; ++q) { const pair_t v = sm[tile_pair(base + q, c)]; ax[q] = v.x; ay[q] = v.y; }
+		dft4<false>(ax[0], ax[1], ax[2], ax[3]); dft4<false>(ay[0], ay[1], ay[2], ay[3]);
+		#pragma unroll
+		for (u32 k = 0; k < 4; ++k)
+		{
+			const u64 f = boundary_tw(t, (u64)(K0 + k * Kstep) * colscale, false);
+			pair_t o; o.x = gl::mul(ax[k], f); o.y = gl::mul(ay[k], f);
+			gdst[gcol + (size_t)(base + k) * A.stride] = o;
+		}
+	}
+}
+
+// ---- the big radix-16 stage (s = 64 rows for T = 4): group G of four columns j = 4 G .. 4 G + 3, rows j + 64 q
+// forward: FROMG = read the rows from global memory (first pass of an operation) instead of the tile
+template <bool FROMG> __device__ __forceinline__ void fwd_big_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 c0, u32 wl)
+{
+	const u32 lane = wl & 1, c = (wl >> 1) & 3, j = 4 * G + (wl >> 3);
+	u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)j * PITCH_W + 2 * c + lane;
+	u64 a[16];
+	if (FROMG)
+	{
+		const u64 *g = reinterpret_cast<const u64 *>(A.src + (size_t)c0 + c + (size_t)j * A.stride) + lane;
+		const size_t gs = 2 * (size_t)64 * A.stride;
+		#pragma unroll
+		for (int q = 0; q < 16; ++q) a[q] = g[q * gs];
+	}
+	else ld16_nat<64 * PITCH_W>(a, p);
+	dft16<false>(a);
+	tw16<64>(a, A.tw + A.st[0].toff + j);
+	st16_sw<64 * PITCH_W>(p, a);
+}
+
+// inverse big stage + unweight (x 1/(w m)), then for the 64 rows this warp has just completed: carry, publish, wait
+// for the run before, absorb -- one thread per row -- and re-weight (coalesced; to the register unless the chain
+// keeps the parked transform as the state, and back into the tile when the forward pass follows)
+template <bool FWD_FOLLOWS> __device__ __forceinline__ void inv_big_carry_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl)
+{
+	const Tables &t = A.t;
+	constexpr u32 R = 1024;
+	{
+		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = 4 * G + (wl >> 3);
+		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)j * PITCH_W + 2 * c + lane;
+		u64 a[16];
+		ld16_sw<64 * PITCH_W>(a, p);
+		tw16<64>(a, A.twi + A.st[0].toff + j);
+		dft16<true>(a);
+		const u64 *wp = t.winvs_tile + 2 * (((size_t)g * R + j) * TILE_C + c) + lane;
+		#pragma unroll
+		for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], wp[(size_t)q * (64 * TILE_C * 2)]);
+		st16_nat<64 * PITCH_W>(p, a);
+	}
+	__syncwarp();
+	// every run of this warp is carried and PUBLISHED before any of its threads waits: a tile never holds back a
+	// carry its successor needs while it waits for its own predecessor (tile 0 waits for the last tile: end-around)
+	#pragma unroll 1
+	for (u32 u = 0; u < 2; ++u)
+	{
+		const u32 rr = wl + 32 * u, row = 4 * G + (rr & 3) + 64 * (rr >> 2);
+		u64 v[RUN];
+		#pragma unroll
+		for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
+		const u32 j0 = 2 * (row * A.stride + c0);
+		const u64 cout = carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
+		marin_st_slot(&A.slots[(size_t)g * R + row], cout, A.epoch);
+		#pragma unroll
+		for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
+	}
+	#pragma unroll 1
+	for (u32 u = 0; u < 2; ++u)
+	{
+		const u32 rr = wl + 32 * u, row = 4 * G + (rr & 3) + 64 * (rr >> 2);
+		const u64 cin = wait_slot_fast(A, slot_before(A, g, row));
+		if (cin == 0) continue;
+		const pair_t p0 = sm[tile_pair(row, 0)], p1 = sm[tile_pair(row, 1)];
+		u64 d[4] = {p0.x, p0.y, p1.x, p1.y};
+		carry_absorb(d, 4, t.wbase, run_bits(t, 2 * (row * A.stride + c0), 4), cin);
+		pair_t q0, q1; q0.x = d[0]; q0.y = d[1]; q1.x = d[2]; q1.y = d[3];
+		sm[tile_pair(row, 0)] = q0; sm[tile_pair(row, 1)] = q1;
+	}
+	__syncwarp();
+	const pair_t *wt = reinterpret_cast<const pair_t *>(t.w_tile) + (size_t)g * R * TILE_C;
+	#pragma unroll 4
+	for (u32 u = 0; u < 8; ++u)
+	{
+		const u32 ri = (wl >> 2) + 8 * u, c = wl & 3, row = 4 * G + (ri & 3) + 64 * (ri >> 2);
+		const pair_t w = wt[(size_t)row * TILE_C + c];
+		const pair_t d = sm[tile_pair(row, c)];
+		pair_t o; o.x = mul_small((u32)d.x, w.x); o.y = mul_small((u32)d.y, w.y);
+		if (!A.skip_dst) A.dst[(size_t)row * A.stride + c0 + c] = o;
+		if (FWD_FOLLOWS) sm[tile_pair(row, c)] = o;
+	}
+}
+
+// inverse strided pass with carry (level 0), optionally followed by the forward strided pass of the next squaring
+template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_inv_fast_T4(const __grid_constant__ StridedArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	__shared__ u32 s_tile;
+	// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket
+	if (threadIdx.x == 0) s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
+	__syncthreads();
+	const u32 g = s_tile, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) inv_small_T4(A, sm, warp + 8 * it, c0, wl);
+	__syncthreads();
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) inv_big_carry_T4<FWD_FOLLOWS>(A, sm, warp + 8 * it, g, c0, wl);
+	if (!FWD_FOLLOWS) return;
+	__syncthreads();
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) fwd_big_T4<false>(A, sm, warp + 8 * it, c0, wl);
+	__syncthreads();
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.fwd_dst, warp + 8 * it, c0, wl);
+}
+
+// forward strided pass from a register in global memory
+__global__ void __launch_bounds__(STR_THREADS, 2) k_fwd_fast_T4(const __grid_constant__ StridedArgs A)
+{
+	extern __shared__ __align__(16) unsigned char smraw[];
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	const u32 g = blockIdx.x, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) fwd_big_T4<true>(A, sm, warp + 8 * it, c0, wl);
+	__syncthreads();
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.dst, warp + 8 * it, c0, wl);
+}
+
+}} // namespace marin::fast
+#endif
