@@ -263,15 +263,15 @@ struct CudaBackend
 	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
 	void sync() { use(); CK(cudaStreamSynchronize(st)); }
 
-	// Keep a buffer (the parked transform a squaring chain ping-pongs through) resident in L2: B200's 126 MB L2 holds
-	// a 64 MiB register, but the weight tables streaming through would evict it between kernels.  The persisting
-	// set-aside is taken from every other kernel's L2 (measured at n = 2^23: add 58 -> 85 us, copy 25 -> 52 us), so
-	// it is switched on only while a long squaring chain runs (persist_on / persist_off, driven by the engine core)
-	// and it buys that chain 1.8 %.
+	// Optional (MARIN_B200_L2_PERSIST=1): pin the parked transform of a squaring chain in L2 with an access-policy
+	// window.  It bought the round-1 kernels 1.8 %; with the specialised kernels (which already mark the weight
+	// streams and the dead tile input evict-first) it costs 15 % (374 vs 326 us per squaring at n = 2^23: the
+	// set-aside starves everything else), and the limit is device-global, so engines sharing a GPU would fight
+	// over it.  Off by default.
 	void persist(void *p, size_t bytes)
 	{
 		use();
-		if (getenv("MARIN_B200_NO_L2_PERSIST")) return;
+		if (!getenv("MARIN_B200_L2_PERSIST")) return;
 		int maxPersist = 0, maxWindow = 0;
 		cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
 		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);

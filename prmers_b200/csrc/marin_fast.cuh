@@ -218,38 +218,52 @@ __device__ __forceinline__ u64 wait_slot_fast(const StridedArgs &A, size_t idx)
 	}
 }
 
+// streaming loads: data read exactly once per launch (tile input, weight streams) must not evict the twiddle tables
+// from L1 -- ld.global.cs allocates evict-first
+__device__ __forceinline__ pair_t ld_stream(const pair_t *p) { return __ldcs(reinterpret_cast<const ulonglong2 *>(p)); }
+__device__ __forceinline__ u64 ld_stream(const u64 *p) { return __ldcs(p); }
+
+// Boundary twiddles of a pair butterfly: rows base + q have frequency indices K0 + q Kstep, so the four factors are
+// f0 g^q with f0 = w_m^(+-K0 colscale) (one product of two table entries) and g = w_m^(+-Kstep colscale), a per-thread
+// constant (a thread keeps its column): two table loads per butterfly instead of eight, same number of products.
+struct BoundaryPow { u64 g1, g2, g3; };
+__device__ __forceinline__ BoundaryPow boundary_pow(const Tables &t, u64 colscale, u32 Kstep, bool inv)
+{
+	BoundaryPow b;
+	b.g1 = boundary_tw(t, (u64)Kstep * colscale, inv);
+	b.g2 = gl::mul(b.g1, b.g1);
+	b.g3 = gl::mul(b.g2, b.g1);
+	return b;
+}
+
 // ---- the small stages of one block of 16 T rows (warp-local), T = 4: radix 16 with s = 4, then radix 4 on whole pairs
 
-// inverse direction: global -> radix-4 (boundary twiddle first) -> shared -> radix-16 (s = 4)
-__device__ __forceinline__ void inv_small_T4(const StridedArgs &A, pair_t *sm, u32 Bk, u32 c0, u32 wl)
+// inverse direction: global -> radix-4 (boundary twiddle first) -> shared -> radix-16 (s = 4); v = the eight pairs of
+// this thread's two pair butterflies, loaded by the caller well ahead of time
+__device__ __forceinline__ void inv_small_T4(const StridedArgs &A, pair_t *sm, u32 Bk, u32 c0, u32 wl, const pair_t (&v)[2][4], const BoundaryPow &bp)
 {
 	const Tables &t = A.t;
-	constexpr u32 Kstep = 256;
-	#pragma unroll 1
+	const u32 c = wl & 3;
+	const u64 colscale = (u64)(c0 + c) * A.escale;
+	#pragma unroll
 	for (u32 i = 0; i < 2; ++i)
 	{
-		const u32 pb = wl + 32 * i, c = pb & 3, base = 64 * Bk + 4 * (pb >> 2);
-		const size_t gcol = (size_t)c0 + c;
-		const u64 colscale = (u64)(c0 + c) * A.escale;
-		const u32 K0 = A.rowK[base];
-		pair_t v[4];
-		#pragma unroll
-		for (u32 q = 0; q < 4; ++q) v[q] = A.src[gcol + (size_t)(base + q) * A.stride];
+		const u32 base = 64 * Bk + 4 * ((wl + 32 * i) >> 2);
+		const u64 f0 = boundary_tw(t, (u64)A.rowK[base] * colscale, true);
+		const u64 f1 = gl::mul(f0, bp.g1), f2 = gl::mul(f0, bp.g2), f3 = gl::mul(f0, bp.g3);
 		u64 ax[4], ay[4];
-		#pragma unroll
-		for (u32 q = 0; q < 4; ++q)
-		{
-			const u64 f = boundary_tw(t, (u64)(K0 + q * Kstep) * colscale, true);
-			ax[q] = gl::mul(v[q].x, f); ay[q] = gl::mul(v[q].y, f);
-		}
+		ax[0] = gl::mul(v[i][0].x, f0); ay[0] = gl::mul(v[i][0].y, f0);
+		ax[1] = gl::mul(v[i][1].x, f1); ay[1] = gl::mul(v[i][1].y, f1);
+		ax[2] = gl::mul(v[i][2].x, f2); ay[2] = gl::mul(v[i][2].y, f2);
+		ax[3] = gl::mul(v[i][3].x, f3); ay[3] = gl::mul(v[i][3].y, f3);
 		dft4<true>(ax[0], ax[1], ax[2], ax[3]); dft4<true>(ay[0], ay[1], ay[2], ay[3]);
 		#pragma unroll
 		for (u32 q = 0; q < 4; ++q) { pair_t o; o.x = ax[q]; o.y = ay[q]; sm[tile_pair(base + q, c)] = o; }
 	}
 	__syncwarp();
 	{
-		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = wl >> 3;
-		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * c + lane;
+		const u32 lane = wl & 1, cc = (wl >> 1) & 3, j = wl >> 3;
+		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * cc + lane;
 		u64 a[16];
 		ld16_sw<4 * PITCH_W>(a, p);
 		tw16<4>(a, A.twi + A.st[1].toff + j);
@@ -257,15 +271,25 @@ __device__ __forceinline__ void inv_small_T4(const StridedArgs &A, pair_t *sm, u
 		st16_nat<4 * PITCH_W>(p, a);
 	}
 }
+__device__ __forceinline__ void inv_small_load_T4(const StridedArgs &A, u32 Bk, u32 c0, u32 wl, pair_t (&v)[2][4])
+{
+	const size_t gcol = (size_t)c0 + (wl & 3);
+	#pragma unroll
+	for (u32 i = 0; i < 2; ++i)
+	{
+		const u32 base = 64 * Bk + 4 * ((wl + 32 * i) >> 2);
+		#pragma unroll
+		for (u32 q = 0; q < 4; ++q) v[i][q] = ld_stream(A.src + gcol + (size_t)(base + q) * A.stride);
+	}
+}
 
 // forward direction: shared -> radix-16 (s = 4) -> shared -> radix-4 on pairs, boundary twiddle -> global
-__device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, pair_t *gdst, u32 Bk, u32 c0, u32 wl)
+__device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, pair_t *gdst, u32 Bk, u32 c0, u32 wl, const BoundaryPow &bp)
 {
 	const Tables &t = A.t;
-	constexpr u32 Kstep = 256;
 	{
-		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = wl >> 3;
-		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * c + lane;
+		const u32 lane = wl & 1, cc = (wl >> 1) & 3, j = wl >> 3;
+		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * cc + lane;
 		u64 a[16];
 		ld16_nat<4 * PITCH_W>(a, p);
 		dft16<false>(a);
@@ -273,24 +297,24 @@ __device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, p
 		st16_sw<4 * PITCH_W>(p, a);
 	}
 	__syncwarp();
-	#pragma unroll 1
+	const u32 c = wl & 3;
+	const size_t gcol = (size_t)c0 + c;
+	const u64 colscale = (u64)(c0 + c) * A.escale;
+	#pragma unroll
 	for (u32 i = 0; i < 2; ++i)
 	{
-		const u32 pb = wl + 32 * i, c = pb & 3, base = 64 * Bk + 4 * (pb >> 2);
-		const size_t gcol = (size_t)c0 + c;
-		const u64 colscale = (u64)(c0 + c) * A.escale;
-		const u32 K0 = A.rowK[base];
+		const u32 base = 64 * Bk + 4 * ((wl + 32 * i) >> 2);
+		const u64 f0 = boundary_tw(t, (u64)A.rowK[base] * colscale, false);
 		u64 ax[4], ay[4];
 		#pragma unroll
 		for (u32 q = 0; q < 4; ++q) { const pair_t v = sm[tile_pair(base + q, c)]; ax[q] = v.x; ay[q] = v.y; }
 		dft4<false>(ax[0], ax[1], ax[2], ax[3]); dft4<false>(ay[0], ay[1], ay[2], ay[3]);
-		#pragma unroll
-		for (u32 k = 0; k < 4; ++k)
-		{
-			const u64 f = boundary_tw(t, (u64)(K0 + k * Kstep) * colscale, false);
-			pair_t o; o.x = gl::mul(ax[k], f); o.y = gl::mul(ay[k], f);
-			gdst[gcol + (size_t)(base + k) * A.stride] = o;
-		}
+		const u64 f1 = gl::mul(f0, bp.g1), f2 = gl::mul(f0, bp.g2), f3 = gl::mul(f0, bp.g3);
+		pair_t o;
+		o.x = gl::mul(ax[0], f0); o.y = gl::mul(ay[0], f0); gdst[gcol + (size_t)(base + 0) * A.stride] = o;
+		o.x = gl::mul(ax[1], f1); o.y = gl::mul(ay[1], f1); gdst[gcol + (size_t)(base + 1) * A.stride] = o;
+		o.x = gl::mul(ax[2], f2); o.y = gl::mul(ay[2], f2); gdst[gcol + (size_t)(base + 2) * A.stride] = o;
+		o.x = gl::mul(ax[3], f3); o.y = gl::mul(ay[3], f3); gdst[gcol + (size_t)(base + 3) * A.stride] = o;
 	}
 }
 
@@ -314,28 +338,28 @@ template <bool FROMG> __device__ __forceinline__ void fwd_big_T4(const StridedAr
 	st16_sw<64 * PITCH_W>(p, a);
 }
 
-// inverse big stage + unweight (x 1/(w m)), then for the 64 rows this warp has just completed: carry, publish, wait
-// for the run before, absorb -- one thread per row -- and re-weight (coalesced; to the register unless the chain
-// keeps the parked transform as the state, and back into the tile when the forward pass follows)
-template <bool FWD_FOLLOWS> __device__ __forceinline__ void inv_big_carry_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl)
+// inverse big stage + unweight (x 1/(w m)), then, for the 64 rows this warp has just completed, carry and publish:
+// one thread per row.  The 16 unweighting factors (a stream from HBM) are requested before the butterfly starts.
+__device__ __forceinline__ void inv_big_carry_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl)
 {
 	const Tables &t = A.t;
 	constexpr u32 R = 1024;
 	{
 		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = 4 * G + (wl >> 3);
 		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)j * PITCH_W + 2 * c + lane;
+		const u64 *wp = t.winvs_tile + 2 * (((size_t)g * R + j) * TILE_C + c) + lane;
+		u64 wv[16];
+		#pragma unroll
+		for (int q = 0; q < 16; ++q) wv[q] = ld_stream(wp + (size_t)q * (64 * TILE_C * 2));
 		u64 a[16];
 		ld16_sw<64 * PITCH_W>(a, p);
 		tw16<64>(a, A.twi + A.st[0].toff + j);
 		dft16<true>(a);
-		const u64 *wp = t.winvs_tile + 2 * (((size_t)g * R + j) * TILE_C + c) + lane;
 		#pragma unroll
-		for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], wp[(size_t)q * (64 * TILE_C * 2)]);
+		for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], wv[q]);
 		st16_nat<64 * PITCH_W>(p, a);
 	}
 	__syncwarp();
-	// every run of this warp is carried and PUBLISHED before any of its threads waits: a tile never holds back a
-	// carry its successor needs while it waits for its own predecessor (tile 0 waits for the last tile: end-around)
 	#pragma unroll 1
 	for (u32 u = 0; u < 2; ++u)
 	{
@@ -348,6 +372,24 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void inv_big_carry_T4(con
 		marin_st_slot(&A.slots[(size_t)g * R + row], cout, A.epoch);
 		#pragma unroll
 		for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
+	}
+}
+
+// second half, after EVERY run of the tile's warp has been published (a tile never holds back a carry its successor
+// needs while it waits for its own predecessor; tile 0 waits for the last tile: end-around): wait for the run before
+// each row in the previous tile, absorb, re-weight (coalesced; to the register unless the chain keeps the parked
+// transform as the state, back into the tile when the forward pass follows).  The weights are requested before the wait.
+template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl)
+{
+	const Tables &t = A.t;
+	constexpr u32 R = 1024;
+	const pair_t *wt = reinterpret_cast<const pair_t *>(t.w_tile) + (size_t)g * R * TILE_C;
+	pair_t w[8];
+	#pragma unroll
+	for (u32 u = 0; u < 8; ++u)
+	{
+		const u32 ri = (wl >> 2) + 8 * u, row = 4 * G + (ri & 3) + 64 * (ri >> 2);
+		w[u] = ld_stream(wt + (size_t)row * TILE_C + (wl & 3));
 	}
 	#pragma unroll 1
 	for (u32 u = 0; u < 2; ++u)
@@ -362,14 +404,12 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void inv_big_carry_T4(con
 		sm[tile_pair(row, 0)] = q0; sm[tile_pair(row, 1)] = q1;
 	}
 	__syncwarp();
-	const pair_t *wt = reinterpret_cast<const pair_t *>(t.w_tile) + (size_t)g * R * TILE_C;
-	#pragma unroll 4
+	#pragma unroll
 	for (u32 u = 0; u < 8; ++u)
 	{
 		const u32 ri = (wl >> 2) + 8 * u, c = wl & 3, row = 4 * G + (ri & 3) + 64 * (ri >> 2);
-		const pair_t w = wt[(size_t)row * TILE_C + c];
 		const pair_t d = sm[tile_pair(row, c)];
-		pair_t o; o.x = mul_small((u32)d.x, w.x); o.y = mul_small((u32)d.y, w.y);
+		pair_t o; o.x = mul_small((u32)d.x, w[u].x); o.y = mul_small((u32)d.y, w[u].y);
 		if (!A.skip_dst) A.dst[(size_t)row * A.stride + c0 + c] = o;
 		if (FWD_FOLLOWS) sm[tile_pair(row, c)] = o;
 	}
@@ -385,18 +425,29 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	if (threadIdx.x == 0) s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
 	__syncthreads();
 	const u32 g = s_tile, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) inv_small_T4(A, sm, warp + 8 * it, c0, wl);
+	const u64 colscale = (u64)(c0 + (wl & 3)) * A.escale;
+	{
+		// all sixteen pairs of this thread's four boundary butterflies are requested at once
+		pair_t v0[2][4], v1[2][4];
+		inv_small_load_T4(A, warp, c0, wl, v0);
+		inv_small_load_T4(A, warp + 8, c0, wl, v1);
+		const BoundaryPow bpi = boundary_pow(A.t, colscale, 256, true);
+		inv_small_T4(A, sm, warp, c0, wl, v0, bpi);
+		inv_small_T4(A, sm, warp + 8, c0, wl, v1, bpi);
+	}
 	__syncthreads();
-	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) inv_big_carry_T4<FWD_FOLLOWS>(A, sm, warp + 8 * it, g, c0, wl);
+	inv_big_carry_T4(A, sm, warp, g, c0, wl);
+	inv_big_carry_T4(A, sm, warp + 8, g, c0, wl);
+	absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp, g, c0, wl);
+	absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp + 8, g, c0, wl);
 	if (!FWD_FOLLOWS) return;
 	__syncthreads();
 	#pragma unroll 1
 	for (u32 it = 0; it < 2; ++it) fwd_big_T4<false>(A, sm, warp + 8 * it, c0, wl);
 	__syncthreads();
+	const BoundaryPow bpf = boundary_pow(A.t, colscale, 256, false);
 	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.fwd_dst, warp + 8 * it, c0, wl);
+	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.fwd_dst, warp + 8 * it, c0, wl, bpf);
 }
 
 // forward strided pass from a register in global memory
@@ -408,8 +459,9 @@ __global__ void __launch_bounds__(STR_THREADS, 2) k_fwd_fast_T4(const __grid_con
 	#pragma unroll 1
 	for (u32 it = 0; it < 2; ++it) fwd_big_T4<true>(A, sm, warp + 8 * it, c0, wl);
 	__syncthreads();
+	const BoundaryPow bpf = boundary_pow(A.t, (u64)(c0 + (wl & 3)) * A.escale, 256, false);
 	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.dst, warp + 8 * it, c0, wl);
+	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.dst, warp + 8 * it, c0, wl, bpf);
 }
 
 }} // namespace marin::fast
