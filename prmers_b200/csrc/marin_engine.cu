@@ -209,8 +209,8 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
 		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
 		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
-		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
+		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
+		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
 		use_fast = getenv("MARIN_B200_NO_FAST") == nullptr;
 	}
@@ -351,8 +351,8 @@ struct CudaBackend
 		use();
 		if (use_fast && A.with_carry && A.ticket && fast_str_shape(A) && grid == A.tiles)
 		{
-			if (A.fwd_dst) launch_windowed(fast::k_inv_fast_T4<true>, A, grid, fast::STR_THREADS, fast::SC<4>::SMEM);
-			else launch_windowed(fast::k_inv_fast_T4<false>, A, grid, fast::STR_THREADS, fast::SC<4>::SMEM);
+			if (A.fwd_dst) launch_windowed(fast::k_inv_fast_T4<true>, A, grid, fast::STR_THREADS, fast::INV_SMEM_T4);
+			else launch_windowed(fast::k_inv_fast_T4<false>, A, grid, fast::STR_THREADS, fast::INV_SMEM_T4);
 			post(); return;
 		}
 		launch_windowed(k_strided<true>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post();

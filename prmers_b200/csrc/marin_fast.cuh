@@ -219,9 +219,11 @@ __device__ __forceinline__ u64 wait_slot_fast(const StridedArgs &A, size_t idx)
 }
 
 // streaming loads: data read exactly once per launch (tile input, weight streams) must not evict the twiddle tables
-// from L1 -- ld.global.cs allocates evict-first
-__device__ __forceinline__ pair_t ld_stream(const pair_t *p) { return __ldcs(reinterpret_cast<const ulonglong2 *>(p)); }
-__device__ __forceinline__ u64 ld_stream(const u64 *p) { return __ldcs(p); }
+// from L1 (no allocation there) (no allocation there)
+__device__ __forceinline__ pair_t ld_stream(const pair_t *p)
+{ pair_t r; asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p)); return r; }
+__device__ __forceinline__ u64 ld_stream(const u64 *p)
+{ u64 r; asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p)); return r; }
 
 // Boundary twiddles of a pair butterfly: rows base + q have frequency indices K0 + q Kstep, so the four factors are
 // f0 g^q with f0 = w_m^(+-K0 colscale) (one product of two table entries) and g = w_m^(+-Kstep colscale), a per-thread
@@ -237,51 +239,6 @@ __device__ __forceinline__ BoundaryPow boundary_pow(const Tables &t, u64 colscal
 }
 
 // ---- the small stages of one block of 16 T rows (warp-local), T = 4: radix 16 with s = 4, then radix 4 on whole pairs
-
-// inverse direction: global -> radix-4 (boundary twiddle first) -> shared -> radix-16 (s = 4); v = the eight pairs of
-// this thread's two pair butterflies, loaded by the caller well ahead of time
-__device__ __forceinline__ void inv_small_T4(const StridedArgs &A, pair_t *sm, u32 Bk, u32 c0, u32 wl, const pair_t (&v)[2][4], const BoundaryPow &bp)
-{
-	const Tables &t = A.t;
-	const u32 c = wl & 3;
-	const u64 colscale = (u64)(c0 + c) * A.escale;
-	#pragma unroll
-	for (u32 i = 0; i < 2; ++i)
-	{
-		const u32 base = 64 * Bk + 4 * ((wl + 32 * i) >> 2);
-		const u64 f0 = boundary_tw(t, (u64)A.rowK[base] * colscale, true);
-		const u64 f1 = gl::mul(f0, bp.g1), f2 = gl::mul(f0, bp.g2), f3 = gl::mul(f0, bp.g3);
-		u64 ax[4], ay[4];
-		ax[0] = gl::mul(v[i][0].x, f0); ay[0] = gl::mul(v[i][0].y, f0);
-		ax[1] = gl::mul(v[i][1].x, f1); ay[1] = gl::mul(v[i][1].y, f1);
-		ax[2] = gl::mul(v[i][2].x, f2); ay[2] = gl::mul(v[i][2].y, f2);
-		ax[3] = gl::mul(v[i][3].x, f3); ay[3] = gl::mul(v[i][3].y, f3);
-		dft4<true>(ax[0], ax[1], ax[2], ax[3]); dft4<true>(ay[0], ay[1], ay[2], ay[3]);
-		#pragma unroll
-		for (u32 q = 0; q < 4; ++q) { pair_t o; o.x = ax[q]; o.y = ay[q]; sm[tile_pair(base + q, c)] = o; }
-	}
-	__syncwarp();
-	{
-		const u32 lane = wl & 1, cc = (wl >> 1) & 3, j = wl >> 3;
-		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * cc + lane;
-		u64 a[16];
-		ld16_sw<4 * PITCH_W>(a, p);
-		tw16<4>(a, A.twi + A.st[1].toff + j);
-		dft16<true>(a);
-		st16_nat<4 * PITCH_W>(p, a);
-	}
-}
-__device__ __forceinline__ void inv_small_load_T4(const StridedArgs &A, u32 Bk, u32 c0, u32 wl, pair_t (&v)[2][4])
-{
-	const size_t gcol = (size_t)c0 + (wl & 3);
-	#pragma unroll
-	for (u32 i = 0; i < 2; ++i)
-	{
-		const u32 base = 64 * Bk + 4 * ((wl + 32 * i) >> 2);
-		#pragma unroll
-		for (u32 q = 0; q < 4; ++q) v[i][q] = ld_stream(A.src + gcol + (size_t)(base + q) * A.stride);
-	}
-}
 
 // forward direction: shared -> radix-16 (s = 4) -> shared -> radix-4 on pairs, boundary twiddle -> global
 __device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, pair_t *gdst, u32 Bk, u32 c0, u32 wl, const BoundaryPow &bp)
@@ -338,43 +295,6 @@ template <bool FROMG> __device__ __forceinline__ void fwd_big_T4(const StridedAr
 	st16_sw<64 * PITCH_W>(p, a);
 }
 
-// inverse big stage + unweight (x 1/(w m)), then, for the 64 rows this warp has just completed, carry and publish:
-// one thread per row.  The 16 unweighting factors (a stream from HBM) are requested before the butterfly starts.
-__device__ __forceinline__ void inv_big_carry_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl)
-{
-	const Tables &t = A.t;
-	constexpr u32 R = 1024;
-	{
-		const u32 lane = wl & 1, c = (wl >> 1) & 3, j = 4 * G + (wl >> 3);
-		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)j * PITCH_W + 2 * c + lane;
-		const u64 *wp = t.winvs_tile + 2 * (((size_t)g * R + j) * TILE_C + c) + lane;
-		u64 wv[16];
-		#pragma unroll
-		for (int q = 0; q < 16; ++q) wv[q] = ld_stream(wp + (size_t)q * (64 * TILE_C * 2));
-		u64 a[16];
-		ld16_sw<64 * PITCH_W>(a, p);
-		tw16<64>(a, A.twi + A.st[0].toff + j);
-		dft16<true>(a);
-		#pragma unroll
-		for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], wv[q]);
-		st16_nat<64 * PITCH_W>(p, a);
-	}
-	__syncwarp();
-	#pragma unroll 1
-	for (u32 u = 0; u < 2; ++u)
-	{
-		const u32 rr = wl + 32 * u, row = 4 * G + (rr & 3) + 64 * (rr >> 2);
-		u64 v[RUN];
-		#pragma unroll
-		for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
-		const u32 j0 = 2 * (row * A.stride + c0);
-		const u64 cout = carry_run(v, RUN, t.wbase, run_bits(t, j0, RUN), A.a, 0);
-		marin_st_slot(&A.slots[(size_t)g * R + row], cout, A.epoch);
-		#pragma unroll
-		for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
-	}
-}
-
 // second half, after EVERY run of the tile's warp has been published (a tile never holds back a carry its successor
 // needs while it waits for its own predecessor; tile 0 waits for the last tile: end-around): wait for the run before
 // each row in the previous tile, absorb, re-weight (coalesced; to the register unless the chain keeps the parked
@@ -415,39 +335,212 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(c
 	}
 }
 
-// inverse strided pass with carry (level 0), optionally followed by the forward strided pass of the next squaring
+// ---- radix-16 stages with run-time strides: ONE copy of the inverse and ONE of the forward butterfly code serves both
+// stages of a pass.  Warps run different phases at the same time here (that is the point of the warp-local phases), so
+// the code they cover together must fit the instruction cache: with every stage unrolled separately the kernel was
+// 170 KB and 21 % of its stall samples were "no instruction"; 15 address adds per butterfly are the cheaper price.
+__device__ __forceinline__ void ld16_sw_rt(u64 *a, const u64 *p, u32 stw)
+{
+	#pragma unroll
+	for (int q = 0; q < 16; ++q) a[sw16(q)] = p[q * stw];
+}
+__device__ __forceinline__ void ld16_nat_rt(u64 *a, const u64 *p, u32 stw)
+{
+	#pragma unroll
+	for (int q = 0; q < 16; ++q) a[q] = p[q * stw];
+}
+__device__ __forceinline__ void st16_nat_rt(u64 *p, const u64 *a, u32 stw)
+{
+	#pragma unroll
+	for (int k = 0; k < 16; ++k) p[k * stw] = a[k];
+}
+__device__ __forceinline__ void st16_sw_rt(u64 *p, const u64 *a, u32 stw)
+{
+	#pragma unroll
+	for (int k = 0; k < 16; ++k) p[k * stw] = a[sw16(k)];
+}
+__device__ __forceinline__ void tw16_rt(u64 *a, const u64 *tw, u32 tws)
+{
+	#pragma unroll
+	for (int k = 1; k < 16; ++k) a[sw16(k)] = gl::mul(a[sw16(k)], tw[(k - 1) * tws]);
+}
+
+// carry and publish the 64 rows of group G (one thread per row, two rows per thread)
+__device__ __forceinline__ void carry_publish_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl, u32 bits0, u32 bits1)
+{
+	const Tables &t = A.t;
+	#pragma unroll 1
+	for (u32 u = 0; u < 2; ++u)
+	{
+		const u32 bits = u ? bits1 : bits0;
+		const u32 rr = wl + 32 * u, row = 4 * G + (rr & 3) + 64 * (rr >> 2);
+		u64 v[RUN];
+		#pragma unroll
+		for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
+		const u64 cout = carry_run(v, RUN, t.wbase, bits, A.a, 0);
+		marin_st_slot(&A.slots[(size_t)g * 1024 + row], cout, A.epoch);
+		#pragma unroll
+		for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
+	}
+}
+
+// inverse strided pass with carry (level 0), optionally followed by the forward strided pass of the next squaring.
+// Shared memory: the tile, then the stage twiddles of the pass (inverse, forward: 2 x 1020 words) -- L1 is a stream of
+// tile inputs and weights here and a twiddle that misses costs an L2 round trip in the middle of a butterfly.
+static constexpr u32 STR_TW = 15 * 64 + 15 * 4;               // stage twiddles of one direction, R = 1024
+static constexpr u32 INV_SMEM_T4 = SC<4>::SMEM + 2 * STR_TW * 8;
+
 template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_inv_fast_T4(const __grid_constant__ StridedArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	u64 *twsm = reinterpret_cast<u64 *>(smraw + SC<4>::SMEM);
 	__shared__ u32 s_tile;
 	// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket
 	if (threadIdx.x == 0) s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
+	for (u32 i = threadIdx.x; i < STR_TW; i += STR_THREADS) { twsm[i] = A.twi[i]; if (FWD_FOLLOWS) twsm[STR_TW + i] = A.tw[i]; }
 	__syncthreads();
+	const Tables &t = A.t;
 	const u32 g = s_tile, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const u64 colscale = (u64)(c0 + (wl & 3)) * A.escale;
+	const u32 c = wl & 3;                                      // column of this thread in the pair-wise radix-4 stages
+	const u64 colscale = (u64)(c0 + c) * A.escale;
+	const u32 lane = wl & 1, cc = (wl >> 1) & 3, jq = wl >> 3; // radix-16 stages: lane of the pair, column, butterfly of four
+	u64 *smw = reinterpret_cast<u64 *>(sm) + 2 * cc + lane;
+	const size_t gcol = (size_t)c0 + c;
 	{
-		// all sixteen pairs of this thread's four boundary butterflies are requested at once
-		pair_t v0[2][4], v1[2][4];
-		inv_small_load_T4(A, warp, c0, wl, v0);
-		inv_small_load_T4(A, warp + 8, c0, wl, v1);
-		const BoundaryPow bpi = boundary_pow(A.t, colscale, 256, true);
-		inv_small_T4(A, sm, warp, c0, wl, v0, bpi);
-		inv_small_T4(A, sm, warp + 8, c0, wl, v1, bpi);
+		// ---- inverse: [radix 4 on pairs from global, radix 16 (s = 4)] per block of 64 rows, block barrier,
+		//      [radix 16 (s = 64) + unweight, carry, publish] per group of 4 columns.
+		// ONE register array serves as the queue of prefetched boundary inputs (two butterflies = 8 pairs, requested two
+		// butterflies ahead of their use) in the first two phases and as the 16 unweighting factors in the last two.
+		u64 pf[16];
+		#pragma unroll
+		for (u32 i = 0; i < 2; ++i)
+			#pragma unroll
+			for (u32 q = 0; q < 4; ++q)
+			{
+				const pair_t x = ld_stream(A.src + gcol + (size_t)(64 * warp + 4 * ((wl + 32 * i) >> 2) + q) * A.stride);
+				pf[8 * i + 2 * q] = x.x; pf[8 * i + 2 * q + 1] = x.y;
+			}
+		// boundary twiddles: f0 of the four butterflies (two random table reads each) formed up front, in use order
+		u64 fq[4];
+		#pragma unroll
+		for (u32 b = 0; b < 4; ++b)
+			fq[b] = boundary_tw(t, (u64)A.rowK[64 * (warp + 8 * (b >> 1)) + 4 * ((wl + 32 * (b & 1)) >> 2)] * colscale, true);
+		const BoundaryPow bp = boundary_pow(t, colscale, 256, true);
+		#pragma unroll 1
+		for (u32 ph = 0; ph < 4; ++ph)
+		{
+			const u32 blk = warp + 8 * (ph & 1);
+			const bool big = ph >= 2;
+			if (ph == 2) __syncthreads();
+			u32 bits0 = 0, bits1 = 0;
+			if (!big)
+			{
+				#pragma unroll 1
+				for (u32 i = 0; i < 2; ++i)
+				{
+					const u32 base = 64 * blk + 4 * ((wl + 32 * i) >> 2);
+					const u64 f0 = fq[0];
+					const u64 f1 = gl::mul(f0, bp.g1), f2 = gl::mul(f0, bp.g2), f3 = gl::mul(f0, bp.g3);
+					u64 ax[4], ay[4];
+					ax[0] = gl::mul(pf[0], f0); ay[0] = gl::mul(pf[1], f0);
+					ax[1] = gl::mul(pf[2], f1); ay[1] = gl::mul(pf[3], f1);
+					ax[2] = gl::mul(pf[4], f2); ay[2] = gl::mul(pf[5], f2);
+					ax[3] = gl::mul(pf[6], f3); ay[3] = gl::mul(pf[7], f3);
+					dft4<true>(ax[0], ax[1], ax[2], ax[3]); dft4<true>(ay[0], ay[1], ay[2], ay[3]);
+					#pragma unroll
+					for (u32 q = 0; q < 4; ++q) { pair_t o; o.x = ax[q]; o.y = ay[q]; sm[tile_pair(base + q, c)] = o; }
+					fq[0] = fq[1]; fq[1] = fq[2]; fq[2] = fq[3];
+					#pragma unroll
+					for (u32 q = 0; q < 8; ++q) pf[q] = pf[8 + q];
+					if (ph == 0)
+					{
+						const u32 nbase = 64 * (warp + 8) + 4 * ((wl + 32 * i) >> 2);
+						#pragma unroll
+						for (u32 q = 0; q < 4; ++q)
+						{
+							const pair_t x = ld_stream(A.src + gcol + (size_t)(nbase + q) * A.stride);
+							pf[8 + 2 * q] = x.x; pf[8 + 2 * q + 1] = x.y;
+						}
+					}
+				}
+				__syncwarp();
+			}
+			else
+			{
+				// the 16 unweighting factors (a stream from HBM) and the width bits of this thread's two carry rows are
+				// requested before the butterfly starts
+				const u64 *wp = t.winvs_tile + 2 * (((size_t)g * 1024 + 4 * blk + jq) * TILE_C + cc) + lane;
+				#pragma unroll
+				for (int q = 0; q < 16; ++q) pf[q] = ld_stream(wp + (size_t)q * (64 * TILE_C * 2));
+				bits0 = run_bits(t, 2 * ((4 * blk + (wl & 3) + 64 * (wl >> 2)) * A.stride + c0), RUN);
+				bits1 = run_bits(t, 2 * ((4 * blk + (wl & 3) + 64 * ((wl + 32) >> 2)) * A.stride + c0), RUN);
+			}
+			const u32 row0 = big ? 4 * blk + jq : 64 * blk + jq;
+			const u32 stw = (big ? 64u : 4u) * PITCH_W, tws = big ? 64u : 4u;
+			const u64 *tw = twsm + (big ? 4 * blk : 960u) + jq;
+			u64 *p = smw + (size_t)row0 * PITCH_W;
+			u64 a[16];
+			ld16_sw_rt(a, p, stw);
+			tw16_rt(a, tw, tws);
+			dft16<true>(a);
+			if (big)
+			{
+				#pragma unroll
+				for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], pf[q]);
+			}
+			st16_nat_rt(p, a, stw);
+			if (big) { __syncwarp(); carry_publish_T4(A, sm, blk, g, c0, wl, bits0, bits1); }
+		}
 	}
-	__syncthreads();
-	inv_big_carry_T4(A, sm, warp, g, c0, wl);
-	inv_big_carry_T4(A, sm, warp + 8, g, c0, wl);
-	absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp, g, c0, wl);
-	absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp + 8, g, c0, wl);
+	#pragma unroll 1
+	for (u32 it = 0; it < 2; ++it) absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp + 8 * it, g, c0, wl);
 	if (!FWD_FOLLOWS) return;
 	__syncthreads();
+	// ---- forward pass of the next squaring: radix 16 (s = 64) per group, block barrier, [radix 16 (s = 4), radix 4 on
+	//      pairs + boundary twiddle -> global] per block
+	u64 fq[4];
+	#pragma unroll
+	for (u32 b = 0; b < 4; ++b)
+		fq[b] = boundary_tw(t, (u64)A.rowK[64 * (warp + 8 * (b >> 1)) + 4 * ((wl + 32 * (b & 1)) >> 2)] * colscale, false);
+	const BoundaryPow bpf = boundary_pow(t, colscale, 256, false);
 	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) fwd_big_T4<false>(A, sm, warp + 8 * it, c0, wl);
-	__syncthreads();
-	const BoundaryPow bpf = boundary_pow(A.t, colscale, 256, false);
-	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.fwd_dst, warp + 8 * it, c0, wl, bpf);
+	for (u32 ph = 0; ph < 4; ++ph)
+	{
+		const u32 blk = warp + 8 * (ph & 1);
+		const bool big = ph < 2;
+		if (ph == 2) __syncthreads();
+		const u32 row0 = big ? 4 * blk + jq : 64 * blk + jq;
+		const u32 stw = (big ? 64u : 4u) * PITCH_W, tws = big ? 64u : 4u;
+		const u64 *tw = twsm + STR_TW + (big ? 4 * blk : 960u) + jq;
+		u64 *p = smw + (size_t)row0 * PITCH_W;
+		u64 a[16];
+		ld16_nat_rt(a, p, stw);
+		dft16<false>(a);
+		tw16_rt(a, tw, tws);
+		st16_sw_rt(p, a, stw);
+		if (!big)
+		{
+			__syncwarp();
+			#pragma unroll 1
+			for (u32 i = 0; i < 2; ++i)
+			{
+				const u32 base = 64 * blk + 4 * ((wl + 32 * i) >> 2);
+				const u64 f0 = fq[0];
+				fq[0] = fq[1]; fq[1] = fq[2]; fq[2] = fq[3];
+				u64 ax[4], ay[4];
+				#pragma unroll
+				for (u32 q = 0; q < 4; ++q) { const pair_t pv = sm[tile_pair(base + q, c)]; ax[q] = pv.x; ay[q] = pv.y; }
+				dft4<false>(ax[0], ax[1], ax[2], ax[3]); dft4<false>(ay[0], ay[1], ay[2], ay[3]);
+				const u64 f1 = gl::mul(f0, bpf.g1), f2 = gl::mul(f0, bpf.g2), f3 = gl::mul(f0, bpf.g3);
+				pair_t o;
+				o.x = gl::mul(ax[0], f0); o.y = gl::mul(ay[0], f0); A.fwd_dst[gcol + (size_t)(base + 0) * A.stride] = o;
+				o.x = gl::mul(ax[1], f1); o.y = gl::mul(ay[1], f1); A.fwd_dst[gcol + (size_t)(base + 1) * A.stride] = o;
+				o.x = gl::mul(ax[2], f2); o.y = gl::mul(ay[2], f2); A.fwd_dst[gcol + (size_t)(base + 2) * A.stride] = o;
+				o.x = gl::mul(ax[3], f3); o.y = gl::mul(ay[3], f3); A.fwd_dst[gcol + (size_t)(base + 3) * A.stride] = o;
+			}
+		}
+	}
 }
 
 // forward strided pass from a register in global memory
