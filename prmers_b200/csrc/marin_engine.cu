@@ -98,6 +98,51 @@ __global__ void __launch_bounds__(LIN_BLOCK) k_lin_pairs(const __grid_constant__
 	if (i < npairs) lin_pair_finish(A, i, u0, u1, w0, w1, threadIdx.x ? cs[threadIdx.x - 1] : ((gridDim.x == 1) ? cs[npairs - 1] : A.carry[blockIdx.x]));
 }
 
+// S = A + B and D = A - B (+ copies) in one pass over the registers (marin.cl:1891-2154)
+__global__ void k_addsub_boundary(const __grid_constant__ LinArgs A, u32 nblocks)
+{
+	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nblocks) return;
+	const u32 npairs = A.t.n / 2;
+	const u32 first = b * LIN_BLOCK;
+	addsub_pair_carry(A, (first == 0) ? npairs - 1 : first - 1, A.carry[b], A.carry2[b]);
+}
+__global__ void __launch_bounds__(LIN_BLOCK) k_addsub_pairs(const __grid_constant__ LinArgs A)
+{
+	__shared__ u64 cs[LIN_BLOCK], cd[LIN_BLOCK];
+	const u32 npairs = A.t.n / 2;
+	const u32 i = blockIdx.x * LIN_BLOCK + threadIdx.x;
+	u64 us[2] = {0, 0}, ud[2] = {0, 0}; u32 w0 = 1, w1 = 1;
+	if (i < npairs) { addsub_pair_compute(A, i, us, ud, w0, w1); cs[threadIdx.x] = us[1] >> w1; cd[threadIdx.x] = ud[1] >> w1; }
+	__syncthreads();
+	if (i < npairs)
+	{
+		const bool wrap = (gridDim.x == 1);
+		const u64 c_s = threadIdx.x ? cs[threadIdx.x - 1] : (wrap ? cs[npairs - 1] : A.carry[blockIdx.x]);
+		const u64 c_d = threadIdx.x ? cd[threadIdx.x - 1] : (wrap ? cd[npairs - 1] : A.carry2[blockIdx.x]);
+		addsub_pair_finish(A, i, us, ud, w0, w1, c_s, c_d);
+	}
+}
+
+// canonical digits and comparison on the device (see canon_p1_thread / canon_p2_thread)
+__global__ void k_canon_p1(const __grid_constant__ CanonArgs A, u32 count)
+{
+	const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < count) canon_p1_thread(A, r);
+}
+__global__ void k_canon_p2(const __grid_constant__ CanonArgs A, u32 count)
+{
+	const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < count) canon_p2_thread(A, r);
+}
+__global__ void k_canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags)
+{
+	u32 f = 0;
+	for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) f |= canon_cmp_digit(l[j], r[j]);
+	f = __reduce_or_sync(0xffffffffu, f);
+	if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
 // A recorded sequence of engine ops on a single-CTA engine, run by ONE launch: the CTA walks the list, every op is the
 // same phase functions the stand-alone kernels run, separated by block barriers (registers live in global memory; a
 // barrier orders one op's stores before the next op's loads within the CTA).  At these sizes an op is a few
@@ -364,6 +409,18 @@ struct CudaBackend
 		if (nblocks > 1) { k_lin_boundary<<<(nblocks + 127) / 128, 128, 0, st>>>(A, nblocks); post(); }
 		k_lin_pairs<<<nblocks, LIN_BLOCK, 0, st>>>(A); post();
 	}
+	void addsub_pairs(const LinArgs &A)
+	{
+		use();
+		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
+		if (nblocks > 1) { k_addsub_boundary<<<(nblocks + 127) / 128, 128, 0, st>>>(A, nblocks); post(); }
+		k_addsub_pairs<<<nblocks, LIN_BLOCK, 0, st>>>(A); post();
+	}
+	void canon_p1(const CanonArgs &A, u32 count) { use(); k_canon_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
+	void canon_p2(const CanonArgs &A, u32 count) { use(); k_canon_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
+	void canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags) { use(); k_canon_cmp<<<592, 256, 0, st>>>(l, r, n, flags); post(); }
+	// device -> host without waiting (the caller syncs once for several copies)
+	void d2h_async(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); }
 	void lin_p1(const LinArgs &A, u32 count) { use(); k_lin_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void lin_p2(const LinArgs &A, u32 count) { use(); k_lin_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }
@@ -420,14 +477,11 @@ int mb200_sub_u32(void *eng, size_t r, uint32_t a) { GUARD(E(eng)->sub_u32(r, a)
 int mb200_add(void *eng, size_t dst, size_t src) { GUARD(E(eng)->add(dst, src)); }
 int mb200_sub_reg(void *eng, size_t dst, size_t src) { GUARD(E(eng)->sub_reg(dst, src)); }
 
-int mb200_mul_add(void *eng, size_t dst, size_t mul_src, size_t add_src, uint32_t a)
-{ GUARD(E(eng)->mul(dst, mul_src, a); E(eng)->add(dst, add_src)); }
-int mb200_addsub(void *eng, size_t s, size_t d, size_t a, size_t b)
-{ GUARD(E(eng)->copy(s, a); E(eng)->copy(d, a); E(eng)->add(s, b); E(eng)->sub_reg(d, b)); }
-int mb200_addsub_copy(void *eng, size_t s, size_t d, size_t sc, size_t dc, size_t a, size_t b)
-{ GUARD(E(eng)->copy(s, a); E(eng)->copy(d, a); E(eng)->add(s, b); E(eng)->sub_reg(d, b); E(eng)->copy(sc, s); E(eng)->copy(dc, d)); }
-int mb200_square_mul_copy(void *eng, size_t r, size_t c, uint32_t a) { GUARD(E(eng)->square_mul(r, a); E(eng)->copy(c, r)); }
-int mb200_mul_copy(void *eng, size_t dst, size_t src, size_t c, uint32_t a) { GUARD(E(eng)->mul(dst, src, a); E(eng)->copy(c, dst)); }
+int mb200_mul_add(void *eng, size_t dst, size_t mul_src, size_t add_src, uint32_t a) { GUARD(E(eng)->mul_add(dst, mul_src, add_src, a)); }
+int mb200_addsub(void *eng, size_t s, size_t d, size_t a, size_t b) { GUARD(E(eng)->addsub(s, d, a, b)); }
+int mb200_addsub_copy(void *eng, size_t s, size_t d, size_t sc, size_t dc, size_t a, size_t b) { GUARD(E(eng)->addsub(s, d, a, b, sc, dc)); }
+int mb200_square_mul_copy(void *eng, size_t r, size_t c, uint32_t a) { GUARD(E(eng)->square_mul_copy(r, c, a)); }
+int mb200_mul_copy(void *eng, size_t dst, size_t src, size_t c, uint32_t a) { GUARD(E(eng)->mul_copy(dst, src, c, a)); }
 
 int mb200_equal(void *eng, size_t l, size_t r, int *out) { GUARD(*out = E(eng)->equal(l, r) ? 1 : 0); }
 

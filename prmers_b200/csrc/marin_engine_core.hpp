@@ -31,7 +31,11 @@ public:
 		be.memset0(_reg, regs * n * 8);
 		const size_t ncarry = std::max<size_t>(std::max<size_t>(n / pl.D, n / RUN + 1), pl.small ? n / 2 : 0); // recorded linear ops keep one word per pair
 		_carry = (u64 *)be.alloc(ncarry * 8);
+		_carry2 = (u64 *)be.alloc(ncarry * 8);
 		_scratch = (u64 *)be.alloc(n * 8);
+		_canon_D = (n % 16 == 0) ? 16 : ((n % 8 == 0) ? 8 : 4);
+		_cc[0] = (u64 *)be.alloc((n / _canon_D) * 8); _cc[1] = (u64 *)be.alloc((n / _canon_D) * 8);
+		_words = (u32 *)be.alloc(16); be.memset0(_words, 16);   // [0], [1] carries still pending after a canon round, [2] comparison flags
 		_nslots = n / RUN + 1;
 		_slots = (pair_t *)be.alloc(_nslots * 16);   // {carry, epoch} hand-off slots of the inverse strided pass
 		be.memset0(_slots, _nslots * 16);
@@ -75,7 +79,8 @@ public:
 	{
 		be.sync();
 		for (void *p : _owned) be.free(p);
-		be.free(_reg); be.free(_carry); be.free(_scratch); be.free(_slots); be.free(_flags); if (_fwd) be.free(_fwd);
+		be.free(_reg); be.free(_carry); be.free(_carry2); be.free(_scratch); if (_scratch2) { be.free(_scratch2); be.free(_cc2[0]); be.free(_cc2[1]); } be.free(_cc[0]); be.free(_cc[1]); be.free(_words);
+		be.free(_slots); be.free(_flags); if (_fwd) be.free(_fwd);
 	}
 
 	size_t size() const { return pl.n; }
@@ -83,13 +88,17 @@ public:
 	void sync()
 	{
 		blocking("sync");
-		be.sync();
-		if (_flags)
-		{
-			u32 err = 0;
-			be.d2h(&err, _flags + (size_t)(pl.R2 * pl.S / TILE_C), 4);
-			if (err) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
-		}
+		check_device_error();
+	}
+
+	// The error word of the inverse pass (a carry hand-off that timed out poisons the carry it returns and raises this
+	// word): read, after a stream sync, by EVERY call that hands register contents or a comparison to the host, so a
+	// wrong residue cannot leave the engine silently.  Sticky: once set the engine refuses to export anything.
+	void check_device_error()
+	{
+		u32 err = 0;
+		be.d2h(&err, _flags + (size_t)(pl.R2 * pl.S / TILE_C), 4); // synchronises the stream
+		if (err) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
 	}
 
 	// Record the engine calls that follow instead of running them (graph_end returns the id of the recorded sequence,
@@ -193,6 +202,81 @@ public:
 		strided(true, 0, _fwd, R(dst), a, nullptr);
 	}
 
+	// r = r^2 * a (or dst = dst * src * a) and a second copy of the result, stored by the same carry pass
+	// (carry_weight_mul_p1_copy / p2_copy, marin.cl:1731-1769,1824-1851; engine_gpu.h:1131)
+	void square_mul_copy(size_t r, size_t c, u32 a)
+	{
+		check_range(r); check_range(c); check_a(a);
+		if (_recording || c == r) { square_mul(r, a); copy(c, r); return; }
+		check(r); check(c);
+		touch(c); touch(r);
+		if (pl.small) { MidArgs M = mid_args(R(r), nullptr, R(r), MODE_SQR, a); M.dst2 = (pair_t *)R(c); launch_mid(M); return; }
+		materialize();
+		_fwd_reg = (size_t)-1;
+		strided(false, 0, R(r), _fwd, 1, nullptr);
+		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
+		MidArgs M = mid_args(_fwd, nullptr, _fwd, MODE_SQR, a); launch_mid(M);
+		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
+		strided(true, 0, _fwd, R(r), a, nullptr, false, false, R(c));
+	}
+	void mul_copy(size_t dst, size_t src, size_t c, u32 a)
+	{
+		check_range(dst); check_range(src); check_range(c); check_a(a);
+		if (_recording || c == dst || c == src) { mul(dst, src, a); copy(c, dst); return; }
+		check(dst); check(src); check(c);
+		if (dst == src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
+		touch(c);
+		if (pl.small) { MidArgs M = mid_args(R(dst), R(src), R(dst), MODE_MUL, a); M.dst2 = (pair_t *)R(c); launch_mid(M); return; }
+		materialize();
+		if (_fwd_reg != dst) strided(false, 0, R(dst), _fwd, 1, nullptr);
+		touch(dst);
+		_fwd_reg = (size_t)-1;
+		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
+		MidArgs M = mid_args(_fwd, R(src), _fwd, MODE_MUL, a); launch_mid(M);
+		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
+		strided(true, 0, _fwd, R(dst), a, nullptr, false, false, R(c));
+	}
+
+	// dst = dst * mul_src + add_src with the addition inside the carry pass (carry_weight_muladd_p1/p2,
+	// marin.cl:2298-2365); a != 1 multiplies the whole sum in the carry chain, so that case keeps the composition
+	void mul_add(size_t dst, size_t mul_src, size_t add_src, u32 a)
+	{
+		check_range(dst); check_range(mul_src); check_range(add_src); check_a(a);
+		if (_recording || a != 1 || add_src == dst) { mul(dst, mul_src, a); add(dst, add_src); return; }
+		check(dst); check(mul_src); check(add_src);
+		if (dst == mul_src) throw std::runtime_error("marin_b200: mul(dst, src) needs src != dst (src is a multiplicand)");
+		if (pl.small) { MidArgs M = mid_args(R(dst), R(mul_src), R(dst), MODE_MUL, 1); M.add_src = (const pair_t *)R(add_src); launch_mid(M); return; }
+		materialize();
+		if (_fwd_reg != dst) strided(false, 0, R(dst), _fwd, 1, nullptr);
+		touch(dst);
+		_fwd_reg = (size_t)-1;
+		if (pl.R2 > 1) strided(false, 1, _fwd, _fwd, 1, nullptr);
+		MidArgs M = mid_args(_fwd, R(mul_src), _fwd, MODE_MUL, 1); launch_mid(M);
+		if (pl.R2 > 1) strided(true, 1, _fwd, _fwd, 1, nullptr);
+		strided(true, 0, _fwd, R(dst), 1, nullptr, false, false, nullptr, R(add_src));
+	}
+
+	// S = A + B and D = A - B in one pass over the registers, optionally with a second copy of each
+	// (carry_weight_addsub_p1/p2 and their _copy forms, marin.cl:1891-2154; engine_gpu.h:1064-1072).  Outputs may alias
+	// inputs (the Edwards schedules call it in place); S and D must differ.
+	void addsub(size_t s, size_t d, size_t a, size_t b, size_t sc = (size_t)-1, size_t dc = (size_t)-1)
+	{
+		const bool copies = sc != (size_t)-1;
+		check(s); check(d); check(a); check(b);
+		if (copies) { check(sc); check(dc); }
+		if (_recording || s == d || (copies && (sc == dc || sc == d || dc == s || sc == a || sc == b || dc == a || dc == b)))
+		{
+			// the reference's default composition (engine.h:72-79,125-131), also what a recording captures
+			copy(s, a); copy(d, a); add(s, b); sub_reg(d, b);
+			if (copies) { copy(sc, s); copy(dc, d); }
+			return;
+		}
+		touch(s); touch(d);
+		if (copies) { touch(sc); touch(dc); }
+		LinArgs L{_t, R(s), R(b), nullptr, _carry, LIN_ADDSUB, 0, pl.D, R(a), R(d), copies ? R(sc) : nullptr, copies ? R(dc) : nullptr, _carry2};
+		be.addsub_pairs(L);
+	}
+
 	void sub_u32(size_t r, u32 a)
 	{
 		check(r);
@@ -203,20 +287,75 @@ public:
 	void add(size_t dst, size_t src) { check(dst); check(src); if (!rec(PO_ADD, dst, src, 0)) lin(LIN_ADD, dst, src, 0, nullptr); }
 	void sub_reg(size_t dst, size_t src) { check(dst); check(src); if (!rec(PO_SUBREG, dst, src, 0)) lin(LIN_SUBREG, dst, src, 0, nullptr); }
 
-	// canonical digits, value | width << 32: unweight on the device, strong carry on the host exactly as
-	// engine_gpu_flat::get does (engine_gpu.h:1534-1561)
+	// Canonical digits, value | width << 32 (engine_gpu.h:1534-1561 carries serially on the host: 8.4 M digits, ~10 ms).
+	// Here: unweight + strong carry per run of 16 digits, then one round in which every run takes in the carry of the
+	// run before it (end-around); a carry that crosses a whole run (all ones) needs another round, which the host sees
+	// in a 4-byte counter.  After CANON_ROUNDS rounds (a pathological all-ones residue plus a stray unit) the rest is
+	// finished on the host exactly as the reference does.
+	static constexpr u32 CANON_ROUNDS = 8;
+	// first round only, nothing read back: the caller looks at word `slot` of _words later (several of these can be in
+	// flight before one 4-byte read) and calls canon_finish if carries are still pending
+	void canon_start(size_t src, u64 *enc_dev, u64 *cc0, u64 *cc1, u32 slot)
+	{
+		const u32 runs = pl.n / _canon_D;
+		CanonArgs C{_t, R(src), enc_dev, cc0, cc0, _words + slot, _canon_D};
+		be.canon_p1(C, runs);
+		C.cin = cc0; C.cout = cc1;
+		be.canon_p2(C, runs);
+	}
+	// carries cc1[r] (leaving run r) are still pending: more rounds, then the host
+	void canon_finish(u64 *enc_dev, u64 *cc0, u64 *cc1, u32 slot)
+	{
+		const u32 runs = pl.n / _canon_D;
+		CanonArgs C{_t, nullptr, enc_dev, cc0, cc0, _words + slot, _canon_D};
+		u64 *cc[2] = {cc1, cc0};
+		u32 cur = 0;
+		for (u32 round = 1; round < CANON_ROUNDS; ++round)
+		{
+			be.memset0(_words + slot, 4);
+			C.cin = cc[cur]; C.cout = cc[cur ^ 1];
+			be.canon_p2(C, runs);
+			cur ^= 1;
+			u32 pending = 0;
+			be.d2h(&pending, _words + slot, 4);
+			if (pending == 0) return;
+		}
+		std::vector<u64> enc(pl.n), cv(runs);
+		be.d2h(enc.data(), enc_dev, (size_t)pl.n * 8);
+		be.d2h(cv.data(), cc[cur], (size_t)runs * 8);
+		bool any = true;
+		while (any)
+		{
+			any = false;
+			for (u32 r = 0; r < runs; ++r)
+			{
+				u64 c = cv[(r == 0) ? runs - 1 : r - 1];
+				if (c == 0) continue;
+				cv[(r == 0) ? runs - 1 : r - 1] = 0;
+				for (u32 k = r * _canon_D; c != 0; k = (k + 1 == pl.n) ? 0 : k + 1) { const u32 w = width(k); enc[k] = (u64)adc((u32)enc[k], w, c) | ((u64)w << 32); }
+				any = true;
+			}
+		}
+		be.h2d(enc_dev, enc.data(), (size_t)pl.n * 8);
+	}
+	// one blocking read of the four status words: [0], [1] pending carries of two canon_start calls, [2] comparison
+	// flags, and the error word of the inverse pass
+	void read_words(u32 *w4)
+	{
+		be.d2h_async(w4, _words, 12);
+		be.d2h(w4 + 3, _flags + (size_t)(pl.R2 * pl.S / TILE_C), 4); // synchronises the stream
+		if (w4[3]) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
+	}
+
 	void get_digits(size_t src, u64 *enc)
 	{
 		check(src); blocking("get");
-		const u32 n = pl.n;
-		be.unweight(_t, R(src), _scratch, n);
-		be.d2h(enc, _scratch, (size_t)n * 8);
-		// one pass carries and encodes (value | width << 32); the end-around carry (2^p = 1) then ripples from digit 0
-		// through digits that are already canonical, for a handful of digits at most
-		u64 c = 0;
-		for (u32 k = 0; k < n; ++k) { const u32 w = width(k); enc[k] = (u64)adc(enc[k], w, c) | ((u64)w << 32); }
-		while (c != 0)
-			for (u32 k = 0; k < n; ++k) { const u32 w = width(k); enc[k] = (u64)adc((u32)enc[k], w, c) | ((u64)w << 32); if (c == 0) break; }
+		be.memset0(_words, 12);
+		canon_start(src, _scratch, _cc[0], _cc[1], 0);
+		u32 w[4];
+		read_words(w);
+		if (w[0]) canon_finish(_scratch, _cc[0], _cc[1], 0);
+		be.d2h(enc, _scratch, (size_t)pl.n * 8);
 	}
 
 	void set_digits(size_t dst, const u64 *enc)
@@ -226,17 +365,39 @@ public:
 		lin(LIN_SETDIGITS, dst, dst, 0, _scratch);
 	}
 
+	// is_equal (engine.h:148-157 converts both registers to GMP integers on the host): canonical digits of both on the
+	// device, one compare-and-reduce kernel, 4 bytes back.  2^p - 1 (all ones) and 0 are the same residue.
 	bool equal(size_t l, size_t r)
 	{
-		std::vector<u64> a(pl.n), b(pl.n);
-		get_digits(l, a.data()); get_digits(r, b.data());
-		normalize_zero(a); normalize_zero(b);
-		return a == b;
+		check(l); check(r); blocking("is_equal");
+		if (!_scratch2)
+		{
+			_scratch2 = (u64 *)be.alloc((size_t)pl.n * 8);
+			_cc2[0] = (u64 *)be.alloc((pl.n / _canon_D) * 8); _cc2[1] = (u64 *)be.alloc((pl.n / _canon_D) * 8);
+		}
+		u32 w[4];
+		be.memset0(_words, 12);
+		canon_start(l, _scratch, _cc[0], _cc[1], 0);
+		canon_start(r, _scratch2, _cc2[0], _cc2[1], 1);
+		be.canon_cmp(_scratch, _scratch2, pl.n, _words + 2);     // speculative: valid when no carry is pending (the usual case)
+		read_words(w);
+		if (w[0] || w[1])
+		{
+			if (w[0]) canon_finish(_scratch, _cc[0], _cc[1], 0);
+			if (w[1]) canon_finish(_scratch2, _cc2[0], _cc2[1], 1);
+			be.memset0(_words, 12);
+			be.canon_cmp(_scratch, _scratch2, pl.n, _words + 2);
+			read_words(w);
+		}
+		const u32 f = w[2];
+		if (!(f & 1u)) return true;
+		const bool l_zero = !(f & 2u) || !(f & 4u), r_zero = !(f & 8u) || !(f & 16u);
+		return l_zero && r_zero;
 	}
 
-	void get_raw(size_t src, void *buf) { check(src); blocking("get_data"); be.d2h(buf, R(src), (size_t)pl.n * 8); }
+	void get_raw(size_t src, void *buf) { check(src); blocking("get_data"); be.d2h(buf, R(src), (size_t)pl.n * 8); check_device_error(); }
 	void set_raw(size_t dst, const void *buf) { check(dst); blocking("set_data"); touch(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
-	void get_all(void *buf) { blocking("get_checkpoint"); materialize(); be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); }
+	void get_all(void *buf) { blocking("get_checkpoint"); calm(); materialize(); be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); check_device_error(); }
 	void set_all(const void *buf) { blocking("set_checkpoint"); _fwd_reg = _last_sq = _lazy = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
 
 	// single passes of square_mul, for per-kernel timing (3-pass engines only): 0 strided forward,
@@ -275,7 +436,8 @@ public:
 
 private:
 	size_t _regs;
-	u64 *_reg = nullptr, *_carry = nullptr, *_scratch = nullptr;
+	u64 *_reg = nullptr, *_carry = nullptr, *_carry2 = nullptr, *_scratch = nullptr, *_scratch2 = nullptr, *_cc[2] = {nullptr, nullptr}, *_cc2[2] = {nullptr, nullptr};
+	u32 *_words = nullptr, _canon_D = 16;
 	pair_t *_slots = nullptr; size_t _nslots = 0;
 	u32 *_flags = nullptr, _epoch = 0;
 	// speculation for squaring chains: _fwd holds the forward strided pass of register _fwd_reg's current value
@@ -324,13 +486,6 @@ private:
 		return (u32)s & ((1u << w) - 1);
 	}
 
-	void normalize_zero(std::vector<u64> &d) const
-	{
-		// 2^p - 1 (all ones) and 0 are the same residue (engine.h:181-196)
-		for (u32 k = 0; k < pl.n; ++k) if ((u32)d[k] != (1u << width(k)) - 1) return;
-		for (u32 k = 0; k < pl.n; ++k) d[k] &= ~(u64)0xffffffffu;
-	}
-
 	MidArgs mid_args(u64 *x, const u64 *y, u64 *dst, int mode, u32 a)
 	{
 		MidArgs M;
@@ -356,7 +511,7 @@ private:
 
 	// level 0 = strided pass over the whole register (the inverse one carries), level 1 = second strided
 	// pass inside each of the R blocks (only for transforms with more rows than one tile can hold)
-	void strided(bool inv, int level, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst, bool skip_dst = false, bool exact_inverse = false)
+	void strided(bool inv, int level, const u64 *src, u64 *dst, u32 a, u64 *fwd_dst, bool skip_dst = false, bool exact_inverse = false, u64 *dst2 = nullptr, const u64 *add_src = nullptr)
 	{
 		StridedArgs A;
 		std::memset(&A, 0, sizeof(A));
@@ -371,6 +526,7 @@ private:
 		if (!inv) { be.strided_fwd(A, grid, thr, smem); return; }
 		if (exact_inverse) { be.strided_inv(A, grid, thr, smem); return; } // plain, unnormalised: the caller scales by 1/R
 		A.skip_dst = skip_dst ? 1u : 0u;
+		A.dst2 = (pair_t *)dst2; A.add_src = (const pair_t *)add_src;
 		if (level == 0) { A.with_carry = 1; A.flags = _flags; A.epoch = next_epoch(); A.fwd_dst = (pair_t *)fwd_dst; set_ticket(A); }
 		be.strided_inv(A, grid, thr, smem);
 	}

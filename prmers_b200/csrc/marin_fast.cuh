@@ -331,6 +331,7 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(c
 		const pair_t d = sm[tile_pair(row, c)];
 		pair_t o; o.x = mul_small((u32)d.x, w[u].x); o.y = mul_small((u32)d.y, w[u].y);
 		if (!A.skip_dst) A.dst[(size_t)row * A.stride + c0 + c] = o;
+		if (A.dst2) A.dst2[(size_t)row * A.stride + c0 + c] = o;
 		if (FWD_FOLLOWS) sm[tile_pair(row, c)] = o;
 	}
 }
@@ -486,6 +487,13 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 			dft16<true>(a);
 			if (big)
 			{
+				if (!FWD_FOLLOWS && A.add_src) // mul_add: the other register joins while both are weighted (times m: pf carries the 1/m)
+				{
+					const u64 *ap = reinterpret_cast<const u64 *>(A.add_src) + 2 * ((size_t)row0 * A.stride + c0 + cc) + lane;
+					const size_t as = 2 * (size_t)64 * A.stride;
+					#pragma unroll
+					for (int q = 0; q < 16; ++q) a[q] = gl::add(a[q], gl::mul(ap[q * as], (u64)t.m));
+				}
 				#pragma unroll
 				for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], pf[q]);
 			}

@@ -232,7 +232,8 @@ struct Tw { const u64 *tab; u32 s; };
 // outputs (forward) of the stage that touches global memory in a strided pass.
 // The stage that carries the boundary twiddle is the last forward stage (s = 1): its rows base + k have
 // frequency indices K0 + k * Kstep, K0 = rowK[base], Kstep = R / radix.
-struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost; };
+struct Boundary { const Tables *t; u64 colscale; bool twiddle; const u64 *wpost; size_t wstride; u32 K0, Kstep; bool skip_wpost;
+	const u64 *addp; size_t addstride; }; // addp: register added to the product before unweighting (mul_add), element (base + s q) at addp[(base + s q) addstride]
 
 template <int R> HD u32 slot_of(u32 k) { return (R == 16) ? sw16(k) : k; }
 
@@ -293,6 +294,11 @@ template <int R, bool INV> HD void bfly_core(u64 *a, const View &out, u32 base, 
 			const u32 sl = slot_of<R>(k); a[sl] = gl::mul(a[sl], f);
 		}
 
+	// mul_add (carry_weight_muladd, marin.cl:2298-2365): the register to add joins the product while both are still
+	// weighted -- times m, because the unweighting factor below carries the 1/m of the unnormalised transform
+	if (INV && bd && bd->wpost && bd->addp)
+		#pragma unroll
+		for (u32 q = 0; q < R; ++q) a[q] = gl::add(a[q], gl::mul(bd->addp[(size_t)(base + s * q) * bd->addstride], (u64)bd->t->m));
 	if (INV && bd && bd->wpost && !bd->skip_wpost) // unweight (and scale by 1/m) the outputs of the last inverse stage: natural order, coalesced
 		#pragma unroll
 		for (u32 q = 0; q < R; ++q) a[q] = gl::mul(a[q], bd->wpost[(size_t)(base + s * q) * bd->wstride]);
@@ -384,6 +390,8 @@ struct MidArgs     // contiguous pass: one CTA = one block of S pairs (or the wh
 	pair_t *x;          // register to transform (in place)
 	const pair_t *y;    // multiplicand (MODE_MUL)
 	pair_t *dst;        // output register (MODE_FWD), may equal x
+	pair_t *dst2;       // single-CTA engines: also store the finished digits here (square_mul_copy / mul_copy), or null
+	const pair_t *add_src; // single-CTA engines: register added to the product before the carry (mul_add, a = 1), or null
 	int mode;
 	u32 S, nst;
 	Stage st[MAX_STAGES];
@@ -414,6 +422,8 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	unsigned long long *ticket; // carry pass: tiles are handed out in START order (atomic counter, never reset), so the
 	unsigned long long ticket_base; // tile a CTA waits for has always started before it, whatever the block scheduler does
 	u32 skip_dst;       // carry pass of a squaring chain: leave the register alone, the parked transform in fwd_dst is the state
+	pair_t *dst2;       // carry pass: second copy of the finished digits (square_mul_copy / mul_copy, marin.cl:1731-1769), or null
+	const pair_t *add_src; // carry pass: register added to the product before the carry (mul_add, multiplier a = 1 only), or null
 	u32 dbg;            // timing experiments only (builds with -DMARIN_DEBUG_SKIP): bit mask of steps to leave out
 };
 #if defined(MARIN_DEBUG_SKIP)
@@ -504,6 +514,11 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 				const pair_t pv = sm[lin_pair((j0 + i) >> 1)];
 				v[i] = gl::mul(pv.x, t.winvs_nat[j0 + i]);
 				v[i + 1] = gl::mul(pv.y, t.winvs_nat[j0 + i + 1]);
+				if (A.add_src)
+				{
+					const pair_t av = A.add_src[(j0 + i) >> 1];
+					v[i] = gl::add(v[i], gl::mul(av.x, t.winv_nat[j0 + i])); v[i + 1] = gl::add(v[i + 1], gl::mul(av.y, t.winv_nat[j0 + i + 1]));
+				}
 			}
 			smc[r] = carry_run(v, D, t.wbase, run_bits(t, j0, D), A.a, 0);
 			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; sm[lin_pair((j0 + i) >> 1)] = pv; }
@@ -521,6 +536,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 			pair_t pv;
 			pv.x = gl::mul(v[i], t.w_nat[j0 + i]); pv.y = gl::mul(v[i + 1], t.w_nat[j0 + i + 1]);
 			xg[(j0 + i) >> 1] = pv;
+			if (A.dst2) A.dst2[(j0 + i) >> 1] = pv;
 		}
 	}
 }
@@ -592,7 +608,8 @@ template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const St
 		// the last inverse stage of a carry pass also unweights: digit index 2 (row stride + c0 + c) + lane
 		const bool wp = INV && first && out_smem_always;
 		const Boundary bd{&t, (u64)(c0 + c) * A.escale, last, wp ? t.winvs_tile + 2 * ((size_t)(c0 / TILE_C) * A.R * TILE_C + c) + lane : nullptr, 2 * (size_t)TILE_C,
-			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0};
+			last ? A.rowK[base] : 0u, A.R / R, MARIN_DBG(A, 3) != 0,
+			(wp && A.add_src) ? reinterpret_cast<const u64 *>(A.add_src) + 2 * (blockbase + c0 + c) + lane : nullptr, 2 * (size_t)A.stride};
 		if (!INV)
 			bfly<R, false>((first && !in_smem_always) ? Gi : Sv, last ? Go : Sv, base, sg.s, j, tw, t.w5, last ? &bd : nullptr);
 		else // inverse order: the stage that is `last` in forward order comes first and reads global
@@ -632,7 +649,7 @@ HD u32 strided_publish_phase(const StridedArgs &A) { return A.nst; } // every sl
 
 static constexpr u32 SPIN_LIMIT = 1u << 27; // bounded wait: a lost flag raises the error word instead of hanging the GPU
 
-// carry published in slot idx by this launch; bounded wait (an error word instead of a hung GPU)
+// carry published in slot idx by this launch; bounded wait (an error word and a poisoned carry instead of a hung GPU)
 HD u64 wait_slot(const StridedArgs &A, size_t idx, bool backoff)
 {
 	u32 spins = 0;
@@ -640,7 +657,7 @@ HD u64 wait_slot(const StridedArgs &A, size_t idx, bool backoff)
 	{
 		const pair_t v = marin_ld_slot(&A.slots[idx]);
 		if (v.y == (u64)A.epoch) return v.x;
-		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[A.tiles], 1u); return 0; }
+		if (++spins > SPIN_LIMIT) { MARIN_ST_VOLATILE_U32(&A.flags[A.tiles], 1u); return ~0ull; } // poisoned carry + sticky error word: every later read-back throws
 		if (backoff) MARIN_NANOSLEEP(200);
 	}
 }
@@ -726,6 +743,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 					pair_t o; o.x = gl::mul(d.x, w[u].x); o.y = gl::mul(d.y, w[u].y);
 					if (MARIN_DBG(A, 2)) o = d;
 					if (!A.skip_dst) A.dst[blockbase + (size_t)row * A.stride + c0 + c] = o;
+					if (A.dst2) A.dst2[blockbase + (size_t)row * A.stride + c0 + c] = o;
 					if (A.fwd_dst) sm[tile_pair(row, c)] = o;
 				}
 			}
@@ -738,7 +756,7 @@ template <bool INV> HD void strided_phase(const StridedArgs &A, u32 blkid, u32 p
 }
 
 // ---- linear operations on digits (natural order, runs of D digits) -----------------------------
-enum LinOp : int { LIN_ADD = 0, LIN_SUBREG = 1, LIN_SUBSMALL = 2, LIN_SETDIGITS = 3, LIN_SETSMALL = 4 };
+enum LinOp : int { LIN_ADD = 0, LIN_SUBREG = 1, LIN_SUBSMALL = 2, LIN_SETDIGITS = 3, LIN_SETSMALL = 4, LIN_ADDSUB = 5 };
 
 struct LinArgs
 {
@@ -747,6 +765,9 @@ struct LinArgs
 	const u64 *digits;        // LIN_SETDIGITS: encoded digits (low 32 bits used)
 	u64 *carry;               // one per run
 	int op; u32 a; u32 D;
+	// LIN_ADDSUB (one pass for S = A + B and D = A - B, marin.cl:1891-2154): dst = S, dst2 = D, inputs srcA and src (= B);
+	// cpy / cpy2: optional copies of S and D (addsub_copy); carry2: the D carries.  Any output may alias any input.
+	const u64 *srcA; u64 *dst2, *cpy, *cpy2, *carry2;
 };
 
 // digits of the small constant `a` that fall in digit j (a < 2^32)
@@ -845,6 +866,37 @@ HD u64 lin_pair_carry(const LinArgs &A, u32 i)
 	return u1 >> w1;
 }
 
+// ---- addsub on pairs: same single-hop carry, both results from one read of A and B
+HD void addsub_pair_compute(const LinArgs &A, u32 i, u64 *us, u64 *ud, u32 &w0, u32 &w1)
+{
+	const Tables &t = A.t;
+	const u32 j = 2 * i;
+	w0 = digit_width(t, j); w1 = digit_width(t, j + 1);
+	const pair_t x = reinterpret_cast<const pair_t *>(A.srcA)[i], y = reinterpret_cast<const pair_t *>(A.src)[i];
+	const pair_t wi = reinterpret_cast<const pair_t *>(t.winv_nat)[i];
+	const u64 m0 = ((u64)1 << w0) - 1, m1 = ((u64)1 << w1) - 1;
+	us[0] = gl::mul(gl::add(x.x, y.x), wi.x); us[1] = gl::mul(gl::add(x.y, y.y), wi.y);
+	ud[0] = gl::add(gl::mul(gl::sub(x.x, y.x), wi.x), 2 * m0); ud[1] = gl::add(gl::mul(gl::sub(x.y, y.y), wi.y), 2 * m1);
+}
+HD void addsub_pair_finish(const LinArgs &A, u32 i, const u64 *us, const u64 *ud, u32 w0, u32 w1, u64 cs, u64 cd)
+{
+	const pair_t w = reinterpret_cast<const pair_t *>(A.t.w_nat)[i];
+	const u64 m0 = ((u64)1 << w0) - 1, m1 = ((u64)1 << w1) - 1;
+	pair_t o;
+	o.x = gl::mul((us[0] & m0) + cs, w.x); o.y = gl::mul((us[1] & m1) + (us[0] >> w0), w.y);
+	reinterpret_cast<pair_t *>(A.dst)[i] = o;
+	if (A.cpy) reinterpret_cast<pair_t *>(A.cpy)[i] = o;
+	o.x = gl::mul((ud[0] & m0) + cd, w.x); o.y = gl::mul((ud[1] & m1) + (ud[0] >> w0), w.y);
+	reinterpret_cast<pair_t *>(A.dst2)[i] = o;
+	if (A.cpy2) reinterpret_cast<pair_t *>(A.cpy2)[i] = o;
+}
+HD void addsub_pair_carry(const LinArgs &A, u32 i, u64 &cs, u64 &cd)
+{
+	u64 us[2], ud[2]; u32 w0, w1;
+	addsub_pair_compute(A, i, us, ud, w0, w1);
+	cs = us[1] >> w1; cd = ud[1] >> w1;
+}
+
 static constexpr u32 LIN_BLOCK = 256; // pairs per CTA of the fast linear kernel
 
 // x <- x * f, elementwise (the plain inverse strided pass is unnormalised: times 1/R it is the exact inverse)
@@ -852,6 +904,67 @@ HD void scale_thread(u64 *x, u64 f, u32 j, u32 n) { if (j < n) x[j] = gl::mul(x[
 
 // unweighted digit values (not carried) for the host-side canonical export (engine_gpu.h:1534-1561)
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
+
+// ---- canonical digits on the device (engine_gpu.h:1534-1561 does this on the host, serially): each thread unweights a run
+// of CANON_D digits and carries it strongly from a zero carry-in (canon_p1); then every run adds the carry of the run
+// before it (the last one's wraps to digit 0: 2^p = 1) and ripples it as far as it goes inside the run (canon_p2); a carry
+// that leaves a run -- the run was all ones -- is counted in *pending and handled by another canon_p2 round (rare: the host
+// looks at the counter).  Output: value | width << 32, the reference's encoding.
+static constexpr u32 CANON_D = 16;
+struct CanonArgs { Tables t; const u64 *x; u64 *enc; u64 *cin, *cout; u32 *pending; u32 D; };
+
+HD void canon_p1_thread(const CanonArgs &A, u32 r)
+{
+	const Tables &t = A.t;
+	const u32 D = A.D, nruns = t.n / D;
+	if (r >= nruns) return;
+	const u32 j0 = r * D, bits = run_bits(t, j0, D);
+	u64 c = 0;
+	for (u32 i = 0; i < D; ++i)
+	{
+		const u32 w = t.wbase + ((bits >> i) & 1u);
+		const u64 u = gl::mul(A.x[j0 + i], t.winv_nat[j0 + i]);
+		const u64 s = u + c, co = (s < c) ? 1 : 0;
+		c = (s >> w) | (co << (64 - w));
+		A.enc[j0 + i] = (s & (((u64)1 << w) - 1)) | ((u64)w << 32);
+	}
+	A.cout[r] = c;
+}
+
+HD void canon_p2_thread(const CanonArgs &A, u32 r)
+{
+	const Tables &t = A.t;
+	const u32 D = A.D, nruns = t.n / D;
+	if (r >= nruns) return;
+	u64 c = A.cin[(r == 0) ? nruns - 1 : r - 1];
+	const u32 j0 = r * D;
+	for (u32 i = 0; i < D && c != 0; ++i)
+	{
+		const u64 e = A.enc[j0 + i];
+		const u32 w = (u32)(e >> 32);
+		const u64 s = (e & 0xffffffffull) + c; // value < 2^32, c < 2^64 - 2^32 after the first digit; the first add is checked
+		const u64 co = (s < c) ? 1 : 0;
+		c = (s >> w) | (co << (64 - w));
+		A.enc[j0 + i] = (s & (((u64)1 << w) - 1)) | ((u64)w << 32);
+	}
+	A.cout[r] = c;
+	if (c != 0)
+	{
+#if defined(__CUDA_ARCH__)
+		atomicAdd(A.pending, 1u);
+#else
+		*A.pending += 1;
+#endif
+	}
+}
+
+// compare two canonical digit vectors; flags: bit 0 a digit differs, bit 1 l is not all ones, bit 2 l is not zero,
+// bit 3 r is not all ones, bit 4 r is not zero (2^p - 1 and 0 are the same residue, engine.h:181-196)
+HD u32 canon_cmp_digit(u64 el, u64 er)
+{
+	const u32 w = (u32)(el >> 32), vl = (u32)el, vr = (u32)er, ones = (u32)((((u64)1) << w) - 1);
+	return (vl != vr ? 1u : 0u) | (vl != ones ? 2u : 0u) | (vl != 0 ? 4u : 0u) | (vr != ones ? 8u : 0u) | (vr != 0 ? 16u : 0u);
+}
 
 // ---- recorded op sequences for single-CTA engines ("programs"): one kernel launch runs the whole list ------------
 enum ProgCode : u32 { PO_COPY = 0, PO_SQR, PO_SETMUL, PO_MUL, PO_ADD, PO_SUBREG, PO_SUBSMALL, PO_SETSMALL };

@@ -44,7 +44,10 @@ def lib():
                      ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_sub_u32", [vp, sz, u32]),
                      ("emu_add", [vp, sz, sz]), ("emu_sub_reg", [vp, sz, sz]), ("emu_get_digits", [vp, sz, vp]),
                      ("emu_set_digits", [vp, sz, vp]), ("emu_equal", [vp, sz, sz, vp]), ("emu_graph_begin", [vp]),
-                     ("emu_graph_end", [vp, vp]), ("emu_graph_launch", [vp, C.c_int])):
+                     ("emu_graph_end", [vp, vp]), ("emu_graph_launch", [vp, C.c_int]),
+                     ("emu_addsub", [vp, sz, sz, sz, sz]), ("emu_addsub_copy", [vp, sz, sz, sz, sz, sz, sz]),
+                     ("emu_square_mul_copy", [vp, sz, sz, u32]), ("emu_mul_copy", [vp, sz, sz, sz, u32]),
+                     ("emu_mul_add", [vp, sz, sz, sz, u32])):
             getattr(L, f).argtypes = a; getattr(L, f).restype = C.c_int
         L.emu_transform_size.restype = sz; L.emu_transform_size.argtypes = [u32]
         _lib = L
@@ -78,6 +81,11 @@ class EmuEngine:
     def sub(self, r, a): self._ck(lib().emu_sub_u32(self._h, r, a))
     def add(self, d, s): self._ck(lib().emu_add(self._h, d, s))
     def sub_reg(self, d, s): self._ck(lib().emu_sub_reg(self._h, d, s))
+    def addsub(self, s, d, a, b): self._ck(lib().emu_addsub(self._h, s, d, a, b))
+    def addsub_copy(self, s, d, sc, dc, a, b): self._ck(lib().emu_addsub_copy(self._h, s, d, sc, dc, a, b))
+    def square_mul_copy(self, r, c, a=1): self._ck(lib().emu_square_mul_copy(self._h, r, c, a))
+    def mul_add(self, d, ms, as_, a=1): self._ck(lib().emu_mul_add(self._h, d, ms, as_, a))
+    def mul_copy(self, d, s, c, a=1): self._ck(lib().emu_mul_copy(self._h, d, s, c, a))
 
     # recorded op sequences (the emulated k_program)
     def is_single_cta(self): return self.small
@@ -89,6 +97,11 @@ class EmuEngine:
         return gid.value
 
     def graph_launch(self, gid): self._ck(lib().emu_graph_launch(self._h, gid))
+
+    def is_equal(self, l, r):
+        out = C.c_int(0)
+        self._ck(lib().emu_equal(self._h, l, r, C.byref(out)))
+        return bool(out.value)
 
     def get_digits(self, s):
         out = np.zeros(self.n, dtype=np.uint64)

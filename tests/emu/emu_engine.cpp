@@ -76,6 +76,26 @@ struct CpuBackend
 			}
 		}
 	}
+	void addsub_pairs(const LinArgs &A)
+	{
+		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
+		for (u32 b = 0; b < nblocks; ++b) { const u32 first = b * LIN_BLOCK; addsub_pair_carry(A, first == 0 ? npairs - 1 : first - 1, A.carry[b], A.carry2[b]); }
+		std::vector<u64> cs(LIN_BLOCK), cd(LIN_BLOCK);
+		for (u32 b = 0; b < nblocks; ++b)
+		{
+			const u32 cnt = std::min<u32>(LIN_BLOCK, npairs - b * LIN_BLOCK);
+			for (u32 t = 0; t < cnt; ++t) addsub_pair_carry(A, b * LIN_BLOCK + t, cs[t], cd[t]);
+			// all reads of a block come before its writes on the GPU (barrier): keep the results aside, then store
+			std::vector<u64> us(2 * cnt), ud(2 * cnt); std::vector<u32> w(2 * cnt);
+			for (u32 t = 0; t < cnt; ++t) addsub_pair_compute(A, b * LIN_BLOCK + t, &us[2 * t], &ud[2 * t], w[2 * t], w[2 * t + 1]);
+			for (u32 t = 0; t < cnt; ++t)
+				addsub_pair_finish(A, b * LIN_BLOCK + t, &us[2 * t], &ud[2 * t], w[2 * t], w[2 * t + 1], t ? cs[t - 1] : A.carry[b], t ? cd[t - 1] : A.carry2[b]);
+		}
+	}
+	void canon_p1(const CanonArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) canon_p1_thread(A, i); }
+	void canon_p2(const CanonArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) canon_p2_thread(A, i); }
+	void canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags) { u32 f = 0; for (u32 j = 0; j < n; ++j) f |= canon_cmp_digit(l[j], r[j]); *flags |= f; }
+	void d2h_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
 	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { for (u32 j = 0; j < n; ++j) unweight_thread(t, x, out, j); }
@@ -158,6 +178,11 @@ int emu_mul(void *h, size_t d, size_t s, uint32_t a) { GUARD(((Emu *)h)->mul(d, 
 int emu_sub_u32(void *h, size_t r, uint32_t a) { GUARD(((Emu *)h)->sub_u32(r, a)) }
 int emu_add(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->add(d, s)) }
 int emu_sub_reg(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->sub_reg(d, s)) }
+int emu_addsub(void *h, size_t s, size_t d, size_t a, size_t b) { GUARD(((Emu *)h)->addsub(s, d, a, b)) }
+int emu_addsub_copy(void *h, size_t s, size_t d, size_t sc, size_t dc, size_t a, size_t b) { GUARD(((Emu *)h)->addsub(s, d, a, b, sc, dc)) }
+int emu_square_mul_copy(void *h, size_t r, size_t c, uint32_t a) { GUARD(((Emu *)h)->square_mul_copy(r, c, a)) }
+int emu_mul_add(void *h, size_t d, size_t ms, size_t as, uint32_t a) { GUARD(((Emu *)h)->mul_add(d, ms, as, a)) }
+int emu_mul_copy(void *h, size_t d, size_t s, size_t c, uint32_t a) { GUARD(((Emu *)h)->mul_copy(d, s, c, a)) }
 int emu_get_digits(void *h, size_t s, uint64_t *enc) { GUARD(((Emu *)h)->get_digits(s, (u64 *)enc)) }
 int emu_set_digits(void *h, size_t d, const uint64_t *enc) { GUARD(((Emu *)h)->set_digits(d, (const u64 *)enc)) }
 int emu_graph_begin(void *h) { GUARD(((Emu *)h)->graph_begin()) }

@@ -107,6 +107,71 @@ def chain_state_script(e, p, put, val):
     return True
 
 
+def fused_ops_script(e, p, put, val, is_equal=None):
+    """The one-pass kernels behind addsub / addsub_copy / square_mul_copy / mul_copy (marin.cl:1731-2154) against the
+    reference's default compositions (engine.h:65-131), including the in-place calls the Edwards schedules make, a
+    squaring chain parked before them, and the canonical export / comparison corner cases (carry that ripples through
+    runs of all-ones digits, 2^p - 1 == 0).  Shared by the emulated and the GPU tier; needs 10 registers."""
+    m = (1 << p) - 1
+    wd = mo.widths(e.get_size(), p)
+    rng = random.Random(p + 1)
+    a, b, c = (rng.randrange(m) for _ in range(3))
+    put(e, 0, a, wd); put(e, 1, b, wd); put(e, 2, c, wd)
+    e.addsub(3, 4, 0, 1)
+    assert val(e, 3) == (a + b) % m and val(e, 4) == (a - b) % m and val(e, 0) == a and val(e, 1) == b
+    e.addsub(0, 1, 0, 1)                                      # in place: (a, b) <- (a + b, a - b)
+    a, b = (a + b) % m, (a - b) % m
+    assert val(e, 0) == a and val(e, 1) == b
+    e.addsub(1, 0, 0, 1)                                      # crossed outputs
+    a, b = (a - b) % m, (a + b) % m
+    assert val(e, 0) == a and val(e, 1) == b
+    e.addsub_copy(3, 4, 5, 6, 0, 1)
+    assert val(e, 3) == val(e, 5) == (a + b) % m and val(e, 4) == val(e, 6) == (a - b) % m
+    e.addsub_copy(0, 1, 5, 6, 0, 1)                           # in place with copies
+    a, b = (a + b) % m, (a - b) % m
+    assert val(e, 0) == val(e, 5) == a and val(e, 1) == val(e, 6) == b
+    amul = min(3, e.a_max) if hasattr(e, "a_max") else 3
+    for _ in range(3):
+        e.square_mul(2); c = c * c % m                        # leaves register 2 parked on multi-pass engines
+    e.square_mul_copy(2, 8, amul); c = c * c * amul % m
+    assert val(e, 2) == val(e, 8) == c
+    e.square_mul(2); c = c * c % m                            # and the chain restarts cleanly
+    assert val(e, 2) == c and val(e, 8) != c
+    e.set_multiplicand(7, 1)
+    e.mul_copy(2, 7, 9, amul); c = c * b * amul % m
+    assert val(e, 2) == val(e, 9) == c and val(e, 1) == b
+    e.mul_add(2, 7, 0); c = (c * b + a) % m                   # product and sum carried together
+    assert val(e, 2) == c and val(e, 0) == a
+    e.mul_add(2, 7, 0, amul); c = (c * b * amul + a) % m
+    assert val(e, 2) == c
+    # canonical export: all ones is zero; all ones plus one ripples a carry through every run and wraps (2^p = 1)
+    put(e, 3, 0, wd)
+    ones = mo.int_to_digits(0, wd)
+    for k in range(len(ones)):
+        ones[k] = (int(ones[k]) & ~0xffffffff) | ((1 << int(wd[k])) - 1)
+    e.set_digits(4, ones)
+    assert val(e, 4) == 0
+    if is_equal:
+        assert is_equal(e, 3, 4) and is_equal(e, 4, 3) and is_equal(e, 4, 4) and not is_equal(e, 3, 0)
+        e.copy(5, 0)
+        assert is_equal(e, 5, 0)
+        e.add(5, 3)                                           # + 0: another semi-carried image of the same value
+        assert is_equal(e, 5, 0)
+    e.set(5, 1)
+    e.add(4, 5)                                               # (2^p - 1) + 1 = 2^p = 1
+    assert val(e, 4) == 1
+    e.set_digits(4, ones); e.set(5, 2**32 - 1 if p > 40 else 5)
+    e.add(4, 5)
+    assert val(e, 4) == (2**32 - 1 if p > 40 else 5) % m
+    return True
+
+
+@pytest.mark.parametrize("p,force_S", [(127, 0), (701, 0), (9941, 0), (86243, 0), (86243, 64), (216091, 64)])
+def test_fused_ops_and_canonical_corner_cases(p, force_S):
+    e = EmuEngine(p, 10, force_S)
+    assert fused_ops_script(e, p, put, val, lambda eng, l, r: eng.is_equal(l, r))
+
+
 @pytest.mark.parametrize("p,force_S,force_R2", [(86243, 64, 0), (216091, 64, 0), (86243, 8, 16), (216091, 128, 0)])
 def test_chain_state_is_materialised_on_demand(p, force_S, force_R2):
     e = EmuEngine(p, 6, force_S, force_R2)

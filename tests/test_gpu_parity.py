@@ -155,6 +155,85 @@ def test_fused_helpers_match_default_compositions():
     e.close()
 
 
+@pytest.mark.parametrize("p,force_S,force_R2", [(127, 0, 0), (701, 0, 0), (9941, 0, 0), (86243, 0, 0), (86243, 64, 0), (216091, 64, 0),
+                                                (86243, 8, 16), (1362763, 0, 0)])
+def test_fused_kernels_and_device_canonical_export(p, force_S, force_R2):
+    """addsub(+copy), square_mul_copy, mul_copy as single passes; canonical carry and is_equal on the device."""
+    from tests.test_emu_kernels import fused_ops_script
+    e = _engine(p, 10, force_S, force_R2)
+    assert fused_ops_script(e, p, lambda eng, r, x, wd: eng.set_mpz(r, x), val, lambda eng, l, r: eng.is_equal(l, r))
+    e.close()
+
+
+def test_fused_kernels_full_size():
+    """The same at the headline size (n = 2^23, specialised kernels) and at n = 5 * 2^21 (config 4): the fused kernels
+    against the reference's default compositions (engine.h:65-131), canonical digits compared on the device and digit
+    for digit on the host -- no big-integer conversions at this size."""
+    for p in (136279841, 205271257):
+        e = _engine(p, 12)
+        e.set(0, 3); e.set(1, 5)
+        for _ in range(30):
+            e.square_mul(0); e.square_mul(1, 3)
+        # compositions into 2..5
+        e.copy(2, 0); e.copy(3, 0); e.add(2, 1); e.sub_reg(3, 1)
+        e.addsub(4, 5, 0, 1)
+        assert e.is_equal(2, 4) and e.is_equal(3, 5) and not e.is_equal(4, 5)
+        assert np.array_equal(e.get(2), e.get(4)) and np.array_equal(e.get(3), e.get(5))
+        e.copy(6, 0); e.copy(7, 1)
+        e.addsub_copy(6, 7, 8, 9, 6, 7)                       # in place, with copies
+        assert e.is_equal(6, 2) and e.is_equal(7, 3) and e.is_equal(8, 2) and e.is_equal(9, 3)
+        e.copy(2, 0); e.square_mul(2, 3); e.copy(3, 2)
+        e.copy(4, 0)
+        for _ in range(3):
+            e.square_mul(10)                                  # another register parked in between
+        e.square_mul_copy(4, 5, 3)
+        assert e.is_equal(4, 2) and e.is_equal(5, 2) and np.array_equal(e.get(5), e.get(3))
+        e.set_multiplicand(11, 1)
+        e.copy(2, 0); e.mul(2, 11, 3); e.copy(3, 2)
+        e.copy(4, 0); e.mul_copy(4, 11, 5, 3)
+        assert e.is_equal(4, 2) and e.is_equal(5, 3)
+        e.copy(2, 0); e.mul(2, 11); e.add(2, 1)
+        e.copy(4, 0); e.mul_add(4, 11, 1)
+        assert e.is_equal(4, 2)
+        e.close()
+
+
+def test_specialised_kernels_match_generic_kernels_bit_for_bit():
+    """marin_fast.cuh against the generic phase functions: identical raw register images (MARIN_B200_NO_FAST=1)."""
+    import prmers_b200 as pb
+    p = 136279841
+    imgs = []
+    for fast in (True, False):
+        if not fast:
+            os.environ["MARIN_B200_NO_FAST"] = "1"
+        try:
+            e = pb.Engine(p, 4)
+        finally:
+            os.environ.pop("MARIN_B200_NO_FAST", None)
+        out = []
+
+        def raw(r):
+            b = bytearray(e.get_register_data_size())
+            assert e.get_data(b, r)
+            return bytes(b)
+        e.set(0, 3)
+        for _ in range(30):
+            e.square_mul(0)
+        e.copy(1, 0)
+        for _ in range(5):
+            e.square_mul(0)
+        out.append(raw(0))
+        e.square_mul(0, 3); out.append(raw(0))
+        e.set_multiplicand(2, 1); out.append(raw(2))
+        e.mul(0, 2, 1); out.append(raw(0))
+        e.mul(1, 2, 3); out.append(raw(1))
+        e.square_mul_copy(1, 3, 1); out.append(raw(1)); out.append(raw(3))
+        imgs.append(out)
+        e.close()
+    for i, (x, y) in enumerate(zip(*imgs)):
+        assert x == y, f"step {i}"
+
+
 def test_m127_lucas_lehmer_and_m86243_prp():
     """BASELINE config 1: LL M127 and PRP p = 86243, bit-exact residue plumbing."""
     e = _engine(127, 2)

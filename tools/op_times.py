@@ -29,6 +29,13 @@ for p, regs in CASES:
         "sub_reg": t(e, lambda: e.sub_reg(3, 1), cnt),
         "sub(2)": t(e, lambda: e.sub(3, 2), cnt),
         "copy": t(e, lambda: e.copy(5, 1), cnt),
+        "addsub": t(e, lambda: e.addsub(5, 6, 1, 3), cnt),
+        "addsub_copy": t(e, lambda: e.addsub_copy(5, 6, 4, 7, 1, 3), cnt),
+        "square_mul_copy": t(e, lambda: e.square_mul_copy(0, 5), cnt),
+        "mul_copy": t(e, lambda: e.mul_copy(3, 2, 5), cnt),
+        "mul_add": t(e, lambda: e.mul_add(3, 2, 1), cnt),
+        "is_equal": t(e, lambda: e.is_equal(0, 1), 20),
+        "get": t(e, lambda: e.get(0), 10),
     }
     print(f"p={p} n={e.get_size()}: " + "  ".join(f"{k} {v:.1f}" for k, v in r.items()) + "  (us/op)", flush=True)
     e.close()
