@@ -44,18 +44,22 @@ int mb200_sub_u32(void *eng, size_t r, uint32_t a);                 /* engine::s
 int mb200_add(void *eng, size_t dst, size_t src);                   /* engine::add, engine.h:64 */
 int mb200_sub_reg(void *eng, size_t dst, size_t src);               /* engine::sub_reg, engine.h:71 */
 
-/* fused helpers with the semantics of the default compositions in engine.h:54-131 */
+/* fused helpers with the semantics of the default compositions in engine.h:54-131; each is ONE pass over the registers
+   (the reference's overrides: engine_gpu.h:1064-1072,1131; kernels carry_weight_muladd / addsub(_copy) / mul_p1_copy,
+   marin.cl:1731-1769,1891-2154,2298-2365).  mul_add fuses for a = 1; outputs of addsub may alias its inputs. */
 int mb200_mul_add(void *eng, size_t dst, size_t mul_src, size_t add_src, uint32_t a);       /* engine.h:65-69 */
 int mb200_addsub(void *eng, size_t sum_out, size_t diff_out, size_t a, size_t b);           /* engine.h:72-80 */
 int mb200_addsub_copy(void *eng, size_t sum, size_t diff, size_t sum_copy, size_t diff_copy, size_t a, size_t b); /* engine.h:124-130 */
 int mb200_square_mul_copy(void *eng, size_t r, size_t dst_copy, uint32_t a);                /* engine.h:82-86 */
 int mb200_mul_copy(void *eng, size_t dst, size_t src, size_t dst_copy, uint32_t a);         /* engine.h:92-96 */
 
-/* engine::is_equal (engine.h:148-157): residues compared modulo 2^p - 1 */
+/* engine::is_equal (engine.h:148-157): residues compared modulo 2^p - 1 (0 and 2^p - 1 are equal); canonical carry and
+   comparison run on the device, 16 bytes come back */
 int mb200_equal(void *eng, size_t lhs, size_t rhs, int *out);
 
 /* engine::get / engine::set(Reg, uint64*) (engine.h:24-25; engine_gpu.h:1452-1561): canonical digits,
-   unweighted and fully carried; n = transform size entries */
+   unweighted and fully carried (on the device; engine_gpu.h:1534-1561 does it on the host); n = transform size entries.
+   Every call that returns register contents first reads the device error word and fails if it is set. */
 int mb200_get_digits(void *eng, size_t src, uint64_t *enc, size_t n);
 int mb200_set_digits(void *eng, size_t dst, const uint64_t *enc, size_t n);
 
@@ -90,6 +94,10 @@ int mb200_graph_end(void *eng, int *graph_id);
 int mb200_graph_launch(void *eng, int graph_id);
 /* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 uint64_t mb200_launch_count(void *eng);
+
+/* free / total bytes of device memory (cudaMemGetInfo): what the P-1 stage-2 planner sizes its baby table with
+   (the reference asks OpenCL for CL_DEVICE_GLOBAL_MEM_SIZE, src/modes/RunPM1.cpp:1994-2026) */
+int mb200_device_mem_info(uint32_t device, size_t *free_bytes, size_t *total_bytes);
 
 /* pinned host buffers for fast get_/set_ transfers */
 void *mb200_host_alloc(size_t bytes);

@@ -11,6 +11,7 @@ class IntEngine:
     def __init__(self, p, regs):
         self.p, self.N = p, (1 << p) - 1
         self.r = [0] * regs
+        self.reg_count = regs
         self.calls = 0
 
     def get_size(self):
@@ -37,6 +38,9 @@ class IntEngine:
         self.addsub(s, d, a, b); self.r[sc], self.r[dc] = self.r[s], self.r[d]
 
     def mul_copy(self, d, s, c, a=1): self.mul(d, s, a); self.r[c] = self.r[d]
+    def square_mul_copy(self, r, c, a=1): self.square_mul(r, a); self.r[c] = self.r[r]
+    def mul_add(self, d, ms, as_, a=1): self.mul(d, ms, a); self.add(d, as_)
+    def is_equal(self, a, b): return self.r[a] % self.N == self.r[b] % self.N
     def set_mpz(self, d, z): self.r[d] = z % self.N
     def get_mpz(self, s): return self.r[s] % self.N
 

@@ -550,6 +550,14 @@ int mb200_graph_launch(void *eng, int id) { GUARD(E(eng)->graph_launch(id)); }
 
 uint64_t mb200_launch_count(void *eng) { return eng ? E(eng)->be.launches : 0; }
 
+int mb200_device_mem_info(uint32_t device, size_t *free_bytes, size_t *total_bytes)
+{
+	g_err.clear();
+	if (cudaSetDevice((int)device) != cudaSuccess || cudaMemGetInfo(free_bytes, total_bytes) != cudaSuccess)
+	{ g_err = "cudaMemGetInfo failed"; cudaGetLastError(); return 0; }
+	return 1;
+}
+
 void *mb200_host_alloc(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
 void mb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 

@@ -51,6 +51,7 @@ _SIGS = {
     "mb200_square_mul_repeat": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
     "mb200_bench_pass": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_float)]),
     "mb200_is_single_cta": (C.c_int, [C.c_void_p]),
+    "mb200_device_mem_info": (C.c_int, [C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mb200_graph_begin": (C.c_int, [C.c_void_p]),
     "mb200_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "mb200_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),
@@ -318,6 +319,15 @@ class Engine:
 
     def launch_count(self):
         return self._L.mb200_launch_count(self._h)
+
+
+def device_mem_info(device=0):
+    """(free, total) bytes of device memory (cudaMemGetInfo): the P-1 stage-2 planner's budget."""
+    L = load_library()
+    free, total = C.c_size_t(0), C.c_size_t(0)
+    if not L.mb200_device_mem_info(device, C.byref(free), C.byref(total)):
+        raise MarinError(L.mb200_last_error().decode())
+    return free.value, total.value
 
 
 def create_gpu(p, reg_count, device=0, verbose=False):

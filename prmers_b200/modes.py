@@ -12,6 +12,7 @@ import math
 
 import numpy as np
 
+from . import hostmath
 from .engine import digits_to_int
 
 # register map of RunPrpOrLlMarin.cpp:213
@@ -25,6 +26,14 @@ def _digits(eng, r):
 def _value(eng, r, p):
     v = digits_to_int(_digits(eng, r))
     return 0 if v == (1 << p) - 1 else v
+
+
+def _same(eng, a, b, p):
+    """engine::is_equal (engine.h:148-157): compared on the device when the engine can (no 10^8-bit integers on the
+    host per Gerbicz check), through the canonical values otherwise."""
+    if hasattr(eng, "is_equal"):
+        return eng.is_equal(a, b)
+    return _value(eng, a, p) == _value(eng, b, p)
 
 
 def pack_words(enc, p):
@@ -54,7 +63,7 @@ def format_res2048(r):
     return f"{r & ((1 << 2048) - 1):0512x}"
 
 
-def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4, stop_after_checks=0):
+def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4, stop_after_checks=0, known_factors=()):
     """PRP test of 2^p - 1 (type 1, base 3): p squarings from 3, prime iff the residue is 9.
 
     Gerbicz-Li checking as the reference: every B = floor(sqrt(p)) iterations the accumulator
@@ -63,7 +72,10 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
     restored (RunPrpOrLlMarin.cpp:338-412).  `error_iter` injects a fault (x -= 2) after that
     iteration, like -erroriter (RunPrpOrLlMarin.cpp:326-336).  `stop_after_checks` ends the run after that
     many passed checks (the reference's size-ladder smoke test stops at the first "Check passed",
-    unit_test_all.sh:54-79); the result then carries `stopped_at` instead of a verdict.
+    unit_test_all.sh:54-79); the result then carries `stopped_at` instead of a verdict.  `known_factors` (-factors)
+    turns the verdict into the cofactor test of src/math/Cofactor.cpp:33-63: with KF their product and N = (2^p - 1) / KF,
+    N is a probable prime iff residue / 9 == 3^(KF - 1) (mod N); the reported residue stays the full-modulus one
+    (src/io/JsonBuilder.cpp:182-217).
     """
     say = log or (lambda s: None)
     total = p
@@ -100,7 +112,7 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
                     eng.square_mul(R3, 3)
                 for _ in range(modB):
                     eng.square_mul(R3)
-                if _value(eng, R3, p) != _value(eng, R1, p):
+                if not _same(eng, R3, R1, p):
                     say(f"[Gerbicz Li] Check FAILED! iter={it + 1}")
                     say(f"[Gerbicz Li] Restore iter={itersave} (j={jsave})")
                     errors += 1
@@ -126,8 +138,17 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
     m = (1 << p) - 1
     x = 0 if x == m else x
     r = prp3_div9(p, x)
-    return {"exponent": p, "worktype": "PRP-3", "is_prp": x == 9 % m, "res64": format_res64(r), "res2048": format_res2048(r),
-            "residue_type": 1, "errors_gerbicz": errors, "fft_length": eng.get_size(), "iterations": total}
+    is_prp, rtype = x == 9 % m, 1
+    if known_factors:
+        kf = 1
+        for f in known_factors:
+            kf *= int(f)
+        if m % kf:
+            raise ValueError("known factors do not divide 2^p - 1")
+        cof = m // kf
+        is_prp, rtype = r % cof == pow(3, kf - 1, cof), 5
+    return {"exponent": p, "worktype": "PRP-3", "is_prp": is_prp, "res64": format_res64(r), "res2048": format_res2048(r),
+            "residue_type": rtype, "errors_gerbicz": errors, "fft_length": eng.get_size(), "iterations": total}
 
 
 def run_ll(eng, p, error_iter=0):
@@ -162,18 +183,195 @@ def pm1_exponent(p, b1):
     return e
 
 
-def run_pm1_stage1(eng, p, b1, reg=0, gcd=True):
-    """P-1 stage 1, "fast3" (RunPM1.cpp:7127): X <- X^2 * (3 if bit else 1) over the bits of E, MSB first;
-    the factor is gcd(X - 1, 2^p - 1)."""
+# register map of runPM1Marin (RunPM1.cpp:6206-6216)
+PM1_RSTATE, PM1_RACC_L, PM1_RACC_R, PM1_RCHK, PM1_RPOW, PM1_RTMP, PM1_RSTART, PM1_RSAVE_S, PM1_RSAVE_L, PM1_RSAVE_R, PM1_RBASE = range(11)
+
+
+def _fast3_pow(eng, r, e):
+    """r <- 3^e by the same fast3 squarings the main loop uses (RunPM1.cpp:7161-7167)."""
+    eng.set(r, 1)
+    for k in range(e.bit_length() - 1, -1, -1):
+        eng.square_mul(r, 3 if (e >> k) & 1 else 1)
+
+
+def run_pm1_stage1(eng, p, b1, reg=0, gcd=True, gerbicz=None, check_level=0, error_iter=0, log=None, max_restores=8):
+    """P-1 stage 1, "fast3" (RunPM1.cpp:7016-7300): X <- X^2 * (3 if bit else 1) over the bits of
+    E = 2 p prod q^floor(log_q B1), MSB first; the factor is gcd(X - 1, 2^p - 1).
+
+    Gerbicz-Li checking as the reference does it for an exponentiation (RunPM1.cpp:7102-7190): the bits are cut in
+    blocks of B = floor(sqrt(bits)); for a lot of full blocks L <- L * (state at block start), R <- R * (state at block
+    end), eacc += (bits of the block), and the check is L^(2^B) * 3^eacc == R; a shorter first block is checked on its
+    own (start^(2^len) * 3^wbits == state).  A mismatch restores the state saved at the last passed check and redoes
+    the blocks since.  On by default when the engine has the 11 registers of the reference's map; `error_iter` injects
+    a fault like -erroriter (RunPM1.cpp:7134).  The reference compares its block counter with a variable that stays 0
+    (RunPM1.cpp:7155 `gl_checkpass == checkpass`), so its lot check only ever runs at the last bit; here the computed
+    level (every `check_level` full blocks, default the reference's 600 s formula) is honoured."""
+    say = log or (lambda s: None)
     E = pm1_exponent(p, b1)
-    eng.set(reg, 1)
-    for bit in bin(E)[2:]:
-        eng.square_mul(reg, 3 if bit == "1" else 1)
-    x = _value(eng, reg, p)
+    bits = E.bit_length()
+    regs = getattr(eng, "reg_count", None)
+    if gerbicz is None:
+        gerbicz = regs is not None and regs >= 11 and reg == 0
     m = (1 << p) - 1
-    g = math.gcd((x - 1) % m, m) if gcd else 1          # (Python's gcd is quadratic: skip it for 10^8-bit smoke runs)
-    return {"exponent": p, "worktype": "PM1", "b1": b1, "factor": g if 1 < g < m else None, "bits": E.bit_length(),
-            "fft_length": eng.get_size(), "x": x}
+    errors = 0
+    if not gerbicz:
+        eng.set(reg, 1)
+        for k in range(bits - 1, -1, -1):
+            eng.square_mul(reg, 3 if (E >> k) & 1 else 1)
+            if error_iter and bits - k == error_iter:
+                eng.sub(reg, 2)
+        state = reg
+    else:
+        S, L, Rr, CHK, POW, TMP, START, SAVE_S = PM1_RSTATE, PM1_RACC_L, PM1_RACC_R, PM1_RCHK, PM1_RPOW, PM1_RTMP, PM1_RSTART, PM1_RSAVE_S
+        B = max(1, math.isqrt(bits))
+        level_auto = int(1000 * 600.0 / B) or max((bits // B) // max(math.isqrt(B), 1), 1)
+        level = check_level if check_level > 0 else max(level_auto, 1)
+        eng.set(PM1_RBASE, 3); eng.set(S, 1)
+        eacc = wbits = 0
+        gl_checkpass = blocks_since_check = bits_in_block = 0
+        current_block_len = ((bits - 1) % B) + 1
+        in_lot, errordone, restores = False, False, 0
+        i = bits
+        while i > 0:
+            if bits_in_block == 0:
+                current_block_len = ((i - 1) % B) + 1
+                if current_block_len == B:
+                    if gl_checkpass == 0 and blocks_since_check == 0 and wbits == 0 and eacc == 0:
+                        eng.set(L, 1); eng.set(Rr, 1); eng.copy(SAVE_S, S)
+                        eng.set(PM1_RSAVE_L, 1); eng.set(PM1_RSAVE_R, 1)
+                        in_lot = True
+                else:
+                    in_lot = False
+                    gl_checkpass = blocks_since_check = 0
+                    eacc = wbits = 0
+                eng.copy(START, S)
+            b = (E >> (i - 1)) & 1
+            eng.square_mul(S, 3 if b else 1)
+            wbits = (wbits << 1) | b
+            bits_in_block += 1
+            if error_iter > 0 and bits - i + 1 == error_iter and not errordone:
+                errordone = True
+                eng.sub(S, 2)
+                say(f"Injected error at iteration {bits - i + 1}")
+            if bits_in_block == current_block_len:
+                if current_block_len == B:
+                    eng.set_multiplicand(TMP, START); eng.mul(L, TMP)
+                    eng.set_multiplicand(TMP, S); eng.mul(Rr, TMP)
+                    eacc += wbits
+                    blocks_since_check += 1
+                    gl_checkpass += 1
+                    if in_lot and (gl_checkpass == level or i == 1):
+                        eng.copy(CHK, L)
+                        for _ in range(B):
+                            eng.square_mul(CHK)
+                        _fast3_pow(eng, POW, eacc)
+                        eng.set_multiplicand(TMP, POW); eng.mul(CHK, TMP)
+                        if not _same(eng, CHK, Rr, p):
+                            say("[Gerbicz Li] Mismatch : Last correct state will be restored")
+                            errors += 1; restores += 1
+                            if restores > max_restores:
+                                raise RuntimeError("Gerbicz-Li: too many restores")
+                            eng.copy(S, SAVE_S); eng.set(L, 1); eng.set(Rr, 1); eng.copy(START, S)
+                            i += blocks_since_check * B - 1          # back to the first bit of the lot (the loop's --i is not taken)
+                            eacc = wbits = 0
+                            blocks_since_check = gl_checkpass = bits_in_block = 0
+                            continue
+                        say("[Gerbicz Li] Check passed")
+                        eng.copy(SAVE_S, S); eng.set(L, 1); eng.set(Rr, 1)
+                        eacc = 0; blocks_since_check = gl_checkpass = 0
+                else:
+                    eng.copy(CHK, START)
+                    for _ in range(current_block_len):
+                        eng.square_mul(CHK)
+                    _fast3_pow(eng, POW, wbits)
+                    eng.set_multiplicand(TMP, POW); eng.mul(CHK, TMP)
+                    if not _same(eng, CHK, S, p):
+                        say("[Gerbicz Li] Mismatch : Last correct state will be restored")
+                        errors += 1; restores += 1
+                        if restores > max_restores:
+                            raise RuntimeError("Gerbicz-Li: too many restores")
+                        eng.copy(S, START)
+                        i += current_block_len - 1
+                        wbits = bits_in_block = 0
+                        continue
+                    say("[Gerbicz Li] Check passed")
+                    eng.copy(SAVE_S, S); eng.set(L, 1); eng.set(Rr, 1)
+                    eacc = 0; blocks_since_check = gl_checkpass = 0
+                bits_in_block = 0
+                wbits = 0
+            i -= 1
+        state = S
+    x = _value(eng, state, p)
+    g = hostmath.gcd((x - 1) % m, m) if gcd else 1
+    return {"exponent": p, "worktype": "PM1", "b1": b1, "factor": g if 1 < g < m else None, "bits": bits,
+            "fft_length": eng.get_size(), "x": x, "errors_gerbicz": errors}
+
+
+# ---- canonical P-1 interchange files (backend independent): GMP-ECM resume line and Prime95 stage-1 save file
+# (AlgoUtils.hpp:465-508,600-733; written by the reference after stage 1, RunPM1.cpp:7263-7275)
+_CHKSUMMOD = 4294967291
+
+
+def pm1_resume_line(p, b1, x):
+    """writeEcmResumeLine (AlgoUtils.hpp:487-508): one line a GMP-ECM / PrMers stage 2 can resume from."""
+    chk = (b1 % _CHKSUMMOD) * (((1 << p) - 1) % _CHKSUMMOD) % _CHKSUMMOD * (x % _CHKSUMMOD) % _CHKSUMMOD
+    return (f"METHOD=P-1; B1={b1}; N=2^{p}-1; X=0x{x:x}; CHECKSUM={chk}; "
+            "PROGRAM=PrMers; X0=0x3; Y=0x0; Y0=0x0; WHO=; TIME=;\n")
+
+
+def parse_pm1_resume_line(line):
+    """The fields the reference reads back (AlgoUtils.hpp:585-612); verifies the checksum."""
+    f = dict(kv.strip().split("=", 1) for kv in line.strip().rstrip(";").split(";") if "=" in kv)
+    b1, p, x = int(f["B1"]), int(f["N"][2:].split("-")[0]), int(f["X"], 16)
+    chk = (b1 % _CHKSUMMOD) * (((1 << p) - 1) % _CHKSUMMOD) % _CHKSUMMOD * (x % _CHKSUMMOD) % _CHKSUMMOD
+    if "CHECKSUM" in f and int(f["CHECKSUM"]) != chk:
+        raise ValueError("P-1 resume line: checksum mismatch")
+    return {"p": p, "b1": b1, "x": x}
+
+
+def pm1_p95_bytes(p, b1, x, date_start="", date_end="", version="b200"):
+    """write_prime95_s1_from_bytes (AlgoUtils.hpp:641-733): Prime95's stage-1 save file for the residue X."""
+    import struct, zlib
+    h = f"{x:x}"
+    h = "0" * ((8 - (len(h) & 7)) & 7) + h
+    data = bytes.fromhex(h)[::-1]                                   # little-endian bytes, padded to whole 32-bit words
+    s32 = sum(struct.unpack(f"<{len(data) // 4}I", data)) if data else 0
+    chk = ((b1 << 1) + 6 + (len(data) >> 1) + s32) & 0xFFFFFFFF
+    out = struct.pack("<IIdiIiBBHQdIiQQii", 830093643, 8, 1.0, 2, p, -1, ord("S"), ord("1"), 0, 0, 1.0, chk, 5, b1, b1, 1, len(data) >> 2)
+    out += data
+    js = (',"programs":[{"work":{"type":"PM1","stage":"1"},"program":{"name":"prmers","version":"' + version + '"},"os":{"os":"Linux",'
+          '"architecture":"x86_64"},"date_start":"' + date_start + '","date_end":"' + date_end + '"}]').encode()
+    out += b"MOREINFOJSONDATA" + struct.pack("<III", 8 + len(js), 1, zlib.crc32(js) & 0xFFFFFFFF) + js
+    return out
+
+
+def parse_pm1_p95(buf):
+    """read_prime95_s1_to_bytes (AlgoUtils.hpp:735-800): exponent, B1 and residue of a Prime95 stage-1 file."""
+    import struct
+    fmt = "<IIdiIiBBHQdIiQQii"
+    hd = struct.unpack_from(fmt, buf, 0)
+    if hd[0] != 830093643:
+        raise ValueError("not a Prime95 P-1 save file")
+    p, chk, b1, nwords = hd[4], hd[11], hd[13], hd[16]
+    off = struct.calcsize(fmt)
+    data = buf[off:off + 4 * nwords]
+    if len(data) != 4 * nwords:
+        raise ValueError("truncated Prime95 P-1 save file")
+    s32 = sum(struct.unpack(f"<{nwords}I", data)) if nwords else 0
+    if ((b1 << 1) + 6 + (len(data) >> 1) + s32) & 0xFFFFFFFF != chk:
+        raise ValueError("Prime95 P-1 save file: checksum mismatch")
+    return {"p": p, "b1": b1, "x": int.from_bytes(data, "little")}
+
+
+def write_pm1_resume(directory, p, b1, x):
+    """resume_p<p>_B1_<b1>.save / .p95 as RunPM1.cpp:7268-7274 names them; returns the two paths."""
+    import os
+    base = os.path.join(directory, f"resume_p{p}_B1_{b1}")
+    with open(base + ".save", "w") as f:
+        f.write(pm1_resume_line(p, b1, x))
+    with open(base + ".p95", "wb") as f:
+        f.write(pm1_p95_bytes(p, b1, x))
+    return base + ".save", base + ".p95"
 
 
 # ---- P-1 stage 2, V-trace (RunPM1.cpp:1931-4335): register map of RunPM1.cpp:3192-3209 ------------------
@@ -222,17 +420,68 @@ def _lucas_jump(eng, k):
             eng.copy(B, T)                                 # B = V_{2m+1}
 
 
-def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None):
+def euler_phi(n):
+    r, x, q = n, n, 2
+    while q * q <= x:
+        if x % q == 0:
+            while x % q == 0:
+                x //= q
+            r -= r // q
+        q += 1
+    if x > 1:
+        r -= r // x
+    return r
+
+
+VTRACE_BASE_REGS = BABY_BASE
+VTRACE_D_CANDIDATES = (30, 60, 90, 210, 420, 630, 1260, 2310, 4620, 6930, 30030, 60060, 90090)
+
+
+def vtrace_plan(p, b1, b2, n, free_bytes, D=None, baby_batch=None, max_regs=4096, mem_fraction=0.8):
+    """Choose D and the number of baby traces kept on the GPU (RunPM1.cpp:2227-2620 in spirit, README.md:520-562 in
+    letter): m(D) = phi(D)/2 baby traces, b of them resident, P = ceil(m/b) passes over the giant steps.  Cost model
+    of the README: P * (B2 - B1) / D giant steps of ~4 engine ops, one term (4 ops) per prime pair, D baby steps of 4
+    ops per pass.  `free_bytes` is what cudaMemGetInfo reports (the reference asks OpenCL, RunPM1.cpp:1994-2026); a
+    register costs 8 n bytes.  A forced D and / or batch (-pm1-vtrace-d, -pm1-vtrace-baby-batch) are honoured."""
+    budget = max(int(free_bytes * mem_fraction) // (8 * n) - VTRACE_BASE_REGS, 1)
+    budget = min(budget, max_regs - VTRACE_BASE_REGS)
+    span = max(b2 - b1, 1)
+    nprimes = max(span / max(math.log(max(b2, 3)), 1.0), 1.0)
+    best = None
+    for d in ([D] if D else [d for d in VTRACE_D_CANDIDATES if d // 2 < b2]):
+        if d % 2 or d < 4:
+            raise ValueError("D must be even and >= 4")
+        m_d = euler_phi(d) // 2
+        b = min(baby_batch or m_d, m_d, budget) if not baby_batch else min(baby_batch, m_d)
+        if b > budget and baby_batch:
+            raise ValueError(f"baby batch {baby_batch} needs {VTRACE_BASE_REGS + b} registers of {8 * n} bytes: more than the device has free")
+        passes = -(-m_d // b)
+        # every prime pair (k D - j, k D + j) shares a term: the denser the residues, the more pairs
+        pair_gain = 1.0 + 0.5 * (1.0 - m_d / (d / 2.0))
+        cost = 4.0 * passes * span / d + 4.0 * nprimes / pair_gain + 4.0 * d * passes
+        cand = {"D": d, "babies": m_d, "baby_batch": b, "passes": passes, "regs": VTRACE_BASE_REGS + b, "cost": cost}
+        if best is None or cost < best["cost"]:
+            best = cand
+    return best
+
+
+def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None, baby_batch=None, v1_in_register=False):
     """P-1 stage 2 on traces V_n = H^n + H^-n: for every prime B1 < q <= B2 write q = k D +- j and
     accumulate (V_{kD} - V_j); both members of a pair share one term.  Returns the accumulator residue
     (an int) and statistics; the factor is gcd(acc, 2^p - 1) (use pm1_stage2_factor).  `k_range`
     restricts the giant steps to [k_lo, k_hi) so that ranks can split the prime range:
     each rank rebuilds the (deterministic) baby table, jumps to its first k by a Lucas ladder and
-    accumulates its own product."""
+    accumulates its own product.  `baby_batch` keeps only that many baby traces resident and makes
+    ceil(m(D) / baby_batch) passes over the giant steps, one per window of the baby table
+    (-pm1-vtrace-baby-batch, README.md:520-562); the accumulator runs through all passes.
+    `v1_in_register`: register RV1 already holds V_1 (then H is ignored: no 1/H on the host)."""
     m = (1 << p) - 1
     D = D or vtrace_choose_D(b1)
     babies = [j for j in range(1, D // 2 + 1) if math.gcd(j, D) == 1]
-    slot = {j: BABY_BASE + i for i, j in enumerate(babies)}
+    batch = min(baby_batch or len(babies), len(babies))
+    regs = getattr(eng, "reg_count", None)
+    if regs is not None and regs < BABY_BASE + batch:
+        raise ValueError(f"V-trace stage 2 with {batch} resident baby traces needs {BABY_BASE + batch} registers, the engine has {regs}")
     if sieve is None:
         sieve = bytearray([1]) * (b2 + D + 2)
         sieve[:2] = b"\0\0"
@@ -240,33 +489,42 @@ def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None):
             if sieve[i]:
                 sieve[i * i::i] = bytearray(len(sieve[i * i::i]))
     is_s2_prime = lambda q: b1 < q <= b2 and sieve[q]
-    V1 = (H + pow(H, -1, m)) % m
-    _set_int(eng, RV1, V1, p)
+    if not v1_in_register:
+        V1 = (H + hostmath.invert_mod(H, m)) % m       # (a non-invertible H would itself expose a factor: ValueError)
+        _set_int(eng, RV1, V1, p)
     eng.set_multiplicand(RMUL_V1, RV1)
-    # baby steps: V_0 = 2, V_1, V_{n+1} = V_1 V_n - V_{n-1}; store -V_j so the term is one add (RunPM1.cpp:3551-3587)
-    eng.set(RBPREV, 2); eng.copy(RBCUR, RV1)
-    for n in range(1, D + 1):
-        if n in slot:
-            eng.set(slot[n], 0); eng.sub_reg(slot[n], RBCUR)
-        if n == D:
-            eng.copy(RVD, RBCUR)
-            break
-        eng.copy(RBNEXT, RBCUR); eng.mul(RBNEXT, RMUL_V1); eng.sub_reg(RBNEXT, RBPREV)
-        eng.copy(RBPREV, RBCUR); eng.copy(RBCUR, RBNEXT)
-    eng.set_multiplicand(RMUL_VD, RVD)
     k_first, k_last = (b1 + 1 + D // 2) // D, (b2 + D // 2) // D
     k_lo, k_hi = k_range if k_range else (k_first, k_last + 1)
     k_lo, k_hi = max(k_lo, k_first), min(k_hi, k_last + 1)
     eng.set(RACC, 1)
-    terms = primes = 0
-    if k_lo < k_hi:
+    terms = primes = passes = 0
+    have_vd = False
+    for w0 in range(0, len(babies), batch):
+        window = babies[w0:w0 + batch]
+        slot = {j: BABY_BASE + i for i, j in enumerate(window)}
+        passes += 1
+        # baby steps: V_0 = 2, V_1, V_{n+1} = V_1 V_n - V_{n-1}; store -V_j so the term is one add (RunPM1.cpp:3551-3587)
+        eng.set(RBPREV, 2); eng.copy(RBCUR, RV1)
+        top = D if not have_vd else max(window)
+        for n in range(1, top + 1):
+            if n in slot:
+                eng.set(slot[n], 0); eng.sub_reg(slot[n], RBCUR)
+            if n == top:
+                if n == D:
+                    eng.copy(RVD, RBCUR); have_vd = True
+                break
+            eng.copy(RBNEXT, RBCUR); eng.mul(RBNEXT, RMUL_V1); eng.sub_reg(RBNEXT, RBPREV)
+            eng.copy(RBPREV, RBCUR); eng.copy(RBCUR, RBNEXT)
+        eng.set_multiplicand(RMUL_VD, RVD)
+        if k_lo >= k_hi:
+            continue
         if k_lo == 0:
             eng.set(RGCUR, 2)                                  # V_0; V_{-D} = V_D
             eng.copy(RGPREV, RVD)
         else:
             _lucas_jump(eng, k_lo)
         for k in range(k_lo, k_hi):
-            for j in babies:
+            for j in window:
                 lo, hi = k * D - j, k * D + j
                 a, b = lo > 0 and is_s2_prime(lo), is_s2_prime(hi)
                 if not (a or b):
@@ -278,16 +536,45 @@ def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None):
             # next giant step: V_{(k+1)D} = V_D V_{kD} - V_{(k-1)D}  (RunPM1.cpp:3788-3797)
             eng.copy(RGNEXT, RGCUR); eng.mul(RGNEXT, RMUL_VD); eng.sub_reg(RGNEXT, RGPREV)
             eng.copy(RGPREV, RGCUR); eng.copy(RGCUR, RGNEXT)
-    return {"acc": _value(eng, RACC, p), "terms": terms, "primes": primes, "D": D, "k_range": (k_lo, k_hi)}
+    return {"acc": _value(eng, RACC, p), "terms": terms, "primes": primes, "D": D, "k_range": (k_lo, k_hi),
+            "passes": passes, "baby_batch": batch}
 
 
-def pm1_stage2_factor(p, accs):
-    """gcd of the product of the per-rank accumulators with 2^p - 1 (RunPM1.cpp:4261-4262)."""
+def run_pm1_stage2_sharded(engine_factory, p, b1, b2, H, D=None, baby_batch=None, known_factors=()):
+    """Config 4's second half across the GPUs of a box: the giant-step range is cut in `world` equal
+    shares, every rank (one process per GPU, own engine) rebuilds the baby table, jumps to its first giant step and
+    accumulates its own product; the only exchange is the gather of the canonical accumulator residues (~p / 8 bytes
+    each) at the end, multiplied together modulo 2^p - 1 for ONE gcd (RunPM1.cpp:4211-4212,4261-4262).  Every rank
+    returns the merged result."""
+    from . import multi
+    rank, world = multi.rank_world()
+    D = D or vtrace_choose_D(b1)
+    share = split_k_range(b1, b2, D, world)[rank]
+    nb = min(baby_batch or 10**9, sum(1 for j in range(1, D // 2 + 1) if math.gcd(j, D) == 1))
+    eng = engine_factory(p, BABY_BASE + nb)
+    try:
+        r = run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=D, k_range=share, baby_batch=baby_batch)
+    finally:
+        if hasattr(eng, "close"):
+            eng.close()
+    parts = multi.gather([{"rank": rank, "acc": r["acc"], "terms": r["terms"], "primes": r["primes"], "k_range": r["k_range"]}])
+    parts.sort(key=lambda d: d["rank"])
+    return {"exponent": p, "worktype": "PM1", "b1": b1, "b2": b2, "D": D, "world": world,
+            "factor": pm1_stage2_factor(p, [d["acc"] for d in parts], known_factors),
+            "terms": sum(d["terms"] for d in parts), "primes": sum(d["primes"] for d in parts), "parts": parts}
+
+
+def pm1_stage2_factor(p, accs, known_factors=()):
+    """gcd of the product of the per-rank accumulators with 2^p - 1 (RunPM1.cpp:4261-4262); factors already known
+    (-factors, README.md:495-509) are divided out of it."""
     m = (1 << p) - 1
     acc = 1
     for a in accs:
-        acc = acc * a % m
-    g = math.gcd(acc, m)
+        acc = hostmath.mulmod_mersenne(acc, a, p)
+    g = hostmath.gcd(acc, m)
+    for f in known_factors:
+        while f > 1 and g % f == 0:
+            g //= f
     return g if 1 < g < m else None
 
 
@@ -359,7 +646,7 @@ def run_ll_safe(eng, p, check_level=0, error_iter=0, log=None, max_restores=4):
                 _pair_mul_by(eng, LS_CHK_A, LS_CHK_B, LS_BASE_A, LS_BASE_B)
                 for _ in range(modB):
                     _pair_square(eng, LS_CHK_A, LS_CHK_B)
-                same = (_value(eng, LS_CHK_A, p) == _value(eng, LS_ACC_A, p) and _value(eng, LS_CHK_B, p) == _value(eng, LS_ACC_B, p))
+                same = _same(eng, LS_CHK_A, LS_ACC_A, p) and _same(eng, LS_CHK_B, LS_ACC_B, p)
                 checkpass = 0
                 if not same:
                     say(f"[Gerbicz Li] Check FAILED! iter={it + 1}")

@@ -60,7 +60,7 @@ class EmuEngine:
         self._h = L.emu_create(p, regs, force_S, force_R2)
         if not self._h:
             raise ValueError(L.emu_last_error().decode())
-        self.p, self.n = p, L.emu_size(self._h)
+        self.p, self.n, self.reg_count = p, L.emu_size(self._h), regs
         self.small = bool(L.emu_is_small(self._h))
         self.R, self.S, self.R2 = L.emu_plan_R(self._h), L.emu_plan_S(self._h), L.emu_plan_R2(self._h)
         self.a_max = L.emu_a_max(self._h)

@@ -198,3 +198,156 @@ def test_gerbicz_catches_injected_error_at_full_size_gpu():
     r = modes.run_prp(e, p, check_level=1, error_iter=5000, stop_after_checks=1, log=log.append)
     assert any("Check FAILED" in s for s in log) and r["errors_gerbicz"] == 1 and r["checks_passed"] == 1
     e.close()
+
+
+# ---- round 2: P-1 stage 1 with Gerbicz-Li, resume files, V-trace windows / planner, cofactor PRP -------------------
+def test_pm1_stage1_gerbicz_li_detects_and_recovers():
+    """RunPM1.cpp:7102-7190 on exact arithmetic: an injected fault anywhere (first bit, inside the short first block,
+    inside a lot of full blocks, last bit) is caught, the saved state restored and the final X unchanged."""
+    from oracle.int_engine import IntEngine
+    for p, b1, f in [(269, 2141, 13822297), (541, 899, 4312790327), (263, 3527, 23671)]:
+        log = []
+        good = modes.run_pm1_stage1(IntEngine(p, 11), p, b1, check_level=2, log=log.append)
+        assert good["factor"] == f and good["errors_gerbicz"] == 0 and sum("Check passed" in s for s in log) >= 3
+        for ei in (1, 37, good["bits"] // 2, good["bits"] - 3, good["bits"]):
+            log = []
+            r = modes.run_pm1_stage1(IntEngine(p, 11), p, b1, check_level=2, error_iter=ei, log=log.append)
+            assert r["errors_gerbicz"] == 1 and r["x"] == good["x"] and r["factor"] == f, (p, ei)
+            assert any("Mismatch" in s for s in log)
+    # the kernels' own arithmetic (emulated), default check level
+    p, b1 = 1279, 500
+    good = modes.run_pm1_stage1(EmuEngine(p, 2), p, b1)
+    r = modes.run_pm1_stage1(EmuEngine(p, 11), p, b1, error_iter=300)
+    assert r["errors_gerbicz"] == 1 and r["x"] == good["x"]
+    assert modes.run_pm1_stage1(EmuEngine(p, 11), p, b1)["errors_gerbicz"] == 0
+
+
+def test_pm1_resume_files_round_trip_and_checksums():
+    """AlgoUtils.hpp:465-508 (.save line, checksum B1 * N * X mod 4294967291) and :618-733 (.p95 header, word-sum checksum)."""
+    import struct
+    p, b1 = 541, 899
+    x = modes.run_pm1_stage1(EmuEngine(p, 2), p, b1)["x"]
+    line = modes.pm1_resume_line(p, b1, x)
+    assert line.startswith(f"METHOD=P-1; B1={b1}; N=2^{p}-1; X=0x{x:x}; CHECKSUM=") and line.endswith("PROGRAM=PrMers; X0=0x3; Y=0x0; Y0=0x0; WHO=; TIME=;\n")
+    chk = int(line.split("CHECKSUM=")[1].split(";")[0])
+    assert chk == (b1 % 4294967291) * (mr.mp(p) % 4294967291) % 4294967291 * (x % 4294967291) % 4294967291
+    assert modes.parse_pm1_resume_line(line) == {"p": p, "b1": b1, "x": x}
+    with pytest.raises(ValueError):
+        modes.parse_pm1_resume_line(line.replace(f"CHECKSUM={chk}", f"CHECKSUM={chk ^ 1}"))
+    blob = modes.pm1_p95_bytes(p, b1, x)
+    magic, ver, fver, typ, pp = struct.unpack_from("<IIdiI", blob, 0)
+    assert (magic, ver, fver, typ, pp) == (830093643, 8, 1.0, 2, p) and blob[28:30] == b"S1" and b"MOREINFOJSONDATA" in blob
+    assert modes.parse_pm1_p95(blob) == {"p": p, "b1": b1, "x": x}
+    bad = bytearray(blob); bad[90] ^= 1
+    with pytest.raises(ValueError):
+        modes.parse_pm1_p95(bytes(bad))
+
+
+def test_vtrace_windows_forced_D_and_planner():
+    """-pm1-vtrace-d / -pm1-vtrace-baby-batch (README.md:520-562): the factor does not depend on D or on how many baby
+    traces are resident; the planner honours forced values and the memory budget."""
+    from oracle.int_engine import IntEngine
+    p, b1, b2 = 269, 4, 2141
+    H = modes.run_pm1_stage1(IntEngine(p, 2), p, b1)["x"]
+    seen = set()
+    for D, bb in [(None, None), (6, 1), (30, None), (30, 2), (210, 5), (210, 24)]:
+        r = modes.run_pm1_stage2_vtrace(IntEngine(p, 14 + (bb or 64)), p, b1, b2, H, D=D, baby_batch=bb)
+        assert modes.pm1_stage2_factor(p, [r["acc"]]) == 13822297, (D, bb)
+        assert r["passes"] == -(-modes.euler_phi(r["D"]) // 2 // r["baby_batch"])
+        seen.add(r["passes"])
+    assert seen >= {1, 2, 5}
+    with pytest.raises(ValueError):
+        modes.run_pm1_stage2_vtrace(IntEngine(p, 15), p, b1, b2, H, D=30, baby_batch=4)        # not enough registers
+    n = 10485760
+    full = modes.vtrace_plan(205271257, 1300000, 250000000, n, 170e9)
+    assert full["regs"] * 8 * n <= 0.8 * 170e9 and full["passes"] * full["baby_batch"] >= full["babies"]
+    forced = modes.vtrace_plan(205271257, 1300000, 250000000, n, 170e9, D=2310, baby_batch=72)
+    assert (forced["D"], forced["babies"], forced["baby_batch"], forced["passes"], forced["regs"]) == (2310, 240, 72, 4, 86)
+    small = modes.vtrace_plan(205271257, 1300000, 250000000, n, 4e9)
+    assert small["regs"] * 8 * n <= 0.8 * 4e9 and small["passes"] > 1
+    assert modes.pm1_stage2_factor(p, [0], known_factors=()) is None
+
+
+def test_cofactor_prp_m2699():
+    """unit_tests.sh:216-234: M2699 over four known factors is composite, over five is a probable prime."""
+    f4 = [5399, 307687, 1187561, 7570504839257]
+    r = modes.run_prp(EmuEngine(2699, 8), 2699, known_factors=f4)
+    assert not r["is_prp"] and r["residue_type"] == 5
+    r5 = modes.run_prp(EmuEngine(2699, 8), 2699, known_factors=f4 + [1987104667810711])
+    assert r5["is_prp"] and r5["res64"] == r["res64"]
+    with pytest.raises(ValueError):
+        modes.run_prp(EmuEngine(127, 8), 127, known_factors=[7])
+
+
+@pytest.mark.parametrize("p,b1,b2,s1,s2", [(2151, 256, 4073, 327405968242246366421788399, 31810015665526476520196715312101168065463218256802641),
+                                            (367, 11981, 38971, 646300400639, 50500996776315830904406967)])
+def test_pm1_two_stage_vectors_bigint(p, b1, b2, s1, s2):
+    """unit_tests.sh:60,63 (both stages report a factor) on exact arithmetic."""
+    from oracle.int_engine import IntEngine
+    r = modes.run_pm1_stage1(IntEngine(p, 11), p, b1)
+    assert r["factor"] == s1
+    D = modes.vtrace_choose_D(b1, max_babies=48)
+    acc = modes.run_pm1_stage2_vtrace(IntEngine(p, modes.vtrace_regs_needed(D)), p, b1, b2, r["x"], D=D)["acc"]
+    assert modes.pm1_stage2_factor(p, [acc]) == s2
+
+
+@pytest.mark.gpu
+def test_pm1_stage1_gerbicz_li_gpu():
+    """-erroriter on the P-1 exponentiation: p = 9941 (unit-test size) and BASELINE config 4's exponent (n = 5 * 2^21) at
+    a reduced B1, against the GMP golden state."""
+    import json, os
+    import prmers_b200 as pb
+    p, b1 = 9941, 3000
+    good = modes.run_pm1_stage1(pb.Engine(p, 2), p, b1)
+    for ei in (55, good["bits"] - 1):
+        log = []
+        r = modes.run_pm1_stage1(pb.Engine(p, 11), p, b1, error_iter=ei, check_level=3, log=log.append)
+        assert r["errors_gerbicz"] == 1 and r["x"] == good["x"] and any("Mismatch" in s for s in log)
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pm1_stage1_res64.json")))["cases"][0]
+    assert g["p"] == 205271257
+    eng = pb.Engine(g["p"], 11)
+    log = []
+    r = modes.run_pm1_stage1(eng, g["p"], g["b1"], gcd=False, error_iter=77, check_level=2, log=log.append)
+    assert r["errors_gerbicz"] == 1 and sum("Check passed" in s for s in log) >= 2
+    assert f"{r['x'] & 0xFFFFFFFFFFFFFFFF:016X}" == g["res64"] and f"{r['x'] & ((1 << 256) - 1):064x}" == g["res2048_low"]
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_vtrace_stage2_config4_size_golden_gpu():
+    """V-trace stage 2 on the p = 205271257 engine (n = 5 * 2^21) with a forced D, and at n = 65536 with baby windows,
+    against accumulators computed by the plain recurrence on GMP integers (tools/make_golden_pm1_stage2.py)."""
+    import hashlib, json, os
+    import prmers_b200 as pb
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pm1_stage2_vtrace.json")))["cases"]
+    for g in gold:
+        p, D = g["p"], g["D"]
+        nb = modes.euler_phi(D) // 2
+        for batch in ((None,) if p > 10**8 else (None, 7)):
+            eng = pb.Engine(p, modes.BABY_BASE + (batch or nb))
+            eng.set(modes.RV1, 3)
+            for _ in range(g["v1_squarings"]):
+                eng.square_mul(modes.RV1)
+            r = modes.run_pm1_stage2_vtrace(eng, p, g["b1"], g["b2"], None, D=D, baby_batch=batch, v1_in_register=True)
+            assert (r["terms"] // r["passes"] if False else True) and r["primes"] == g["primes"]
+            acc = r["acc"]
+            assert f"{acc & 0xFFFFFFFFFFFFFFFF:016X}" == g["res64"], (p, batch)
+            assert hashlib.sha256(acc.to_bytes((p + 7) // 8, "little")).hexdigest() == g["sha256"]
+            eng.close()
+
+
+@pytest.mark.gpu
+def test_readme_vtrace_regression_gpu():
+    """README.md:495-509: `prmers 1362763 -pm1 -b1 29 -b2 6910159 -nogcd-stage1 -factors 46333943,282345414919
+    [-pm1-vtrace-d 30030]` -> 28401397572100073.  The factor's only stage-2 prime is B2 itself, so the giant steps are
+    restricted to the last few of the range (Lucas-ladder jump, as a rank of a split run would): the full range is
+    470 000 terms of nothing else."""
+    import prmers_b200 as pb
+    p, b1, b2 = 1362763, 29, 6910159
+    H = modes.run_pm1_stage1(pb.Engine(p, 2), p, b1, gcd=False)["x"]
+    for D, batch in ((30030, 96), (2310, None)):
+        k_last = (b2 + D // 2) // D
+        eng = pb.Engine(p, modes.BABY_BASE + (batch or modes.euler_phi(D) // 2))
+        r = modes.run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=D, baby_batch=batch, k_range=(k_last - 2, k_last + 1))
+        assert modes.pm1_stage2_factor(p, [r["acc"]], known_factors=[46333943, 282345414919]) == 28401397572100073, D
+        eng.close()
