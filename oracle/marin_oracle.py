@@ -20,7 +20,8 @@ def build(force=False):
     """Compile the C oracle (and oracle/_ref when /root/reference is present)."""
     src = os.path.join(_HERE, "marin_oracle.c")
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
-    if force or stale or (os.path.isdir("/root/reference/include/marin") and not os.path.exists(_REF_PATH)):
+    ecm_ref = os.path.join(_HERE, "_ref", "libecm_ref.so")
+    if force or stale or (os.path.isdir("/root/reference/include/marin") and not (os.path.exists(_REF_PATH) and os.path.exists(ecm_ref))):
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
     return _LIB_PATH
 
