@@ -35,8 +35,9 @@ ITERS = 1000            # squarings per step
 METRIC = "PRP iterations/s, M136279841-class exponents (n = 2^23 IBDWT), whole job"
 # steady state of a squaring chain: two launches per square_mul (the inverse pass also runs the next
 # squaring's forward strided pass on the tile it holds); (name, bench_pass id, algorithmic bytes / n)
-PASSES = [("k_mid (contiguous pass: forward, pointwise square, inverse)", 1, 16),
-          ("k_strided<1> (strided inverse + unweight/carry/reweight + next strided forward)", 3, 32)]
+PASSES = [("k_mid_fast<SQR> (contiguous pass: forward, pointwise square, inverse)", 1, 16),
+          ("k_inv_fast_T4<true> (strided inverse + unweight/carry/reweight + next strided forward)", 3, 32)]
+SUMMARY_KEYS = ["k_mid_fast", "k_inv_fast_T4"]          # kernel keys of profiles/ncu_summary.json, same order
 
 
 def measured_peak():
@@ -142,6 +143,107 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_workload(args, rank, local_rank, world):
+    """--workload pm1 | ecm: BASELINE configs 4 and 5, one JSON line each (the default headline line is unchanged)."""
+    import torch
+    import torch.distributed as dist
+    import prmers_b200 as pb
+    from prmers_b200 import ecm, modes, multi
+    dev = torch.device("cuda", local_rank)
+    factory = lambda q, regs: pb.Engine(q, regs, device=local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if args.workload == "pm1":
+        # config 4: p = 205271257 (n = 5 * 2^21); stage 1 is a squaring chain (ms per square_mul); stage 2 = V-trace with a
+        # forced D = 210 and all 24 baby traces resident (-pm1-vtrace-d 210 -pm1-vtrace-baby-batch 24), a bounded slice of
+        # the giant steps right after B1 = 1 300 000 per rank (the ranks split the range as a real run would)
+        p, b1, D, steps_k = 205271257, 1300000, 210, 6 * max(args.steps, 1)
+        eng = factory(p, modes.BABY_BASE + 24)
+        n = eng.get_size()
+        eng.set(modes.RV1, 3)
+        eng.square_mul_repeat(modes.RV1, 40)
+        for _ in range(max(args.warmup, 3)):
+            eng.bench_square_mul(modes.RACC, 50)
+        ms_sq = eng.bench_square_mul(modes.RACC, 300) / 300
+        eng.set(1, 5); eng.square_mul_repeat(1, 20); eng.set_multiplicand(2, 1); eng.sync()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            eng.mul(3, 2)
+        eng.sync()
+        ms_mul = (time.perf_counter() - t0) / 200 * 1e3
+        k_first = (b1 + 1 + D // 2) // D
+        k_lo = k_first + rank * steps_k
+        b2 = (k_first + world * steps_k) * D
+        launches0 = eng.launch_count()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = modes.run_pm1_stage2_vtrace(eng, p, b1, b2, None, D=D, k_range=(k_lo, k_lo + steps_k), v1_in_register=True)
+        dt = multi.max_over_ranks(time.perf_counter() - t0, device=dev)
+        launches = eng.launch_count() - launches0
+        terms = sum(multi.gather([r["terms"]]))
+        if rank == 0:
+            peak, peak_src = measured_peak()
+            line = {"metric": "P-1 stage-2 terms/s, V-trace, p = 205271257 (n = 5 * 2^21), whole job", "value": terms / dt, "unit": "terms/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3 / max(args.steps, 1),
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1)",
+                    "data": "synthetic (V_1 = 3^(2^40) mod Mp; bounds B1 = 1300000, a slice of the giant steps above it)",
+                    "config": {"workload": "BASELINE configs[3]: P-1 p = 205271257, B1 = 1300000, V-trace stage 2 with forced D = 210, 24 resident "
+                                           f"baby traces, {steps_k} giant steps per rank (baby table and Lucas jump included in the time)",
+                               "exponent": p, "transform_size": n, "D": D, "baby_batch": 24, "giant_steps_per_rank": steps_k,
+                               "parallelism": f"giant-step range split over {world} rank(s), no data-path collective"},
+                    "terms": terms, "primes": sum(multi.gather([r["primes"]])) if world == 1 else None,
+                    "ms_per_square_mul": ms_sq, "ms_per_mul": ms_mul, "ms_per_term": dt * 1e3 / max(r["terms"], 1),
+                    "e2e": {"value": terms / dt, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * 8,
+                            "note": "the driver runs through the public API; the accumulator residue is read back at the end"},
+                    "gpu_launches": int(launches), "clocks": sampler.stop(),
+                    "roofline": {"bound": "hbm", "kernel": "mul (3 passes + multiplicand read: 56 n bytes)", "achieved": 56 * n / (ms_mul * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": 56 * n / (ms_mul * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+                    "cpu_baseline": None}
+            print(json.dumps(line), flush=True)
+        eng.close()
+        return
+    # config 5: ECM on M701, B1 = 6000, B2 = 33333, K = 8 curves (twisted Edwards, default family), fixed seed; curve c on rank c mod world
+    # K = 8 is BASELINE's count (one launch now carries all 8: one CTA per curve); K = 296 fills the GPU (2 CTAs per SM)
+    p, b1, b2, K, seed = 701, 6000, 33333, 8, 123456789
+    bfactory = lambda q, regs, b: pb.Engine(q, regs, device=local_rank, batch=b)
+    ecm.run_ecm(factory, p, b1, b2, curves=1, seed=seed, continue_after_factor=True)      # warm-up curve (tables, graphs)
+    t0 = time.perf_counter()
+    seq = ecm.run_ecm(factory, p, b1, b2, curves=K, seed=seed, continue_after_factor=True, curve_indices=multi.assign(list(range(K)), rank, world))
+    dt_seq = multi.max_over_ranks(time.perf_counter() - t0, device=dev)
+    Kbig = 296 * world
+    t0 = time.perf_counter()
+    big = ecm.run_ecm_sharded(factory, p, b1, b2, curves=Kbig, seed=seed, batch_engine_factory=bfactory)
+    dt_big = multi.max_over_ranks(time.perf_counter() - t0, device=dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    reps = max(args.steps, 1)
+    res = None
+    for _ in range(reps):
+        res = ecm.run_ecm_sharded(factory, p, b1, b2, curves=K, seed=seed, batch_engine_factory=bfactory)
+    dt = multi.max_over_ranks(time.perf_counter() - t0, device=dev)
+    if rank == 0:
+        pops = sum(c.get("point_ops", 0) for c in res["curves"])
+        line = {"metric": "ECM curves/s, M701 B1 = 6000 B2 = 33333 (twisted Edwards), whole job", "value": K * reps / dt, "unit": "curves/s",
+                "n_gpus": world, "steps": reps, "warmup": 1, "ms_per_step": dt * 1e3 / reps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1)", "data": "synthetic (fixed -seed 123456789)",
+                "config": {"workload": "BASELINE configs[4]: ECM M701 B1 = 6000 B2 = 33333 K = 8 curves, n = 32, 51 registers per curve, all curves of a rank in lockstep on one batched engine (one CTA per curve)",
+                           "exponent": p, "transform_size": 32, "curves": K, "parallelism": f"curve c on rank c mod {world}"},
+                "point_ops_per_curve": pops / max(len(res["curves"]), 1),
+                "us_per_point_op_launch": dt * 1e6 / reps / max(pops / max(len(res["curves"]), 1), 1),
+                "sequential_one_engine_per_curve": {"curves_per_s": K / dt_seq, "note": "the reference's structure (RunEcmTwistedEdwards.cpp:1736-1830), point ops replayed as one launch each"},
+                "saturating_batch": {"curves": Kbig, "curves_per_s": Kbig / dt_big, "factors_found": sum(1 for c in big["curves"] if c["status"] == "found")},
+                "factors": sorted({str(c["factor"]) for c in res["curves"] if c.get("factor")}),
+                "e2e": {"value": K * reps / dt, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "host loop through the public API, gcds on the host"},
+                "gpu_launches": None, "clocks": sampler.stop(), "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +252,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=ITERS, help="square_mul per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="prp", choices=["prp", "pm1", "ecm"],
+                    help="prp = the headline (default); pm1 = BASELINE config 4 (V-trace stage 2 at n = 5 * 2^21); ecm = config 5 (M701)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -170,6 +274,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload != "prp":
+        run_workload(args, rank, local_rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,13 +338,33 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_iters / float(t.item())
 
+    # ---- the PRP loop itself with Gerbicz-Li on (BASELINE configs[1] says "with Gerbicz checks"): modes.run_prp through
+    # the API until the first check has passed, a check every 2 blocks of B = floor(sqrt p) squarings -- 25x more often
+    # than the reference's default (one per 51 blocks, RunPrpOrLlMarin.cpp:257-268), so this is the pessimistic figure
+    gerbicz = None
+    if rank == 0:
+        from prmers_b200 import modes
+        g_eng = pb.Engine(p, 8, device=local_rank)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = modes.run_prp(g_eng, p, check_level=2, stop_after_checks=1)
+        g_eng.sync()
+        dt = time.perf_counter() - t0
+        B = int(p ** 0.5)
+        gerbicz = {"value": r["stopped_at"] / dt, "unit": "iter/s", "iterations": r["stopped_at"], "seconds": dt,
+                   "block": B, "check_every_blocks": 2, "checks_passed": r["checks_passed"], "errors": r["errors_gerbicz"],
+                   "projected_at_reference_check_interval": value / world / (1.0 + 1.0 / 51 + 3.0 / B),
+                   "note": "modes.run_prp (square_mul; per block copy + set_multiplicand + mul; check = B squarings + device is_equal)"}
+        g_eng.close()
+
     if rank == 0:
         peak, peak_src = measured_peak()
         # per-kernel durations, live, with CUDA events on the launching stream
         passes = []
+        # ... on register 0: the live, dense residue (the data-dependent carry absorption runs as in the real loop)
         for _, which, _ in PASSES:
             cnt = 100
-            passes.append(eng.bench_pass(1, which, cnt) / cnt)            # ms per launch
+            passes.append(eng.bench_pass(0, which, cnt) / cnt)            # ms per launch
         dom = max(range(len(PASSES)), key=lambda i: passes[i])
         alg_bytes = PASSES[dom][2] * n                                    # 8n read + 8n write per pass of the 3-pass count
         achieved = alg_bytes / (passes[dom] * 1e-3) / 1e9
@@ -243,7 +372,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
                 summ = json.load(f)
-            traffic = summ["dram_bytes_per_launch"].get(["k_mid", "k_strided<1>+fwd"][dom])
+            traffic = summ["dram_bytes_per_launch"].get(SUMMARY_KEYS[dom])
             alu_instr = sum(summ["alu_pipe_warp_instructions_per_launch"].values())
         except Exception:
             pass
@@ -261,6 +390,7 @@ def main():
                        "l2": "working set per iteration (64 MiB register + 128 MiB weight tables) exceeds the 126 MB L2; no flush"},
             "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                     "note": "set_digits from pinned host memory + iters x square_mul + get (canonical digits) per step"},
+            "e2e_gerbicz": gerbicz,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": PASSES[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -281,7 +411,7 @@ def main():
             line["roofline_int_alu_pipe"] = {"achieved": alu_instr / (ms_iter * 1e-3), "peak": peak_alu, "unit": "warp-inst/s",
                                              "frac": alu_instr / (ms_iter * 1e-3) / peak_alu,
                                              "alu_warp_instructions_per_square_mul": alu_instr,
-                                             "source": "profiles/ncu_summary.json (ncu capture r1n) + live timing"}
+                                             "source": "profiles/ncu_summary.json (ncu capture) + live timing"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = cpu_baseline(64)

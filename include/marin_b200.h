@@ -29,6 +29,16 @@ size_t mb200_transform_size_for(uint32_t p);
 
 /* engine::create_gpu(q, reg_count, device, verbose) (src/marin/gpu.cpp:52-150, engine.h:301) */
 void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose);
+/* Batched engine (no reference counterpart: the reference creates one engine per ECM curve and runs the curves one
+   after the other, src/modes/RunEcmTwistedEdwards.cpp:1736-1755): `batch` independent register sets ("slabs") of
+   reg_count registers each, driven in lockstep -- every operation below runs on all slabs, one CTA per slab in the
+   same launch.  Single-CTA transform sizes only (n <= 2048: the ECM sizes).  Digits are read / written per slab;
+   mb200_get_digits / mb200_set_digits address slab 0; set_u32 writes the same small value to every slab;
+   mb200_equal is not available on a batched engine. */
+void *mb200_create_batch(uint32_t p, size_t reg_count, uint32_t device, int verbose, uint32_t batch);
+uint32_t mb200_batch(void *eng);
+int mb200_get_digits_slab(void *eng, uint32_t slab, size_t src, uint64_t *enc, size_t n);
+int mb200_set_digits_slab(void *eng, uint32_t slab, size_t dst, const uint64_t *enc, size_t n);
 void mb200_destroy(void *eng);                              /* delete eng */
 size_t mb200_transform_size(void *eng);                     /* engine::get_size, engine.h:40 */
 size_t mb200_register_count(void *eng);

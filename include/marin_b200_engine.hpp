@@ -98,6 +98,7 @@ public:
 class engine_b200 : public engine
 {
 	void *_h;
+	uint32_t _q = 0;
 	static void ck(int ok) { if (!ok) throw std::runtime_error(std::string("marin_b200 error: ") + mb200_last_error()); }
 
 protected:
@@ -106,7 +107,7 @@ protected:
 
 public:
 	engine_b200(const uint32_t q, const size_t reg_count, const size_t device, const bool verbose)
-		: _h(mb200_create(q, reg_count, uint32_t(device), verbose ? 1 : 0))
+		: _h(mb200_create(q, reg_count, uint32_t(device), verbose ? 1 : 0)), _q(q)
 	{
 		if (!_h) throw std::runtime_error(std::string("marin_b200 error: ") + mb200_last_error());
 	}
@@ -134,6 +135,20 @@ public:
 	int graph_end() const { int id = -1; ck(mb200_graph_end(_h, &id)); return id; }
 	void graph_launch(const int id) const { ck(mb200_graph_launch(_h, id)); }
 	bool is_equal(const Reg lhs, const Reg rhs) const override { int out = 0; ck(mb200_equal(_h, lhs, rhs, &out)); return out != 0; }
+#ifdef MARIN_B200_USE_REFERENCE_ENGINE_H
+	// the reference's default set_mpz splits z into digits WITHOUT reducing it (engine.h:205-232: bits above the exponent
+	// are dropped, so 2^q - 1 + 123 becomes 122); reduce first, as the reference's own plugin adapter does
+	// (src/aevum/EngineAevum.cpp:406-414), then let the reference's code do the split
+	void set_mpz(const Reg dst, const mpz_t &z) const override
+	{
+		mpz_t m, r;
+		mpz_init(m); mpz_init(r);
+		mpz_set_ui(m, 1); mpz_mul_2exp(m, m, _q); mpz_sub_ui(m, m, 1);
+		mpz_mod(r, z, m);
+		engine::set_mpz(dst, r);
+		mpz_clear(m); mpz_clear(r);
+	}
+#endif
 
 	size_t get_register_data_size() const override { return mb200_register_data_size(_h); }
 	bool get_data(std::vector<char> &data, const Reg src) const override

@@ -32,8 +32,9 @@ using namespace marin;
 #define MARIN_STR_MINB 2
 #endif
 
-__global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __grid_constant__ MidArgs A)
+__global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __grid_constant__ MidArgs A0)
 {
+	const MidArgs A = slab_of(A0, blockIdx.y);
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	u64 *smc = reinterpret_cast<u64 *>(sm + smem_pairs_lin(A.S));
@@ -66,19 +67,22 @@ template <bool INV> __global__ void __launch_bounds__(MARIN_STR_MAXT, MARIN_STR_
 	}
 }
 
-__global__ void k_lin_p1(const __grid_constant__ LinArgs A, u32 count)
+__global__ void k_lin_p1(const __grid_constant__ LinArgs A0, u32 count)
 {
+	const LinArgs A = slab_of(A0, blockIdx.y);
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < count) lin_p1_thread(A, i);
 }
-__global__ void k_lin_p2(const __grid_constant__ LinArgs A, u32 count)
+__global__ void k_lin_p2(const __grid_constant__ LinArgs A0, u32 count)
 {
+	const LinArgs A = slab_of(A0, blockIdx.y);
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < count) lin_p2_thread(A, i);
 }
 // carry into the first pair of every block, taken from the ORIGINAL register content (runs before k_lin_pairs)
-__global__ void k_lin_boundary(const __grid_constant__ LinArgs A, u32 nblocks)
+__global__ void k_lin_boundary(const __grid_constant__ LinArgs A0, u32 nblocks)
 {
+	const LinArgs A = slab_of(A0, blockIdx.y);
 	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= nblocks) return;
 	const u32 npairs = A.t.n / 2;
@@ -86,8 +90,9 @@ __global__ void k_lin_boundary(const __grid_constant__ LinArgs A, u32 nblocks)
 	A.carry[b] = lin_pair_carry(A, (first == 0) ? npairs - 1 : first - 1);
 }
 
-__global__ void __launch_bounds__(LIN_BLOCK) k_lin_pairs(const __grid_constant__ LinArgs A)
+__global__ void __launch_bounds__(LIN_BLOCK) k_lin_pairs(const __grid_constant__ LinArgs A0)
 {
+	const LinArgs A = slab_of(A0, blockIdx.y);
 	__shared__ u64 cs[LIN_BLOCK];
 	const u32 npairs = A.t.n / 2;
 	const u32 i = blockIdx.x * LIN_BLOCK + threadIdx.x;
@@ -99,16 +104,18 @@ __global__ void __launch_bounds__(LIN_BLOCK) k_lin_pairs(const __grid_constant__
 }
 
 // S = A + B and D = A - B (+ copies) in one pass over the registers (marin.cl:1891-2154)
-__global__ void k_addsub_boundary(const __grid_constant__ LinArgs A, u32 nblocks)
+__global__ void k_addsub_boundary(const __grid_constant__ LinArgs A0, u32 nblocks)
 {
+	const LinArgs A = slab_of(A0, blockIdx.y);
 	const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= nblocks) return;
 	const u32 npairs = A.t.n / 2;
 	const u32 first = b * LIN_BLOCK;
 	addsub_pair_carry(A, (first == 0) ? npairs - 1 : first - 1, A.carry[b], A.carry2[b]);
 }
-__global__ void __launch_bounds__(LIN_BLOCK) k_addsub_pairs(const __grid_constant__ LinArgs A)
+__global__ void __launch_bounds__(LIN_BLOCK) k_addsub_pairs(const __grid_constant__ LinArgs A0)
 {
+	const LinArgs A = slab_of(A0, blockIdx.y);
 	__shared__ u64 cs[LIN_BLOCK], cd[LIN_BLOCK];
 	const u32 npairs = A.t.n / 2;
 	const u32 i = blockIdx.x * LIN_BLOCK + threadIdx.x;
@@ -157,13 +164,15 @@ __global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ Prog
 	__shared__ MidArgs sM;
 	__shared__ LinArgs sL;
 	const u32 tid = threadIdx.x, nthr = blockDim.x, n = A.M.t.n, npairs = n / 2;
-	if (tid == 0) { sM = A.M; sL.t = A.M.t; sL.carry = A.carry; sL.D = A.D; sL.digits = nullptr; }
+	// batched engines (one ECM curve per CTA): CTA x runs the same op list on its own slab of registers
+	u64 *const reg = A.reg + (size_t)blockIdx.x * A.slab_words, *const carry = A.carry + (size_t)blockIdx.x * A.slab_carry;
+	if (tid == 0) { sM = A.M; sM.carry = carry; sM.slab_pairs = 0; sL.t = A.M.t; sL.carry = carry; sL.D = A.D; sL.digits = nullptr; sL.slab_words = 0; sL.srcA = nullptr; sL.dst2 = sL.cpy = sL.cpy2 = sL.carry2 = nullptr; }
 	__syncthreads();
 	for (u32 k = 0; k < A.nops; ++k)
 	{
 		const ProgOp op = A.ops[k];
-		u64 *dst = A.reg + (size_t)op.dst * n;
-		const u64 *src = A.reg + (size_t)op.src * n;
+		u64 *dst = reg + (size_t)op.dst * n;
+		const u64 *src = reg + (size_t)op.src * n;
 		switch (op.code)
 		{
 		case PO_COPY:
@@ -188,13 +197,13 @@ __global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ Prog
 		{
 			if (tid == 0) { sL.dst = dst; sL.src = src; sL.a = op.a; sL.op = (op.code == PO_ADD) ? LIN_ADD : ((op.code == PO_SUBREG) ? LIN_SUBREG : LIN_SUBSMALL); }
 			__syncthreads();
-			for (u32 i = tid; i < npairs; i += nthr) A.carry[i] = lin_pair_carry(sL, i);      // from the ORIGINAL content
+			for (u32 i = tid; i < npairs; i += nthr) carry[i] = lin_pair_carry(sL, i);      // from the ORIGINAL content
 			__syncthreads();
 			for (u32 i = tid; i < npairs; i += nthr)
 			{
 				u64 u0, u1; u32 w0, w1;
 				lin_pair_compute(sL, i, u0, u1, w0, w1);
-				lin_pair_finish(sL, i, u0, u1, w0, w1, A.carry[i ? i - 1 : npairs - 1]);
+				lin_pair_finish(sL, i, u0, u1, w0, w1, carry[i ? i - 1 : npairs - 1]);
 			}
 			break;
 		}
@@ -291,12 +300,12 @@ struct CudaBackend
 		progs.push_back(d); prog_len.push_back((u32)ops.size());
 		return (int)progs.size() - 1;
 	}
-	void prog_launch(int id, ProgArgs A, u32 thr, size_t smem)
+	void prog_launch(int id, ProgArgs A, u32 thr, size_t smem, u32 batch = 1)
 	{
 		if (id < 0 || (size_t)id >= progs.size()) throw std::runtime_error("marin_b200: unknown graph id");
 		use();
 		A.ops = progs[(size_t)id]; A.nops = prog_len[(size_t)id];
-		k_program<<<1, thr, smem, st>>>(A); post();
+		k_program<<<batch, thr, smem, st>>>(A); post();
 	}
 
 	void use() { CK(cudaSetDevice(dev)); }
@@ -354,11 +363,11 @@ struct CudaBackend
 	// kernel's accesses (copies, linear ops) "streaming" misses and slowed them down by up to 2x.
 	cudaAccessPolicyWindow win;
 	bool has_win = false;
-	template <class K, class A> void launch_windowed(K kernel, const A &args, u32 grid, u32 thr, size_t smem)
+	template <class K, class A> void launch_windowed(K kernel, const A &args, u32 grid, u32 thr, size_t smem, u32 gridy = 1)
 	{
 		cudaLaunchConfig_t cfg;
 		memset(&cfg, 0, sizeof(cfg));
-		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+		cfg.gridDim = dim3(grid, gridy); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = smem; cfg.stream = st;
 		cudaLaunchAttribute at[1];
 		at[0].id = cudaLaunchAttributeAccessPolicyWindow;
 		at[0].val.accessPolicyWindow = win;
@@ -369,7 +378,7 @@ struct CudaBackend
 
 	static u32 cap(u32 thr, u32 maxt) { return thr > maxt ? maxt : thr; }
 	static u32 env_u32(const char *name) { const char *s = getenv(name); return s ? (u32)atoi(s) : 0u; }
-	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem)
+	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem, u32 batch = 1)
 	{
 		// timing probes only (results are wrong with a truncated grid): MARIN_B200_MID_GRID / MARIN_B200_MID_THREADS
 		static const u32 fg = env_u32("MARIN_B200_MID_GRID"), ft = env_u32("MARIN_B200_MID_THREADS");
@@ -383,7 +392,7 @@ struct CudaBackend
 			else launch_windowed(fast::k_mid_fast<MODE_FWD>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
 			post(); return;
 		}
-		launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem); post();
+		launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem, batch); post();
 	}
 	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
 	{
@@ -402,27 +411,30 @@ struct CudaBackend
 		}
 		launch_windowed(k_strided<true>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post();
 	}
-	void lin_pairs(const LinArgs &A)
+	void lin_pairs(const LinArgs &A, u32 batch = 1)
 	{
 		use();
 		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
-		if (nblocks > 1) { k_lin_boundary<<<(nblocks + 127) / 128, 128, 0, st>>>(A, nblocks); post(); }
-		k_lin_pairs<<<nblocks, LIN_BLOCK, 0, st>>>(A); post();
+		if (nblocks > 1) { k_lin_boundary<<<dim3((nblocks + 127) / 128, batch), 128, 0, st>>>(A, nblocks); post(); }
+		k_lin_pairs<<<dim3(nblocks, batch), LIN_BLOCK, 0, st>>>(A); post();
 	}
-	void addsub_pairs(const LinArgs &A)
+	void addsub_pairs(const LinArgs &A, u32 batch = 1)
 	{
 		use();
 		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
-		if (nblocks > 1) { k_addsub_boundary<<<(nblocks + 127) / 128, 128, 0, st>>>(A, nblocks); post(); }
-		k_addsub_pairs<<<nblocks, LIN_BLOCK, 0, st>>>(A); post();
+		if (nblocks > 1) { k_addsub_boundary<<<dim3((nblocks + 127) / 128, batch), 128, 0, st>>>(A, nblocks); post(); }
+		k_addsub_pairs<<<dim3(nblocks, batch), LIN_BLOCK, 0, st>>>(A); post();
 	}
+	// registers of every slab: `rows` copies of `bytes`, `pitch` bytes apart
+	void d2d_2d(void *d, const void *s, size_t bytes, size_t pitch, u32 rows)
+	{ use(); CK(cudaMemcpy2DAsync(d, pitch, s, pitch, bytes, rows, cudaMemcpyDeviceToDevice, st)); ++launches; }
 	void canon_p1(const CanonArgs &A, u32 count) { use(); k_canon_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void canon_p2(const CanonArgs &A, u32 count) { use(); k_canon_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
 	void canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags) { use(); k_canon_cmp<<<592, 256, 0, st>>>(l, r, n, flags); post(); }
 	// device -> host without waiting (the caller syncs once for several copies)
 	void d2h_async(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); }
-	void lin_p1(const LinArgs &A, u32 count) { use(); k_lin_p1<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
-	void lin_p2(const LinArgs &A, u32 count) { use(); k_lin_p2<<<(count + 127) / 128, 128, 0, st>>>(A, count); post(); }
+	void lin_p1(const LinArgs &A, u32 count, u32 batch = 1) { use(); k_lin_p1<<<dim3((count + 127) / 128, batch), 128, 0, st>>>(A, count); post(); }
+	void lin_p2(const LinArgs &A, u32 count, u32 batch = 1) { use(); k_lin_p2<<<dim3((count + 127) / 128, batch), 128, 0, st>>>(A, count); post(); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }
 	void scale(u64 *x, u64 f, u32 n) { use(); k_scale<<<(n + 255) / 256, 256, 0, st>>>(x, f, n); post(); }
 	void weights(const WeightArgs &A, u32 n) { use(); k_weights<<<(n + 255) / 256, 256, 0, st>>>(A, n); post(); }
@@ -462,6 +474,25 @@ void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose)
 	catch (...) { g_err = "unknown error"; return nullptr; }
 }
 
+// `batch` independent register sets driven in lockstep, one CTA per set in every launch (single-CTA sizes only)
+void *mb200_create_batch(uint32_t p, size_t reg_count, uint32_t device, int verbose, uint32_t batch)
+{
+	try
+	{
+		g_err.clear();
+		Eng *e = new Eng(p, reg_count, (int)device, 0, 0, batch);
+		if (verbose) fprintf(stderr, "marin_b200: p = %u, n = %u, single-CTA path x %u slabs, %zu registers each, device %u\n", p, e->pl.n, e->batch(), reg_count, device);
+		return e;
+	}
+	catch (const std::exception &ex) { g_err = ex.what(); return nullptr; }
+	catch (...) { g_err = "unknown error"; return nullptr; }
+}
+uint32_t mb200_batch(void *eng) { return eng ? E(eng)->batch() : 0; }
+int mb200_get_digits_slab(void *eng, uint32_t slab, size_t src, uint64_t *enc, size_t n)
+{ GUARD(if (n != E(eng)->size()) throw std::runtime_error("marin_b200: digit count must equal the transform size"); E(eng)->get_digits(src, (u64 *)enc, slab)); }
+int mb200_set_digits_slab(void *eng, uint32_t slab, size_t dst, const uint64_t *enc, size_t n)
+{ GUARD(if (n != E(eng)->size()) throw std::runtime_error("marin_b200: digit count must equal the transform size"); E(eng)->set_digits(dst, (const u64 *)enc, slab)); }
+
 void mb200_destroy(void *eng) { try { delete E(eng); } catch (...) {} }
 size_t mb200_transform_size(void *eng) { return eng ? E(eng)->size() : 0; }
 size_t mb200_register_count(void *eng) { return eng ? E(eng)->regs() : 0; }
@@ -495,7 +526,7 @@ int mb200_get_raw(void *eng, size_t src, void *buf, size_t bytes)
 { if (!eng || bytes != E(eng)->size() * 8) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->get_raw(src, buf)); }
 int mb200_set_raw(void *eng, size_t dst, const void *buf, size_t bytes)
 { if (!eng || bytes != E(eng)->size() * 8) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->set_raw(dst, buf)); }
-size_t mb200_checkpoint_size(void *eng) { return eng ? E(eng)->size() * 8 * E(eng)->regs() : 0; }
+size_t mb200_checkpoint_size(void *eng) { return eng ? E(eng)->size() * 8 * E(eng)->regs() * E(eng)->batch() : 0; }
 int mb200_get_checkpoint(void *eng, void *buf, size_t bytes)
 { if (!eng || bytes != mb200_checkpoint_size(eng)) { g_err = "size mismatch"; return 0; } GUARD(E(eng)->get_all(buf)); }
 int mb200_set_checkpoint(void *eng, const void *buf, size_t bytes)

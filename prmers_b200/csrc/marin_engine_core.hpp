@@ -18,20 +18,27 @@ public:
 	Plan pl;
 	Backend be;
 
-	EngineCore(u32 p, size_t regs, int device, u32 force_S = 0, u32 force_R2 = 0) : be(device), _regs(regs)
+	// batch > 1: `batch` independent register sets ("slabs") driven in lockstep -- every operation runs on all of them,
+	// one CTA per slab in the same launch.  For the single-CTA sizes only (the ECM sizes: one curve per slab, so a B200
+	// works on hundreds of curves in the time of one; the reference creates one engine per curve and runs them one
+	// after the other, RunEcmTwistedEdwards.cpp:1736-1755).  Digits are read and written per slab.
+	EngineCore(u32 p, size_t regs, int device, u32 force_S = 0, u32 force_R2 = 0, u32 batch = 1) : be(device), _regs(regs), _batch(batch ? batch : 1)
 	{
 		std::string err;
 		if (regs == 0) throw std::runtime_error("marin_b200: register count must be >= 1");
 		if (!make_plan(p, pl, err, force_S, force_R2)) throw std::runtime_error("marin_b200: " + err);
+		if (_batch > 1 && !pl.small) throw std::runtime_error("marin_b200: batched engines are for single-CTA transform sizes (n <= 2048) only");
+		if (_batch > 65535) throw std::runtime_error("marin_b200: at most 65535 slabs");
 		HostTables h;
 		build_tables(pl, h);
 		_wbits = h.wbits;
 		const size_t n = pl.n;
-		_reg = (u64 *)be.alloc(regs * n * 8);
-		be.memset0(_reg, regs * n * 8);
+		_reg = (u64 *)be.alloc(_batch * regs * n * 8);
+		be.memset0(_reg, _batch * regs * n * 8);
 		const size_t ncarry = std::max<size_t>(std::max<size_t>(n / pl.D, n / RUN + 1), pl.small ? n / 2 : 0); // recorded linear ops keep one word per pair
-		_carry = (u64 *)be.alloc(ncarry * 8);
-		_carry2 = (u64 *)be.alloc(ncarry * 8);
+		_ncarry = ncarry;
+		_carry = (u64 *)be.alloc(_batch * ncarry * 8);
+		_carry2 = (u64 *)be.alloc(_batch * ncarry * 8);
 		_scratch = (u64 *)be.alloc(n * 8);
 		_canon_D = (n % 16 == 0) ? 16 : ((n % 8 == 0) ? 8 : 4);
 		_cc[0] = (u64 *)be.alloc((n / _canon_D) * 8); _cc[1] = (u64 *)be.alloc((n / _canon_D) * 8);
@@ -85,6 +92,7 @@ public:
 
 	size_t size() const { return pl.n; }
 	size_t regs() const { return _regs; }
+	u32 batch() const { return _batch; }
 	void sync()
 	{
 		blocking("sync");
@@ -124,7 +132,8 @@ public:
 		std::memset(&A, 0, sizeof(A));
 		A.M = mid_args(nullptr, nullptr, nullptr, MODE_SQR, 1);
 		A.reg = _reg; A.D = pl.D; A.carry = _carry;
-		be.prog_launch(id, A, pl.thrMid < 64 ? 64 : pl.thrMid, mid_smem());
+		A.slab_words = (u32)slab_words(); A.slab_carry = (u32)_ncarry;
+		be.prog_launch(id, A, pl.thrMid < 64 ? 64 : pl.thrMid, mid_smem(), _batch);
 	}
 
 	void set_u32(size_t dst, u32 a)
@@ -135,7 +144,14 @@ public:
 		lin(LIN_SETSMALL, dst, dst, a, nullptr);
 	}
 
-	void copy(size_t dst, size_t src) { check(dst); check(src); if (dst != src && !rec(PO_COPY, dst, src, 0)) { touch(dst); be.d2d(R(dst), R(src), pl.n * 8); } }
+	void copy(size_t dst, size_t src)
+	{
+		check(dst); check(src);
+		if (dst == src || rec(PO_COPY, dst, src, 0)) return;
+		touch(dst);
+		if (_batch > 1) be.d2d_2d(R(dst), R(src), (size_t)pl.n * 8, slab_words() * 8, _batch);
+		else be.d2d(R(dst), R(src), pl.n * 8);
+	}
 
 	// r = r^2 * a.  In a chain of squarings of the same register (PRP, LL, P-1 stage 1) the inverse
 	// pass of one squaring also runs the forward strided pass of the next on the tile it still holds in
@@ -274,7 +290,8 @@ public:
 		touch(s); touch(d);
 		if (copies) { touch(sc); touch(dc); }
 		LinArgs L{_t, R(s), R(b), nullptr, _carry, LIN_ADDSUB, 0, pl.D, R(a), R(d), copies ? R(sc) : nullptr, copies ? R(dc) : nullptr, _carry2};
-		be.addsub_pairs(L);
+		if (_batch > 1) { L.slab_words = (u32)slab_words(); L.slab_carry = (u32)_ncarry; }
+		be.addsub_pairs(L, _batch);
 	}
 
 	void sub_u32(size_t r, u32 a)
@@ -295,10 +312,10 @@ public:
 	static constexpr u32 CANON_ROUNDS = 8;
 	// first round only, nothing read back: the caller looks at word `slot` of _words later (several of these can be in
 	// flight before one 4-byte read) and calls canon_finish if carries are still pending
-	void canon_start(size_t src, u64 *enc_dev, u64 *cc0, u64 *cc1, u32 slot)
+	void canon_start(size_t src, u64 *enc_dev, u64 *cc0, u64 *cc1, u32 slot, u32 slab = 0)
 	{
 		const u32 runs = pl.n / _canon_D;
-		CanonArgs C{_t, R(src), enc_dev, cc0, cc0, _words + slot, _canon_D};
+		CanonArgs C{_t, R(src) + (size_t)slab * slab_words(), enc_dev, cc0, cc0, _words + slot, _canon_D};
 		be.canon_p1(C, runs);
 		C.cin = cc0; C.cout = cc1;
 		be.canon_p2(C, runs);
@@ -347,22 +364,22 @@ public:
 		if (w4[3]) throw std::runtime_error("marin_b200: carry hand-off timed out inside the inverse pass (device error flag set)");
 	}
 
-	void get_digits(size_t src, u64 *enc)
+	void get_digits(size_t src, u64 *enc, u32 slab = 0)
 	{
-		check(src); blocking("get");
+		check(src); check_slab(slab); blocking("get");
 		be.memset0(_words, 12);
-		canon_start(src, _scratch, _cc[0], _cc[1], 0);
+		canon_start(src, _scratch, _cc[0], _cc[1], 0, slab);
 		u32 w[4];
 		read_words(w);
 		if (w[0]) canon_finish(_scratch, _cc[0], _cc[1], 0);
 		be.d2h(enc, _scratch, (size_t)pl.n * 8);
 	}
 
-	void set_digits(size_t dst, const u64 *enc)
+	void set_digits(size_t dst, const u64 *enc, u32 slab = 0)
 	{
-		check(dst); blocking("set");
+		check(dst); check_slab(slab); blocking("set");
 		be.h2d(_scratch, enc, (size_t)pl.n * 8);
-		lin(LIN_SETDIGITS, dst, dst, 0, _scratch);
+		lin(LIN_SETDIGITS, dst, dst, 0, _scratch, (int)slab);
 	}
 
 	// is_equal (engine.h:148-157 converts both registers to GMP integers on the host): canonical digits of both on the
@@ -370,6 +387,7 @@ public:
 	bool equal(size_t l, size_t r)
 	{
 		check(l); check(r); blocking("is_equal");
+		if (_batch > 1) throw std::runtime_error("marin_b200: is_equal compares one pair of registers; on a batched engine read the digits per slab");
 		if (!_scratch2)
 		{
 			_scratch2 = (u64 *)be.alloc((size_t)pl.n * 8);
@@ -395,10 +413,10 @@ public:
 		return l_zero && r_zero;
 	}
 
-	void get_raw(size_t src, void *buf) { check(src); blocking("get_data"); be.d2h(buf, R(src), (size_t)pl.n * 8); check_device_error(); }
-	void set_raw(size_t dst, const void *buf) { check(dst); blocking("set_data"); touch(dst); be.h2d(R(dst), buf, (size_t)pl.n * 8); }
-	void get_all(void *buf) { blocking("get_checkpoint"); calm(); materialize(); be.d2h(buf, _reg, _regs * (size_t)pl.n * 8); check_device_error(); }
-	void set_all(const void *buf) { blocking("set_checkpoint"); _fwd_reg = _last_sq = _lazy = (size_t)-1; be.h2d(_reg, buf, _regs * (size_t)pl.n * 8); }
+	void get_raw(size_t src, void *buf, u32 slab = 0) { check(src); check_slab(slab); blocking("get_data"); be.d2h(buf, R(src) + (size_t)slab * slab_words(), (size_t)pl.n * 8); check_device_error(); }
+	void set_raw(size_t dst, const void *buf, u32 slab = 0) { check(dst); check_slab(slab); blocking("set_data"); touch(dst); be.h2d(R(dst) + (size_t)slab * slab_words(), buf, (size_t)pl.n * 8); }
+	void get_all(void *buf) { blocking("get_checkpoint"); calm(); materialize(); be.d2h(buf, _reg, _batch * _regs * (size_t)pl.n * 8); check_device_error(); }
+	void set_all(const void *buf) { blocking("set_checkpoint"); _fwd_reg = _last_sq = _lazy = (size_t)-1; be.h2d(_reg, buf, _batch * _regs * (size_t)pl.n * 8); }
 
 	// single passes of square_mul, for per-kernel timing (3-pass engines only): 0 strided forward,
 	// 1 contiguous middle, 2 strided inverse + carry, 3 carry fix-up
@@ -431,11 +449,14 @@ public:
 	}
 
 	u32 width(u32 k) const { return pl.wbase + ((_wbits[k >> 5] >> (k & 31)) & 1u); }
-	u64 *R(size_t r) { return _reg + r * (size_t)pl.n; }
+	u64 *R(size_t r) { return _reg + r * (size_t)pl.n; }                  // register r of slab 0
+	size_t slab_words() const { return _regs * (size_t)pl.n; }
 	const Tables &tables() const { return _t; }
 
 private:
 	size_t _regs;
+	u32 _batch = 1; size_t _ncarry = 0;
+	void check_slab(u32 slab) const { if (slab >= _batch) throw std::runtime_error("marin_b200: slab index out of range"); }
 	u64 *_reg = nullptr, *_carry = nullptr, *_carry2 = nullptr, *_scratch = nullptr, *_scratch2 = nullptr, *_cc[2] = {nullptr, nullptr}, *_cc2[2] = {nullptr, nullptr};
 	u32 *_words = nullptr, _canon_D = 16;
 	pair_t *_slots = nullptr; size_t _nslots = 0;
@@ -492,12 +513,13 @@ private:
 		std::memset(&M, 0, sizeof(M));
 		fill_mid_args(pl, M);
 		M.t = _t; M.x = (pair_t *)x; M.y = (const pair_t *)y; M.dst = (pair_t *)dst; M.mode = mode; M.a = a; M.carry = _carry;
+		if (_batch > 1) { M.slab_pairs = (u32)(slab_words() / 2); M.slab_carry = (u32)_ncarry; }
 		return M;
 	}
 
 	void launch_mid(const MidArgs &M)
 	{
-		be.mid(M, pl.m / pl.S, pl.thrMid, mid_smem());
+		be.mid(M, pl.m / pl.S, pl.thrMid, mid_smem(), _batch);
 	}
 
 	// any write to a register other than by square_mul drops the parked forward transform of it
@@ -547,13 +569,21 @@ private:
 		return _epoch;
 	}
 
-	void lin(int op, size_t dst, size_t src, u32 a, const u64 *digits)
+	// only_slab >= 0: the operation touches that slab alone (set_digits); otherwise every slab, in lockstep
+	void lin(int op, size_t dst, size_t src, u32 a, const u64 *digits, int only_slab = -1)
 	{
 		touch(dst);
 		LinArgs L{_t, R(dst), R(src), digits, _carry, op, a, pl.D};
-		if (op == LIN_ADD || op == LIN_SUBREG || op == LIN_SUBSMALL) { be.lin_pairs(L); return; }
-		be.lin_p1(L, pl.n / pl.D);
-		be.lin_p2(L, pl.n / pl.D);
+		u32 b = _batch;
+		if (only_slab >= 0)
+		{
+			const size_t o = (size_t)only_slab * slab_words();
+			L.dst += o; L.src += o; L.carry += (size_t)only_slab * _ncarry; b = 1;
+		}
+		else if (_batch > 1) { L.slab_words = (u32)slab_words(); L.slab_carry = (u32)_ncarry; }
+		if (op == LIN_ADD || op == LIN_SUBREG || op == LIN_SUBSMALL) { be.lin_pairs(L, b); return; }
+		be.lin_p1(L, pl.n / pl.D, b);
+		be.lin_p2(L, pl.n / pl.D, b);
 	}
 };
 

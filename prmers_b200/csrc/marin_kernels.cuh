@@ -392,6 +392,7 @@ struct MidArgs     // contiguous pass: one CTA = one block of S pairs (or the wh
 	pair_t *dst;        // output register (MODE_FWD), may equal x
 	pair_t *dst2;       // single-CTA engines: also store the finished digits here (square_mul_copy / mul_copy), or null
 	const pair_t *add_src; // single-CTA engines: register added to the product before the carry (mul_add, a = 1), or null
+	u32 slab_pairs, slab_carry; // batched single-CTA engines (one ECM curve per CTA): CTA y works on the registers of slab y
 	int mode;
 	u32 S, nst;
 	Stage st[MAX_STAGES];
@@ -768,6 +769,7 @@ struct LinArgs
 	// LIN_ADDSUB (one pass for S = A + B and D = A - B, marin.cl:1891-2154): dst = S, dst2 = D, inputs srcA and src (= B);
 	// cpy / cpy2: optional copies of S and D (addsub_copy); carry2: the D carries.  Any output may alias any input.
 	const u64 *srcA; u64 *dst2, *cpy, *cpy2, *carry2;
+	u32 slab_words, slab_carry; // batched engines: CTA y of the grid works on slab y (0 = not batched)
 };
 
 // digits of the small constant `a` that fall in digit j (a < 2^32)
@@ -976,7 +978,28 @@ struct ProgArgs
 	const ProgOp *ops; u32 nops;
 	u32 D;              // digits per run of the set-small path
 	u64 *carry;         // one word per run (set-small), one per pair (linear ops)
+	u32 slab_words, slab_carry; // batched engines: CTA x of the grid runs the program on slab x
 };
+
+// batched engines: the argument block of CTA `y`, every register pointer moved to slab y
+HD MidArgs slab_of(const MidArgs &A, u32 y)
+{
+	MidArgs B = A;
+	if (y == 0 || A.slab_pairs == 0) return B;
+	const size_t o = (size_t)y * A.slab_pairs;
+	if (B.x) B.x += o; if (B.y) B.y += o; if (B.dst) B.dst += o; if (B.dst2) B.dst2 += o; if (B.add_src) B.add_src += o;
+	if (B.carry) B.carry += (size_t)y * A.slab_carry;
+	return B;
+}
+HD LinArgs slab_of(const LinArgs &A, u32 y)
+{
+	LinArgs B = A;
+	if (y == 0 || A.slab_words == 0) return B;
+	const size_t o = (size_t)y * A.slab_words, c = (size_t)y * A.slab_carry;
+	if (B.dst) B.dst += o; if (B.src) B.src += o; if (B.srcA) B.srcA += o; if (B.dst2) B.dst2 += o; if (B.cpy) B.cpy += o; if (B.cpy2) B.cpy2 += o;
+	if (B.carry) B.carry += c; if (B.carry2) B.carry2 += c;
+	return B;
+}
 
 // weight tables: digit j has weight r^((n - p j mod n) mod n), r the n-th root of two (ibdwt.h:111-147)
 struct WeightArgs { u32 p, n; u64 nr2, nr2_inv, inv_m; u64 *w_nat, *winv_nat, *winvs_nat; u64 *w_tile, *winvs_tile; u32 R, stride; };

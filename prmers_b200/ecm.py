@@ -490,7 +490,135 @@ def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), con
     return out
 
 
-def run_ecm_sharded(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), log=None, graphs=None):
+def run_ecm_batched(batch_engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), curve_indices=None, log=None, graphs=None):
+    """Config 5 the B200 way: ALL curves of the call at once on ONE batched engine (`batch_engine_factory(p, 51, B)`,
+    one register slab and one CTA per curve in every launch).  The stage-1 scalar K and the stage-2 chunk scalars are
+    the same for every curve, so the curves run the very same sequence of point operations in lockstep -- a point
+    operation is still one launch, now for B curves; what differs per curve (the curve constants, the base point, the
+    gcds and inversions between the stages) is host work on one slab's digits.  Every curve's residues, status, stage
+    and factor are those run_curve gives it alone (a curve that has finished early keeps being carried along and is
+    ignored).  The reference runs the curves one after the other, one engine each (RunEcmTwistedEdwards.cpp:1736-1830)."""
+    say = log or (lambda s: None)
+    N = (1 << p) - 1
+    idx = list(range(curves) if curve_indices is None else curve_indices)
+    K = stage1_exponent(b1)
+    primes_s2 = ecm_primes(b1, b2)[1] if b2 > b1 else []
+    out = {"exponent": p, "worktype": "ECM", "b1": b1, "b2": b2, "seed": seed, "status": "NF", "factor": None,
+           "curves": [], "k_bits": K.bit_length(), "batch": len(idx)}
+    if not idx:
+        return out
+    eng = batch_engine_factory(p, REGS, len(idx))
+    views = [eng.slab(s) if len(idx) > 1 else eng for s in range(len(idx))]
+    res, cvs = [], []
+    for s, c in enumerate(idx):
+        r = {"curve": c, "curve_seed": mix64(seed, c), "status": "NF", "factor": None, "stage": None, "n": eng.get_size()}
+        try:
+            cv = curve_from_seed(N, r["curve_seed"])
+        except FactorFound as f:
+            r.update(status="found", factor=f.g, stage=0); cv = None
+        else:
+            if cv is None:
+                r["status"] = "nocurve"
+            else:
+                r["sigma"] = cv.get("sigma")
+        res.append(r); cvs.append(cv)
+    alive = [cv is not None for cv in cvs]
+
+    def load_base(s, X, Y):
+        T = X * Y % N
+        for rg, v in ((6, X), (7, Y), (9, T), (47, (N - X) % N), (48, Y), (49, (N - T) % N)):
+            _set_int(views[s], rg, v, p)
+
+    def base_multiplicands():
+        eng.set_multiplicand(43, 16); eng.set_multiplicand(44, 8); eng.set_multiplicand(45, 29)
+        eng.set_multiplicand(46, 9); eng.set_multiplicand(50, 49)
+
+    def finish(s, **kw):
+        res[s].update(**kw); alive[s] = False
+
+    # constants and the starting points (:3069-3090); the small constants are the same in every slab
+    eng.set(0, 0); eng.set(1, 1); eng.set(8, 2)
+    digits = naf(K)
+    neg = bool(digits) and digits[-1] < 0
+    for s, cv in enumerate(cvs):
+        if cv is None:
+            continue
+        aE, dE, X0, Y0 = cv["a"], cv["d"], cv["X0"], cv["Y0"]
+        _set_int(views[s], 16, aE, p); _set_int(views[s], 17, 2 * dE % N, p); _set_int(views[s], 29, dE, p)
+        load_base(s, X0, Y0)
+        T0 = X0 * Y0 % N
+        for rg, v in ((3, (N - X0) % N if neg else X0), (4, Y0), (5, (N - T0) % N if neg else T0)):
+            _set_int(views[s], rg, v, p)
+    base_multiplicands()
+    ops = EdwardsOps(eng, graphs=graphs)
+    _scalar_mul(eng, ops, digits)
+    for s, cv in enumerate(cvs):
+        if not alive[s]:
+            continue
+        v = views[s]
+        if not check_invariant(v, p, cv["a"], cv["d"]):
+            say(f"[ECM] curve {idx[s]}: invariant FAIL")
+            finish(s, status="invariant", stage=1, point_ops=ops.ops)
+            continue
+        T = _value(v, 5, p)
+        g = math.gcd(T, N)
+        res[s]["stage1_T"] = T; res[s]["point_ops"] = ops.ops
+        if g == N:
+            finish(s, status="singular", stage=1); continue
+        if 1 < g < N:
+            finish(s, status="found", factor=g, stage=1); continue
+        Zv, Yv = _value(v, 1, p), _value(v, 4, p)
+        try:
+            if _inv((Zv - Yv) % N, N) is not None:
+                _inv((cv["a"] - cv["d"]) % N, N)
+        except FactorFound as f:
+            finish(s, status="found", factor=f.g, stage=1)
+
+    if b2 > b1 and any(alive):
+        for (i0, i1, echunk) in s2_chunks(primes_s2, s2_chunk_bits(eng.get_size())):
+            if not any(alive):
+                break
+            d2 = naf(echunk)
+            for s in range(len(idx)):
+                if not alive[s]:
+                    continue
+                v = views[s]
+                Xv, Yv, Zv = (_value(v, rg, p) for rg in (3, 4, 1))
+                try:
+                    iz = _inv(Zv, N)
+                except FactorFound as f:
+                    finish(s, status="found", factor=f.g, stage=2); continue
+                if iz is None:
+                    finish(s, status="singular", stage=2); continue
+                Xa, Ya = Xv * iz % N, Yv * iz % N
+                load_base(s, Xa, Ya)
+            base_multiplicands()
+            if d2:
+                eng.set(1, 1)
+                for dst, src in (((3, 47), (4, 48), (5, 49)) if d2[-1] < 0 else ((3, 6), (4, 7), (5, 9))):
+                    eng.copy(dst, src)
+                _scalar_mul(eng, ops, d2)
+            for s in range(len(idx)):
+                if not alive[s]:
+                    continue
+                T = _value(views[s], 5, p)
+                g = math.gcd(T, N)
+                res[s]["stage2_T"] = T; res[s]["point_ops"] = ops.ops
+                if g == N:
+                    finish(s, status="singular", stage=2)
+                elif g > 1:
+                    finish(s, status="found", factor=g, stage=2)
+    if hasattr(eng, "close"):
+        eng.close()
+    known = {int(f) for f in known_factors}
+    out["curves"] = res
+    for r in res:
+        if r["status"] == "found" and r["factor"] not in known and out["status"] != "found":
+            out.update(status="found", factor=r["factor"], curves_tested_for_found=r["curve"] + 1)
+    return out
+
+
+def run_ecm_sharded(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), log=None, graphs=None, batch_engine_factory=None):
     """Config 5 across the GPUs of one box: curve c runs on rank c mod world with its own engine, every
     rank runs ALL of its curves (no cross-GPU stop flag: a curve at these sizes is seconds), the per-curve results are
     gathered and merged in curve order, so the answer -- first new factor by curve index -- is the one a single
@@ -498,8 +626,12 @@ def run_ecm_sharded(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors
     from . import multi
     rank, world = multi.rank_world()
     mine = multi.assign(list(range(curves)), rank, world)
-    local = run_ecm(engine_factory, p, b1, b2, curves=curves, seed=seed, known_factors=known_factors,
-                    continue_after_factor=True, curve_indices=mine, log=log, graphs=graphs)
+    if batch_engine_factory is not None:       # this rank's curves in lockstep on one batched engine (one CTA per curve)
+        local = run_ecm_batched(batch_engine_factory, p, b1, b2, curves=curves, seed=seed, known_factors=known_factors,
+                                curve_indices=mine, log=log, graphs=graphs)
+    else:
+        local = run_ecm(engine_factory, p, b1, b2, curves=curves, seed=seed, known_factors=known_factors,
+                        continue_after_factor=True, curve_indices=mine, log=log, graphs=graphs)
     for c in local["curves"]:
         c["rank"] = rank
     allc = sorted(multi.gather(local["curves"]), key=lambda c: c["curve"])

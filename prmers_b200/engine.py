@@ -52,6 +52,10 @@ _SIGS = {
     "mb200_bench_pass": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_float)]),
     "mb200_is_single_cta": (C.c_int, [C.c_void_p]),
     "mb200_device_mem_info": (C.c_int, [C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mb200_create_batch": (C.c_void_p, [C.c_uint32, C.c_size_t, C.c_uint32, C.c_int, C.c_uint32]),
+    "mb200_batch": (C.c_uint32, [C.c_void_p]),
+    "mb200_get_digits_slab": (C.c_int, [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "mb200_set_digits_slab": (C.c_int, [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t]),
     "mb200_graph_begin": (C.c_int, [C.c_void_p]),
     "mb200_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "mb200_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),
@@ -96,10 +100,16 @@ class MarinError(RuntimeError):
 class Engine:
     """engine::create_gpu(p, reg_count, device, verbose) and the methods of `class engine`."""
 
-    def __init__(self, p, reg_count, device=0, verbose=False):
+    def __init__(self, p, reg_count, device=0, verbose=False, batch=1):
+        """batch > 1: `batch` independent register sets ("slabs") driven in lockstep by every call, one CTA per slab in
+        each launch (single-CTA sizes only: many ECM curves at once); digits are read and written per slab."""
         L = load_library()
         self._L = L
-        self._h = L.mb200_create(p, reg_count, device, 1 if verbose else 0)
+        self.batch = batch
+        if batch > 1:
+            self._h = L.mb200_create_batch(p, reg_count, device, 1 if verbose else 0, batch)
+        else:
+            self._h = L.mb200_create(p, reg_count, device, 1 if verbose else 0)
         if not self._h:
             raise MarinError(L.mb200_last_error().decode())
         self.p = p
@@ -214,30 +224,40 @@ class Engine:
         return bool(out.value)
 
     # -- digits / big integers (engine.h:24-25,173-232) -----------------------------------------
-    def get(self, src, out=None):
+    def get(self, src, out=None, slab=0):
         """Canonical encoded digits (value | width << 32) as a uint64 array."""
         if out is None:
             out = np.empty(self.n, dtype=np.uint64)
-        self._ck(self._L.mb200_get_digits(self._h, src, out.ctypes.data, self.n))
+        if slab:
+            self._ck(self._L.mb200_get_digits_slab(self._h, slab, src, out.ctypes.data, self.n))
+        else:
+            self._ck(self._L.mb200_get_digits(self._h, src, out.ctypes.data, self.n))
         return out
 
-    def set_digits(self, dst, enc):
+    def set_digits(self, dst, enc, slab=0):
         enc = np.ascontiguousarray(enc, dtype=np.uint64)
         if enc.shape != (self.n,):
             raise MarinError("digit count must equal the transform size")
-        self._ck(self._L.mb200_set_digits(self._h, dst, enc.ctypes.data, self.n))
+        if slab:
+            self._ck(self._L.mb200_set_digits_slab(self._h, slab, dst, enc.ctypes.data, self.n))
+        else:
+            self._ck(self._L.mb200_set_digits(self._h, dst, enc.ctypes.data, self.n))
 
     def widths(self):
         return _widths(self.n, self.p)
 
-    def get_mpz(self, src):
+    def get_mpz(self, src, slab=0):
         """Value in [0, 2^p - 1): all-ones (= 2^p - 1) maps to 0 (engine.h:173-203)."""
-        v = digits_to_int(self.get(src))
+        v = digits_to_int(self.get(src, slab=slab))
         return 0 if v == (1 << self.p) - 1 else v
 
-    def set_mpz(self, dst, z):
+    def set_mpz(self, dst, z, slab=0):
         """Reduces z modulo 2^p - 1 first (the reference's default does not, engine.h:205-232)."""
-        self.set_digits(dst, int_to_digits(int(z) % ((1 << self.p) - 1), _widths(self.n, self.p)))
+        self.set_digits(dst, int_to_digits(int(z) % ((1 << self.p) - 1), _widths(self.n, self.p)), slab=slab)
+
+    def slab(self, index):
+        """A per-slab view for the host side of a batched run: digits in and out of ONE slab."""
+        return SlabView(self, index)
 
     def digit(self, src):
         return Digit(self, src)
@@ -319,6 +339,20 @@ class Engine:
 
     def launch_count(self):
         return self._L.mb200_launch_count(self._h)
+
+
+class SlabView:
+    """One slab of a batched engine as seen by host code that reads / writes residues (get, get_mpz, set_mpz, set_digits);
+    the arithmetic itself is issued on the engine, for all slabs at once."""
+
+    def __init__(self, eng, index):
+        self.eng, self.index, self.p, self.n = eng, index, eng.p, eng.n
+
+    def get_size(self): return self.n
+    def get(self, src, out=None): return self.eng.get(src, out=out, slab=self.index)
+    def get_mpz(self, src): return self.eng.get_mpz(src, slab=self.index)
+    def set_mpz(self, dst, z): self.eng.set_mpz(dst, z, slab=self.index)
+    def set_digits(self, dst, enc): self.eng.set_digits(dst, enc, slab=self.index)
 
 
 def device_mem_info(device=0):

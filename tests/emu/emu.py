@@ -36,6 +36,9 @@ def lib():
         vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
         L.emu_last_error.restype = C.c_char_p
         L.emu_create.restype = vp; L.emu_create.argtypes = [u32, sz, u32, u32]
+        L.emu_create_batch.restype = vp; L.emu_create_batch.argtypes = [u32, sz, u32]
+        L.emu_get_digits_slab.restype = C.c_int; L.emu_get_digits_slab.argtypes = [vp, u32, sz, vp]
+        L.emu_set_digits_slab.restype = C.c_int; L.emu_set_digits_slab.argtypes = [vp, u32, sz, vp]
         L.emu_destroy.argtypes = [vp]
         L.emu_size.restype = sz; L.emu_size.argtypes = [vp]
         for f in ("emu_is_small", "emu_plan_R", "emu_plan_S", "emu_plan_R2", "emu_a_max"):
@@ -55,9 +58,10 @@ def lib():
 
 
 class EmuEngine:
-    def __init__(self, p, regs, force_S=0, force_R2=0):
+    def __init__(self, p, regs, force_S=0, force_R2=0, batch=1):
         L = lib()
-        self._h = L.emu_create(p, regs, force_S, force_R2)
+        self.batch = batch
+        self._h = L.emu_create_batch(p, regs, batch) if batch > 1 else L.emu_create(p, regs, force_S, force_R2)
         if not self._h:
             raise ValueError(L.emu_last_error().decode())
         self.p, self.n, self.reg_count = p, L.emu_size(self._h), regs
@@ -103,17 +107,30 @@ class EmuEngine:
         self._ck(lib().emu_equal(self._h, l, r, C.byref(out)))
         return bool(out.value)
 
-    def get_digits(self, s):
+    def get_digits(self, s, slab=0):
         out = np.zeros(self.n, dtype=np.uint64)
-        self._ck(lib().emu_get_digits(self._h, s, out.ctypes.data))
+        self._ck(lib().emu_get_digits_slab(self._h, slab, s, out.ctypes.data))
         return out
 
-    def get(self, s):
-        return self.get_digits(s)
+    def get(self, s, out=None, slab=0):
+        return self.get_digits(s, slab)
+
+    def get_mpz(self, s, slab=0):
+        from oracle import marin_oracle as mo
+        v = mo.digits_to_int(self.get_digits(s, slab))
+        return 0 if v == (1 << self.p) - 1 else v
+
+    def set_mpz(self, d, z, slab=0):
+        from oracle import marin_oracle as mo
+        self.set_digits(d, mo.int_to_digits(int(z) % ((1 << self.p) - 1), mo.widths(self.n, self.p)), slab)
+
+    def slab(self, index):
+        from prmers_b200.engine import SlabView
+        return SlabView(self, index)
 
     def get_size(self):
         return self.n
 
-    def set_digits(self, d, enc):
+    def set_digits(self, d, enc, slab=0):
         enc = np.ascontiguousarray(enc, dtype=np.uint64)
-        self._ck(lib().emu_set_digits(self._h, d, enc.ctypes.data))
+        self._ck(lib().emu_set_digits_slab(self._h, slab, d, enc.ctypes.data))

@@ -27,15 +27,20 @@ struct CpuBackend
 	void persist_on() {}
 	void persist_off() {}
 
-	void mid(const MidArgs &A, u32 grid, u32 thr, size_t smem)
+	void mid(const MidArgs &A0, u32 grid, u32 thr, size_t smem, u32 batch = 1)
 	{
 		std::vector<pair_t> sm(smem / 16 + 1);
-		u64 *smc = (u64 *)(sm.data() + smem_pairs_lin(A.S));
-		const u32 nph = mid_num_phases(A);
-		for (u32 b = 0; b < grid; ++b)
-			for (u32 ph = 0; ph < nph; ++ph)
-				for (u32 t = 0; t < thr; ++t) mid_phase(A, b, ph, t, thr, sm.data(), smc);
+		u64 *smc = (u64 *)(sm.data() + smem_pairs_lin(A0.S));
+		const u32 nph = mid_num_phases(A0);
+		for (u32 y = 0; y < batch; ++y)
+		{
+			const MidArgs A = slab_of(A0, y);
+			for (u32 b = 0; b < grid; ++b)
+				for (u32 ph = 0; ph < nph; ++ph)
+					for (u32 t = 0; t < thr; ++t) mid_phase(A, b, ph, t, thr, sm.data(), smc);
+		}
 	}
+	void d2d_2d(void *d, const void *s, size_t bytes, size_t pitch, u32 rows) { for (u32 r = 0; r < rows; ++r) std::memcpy((char *)d + r * pitch, (const char *)s + r * pitch, bytes); }
 	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
 	{
 		std::vector<pair_t> sm(smem / 16 + 1);
@@ -59,7 +64,9 @@ struct CpuBackend
 		for (u32 ph = park; ph < nph; ++ph)
 			for (u32 t = 0; t < thr; ++t) strided_phase<true>(A, 0, ph, t, thr, sm0.data());
 	}
-	void lin_pairs(const LinArgs &A)
+	void lin_pairs(const LinArgs &A0, u32 batch = 1) { for (u32 y = 0; y < batch; ++y) lin_pairs1(slab_of(A0, y)); }
+	void addsub_pairs(const LinArgs &A0, u32 batch = 1) { for (u32 y = 0; y < batch; ++y) addsub_pairs1(slab_of(A0, y)); }
+	void lin_pairs1(const LinArgs &A)
 	{
 		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
 		for (u32 b = 0; b < nblocks; ++b) { const u32 first = b * LIN_BLOCK; A.carry[b] = lin_pair_carry(A, first == 0 ? npairs - 1 : first - 1); }
@@ -76,7 +83,7 @@ struct CpuBackend
 			}
 		}
 	}
-	void addsub_pairs(const LinArgs &A)
+	void addsub_pairs1(const LinArgs &A)
 	{
 		const u32 npairs = A.t.n / 2, nblocks = (npairs + LIN_BLOCK - 1) / LIN_BLOCK;
 		for (u32 b = 0; b < nblocks; ++b) { const u32 first = b * LIN_BLOCK; addsub_pair_carry(A, first == 0 ? npairs - 1 : first - 1, A.carry[b], A.carry2[b]); }
@@ -96,18 +103,21 @@ struct CpuBackend
 	void canon_p2(const CanonArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) canon_p2_thread(A, i); }
 	void canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags) { u32 f = 0; for (u32 j = 0; j < n; ++j) f |= canon_cmp_digit(l[j], r[j]); *flags |= f; }
 	void d2h_async(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
-	void lin_p1(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); }
-	void lin_p2(const LinArgs &A, u32 count) { for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); }
+	void lin_p1(const LinArgs &A0, u32 count, u32 batch = 1) { for (u32 y = 0; y < batch; ++y) { const LinArgs A = slab_of(A0, y); for (u32 i = 0; i < count; ++i) lin_p1_thread(A, i); } }
+	void lin_p2(const LinArgs &A0, u32 count, u32 batch = 1) { for (u32 y = 0; y < batch; ++y) { const LinArgs A = slab_of(A0, y); for (u32 i = 0; i < count; ++i) lin_p2_thread(A, i); } }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { for (u32 j = 0; j < n; ++j) unweight_thread(t, x, out, j); }
 	// recorded op sequences: the emulated k_program -- the same op order, each op through the same phase functions
 	std::vector<std::vector<ProgOp>> progs;
 	int prog_upload(const std::vector<ProgOp> &ops) { progs.push_back(ops); return (int)progs.size() - 1; }
-	void prog_launch(int id, ProgArgs A, u32 thr, size_t smem)
+	void prog_launch(int id, ProgArgs A0, u32 thr, size_t smem, u32 batch = 1)
 	{
 		if (id < 0 || (size_t)id >= progs.size()) throw std::runtime_error("marin_b200: unknown graph id");
-		const u32 n = A.M.t.n, npairs = n / 2;
+		const u32 n = A0.M.t.n, npairs = n / 2;
+		for (u32 y = 0; y < batch; ++y)
 		for (const ProgOp &op : progs[(size_t)id])
 		{
+			ProgArgs A = A0;
+			A.reg += (size_t)y * A0.slab_words; A.carry += (size_t)y * A0.slab_carry; A.M.carry = A.carry; A.M.slab_pairs = 0;
 			u64 *dst = A.reg + (size_t)op.dst * n;
 			const u64 *src = A.reg + (size_t)op.src * n;
 			LinArgs L{A.M.t, dst, src, nullptr, A.carry, 0, op.a, A.D};
@@ -163,6 +173,12 @@ void *emu_create(uint32_t p, size_t regs, uint32_t force_S, uint32_t force_R2)
 {
 	try { return new Emu(p, regs, 0, force_S, force_R2); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
+void *emu_create_batch(uint32_t p, size_t regs, uint32_t batch)
+{
+	try { return new Emu(p, regs, 0, 0, 0, batch); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+int emu_get_digits_slab(void *h, uint32_t slab, size_t s, uint64_t *enc) { GUARD(((Emu *)h)->get_digits(s, (u64 *)enc, slab)) }
+int emu_set_digits_slab(void *h, uint32_t slab, size_t d, const uint64_t *enc) { GUARD(((Emu *)h)->set_digits(d, (const u64 *)enc, slab)) }
 void emu_destroy(void *h) { delete (Emu *)h; }
 size_t emu_size(void *h) { return ((Emu *)h)->size(); }
 int emu_is_small(void *h) { return ((Emu *)h)->pl.small ? 1 : 0; }

@@ -226,3 +226,67 @@ def test_graph_replay_equals_direct_calls_gpu():
     with pytest.raises(RuntimeError):
         big.graph_begin()                             # multi-pass engines carry per-launch epochs
     assert np.array_equal(e.get(0), e.get(3))
+
+
+# ---- batched engines: all curves of a call in lockstep, one CTA per curve (round 2) --------------------------------------
+def _curve_key(c):
+    return (c["curve"], c["curve_seed"], c["status"], c["factor"], c["stage"], c.get("stage1_T"), c.get("stage2_T"))
+
+
+def test_batched_engine_ops_emulated():
+    """Every register op of a batched engine acts on each slab exactly as a plain engine would (emulated kernels)."""
+    import random
+    p, B = 701, 3
+    m = (1 << p) - 1
+    e = EmuEngine(p, 12, batch=B)
+    rng = random.Random(1)
+    xs, ys = [rng.randrange(m) for _ in range(B)], [rng.randrange(m) for _ in range(B)]
+    for s in range(B):
+        e.set_mpz(0, xs[s], slab=s); e.set_mpz(1, ys[s], slab=s)
+    e.set_multiplicand(2, 1); e.mul(0, 2, 3); e.square_mul(0); e.add(0, 1); e.sub_reg(0, 1); e.sub(0, 2); e.copy(3, 0)
+    e.addsub(4, 5, 0, 1); e.set(6, 7); e.mul_add(3, 2, 6)
+    e.graph_begin(); e.square_mul(0); e.mul(0, 2); e.add(0, 6); g = e.graph_end()
+    want = []
+    for s in range(B):
+        x = xs[s] * ys[s] * 3 % m; x = (x * x - 2) % m
+        assert e.get_mpz(0, slab=s) == x and e.get_mpz(4, slab=s) == (x + ys[s]) % m and e.get_mpz(5, slab=s) == (x - ys[s]) % m
+        assert e.get_mpz(3, slab=s) == (x * ys[s] + 7) % m
+        want.append(x)
+    e.graph_launch(g); e.graph_launch(g)
+    for s in range(B):
+        x = want[s]
+        for _ in range(2):
+            x = (x * x * ys[s] + 7) % m
+        assert e.get_mpz(0, slab=s) == x
+    with pytest.raises(ValueError):
+        EmuEngine(86243, 4, batch=2)                         # multi-pass sizes cannot be batched
+
+
+def test_batched_ecm_equals_sequential_emulated():
+    """run_ecm_batched: every curve's seed, status, stage, factor and T residues equal the sequential run's."""
+    p, b1, b2, K, seed = 701, 300, 900, 5, 123456789
+    seq = ecm.run_ecm(lambda q, r: EmuEngine(q, r), p, b1, b2, curves=K, seed=seed, continue_after_factor=True)
+    bat = ecm.run_ecm_batched(lambda q, r, b: EmuEngine(q, r, batch=b), p, b1, b2, curves=K, seed=seed)
+    assert [_curve_key(c) for c in seq["curves"]] == [_curve_key(c) for c in bat["curves"]]
+    assert (seq["status"], seq["factor"]) == (bat["status"], bat["factor"]) and bat["batch"] == K
+    one = ecm.run_ecm_batched(lambda q, r, b: EmuEngine(q, r, batch=b), p, b1, b2, curves=K, seed=seed, curve_indices=[3])
+    assert _curve_key(one["curves"][0]) == _curve_key(seq["curves"][3])
+
+
+@pytest.mark.gpu
+def test_batched_ecm_config5_gpu():
+    """BASELINE config 5 (M701, B1 = 6000, B2 = 33333, K = 8, seed 123456789) as ONE batched run against the golden
+    per-curve records, and 64 curves at once against the sequential driver on a sample of them."""
+    import prmers_b200 as pb
+    gold = json.load(open(os.path.join(GOLD, "ecm_m701.json")))
+    p, b1, b2, K, seed = gold["p"], gold["b1"], gold["b2"], gold["curves"], gold["seed"]
+    bat = ecm.run_ecm_batched(lambda q, r, b: pb.Engine(q, r, batch=b), p, b1, b2, curves=K, seed=seed)
+    assert len(bat["curves"]) == len(gold["per_curve"]) == 8
+    for c, g in zip(bat["curves"], gold["per_curve"]):
+        assert (str(c["curve_seed"]), c["status"], c["stage"]) == (g["curve_seed"], g["status"], g["stage"])
+        assert (None if c["factor"] is None else str(c["factor"])) == g["factor"]
+        assert sha(c.get("stage1_T")) == g["stage1_T_sha"] and sha(c.get("stage2_T")) == g["stage2_T_sha"]
+    big = ecm.run_ecm_batched(lambda q, r, b: pb.Engine(q, r, batch=b), p, 600, 2000, curves=64, seed=7)
+    for ci in (0, 17, 63):
+        seq = ecm.run_ecm(lambda q, r: pb.Engine(q, r), p, 600, 2000, curves=64, seed=7, continue_after_factor=True, curve_indices=[ci])
+        assert _curve_key(seq["curves"][0]) == _curve_key(big["curves"][ci])

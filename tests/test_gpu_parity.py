@@ -470,3 +470,16 @@ def test_cpp_adapter_conformance():
                     "-L", libdir, "-l:libmarin_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "adapter test passed" in r.stdout, r.stdout + r.stderr
+
+
+def test_cpp_adapter_against_reference_engine_header():
+    """engine_b200 as a subclass of the reference's OWN `engine` (include/marin/engine.h, compiled in the container that
+    holds /root/reference by __graft_entry__.build(); only the binary travels): the reference's get_mpz / set_mpz /
+    default is_equal / pow / digit run over the B200 engine, exponents 31 ... 136279841, GMP as the arithmetic check."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_engine_adapter_refhdr")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/test_engine_adapter_refhdr not built (needs /root/reference: python __graft_entry__.py)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "against the reference engine.h passed" in r.stdout, r.stdout + r.stderr
