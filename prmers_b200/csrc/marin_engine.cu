@@ -260,9 +260,12 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 2048)); // it also keeps its argument blocks in static shared memory
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID5_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID5_SMEM));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID5_SMEM));
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
@@ -273,6 +276,10 @@ struct CudaBackend
 	static bool fast_mid_shape(const MidArgs &A)
 	{
 		return !A.small && A.S == fast::MID_S && A.nst == 3 && A.st[0].radix == 16 && A.st[1].radix == 16 && A.st[2].radix == 16;
+	}
+	static bool fast_mid5_shape(const MidArgs &A)
+	{
+		return !A.small && A.S == fast::MID5_S && A.nst == 4 && A.st[0].radix == 5 && A.st[1].radix == 4 && A.st[2].radix == 16 && A.st[3].radix == 16;
 	}
 	static bool fast_str_shape(const StridedArgs &A)
 	{
@@ -387,9 +394,16 @@ struct CudaBackend
 		use();
 		if (use_fast && !ft && fast_mid_shape(A))
 		{
-			if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
-			else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
-			else launch_windowed(fast::k_mid_fast<MODE_FWD>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR, false>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL, false>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			else launch_windowed(fast::k_mid_fast<MODE_FWD, false>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
+			post(); return;
+		}
+		if (use_fast && !ft && fast_mid5_shape(A))
+		{
+			if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR, true>, A, grid, fast::MID5_THREADS, fast::MID5_SMEM);
+			else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL, true>, A, grid, fast::MID5_THREADS, fast::MID5_SMEM);
+			else launch_windowed(fast::k_mid_fast<MODE_FWD, true>, A, grid, fast::MID5_THREADS, fast::MID5_SMEM);
 			post(); return;
 		}
 		launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem, batch); post();

@@ -87,20 +87,28 @@ template <int TWS> __device__ __forceinline__ void tw16(u64 *a, const u64 *tw)
 
 static constexpr u32 MID_S = 4096, MID_THREADS = 256;
 static constexpr u32 MID_SMEM = (MID_S + MID_S / 16 + 1) * 16;
+// FIVE: rows of S = 5120 = 5 x 4 x 16 x 16 pairs (n = 5 * 2^21: the radix-5 stage of a 5 * 2^k transform lives in the
+// contiguous pass, so the strided passes are the power-of-two kernels below): a radix-5 and a radix-4 stage across the
+// row, then twenty warp-local blocks of 256 pairs; 320 threads, two CTAs per SM.
+static constexpr u32 MID5_S = 5120, MID5_THREADS = 320;
+static constexpr u32 MID5_SMEM = (MID5_S + MID5_S / 16 + 1) * 16;
 
-template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast(const __grid_constant__ MidArgs A)
+template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THREADS : MID_THREADS, FIVE ? 2 : 3) k_mid_fast(const __grid_constant__ MidArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const Tables &t = A.t;
+	constexpr u32 S = FIVE ? MID5_S : MID_S, NW = FIVE ? 10 : 8, NTHR = 32 * NW;
+	constexpr u32 SB = FIVE ? 2 : 1;                 // index of the s = 16 stage in the stage list
 	const u32 tid = threadIdx.x, lane = tid & 1, h = tid >> 1, wl = tid & 31, warp = tid >> 5;
-	const size_t rowbase = (size_t)blockIdx.x * MID_S;
+	const size_t rowbase = (size_t)blockIdx.x * S;
 	u64 *smw = reinterpret_cast<u64 *>(sm) + lane;
-	const u64 *tw0 = t.twS + A.st[0].toff, *tw1 = t.twS + A.st[1].toff;
-	const u64 *twi0 = t.twSi + A.st[0].toff, *twi1 = t.twSi + A.st[1].toff;
+	const u64 *tw0 = t.twS + A.st[0].toff, *tw1 = t.twS + A.st[SB].toff;
+	const u64 *twi0 = t.twSi + A.st[0].toff, *twi1 = t.twSi + A.st[SB].toff;
 
-	// ---- F0: elements j + 256 q of the row, straight from global memory
+	if (!FIVE)
 	{
+		// ---- F0: elements j + 256 q of the row, straight from global memory
 		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
 		#pragma unroll 1
 		for (u32 it = 0; it < 2; ++it)
@@ -113,6 +121,35 @@ template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast
 			st16_sw<544>(smw + 2 * (j + (j >> 4)), a);
 		}
 	}
+	else
+	{
+		// ---- F0: radix 5, elements j + 1024 q from global memory; F1: radix 4 (s = 256) inside each fifth of the row
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 j = h; j < 1024; j += NTHR / 2)
+		{
+			u64 a[5];
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) a[q] = g[2 * (j + 1024 * q)];
+			dft5(a, t.w5);
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) a[k] = gl::mul(a[k], tw0[(k - 1) * 1024 + j]);
+			u64 *o = smw + 2 * (j + (j >> 4));
+			#pragma unroll
+			for (int k = 0; k < 5; ++k) o[k * 2176] = a[k];
+		}
+		__syncthreads();
+		const u64 *twq = t.twS + A.st[1].toff;
+		#pragma unroll 1
+		for (u32 rb = h; rb < 1280; rb += NTHR / 2)
+		{
+			const u32 j = rb & 255, base = (rb >> 8) * 1024 + j;
+			u64 *o = smw + 2 * (base + (base >> 4));
+			u64 a0 = o[0], a1 = o[544], a2 = o[1088], a3 = o[1632];
+			dft4<false>(a0, a1, a2, a3);
+			o[0] = a0; o[544] = gl::mul(a1, twq[j]); o[1088] = gl::mul(a2, twq[256 + j]); o[1632] = gl::mul(a3, twq[512 + j]);
+		}
+	}
 	__syncthreads();
 
 	// ---- warp-local part: blocks of 256 pairs
@@ -120,9 +157,9 @@ template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast
 	#pragma unroll 1
 	for (u32 it = 0; it < 2; ++it)
 	{
-		const u32 Bk = warp + 8 * it;
+		const u32 Bk = warp + NW * it;
 		u64 *blk = smw + 2 * (272 * Bk);
-		{	// F1: s = 16
+		{	// s = 16
 			u64 a[16];
 			ld16_nat<34>(a, blk + 2 * jl);
 			dft16<false>(a);
@@ -130,7 +167,7 @@ template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast
 			st16_sw<34>(blk + 2 * jl, a);
 		}
 		__syncwarp();
-		{	// F2: s = 1, no twiddles
+		{	// s = 1, no twiddles
 			u64 a[16];
 			ld16_nat<2>(a, blk + 2 * (17 * jl));
 			dft16<false>(a);
@@ -157,14 +194,14 @@ template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast
 			}
 		}
 		__syncwarp();
-		{	// I2: s = 1
+		{	// inverse, s = 1
 			u64 a[16];
 			ld16_sw<2>(a, blk + 2 * (17 * jl));
 			dft16<true>(a);
 			st16_nat<2>(blk + 2 * (17 * jl), a);
 		}
 		__syncwarp();
-		{	// I1: s = 16
+		{	// inverse, s = 16
 			u64 a[16];
 			ld16_sw<34>(a, blk + 2 * jl);
 			tw16<16>(a, twi1 + jl);
@@ -175,8 +212,9 @@ template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast
 	if (MODE == MODE_FWD) return;
 	__syncthreads();
 
-	// ---- I0: s = 256, back to global memory (in place)
+	if (!FIVE)
 	{
+		// ---- I0: s = 256, back to global memory (in place)
 		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
 		#pragma unroll 1
 		for (u32 it = 0; it < 2; ++it)
@@ -187,6 +225,33 @@ template <int MODE> __global__ void __launch_bounds__(MID_THREADS, 3) k_mid_fast
 			tw16<256>(a, twi0 + j);
 			dft16<true>(a);
 			st16_nat<512>(g + 2 * j, a);
+		}
+	}
+	else
+	{
+		const u64 *twq = t.twSi + A.st[1].toff;
+		#pragma unroll 1
+		for (u32 rb = h; rb < 1280; rb += NTHR / 2)
+		{
+			const u32 j = rb & 255, base = (rb >> 8) * 1024 + j;
+			u64 *o = smw + 2 * (base + (base >> 4));
+			u64 a0 = o[0], a1 = gl::mul(o[544], twq[j]), a2 = gl::mul(o[1088], twq[256 + j]), a3 = gl::mul(o[1632], twq[512 + j]);
+			dft4<true>(a0, a1, a2, a3);
+			o[0] = a0; o[544] = a1; o[1088] = a2; o[1632] = a3;
+		}
+		__syncthreads();
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 j = h; j < 1024; j += NTHR / 2)
+		{
+			const u64 *o = smw + 2 * (j + (j >> 4));
+			u64 a[5];
+			a[0] = o[0];
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) a[k] = gl::mul(o[k * 2176], twi0[(k - 1) * 1024 + j]);
+			dft5(a, t.w5i);
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) g[2 * (j + 1024 * q)] = a[q];
 		}
 	}
 }

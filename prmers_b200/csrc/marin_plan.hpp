@@ -28,6 +28,8 @@ inline size_t transform_size(uint32_t exponent)
 static constexpr u32 SMALL_MAX_PAIRS = 1024;  // one CTA does the whole operation up to here; beyond, the grid-wide passes win
                                               // (B200, us per squaring: n = 4096 one CTA 36 / three passes 24, n = 10240 79 / 33, n = 16384 119 / 30)
 static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
+static constexpr u32 MID_S5 = 5120;           // 5 * 2^k transforms with 1024 rows: the radix-5 stage moves into the contiguous pass
+                                              // (85 KiB rows), and the strided passes are the specialised R = 1024 kernels
 static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 9 pairs * 16 B = 180 KiB
 
 struct Plan
@@ -99,10 +101,11 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 		pl.small = false;
 		const u32 five = (m % 5 == 0) ? 5 : 1;
 		if (force_S) { pl.S = force_S; pl.R = m / force_S; }
+		else if (five == 5 && m == 1024u * MID_S5) { pl.S = MID_S5; pl.R = 1024; }   // n = 5 * 2^21 (p ~ 1.7e8 .. 2.1e8)
 		else if (m / five >= ((five == 5) ? 16u : 64u) * MID_S) { pl.S = MID_S; pl.R = m / MID_S; }
 		else if (five == 5) { pl.R = 80; pl.S = m / pl.R; }
 		else { pl.R = (m > 8192) ? 64 : 8; pl.S = m / pl.R; } // measured at n = 4096 and n = 16384: few long rows win (latency, not throughput)
-		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || (pl.S & (pl.S - 1)) != 0 || pl.R < 2) { err = "bad forced split"; return false; }
+		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || ((pl.S & (pl.S - 1)) != 0 && pl.S != MID_S5) || pl.R < 2) { err = "bad forced split"; return false; }
 		// more rows than one tile can hold: split them over two strided passes, R = RA * RB, the radix-5
 		// factor (if any) staying in the first
 		if (pl.R > MAX_R || force_R2)
@@ -113,7 +116,7 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 			if (rb < 2 || Rall % rb != 0 || (rb & (rb - 1)) != 0 || Rall / rb < 2) { err = "bad second-level split"; return false; }
 			pl.R2 = rb; pl.R = Rall / rb;
 		}
-		if (pl.R > MAX_R || pl.S > MID_S) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
+		if (pl.R > MAX_R || pl.S > MID_S5) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
 		pl.nstS = factor_stages(pl.S, pl.stS, true);
 		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0);
 		pl.thrMid = round_threads(pl.S / 8, 512);
