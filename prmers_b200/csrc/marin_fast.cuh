@@ -450,6 +450,32 @@ __device__ __forceinline__ void carry_publish_T4(const StridedArgs &A, pair_t *s
 	}
 }
 
+// ---- bulk asynchronous copy (the TMA engine's 1-D form, cp.async.bulk; UBLKCP in SASS) with an mbarrier: one thread
+// arms the barrier with the byte count and issues the copies, the data lands in shared memory without passing through
+// any thread's registers, and whoever needs it waits on the barrier's phase
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, u32 bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tMBAR_WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra MBAR_DONE_%=;\n\tbra MBAR_WAIT_%=;\n\tMBAR_DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // inverse strided pass with carry (level 0), optionally followed by the forward strided pass of the next squaring.
 // Shared memory: the tile, then the stage twiddles of the pass (inverse, forward: 2 x 1020 words) -- L1 is a stream of
 // tile inputs and weights here and a twiddle that misses costs an L2 round trip in the middle of a butterfly.
@@ -462,9 +488,17 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	u64 *twsm = reinterpret_cast<u64 *>(smraw + SC<4>::SMEM);
 	__shared__ u32 s_tile;
-	// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket
-	if (threadIdx.x == 0) s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
-	for (u32 i = threadIdx.x; i < STR_TW; i += STR_THREADS) { twsm[i] = A.twi[i]; if (FWD_FOLLOWS) twsm[STR_TW + i] = A.tw[i]; }
+	__shared__ __align__(8) unsigned long long s_bar;
+	if (threadIdx.x == 0)
+	{
+		// the stage twiddles come in by bulk asynchronous copy while the tile's first loads are in flight
+		mbar_init(&s_bar, 1);
+		mbar_expect_tx(&s_bar, (FWD_FOLLOWS ? 2u : 1u) * STR_TW * 8);
+		bulk_g2s(twsm, A.twi, STR_TW * 8, &s_bar);
+		if (FWD_FOLLOWS) bulk_g2s(twsm + STR_TW, A.tw, STR_TW * 8, &s_bar);
+		// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket
+		s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
+	}
 	__syncthreads();
 	const Tables &t = A.t;
 	const u32 g = s_tile, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -548,6 +582,7 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 			u64 *p = smw + (size_t)row0 * PITCH_W;
 			u64 a[16];
 			ld16_sw_rt(a, p, stw);
+			if (ph == 0) mbar_wait(&s_bar, 0);                   // the twiddles have landed (long ago: this is the first use)
 			tw16_rt(a, tw, tws);
 			dft16<true>(a);
 			if (big)
