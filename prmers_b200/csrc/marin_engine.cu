@@ -237,6 +237,56 @@ __global__ void k_weights(const __grid_constant__ WeightArgs A, u32 n)
 	if (j < n) weight_thread(A, j);
 }
 
+// Load-time self-test of the field arithmetic: the device paths of gl64.cuh are carry-chain PTX whose correctness rests
+// on how ptxas lowers add.cc / sub.cc / madc sequences (a borrow after sub.cc is read by madc as "carry = no borrow"); the
+// host paths are plain C.  Every engine's first creation in a process runs both on edge values and refuses to go on if
+// they differ -- a toolkit that lowers the chains differently fails here, loudly, instead of producing wrong residues.
+__global__ void k_selftest(const u64 *a, const u64 *b, u64 *out, u32 cnt)
+{
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cnt) return;
+	const u64 x = a[i], y = b[i];
+	u64 *o = out + (size_t)i * 12;
+	o[0] = gl::add(x, y); o[1] = gl::sub(x, y); o[2] = gl::mul(x, y); o[3] = gl::pminus(x); o[4] = gl::add_lazy(x, y);
+	o[5] = gl::mul_pow2<12>(x); o[6] = gl::mul_pow2<48>(x); o[7] = gl::mul_pow2<60>(x); o[8] = gl::mul_pow2<84>(x); o[9] = gl::mul_pow2<180>(x);
+	o[10] = gl::reduce128(x, y); o[11] = fast::mul_small((u32)y, x);
+}
+static void selftest_host(u64 x, u64 y, u64 *o)
+{
+	o[0] = gl::add(x, y); o[1] = gl::sub(x, y); o[2] = gl::mul(x, y); o[3] = gl::pminus(x); o[4] = gl::add_lazy(x, y);
+	o[5] = gl::mul_pow2<12>(x); o[6] = gl::mul_pow2<48>(x); o[7] = gl::mul_pow2<60>(x); o[8] = gl::mul_pow2<84>(x); o[9] = gl::mul_pow2<180>(x);
+	o[10] = gl::reduce128(x, y); o[11] = gl::mul((u64)(u32)y, x);
+}
+static void field_selftest(cudaStream_t st)
+{
+	const u64 P = gl::P;
+	const u64 edge[] = {0, 1, 2, 0xffffffffull, 0x100000000ull, 0x100000001ull, 0xfffffffeffffffffull, 0xffffffff00000000ull /* P - 1 */,
+		P - 2, P - 0xffffffffull, 0x8000000000000000ull, 0x7fffffffffffffffull, 0xfffffffe00000001ull, 0x00000001ffffffffull, 0xdeadbeefcafef00dull % P, 0x0123456789abcdefull};
+	const u32 ne = sizeof(edge) / sizeof(edge[0]), cnt = ne * ne;
+	std::vector<u64> a(cnt), b(cnt), got((size_t)cnt * 12), want((size_t)cnt * 12);
+	for (u32 i = 0; i < ne; ++i) for (u32 j = 0; j < ne; ++j) { a[i * ne + j] = edge[i]; b[i * ne + j] = edge[j]; }
+	u64 *da = nullptr, *db = nullptr, *dout = nullptr;
+	CK(cudaMalloc(&da, cnt * 8)); CK(cudaMalloc(&db, cnt * 8)); CK(cudaMalloc(&dout, (size_t)cnt * 12 * 8));
+	CK(cudaMemcpyAsync(da, a.data(), cnt * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(db, b.data(), cnt * 8, cudaMemcpyHostToDevice, st));
+	k_selftest<<<(cnt + 127) / 128, 128, 0, st>>>(da, db, dout, cnt);
+	CK(cudaMemcpyAsync(got.data(), dout, (size_t)cnt * 12 * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	cudaFree(da); cudaFree(db); cudaFree(dout);
+	for (u32 k = 0; k < cnt; ++k)
+	{
+		selftest_host(a[k], b[k], &want[(size_t)k * 12]);
+		for (u32 f = 0; f < 12; ++f)
+		{
+			// add / sub / mul / shifts are defined on canonical inputs only (< P); reduce128, pminus (<= P), add_lazy and mul take anything
+			const bool canon = a[k] < P && b[k] < P;
+			if (!canon && (f == 0 || f == 1 || (f >= 5 && f <= 9) || f == 4 || f == 3 || f == 11)) continue;
+			if (got[(size_t)k * 12 + f] != want[(size_t)k * 12 + f])
+				throw std::runtime_error("marin_b200: field arithmetic self-test failed (device and host disagree on op " + std::to_string(f) +
+					"): this build of the kernels is not usable with this toolkit / driver");
+		}
+	}
+}
+
 // ------------------------------------------------------------------ backend
 
 struct CudaBackend
@@ -270,6 +320,8 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
 		use_fast = getenv("MARIN_B200_NO_FAST") == nullptr;
+		static bool tested[64] = {false};
+		if (dev < 64 && !tested[dev]) { field_selftest(st); tested[dev] = true; }
 	}
 	bool use_fast = true; // the specialised kernels of marin_fast.cuh (same results; MARIN_B200_NO_FAST=1 runs the generic ones: tests, A/B timing)
 
@@ -323,6 +375,7 @@ struct CudaBackend
 	void d2h(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
 	void d2d(void *d, const void *s, size_t b) { use(); CK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st)); ++launches; }
 	void sync() { use(); CK(cudaStreamSynchronize(st)); }
+	void sync_nothrow() noexcept { cudaSetDevice(dev); cudaStreamSynchronize(st); }
 
 	// Optional (MARIN_B200_L2_PERSIST=1): pin the parked transform of a squaring chain in L2 with an access-policy
 	// window.  It bought the round-1 kernels 1.8 %; with the specialised kernels (which already mark the weight

@@ -33,20 +33,20 @@ public:
 		build_tables(pl, h);
 		_wbits = h.wbits;
 		const size_t n = pl.n;
-		_reg = (u64 *)be.alloc(_batch * regs * n * 8);
+		_reg = (u64 *)dev_alloc(_batch * regs * n * 8);
 		be.memset0(_reg, _batch * regs * n * 8);
 		const size_t ncarry = std::max<size_t>(std::max<size_t>(n / pl.D, n / RUN + 1), pl.small ? n / 2 : 0); // recorded linear ops keep one word per pair
 		_ncarry = ncarry;
-		_carry = (u64 *)be.alloc(_batch * ncarry * 8);
-		_carry2 = (u64 *)be.alloc(_batch * ncarry * 8);
-		_scratch = (u64 *)be.alloc(n * 8);
+		_carry = (u64 *)dev_alloc(_batch * ncarry * 8);
+		_carry2 = (u64 *)dev_alloc(_batch * ncarry * 8);
+		_scratch = (u64 *)dev_alloc(n * 8);
 		_canon_D = (n % 16 == 0) ? 16 : ((n % 8 == 0) ? 8 : 4);
-		_cc[0] = (u64 *)be.alloc((n / _canon_D) * 8); _cc[1] = (u64 *)be.alloc((n / _canon_D) * 8);
-		_words = (u32 *)be.alloc(16); be.memset0(_words, 16);   // [0], [1] carries still pending after a canon round, [2] comparison flags
+		_cc[0] = (u64 *)dev_alloc((n / _canon_D) * 8); _cc[1] = (u64 *)dev_alloc((n / _canon_D) * 8);
+		_words = (u32 *)dev_alloc(16); be.memset0(_words, 16);   // [0], [1] carries still pending after a canon round, [2] comparison flags
 		_nslots = n / RUN + 1;
-		_slots = (pair_t *)be.alloc(_nslots * 16);   // {carry, epoch} hand-off slots of the inverse strided pass
+		_slots = (pair_t *)dev_alloc(_nslots * 16);   // {carry, epoch} hand-off slots of the inverse strided pass
 		be.memset0(_slots, _nslots * 16);
-		if (!pl.small) { _fwd = (u64 *)be.alloc(n * 8); be.persist(_fwd, n * 8); _inv_R = gl::inv(pl.R); }
+		if (!pl.small) { _fwd = (u64 *)dev_alloc(n * 8); be.persist(_fwd, n * 8); _inv_R = gl::inv(pl.R); }
 		Tables &t = _t;
 		std::memset(&t, 0, sizeof(t));
 		t.p = pl.p; t.n = pl.n; t.m = pl.m; t.wbase = pl.wbase; t.inv_m = h.inv_m;
@@ -68,15 +68,14 @@ public:
 		for (int i = 0; i < 4; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
 		// natural-order tables for the linear and single-CTA kernels; multi-pass engines unweight / reweight from
 		// the tile-ordered copies instead
-		u64 *w_nat = (u64 *)be.alloc(n * 8), *winv_nat = (u64 *)be.alloc(n * 8);
-		u64 *winvs_nat = pl.small ? (u64 *)be.alloc(n * 8) : nullptr;
-		u64 *w_tile = pl.small ? nullptr : (u64 *)be.alloc(n * 8), *winvs_tile = pl.small ? nullptr : (u64 *)be.alloc(n * 8);
-		for (u64 *q : {w_nat, winv_nat, winvs_nat, w_tile, winvs_tile}) if (q) _owned.push_back(q);
+		u64 *w_nat = (u64 *)dev_alloc(n * 8), *winv_nat = (u64 *)dev_alloc(n * 8);
+		u64 *winvs_nat = pl.small ? (u64 *)dev_alloc(n * 8) : nullptr;
+		u64 *w_tile = pl.small ? nullptr : (u64 *)dev_alloc(n * 8), *winvs_tile = pl.small ? nullptr : (u64 *)dev_alloc(n * 8);
 		WeightArgs W{pl.p, pl.n, h.nr2, h.nr2_inv, h.inv_m, w_nat, winv_nat, winvs_nat, w_tile, winvs_tile, pl.R, pl.small ? 1u : pl.R2 * pl.S};
 		be.weights(W, pl.n);
 		t.w_nat = w_nat; t.winv_nat = winv_nat; t.winvs_nat = winvs_nat; t.w_tile = w_tile; t.winvs_tile = winvs_tile;
 		const size_t nflags = (size_t)(pl.R2 * pl.S / TILE_C) + 4; // published[tiles], error word, then the 8-byte aligned 64-bit tile ticket
-		_flags = (u32 *)be.alloc(nflags * 4);
+		_flags = (u32 *)dev_alloc(nflags * 4);
 		be.memset0(_flags, nflags * 4);
 		_nflags = nflags;
 		be.sync();
@@ -84,10 +83,7 @@ public:
 
 	~EngineCore()
 	{
-		be.sync();
-		for (void *p : _owned) be.free(p);
-		be.free(_reg); be.free(_carry); be.free(_carry2); be.free(_scratch); if (_scratch2) { be.free(_scratch2); be.free(_cc2[0]); be.free(_cc2[1]); } be.free(_cc[0]); be.free(_cc[1]); be.free(_words);
-		be.free(_slots); be.free(_flags); if (_fwd) be.free(_fwd);
+		be.sync_nothrow();   // a destructor must not throw: a sticky CUDA error here is reported by whoever created the next engine
 	}
 
 	size_t size() const { return pl.n; }
@@ -390,8 +386,8 @@ public:
 		if (_batch > 1) throw std::runtime_error("marin_b200: is_equal compares one pair of registers; on a batched engine read the digits per slab");
 		if (!_scratch2)
 		{
-			_scratch2 = (u64 *)be.alloc((size_t)pl.n * 8);
-			_cc2[0] = (u64 *)be.alloc((pl.n / _canon_D) * 8); _cc2[1] = (u64 *)be.alloc((pl.n / _canon_D) * 8);
+			_scratch2 = (u64 *)dev_alloc((size_t)pl.n * 8);
+			_cc2[0] = (u64 *)dev_alloc((pl.n / _canon_D) * 8); _cc2[1] = (u64 *)dev_alloc((pl.n / _canon_D) * 8);
 		}
 		u32 w[4];
 		be.memset0(_words, 12);
@@ -474,13 +470,21 @@ private:
 	const u64 *_twR = nullptr, *_twRi = nullptr, *_twR2 = nullptr, *_twR2i = nullptr;
 	const u32 *_rowK = nullptr, *_rowK2 = nullptr;
 	std::vector<u32> _wbits;
-	std::vector<void *> _owned;
+
+	// every device allocation of the engine: owned from the moment it exists, so a constructor that throws half-way
+	// (out of memory on a later table) leaves nothing behind -- Allocs frees in its own destructor, which runs for a
+	// partially constructed engine too
+	struct Allocs
+	{
+		Backend *be = nullptr; std::vector<void *> v;
+		~Allocs() { if (be) for (void *q : v) be->free(q); }
+	} _allocs;
+	void *dev_alloc(size_t bytes) { _allocs.be = &be; void *d = be.alloc(bytes ? bytes : 8); _allocs.v.push_back(d); return d; }
 
 	void *upload(const void *src, size_t bytes)
 	{
-		void *d = be.alloc(bytes ? bytes : 8);
+		void *d = dev_alloc(bytes ? bytes : 8);
 		if (bytes) be.h2d(d, src, bytes);
-		_owned.push_back(d);
 		return d;
 	}
 

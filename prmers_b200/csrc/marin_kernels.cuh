@@ -34,7 +34,11 @@ struct alignas(16) pair_t { u64 x, y; };
 #define MARIN_LD_CG_U64(p) __ldcg((const unsigned long long *)(p))
 #define MARIN_NANOSLEEP(ns) __nanosleep(ns)
 // 16-byte {carry, epoch} slots: one vector store publishes value and tag together (the single-word
-// status+value of a decoupled look-back), one vector load reads both
+// status+value of a decoupled look-back), one vector load reads both.  ASSUMPTION: an aligned 16-byte st.v2.u64 /
+// ld.v2.u64 is performed as one access (not torn) on sm_100 -- the PTX memory model only promises that for scalar
+// accesses, but the hardware moves aligned 16-byte vectors in one transaction and CUB's decoupled look-back relies on
+// the same behaviour.  If that ever changes the parity tests catch it (a torn read would inject a stale carry), and the
+// fix is the .b128 relaxed.gpu form or carry-then-epoch with st.release / ld.acquire.
 static __device__ __forceinline__ void marin_st_slot(ulonglong2 *p, unsigned long long v, unsigned long long tag)
 { asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(v), "l"(tag) : "memory"); }
 static __device__ __forceinline__ ulonglong2 marin_ld_slot(const ulonglong2 *p)
@@ -111,7 +115,7 @@ HD u64 boundary_tw(const Tables &t, u64 e, bool inv)
 // element i lives at p[2 * (i * mul + ((i >> 4) & pad))]; p already includes column and lane.
 //   global / linear:           mul = pair stride, pad = 0
 //   shared, contiguous pass:   mul = 1, pad = ~0   (one pair of padding per 16: conflict-free radix-16 stages)
-//   shared, strided tile:      mul = TILE_PITCH (9 pairs per row of 8: conflict-free row-wise carry), pad = 0
+//   shared, strided tile:      mul = TILE_PITCH (5 pairs per row of 4: conflict-free row-wise carry), pad = 0
 // Adjacent threads take the two lanes of the same pair, so a warp touches 16 consecutive pairs.
 static constexpr u32 TILE_PITCH = TILE_C + 1;
 struct View
@@ -402,7 +406,7 @@ struct MidArgs     // contiguous pass: one CTA = one block of S pairs (or the wh
 	u64 *carry;
 };
 
-struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
+struct StridedArgs // strided pass: one CTA = R rows x TILE_C (4) pair-columns
 {
 	Tables t;
 	const pair_t *src; pair_t *dst; // src == dst for in-place
@@ -413,7 +417,7 @@ struct StridedArgs // strided pass: one CTA = R rows x 8 pair-columns
 	u32 Lb;             // block length in pairs (= R * stride)
 	u32 stride;         // pairs between rows
 	u32 escale;         // m / Lb
-	u32 tiles;          // stride / 8 tiles per block
+	u32 tiles;          // stride / TILE_C tiles per block
 	u32 a;              // multiplier for the carry
 	pair_t *slots;      // slots[g * R + row] = {carry out of that run, epoch of the launch that wrote it}
 	u32 with_carry;
@@ -543,7 +547,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 }
 
 // ---- strided passes ----------------------------------------------------------------------------
-// Tile = R rows x 8 pair columns; butterfly id b -> column c = b & 7 (fastest: 128 B rows), row-butterfly b >> 3.
+// Tile = R rows x TILE_C (4) pair columns (64-byte row segments); butterfly id b -> lane b & 1, column (b >> 1) & 3, row-butterfly b >> 3.
 
 template <int R, bool INV> HD void run_stage_tile(const StridedArgs &A, const Stage &sg, bool first, bool last, size_t blockbase /*pairs*/, u32 c0,
 	pair_t *sm, u32 tid, u32 nthr, const pair_t *gsrc, pair_t *gdst, bool in_smem_always, bool out_smem_always)

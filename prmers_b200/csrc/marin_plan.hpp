@@ -30,7 +30,7 @@ static constexpr u32 SMALL_MAX_PAIRS = 1024;  // one CTA does the whole operatio
 static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
 static constexpr u32 MID_S5 = 5120;           // 5 * 2^k transforms with 1024 rows: the radix-5 stage moves into the contiguous pass
                                               // (85 KiB rows), and the strided passes are the specialised R = 1024 kernels
-static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 9 pairs * 16 B = 180 KiB
+static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 5 pairs (4 + 1 of padding) * 16 B = 100 KiB, two CTAs per SM
 
 struct Plan
 {

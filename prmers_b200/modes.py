@@ -63,7 +63,8 @@ def format_res2048(r):
     return f"{r & ((1 << 2048) - 1):0512x}"
 
 
-def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4, stop_after_checks=0, known_factors=()):
+def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_restores=4, stop_after_checks=0, known_factors=(),
+            checkpoint_path=None, backup_every=0, stop_at=None):
     """PRP test of 2^p - 1 (type 1, base 3): p squarings from 3, prime iff the residue is 9.
 
     Gerbicz-Li checking as the reference: every B = floor(sqrt(p)) iterations the accumulator
@@ -76,21 +77,39 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
     turns the verdict into the cofactor test of src/math/Cofactor.cpp:33-63: with KF their product and N = (2^p - 1) / KF,
     N is a probable prime iff residue / 9 == 3^(KF - 1) (mod N); the reported residue stays the full-modulus one
     (src/io/JsonBuilder.cpp:182-217).
+    Checkpoints (RunPrpOrLlMarin.cpp:153-226,296-320): with `checkpoint_path` the run resumes from that file (or its
+    `.old`) when it holds this exponent, this mode and THIS backend's tag, saves every `backup_every` iterations (the
+    reference saves on a timer, -t seconds) and, at iteration `stop_at` (a stand-in for the reference's SIGINT
+    handler), saves and returns {"interrupted": iteration}.  The restored state becomes the last verified one, as the
+    reference does (`copy(R4, R0); copy(R5, R1)` after the restore).
     """
+    from . import checkpoint as ckpt
     say = log or (lambda s: None)
     total = p
     B = max(int(math.isqrt(p)), 1)
     level_auto = int(1000 * 600.0 / B) or max((total // B) // max(int(math.isqrt(B)), 1), 1)
     level = check_level if check_level > 0 else max(level_auto, 1)
-    eng.set(R1, 1)
-    eng.set(R0, 3)
+    ri = 0
+    if checkpoint_path:
+        got = ckpt.load_latest(checkpoint_path, eng, p, ckpt.MODE_PRP)
+        if got:
+            ri = got[0]
+            say(f"Resuming from a checkpoint at iteration {ri}.")
+    if ri == 0:
+        eng.set(R1, 1)
+        eng.set(R0, 3)
     eng.copy(R4, R0); eng.copy(R5, R1)
     eng.set(RBASE, 3)
     eng.set_multiplicand(RTMP, RBASE)
-    itersave, jsave = 0, total - 1
+    itersave, jsave = (ri - 1, total - ri) if ri else (0, total - 1)
     checkpass, errors, restores, errordone, passed = 0, 0, 0, False, 0
-    it, j = 0, total - 1
+    it, j = ri, total - 1 - ri
     while it < total:
+        if checkpoint_path and it > ri and ((stop_at is not None and it == stop_at) or (backup_every and it % backup_every == 0)):
+            ckpt.save(checkpoint_path, eng, p, it, mode=ckpt.MODE_PRP)
+            if stop_at is not None and it == stop_at:
+                say(f"Interrupted by user, state saved at iteration {it}")
+                return {"exponent": p, "worktype": "PRP-3", "interrupted": it, "errors_gerbicz": errors, "fft_length": eng.get_size()}
         eng.square_mul(R0)
         if error_iter > 0 and it + 1 == error_iter and not errordone:
             errordone = True
@@ -121,7 +140,7 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
                         raise RuntimeError("Gerbicz-Li: too many restores")
                     eng.copy(R0, R4); eng.copy(R1, R5)
                     it, j, checkpass = itersave, jsave, 0
-                    if it == 0:
+                    if it == 0 and ri == 0:
                         continue            # restart from the very beginning (iter = -1 + 1)
                     it += 1; j -= 1
                     continue

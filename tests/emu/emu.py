@@ -53,6 +53,9 @@ def lib():
                      ("emu_mul_add", [vp, sz, sz, sz, u32])):
             getattr(L, f).argtypes = a; getattr(L, f).restype = C.c_int
         L.emu_transform_size.restype = sz; L.emu_transform_size.argtypes = [u32]
+        L.emu_checkpoint_size.restype = sz; L.emu_checkpoint_size.argtypes = [vp]
+        L.emu_get_checkpoint.restype = C.c_int; L.emu_get_checkpoint.argtypes = [vp, vp]
+        L.emu_set_checkpoint.restype = C.c_int; L.emu_set_checkpoint.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -101,6 +104,22 @@ class EmuEngine:
         return gid.value
 
     def graph_launch(self, gid): self._ck(lib().emu_graph_launch(self._h, gid))
+
+    def get_checkpoint_size(self): return lib().emu_checkpoint_size(self._h)
+
+    def get_checkpoint(self, data):
+        if len(data) != self.get_checkpoint_size():
+            return False
+        buf = (C.c_char * len(data)).from_buffer(data)
+        self._ck(lib().emu_get_checkpoint(self._h, C.addressof(buf)))
+        return True
+
+    def set_checkpoint(self, data):
+        if len(data) != self.get_checkpoint_size():
+            return False
+        buf = (C.c_char * len(data)).from_buffer_copy(bytes(data))
+        self._ck(lib().emu_set_checkpoint(self._h, C.addressof(buf)))
+        return True
 
     def is_equal(self, l, r):
         out = C.c_int(0)

@@ -23,6 +23,7 @@ struct CpuBackend
 	void d2h(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 	void d2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 	void sync() {}
+	void sync_nothrow() noexcept {}
 	void persist(void *, size_t) {}
 	void persist_on() {}
 	void persist_off() {}
@@ -205,5 +206,8 @@ int emu_graph_begin(void *h) { GUARD(((Emu *)h)->graph_begin()) }
 int emu_graph_end(void *h, int *id) { GUARD(*id = ((Emu *)h)->graph_end()) }
 int emu_graph_launch(void *h, int id) { GUARD(((Emu *)h)->graph_launch(id)) }
 int emu_equal(void *h, size_t l, size_t r, int *out) { GUARD(*out = ((Emu *)h)->equal(l, r) ? 1 : 0) }
+size_t emu_checkpoint_size(void *h) { Emu *e = (Emu *)h; return e->size() * 8 * e->regs() * e->batch(); }
+int emu_get_checkpoint(void *h, void *buf) { GUARD(((Emu *)h)->get_all(buf)) }
+int emu_set_checkpoint(void *h, const void *buf) { GUARD(((Emu *)h)->set_all(buf)) }
 size_t emu_transform_size(uint32_t p) { return transform_size(p); }
 }

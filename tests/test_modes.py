@@ -1,5 +1,7 @@
 """The mode loops (prmers_b200/modes.py) on the kernel emulator (CPU tier) and, marked gpu, on the CUDA
 engine: known answers of the reference's unit_tests.sh."""
+import os
+
 import pytest
 
 from oracle import mersenne_ref as mr
@@ -351,3 +353,30 @@ def test_readme_vtrace_regression_gpu():
         r = modes.run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=D, baby_batch=batch, k_range=(k_last - 2, k_last + 1))
         assert modes.pm1_stage2_factor(p, [r["acc"]], known_factors=[46333943, 282345414919]) == 28401397572100073, D
         eng.close()
+
+
+def test_prp_checkpoint_resume_emulated(tmp_path):
+    """RunPrpOrLlMarin.cpp:153-226,296-320: interrupt -> checkpoint (backend tag 3) -> a fresh engine resumes and ends
+    with the same residue; periodic backups rotate .old; a fault after the resume is still caught and rolled back to
+    the restored state; a foreign or damaged file is ignored."""
+    from prmers_b200 import checkpoint as ckpt
+    p = 1279
+    path = str(tmp_path / ckpt.checkpoint_name(p))
+    full = modes.run_prp(EmuEngine(p, 8), p, check_level=2)
+    log = []
+    r = modes.run_prp(EmuEngine(p, 8), p, check_level=2, checkpoint_path=path, backup_every=200, stop_at=777, log=log.append)
+    assert r == {"exponent": p, "worktype": "PRP-3", "interrupted": 777, "errors_gerbicz": 0, "fft_length": r["fft_length"]}
+    assert os.path.exists(path) and os.path.exists(path + ".old")
+    log = []
+    r2 = modes.run_prp(EmuEngine(p, 8), p, check_level=2, checkpoint_path=path, log=log.append)
+    assert "Resuming from a checkpoint at iteration 777." in log
+    assert r2["is_prp"] and r2["res64"] == full["res64"] and r2["errors_gerbicz"] == 0
+    log = []
+    r3 = modes.run_prp(EmuEngine(p, 8), p, check_level=2, checkpoint_path=path, error_iter=900, log=log.append)
+    assert r3["errors_gerbicz"] == 1 and r3["res64"] == full["res64"] and any(s.startswith("[Gerbicz Li] Restore iter=") for s in log)
+    # a checkpoint of another exponent / a damaged one is not loaded: the run starts from scratch
+    blob = bytearray(open(path, "rb").read()); blob[40] ^= 1
+    open(path, "wb").write(bytes(blob)); os.remove(path + ".old")
+    log = []
+    r4 = modes.run_prp(EmuEngine(p, 8), p, check_level=2, checkpoint_path=path, log=log.append)
+    assert not any("Resuming" in s for s in log) and r4["res64"] == full["res64"]
