@@ -105,18 +105,18 @@ def cpu_baseline(sample_iters, p=HEADLINE_P):
     dt = time.perf_counter() - t0
     return {"value": sample_iters / dt, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"{sample_iters} square_mul at p = {p} (n = {o.n}) after 6 warm-up squarings, "
-                      f"oracle/marin_oracle.c with OpenMP; the reference's OpenCL path needs PoCL + OpenCL/GMP "
-                      f"headers, absent from this image"}, o
+                      f"oracle/marin_oracle.c (cache-blocked two-pass NTT, OpenMP over all host threads); the reference's OpenCL path "
+                      f"needs PoCL + OpenCL / GMP headers: the GPU box has none of them (profiles/r2/probe_box.log)"}, o
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (the stock
-    binary cannot be built here: no CL/cl.h, no gmp.h, no PoCL)."""
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the stock binary cannot be
+    built on the GPU box: no CL/cl.h, no gmp.h, no PoCL -- probed, profiles/r2/probe_box.log)."""
     if rank != 0:
         return
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())      # torchrun pins it to 1; the reference arm uses every core
     from oracle import marin_oracle as mo
-    sample = 2
+    sample = 8
     o = mo.OracleEngine(HEADLINE_P, 1)
     o.set(0, 3)
     for _ in range(4):
@@ -137,7 +137,8 @@ def run_reference(args, rank):
             "config": {"workload": f"PRP M{HEADLINE_P}, n = 2^23 Marin IBDWT, {sample} square_mul per step (bounded sample)",
                        "exponent": HEADLINE_P, "transform_size": o.n},
             "cpu_baseline": {"value": v, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{sample} square_mul per step on all host threads (OpenMP), oracle/marin_oracle.c"},
+                             "sample": f"{sample} square_mul per step on all host threads (OpenMP), oracle/marin_oracle.c with the "
+                                       f"cache-blocked two-pass NTT; no PoCL / OpenCL / GMP headers on the box (profiles/r2/probe_box.log)"},
             "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

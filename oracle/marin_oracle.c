@@ -151,8 +151,109 @@ typedef struct
 	uint64_t *tmp; /* n */
 } mo_engine;
 
+/* The same radix-2 levels, cache-blocked for large m (bench.py's CPU baseline should not be a strawman: the plain
+   loops below stream the whole array through memory once per level, 23 times at m = 2^23).  m = R * C, R = 2^t rows:
+   the top t levels (stride >= C) are done on tiles of R rows x 8 columns (one cache line per row: the tile stays in
+   L2 for all t levels), the remaining levels inside the R contiguous blocks of C elements (each stays in L1/L2).  Two
+   passes over memory instead of log2 m.  Butterflies, twiddles and level order are exactly those of the plain loops,
+   so the results are bit-identical. */
+#define MO_TILE 8
+static int blocked_split(size_t m, size_t *R, size_t *C)
+{
+	if (m < ((size_t)1 << 16) || getenv("MO_NO_BLOCK")) return 0;
+	size_t lg = 0; while (((size_t)1 << lg) < m) ++lg;
+	*R = (size_t)1 << (lg / 2); *C = m / *R;
+	return 1;
+}
+
+static void fwd_pow2_blocked(uint64_t *x, size_t m, const uint64_t *tw, size_t R, size_t C)
+{
+	#pragma omp parallel
+	{
+		uint64_t *tile = (uint64_t *)malloc(R * MO_TILE * 8);
+		#pragma omp for schedule(static)
+		for (size_t c0 = 0; c0 < C; c0 += MO_TILE)
+		{
+			for (size_t r = 0; r < R; ++r) memcpy(tile + r * MO_TILE, x + r * C + c0, MO_TILE * 8);
+			for (size_t hr = R / 2, step = 1; hr >= 1; hr /= 2, step *= 2)         /* half = hr * C elements */
+				for (size_t blk = 0; blk < R / (2 * hr); ++blk)
+					for (size_t rr = 0; rr < hr; ++rr)
+					{
+						uint64_t *p0 = tile + (blk * 2 * hr + rr) * MO_TILE, *p1 = p0 + hr * MO_TILE;
+						const size_t jbase = rr * C + c0;
+						for (size_t c = 0; c < MO_TILE; ++c)
+						{
+							const uint64_t a = p0[c], b = p1[c];
+							p0[c] = mo_mod_add(a, b);
+							p1[c] = mo_mod_mul(mo_mod_sub(a, b), tw[(jbase + c) * step]);
+						}
+					}
+			for (size_t r = 0; r < R; ++r) memcpy(x + r * C + c0, tile + r * MO_TILE, MO_TILE * 8);
+		}
+		free(tile);
+		#pragma omp for schedule(static)
+		for (size_t b = 0; b < R; ++b)
+		{
+			uint64_t *y = x + b * C;
+			for (size_t half = C / 2, step = R; half >= 1; half /= 2, step *= 2)
+				for (size_t base = 0; base < C; base += 2 * half)
+					for (size_t j = 0; j < half; ++j)
+					{
+						const size_t i0 = base + j, i1 = i0 + half;
+						const uint64_t a = y[i0], bb = y[i1];
+						y[i0] = mo_mod_add(a, bb);
+						y[i1] = mo_mod_mul(mo_mod_sub(a, bb), tw[j * step]);
+					}
+		}
+	}
+}
+
+static void inv_pow2_blocked(uint64_t *x, size_t m, const uint64_t *twi, size_t R, size_t C)
+{
+	#pragma omp parallel
+	{
+		#pragma omp for schedule(static)
+		for (size_t b = 0; b < R; ++b)
+		{
+			uint64_t *y = x + b * C;
+			for (size_t half = 1, step = m / 2; half <= C / 2; half *= 2, step /= 2)
+				for (size_t base = 0; base < C; base += 2 * half)
+					for (size_t j = 0; j < half; ++j)
+					{
+						const size_t i0 = base + j, i1 = i0 + half;
+						const uint64_t a = y[i0], bb = mo_mod_mul(y[i1], twi[j * step]);
+						y[i0] = mo_mod_add(a, bb);
+						y[i1] = mo_mod_sub(a, bb);
+					}
+		}
+		uint64_t *tile = (uint64_t *)malloc(R * MO_TILE * 8);
+		#pragma omp for schedule(static)
+		for (size_t c0 = 0; c0 < C; c0 += MO_TILE)
+		{
+			for (size_t r = 0; r < R; ++r) memcpy(tile + r * MO_TILE, x + r * C + c0, MO_TILE * 8);
+			for (size_t hr = 1, step = R / 2; hr <= R / 2; hr *= 2, step /= 2)             /* half = hr * C, twiddle step = m / (2 half) */
+				for (size_t blk = 0; blk < R / (2 * hr); ++blk)
+					for (size_t rr = 0; rr < hr; ++rr)
+					{
+						uint64_t *p0 = tile + (blk * 2 * hr + rr) * MO_TILE, *p1 = p0 + hr * MO_TILE;
+						const size_t jbase = rr * C + c0;
+						for (size_t c = 0; c < MO_TILE; ++c)
+						{
+							const uint64_t a = p0[c], bb = mo_mod_mul(p1[c], twi[(jbase + c) * step]);
+							p0[c] = mo_mod_add(a, bb);
+							p1[c] = mo_mod_sub(a, bb);
+						}
+					}
+			for (size_t r = 0; r < R; ++r) memcpy(x + r * C + c0, tile + r * MO_TILE, MO_TILE * 8);
+		}
+		free(tile);
+	}
+}
+
 static void fwd_pow2(uint64_t *x, size_t m, const uint64_t *tw)
 {
+	size_t R, C;
+	if (blocked_split(m, &R, &C)) { fwd_pow2_blocked(x, m, tw, R, C); return; }
 	/* radix-2 decimation in frequency, natural in, bit-reversed out */
 	for (size_t half = m / 2, step = 1; half >= 1; half /= 2, step *= 2)
 	{
@@ -169,6 +270,8 @@ static void fwd_pow2(uint64_t *x, size_t m, const uint64_t *tw)
 
 static void inv_pow2(uint64_t *x, size_t m, const uint64_t *twi)
 {
+	size_t R, C;
+	if (blocked_split(m, &R, &C)) { inv_pow2_blocked(x, m, twi, R, C); return; }
 	/* radix-2 decimation in time, bit-reversed in, natural out, unnormalised */
 	for (size_t half = 1, step = m / 2; half <= m / 2; half *= 2, step /= 2)
 	{
