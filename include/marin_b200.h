@@ -113,6 +113,30 @@ int mb200_device_mem_info(uint32_t device, size_t *free_bytes, size_t *total_byt
 void *mb200_host_alloc(size_t bytes);
 void mb200_host_free(void *p);
 
+/* The reference's own plugin ABI, exported by the same library (third_party/aevum/src/EngineApi.h:28-62; loader
+   src/aevum/EngineAevum.cpp:89-243): with AEVUM_ENGINE_LIB=<path>/libmarin_b200.so the reference's unmodified
+   `engine_aevum` adapter (-aevum / engine::gpu_backend::aevum) runs on this engine.  Residues cross as ceil(p / 32)
+   packed little-endian 32-bit words; `prepare` is set_multiplicand; fft_spec and tune_dir are ignored. */
+const char *aevum_engine_version(void);
+const char *aevum_engine_last_error(void);
+int aevum_engine_resolve_fft(uint32_t exponent, const char *fft_spec, char *output, size_t output_size);
+void *aevum_engine_create(uint32_t exponent, size_t register_count, uint32_t device, int verbose, const char *fft_spec, const char *tune_dir);
+void aevum_engine_destroy(void *handle);
+size_t aevum_engine_transform_size(void *handle);
+size_t aevum_engine_word_count(void *handle);
+int aevum_engine_sync(void *handle);
+int aevum_engine_set_u32(void *handle, size_t dst, uint32_t value);
+int aevum_engine_set_words(void *handle, size_t dst, const uint32_t *words, size_t count);
+int aevum_engine_get_words(void *handle, size_t src, uint32_t *words, size_t count);
+int aevum_engine_copy(void *handle, size_t dst, size_t src);
+int aevum_engine_prepare(void *handle, size_t dst, size_t src);
+int aevum_engine_square_mul(void *handle, size_t reg, uint32_t factor);
+int aevum_engine_mul(void *handle, size_t dst, size_t src, uint32_t factor);
+int aevum_engine_add(void *handle, size_t dst, size_t src);
+int aevum_engine_sub_reg(void *handle, size_t dst, size_t src);
+int aevum_engine_sub_u32(void *handle, size_t dst, uint32_t value);
+int aevum_engine_equal(void *handle, size_t lhs, size_t rhs, int *equal_out);
+
 #ifdef __cplusplus
 }
 #endif

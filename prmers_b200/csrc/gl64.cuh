@@ -2,7 +2,7 @@
 //
 // Replaces the device field helpers of the reference (kernels/marin.cl:111-148, host twins
 // include/marin/arith.h:24-72).  Every function takes and returns CANONICAL values (< P) unless
-// its name says "lazy"; the device versions are carry-chain PTX on 32-bit halves (IADD3 / IMAD.WIDE
+// its name says otherwise; the device versions are carry-chain PTX on 32-bit halves (IADD3 / IMAD.WIDE
 // in SASS, no tensor cores: this is modular integer arithmetic), the host versions are portable C
 // with identical results so that the kernels can be emulated on a CPU by the tests.
 //
@@ -77,26 +77,6 @@ HD u64 add(u64 a, u64 b)
 #else
 	const u64 s = a + b;
 	return (s < a || s >= P) ? s + EPS : s;
-#endif
-}
-
-// ---- a + b for canonical inputs, result only congruent (may lie in [P, 2^64)); feed to mul only
-HD u64 add_lazy(u64 a, u64 b)
-{
-#if defined(__CUDA_ARCH__)
-	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), s0, s1, m;
-	asm("add.cc.u32 %0, %3, %5;\n\t"
-		"addc.cc.u32 %1, %4, %6;\n\t"
-		"subc.u32 %2, 0, 0;\n\t"             // m = carry ? 0 : 0xffffffff ... (see below)
-		: "=&r"(s0), "=&r"(s1), "=&r"(m) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-	// subc after an add chain reads CF as borrow-in: m = 0 - 0 - CF = carry ? 0xffffffff : 0
-	asm("add.cc.u32 %0, %0, %2;\n\t"
-		"addc.u32 %1, %1, 0;\n\t"
-		: "+r"(s0), "+r"(s1) : "r"(m));
-	return ((u64)s1 << 32) | s0;
-#else
-	const u64 s = a + b;
-	return (s < a) ? s + EPS : s;
 #endif
 }
 

@@ -241,19 +241,20 @@ __global__ void k_weights(const __grid_constant__ WeightArgs A, u32 n)
 // on how ptxas lowers add.cc / sub.cc / madc sequences (a borrow after sub.cc is read by madc as "carry = no borrow"); the
 // host paths are plain C.  Every engine's first creation in a process runs both on edge values and refuses to go on if
 // they differ -- a toolkit that lowers the chains differently fails here, loudly, instead of producing wrong residues.
+// (Its first run caught one: an unused helper whose subc-after-add.cc mask came out inverted on the device.  Removed.)
 __global__ void k_selftest(const u64 *a, const u64 *b, u64 *out, u32 cnt)
 {
 	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= cnt) return;
 	const u64 x = a[i], y = b[i];
 	u64 *o = out + (size_t)i * 12;
-	o[0] = gl::add(x, y); o[1] = gl::sub(x, y); o[2] = gl::mul(x, y); o[3] = gl::pminus(x); o[4] = gl::add_lazy(x, y);
+	o[0] = gl::add(x, y); o[1] = gl::sub(x, y); o[2] = gl::mul(x, y); o[3] = gl::pminus(x); o[4] = gl::neg(x);
 	o[5] = gl::mul_pow2<12>(x); o[6] = gl::mul_pow2<48>(x); o[7] = gl::mul_pow2<60>(x); o[8] = gl::mul_pow2<84>(x); o[9] = gl::mul_pow2<180>(x);
 	o[10] = gl::reduce128(x, y); o[11] = fast::mul_small((u32)y, x);
 }
 static void selftest_host(u64 x, u64 y, u64 *o)
 {
-	o[0] = gl::add(x, y); o[1] = gl::sub(x, y); o[2] = gl::mul(x, y); o[3] = gl::pminus(x); o[4] = gl::add_lazy(x, y);
+	o[0] = gl::add(x, y); o[1] = gl::sub(x, y); o[2] = gl::mul(x, y); o[3] = gl::pminus(x); o[4] = gl::neg(x);
 	o[5] = gl::mul_pow2<12>(x); o[6] = gl::mul_pow2<48>(x); o[7] = gl::mul_pow2<60>(x); o[8] = gl::mul_pow2<84>(x); o[9] = gl::mul_pow2<180>(x);
 	o[10] = gl::reduce128(x, y); o[11] = gl::mul((u64)(u32)y, x);
 }
@@ -277,7 +278,7 @@ static void field_selftest(cudaStream_t st)
 		selftest_host(a[k], b[k], &want[(size_t)k * 12]);
 		for (u32 f = 0; f < 12; ++f)
 		{
-			// add / sub / mul / shifts are defined on canonical inputs only (< P); reduce128, pminus (<= P), add_lazy and mul take anything
+			// add / sub / mul / shifts are defined on canonical inputs only (< P); reduce128 and mul take anything
 			const bool canon = a[k] < P && b[k] < P;
 			if (!canon && (f == 0 || f == 1 || (f >= 5 && f <= 9) || f == 4 || f == 3 || f == 11)) continue;
 			if (got[(size_t)k * 12 + f] != want[(size_t)k * 12 + f])
@@ -655,6 +656,72 @@ int mb200_device_mem_info(uint32_t device, size_t *free_bytes, size_t *total_byt
 	{ g_err = "cudaMemGetInfo failed"; cudaGetLastError(); return 0; }
 	return 1;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's plugin ABI (third_party/aevum/src/EngineApi.h:28-62), exported by this library as well, so that the
+// reference's own run-time loader (src/aevum/EngineAevum.cpp:89-243: dlopen of $AEVUM_ENGINE_LIB, the 19 symbols below)
+// and its `engine_aevum` adapter drive the B200 engine UNCHANGED.  Differences from mb200_*: create takes an FFT spec
+// and a tune directory (ignored here: the transform size is the planner's), set_multiplicand is called `prepare`, and
+// residues cross the boundary as packed little-endian 32-bit words (ceil(p / 32) of them), not digits.
+static void words_from_digits(Eng *e, const std::vector<u64> &enc, uint32_t *words, size_t count)
+{
+	memset(words, 0, count * 4);
+	bool all_ones = true;
+	for (u32 k = 0; k < e->pl.n; ++k) if ((u32)enc[k] != (u32)((((u64)1) << e->width(k)) - 1)) { all_ones = false; break; }
+	if (all_ones) return;                                   // 2^p - 1 is 0
+	size_t bit = 0;
+	for (u32 k = 0; k < e->pl.n; ++k)
+	{
+		const u32 w = e->width(k);
+		const u64 v = (u32)enc[k];
+		const size_t wi = bit / 32; const u32 sh = (u32)(bit % 32);
+		if (wi < count) words[wi] |= (uint32_t)(v << sh);
+		if (sh + w > 32 && wi + 1 < count) words[wi + 1] |= (uint32_t)(v >> (32 - sh));
+		bit += w;
+	}
+}
+static void digits_from_words(Eng *e, const uint32_t *words, size_t count, std::vector<u64> &enc)
+{
+	size_t bit = 0;
+	for (u32 k = 0; k < e->pl.n; ++k)
+	{
+		const u32 w = e->width(k);
+		const size_t wi = bit / 32; const u32 sh = (u32)(bit % 32);
+		u64 chunk = (wi < count) ? words[wi] : 0;
+		if (wi + 1 < count) chunk |= (u64)words[wi + 1] << 32;
+		enc[k] = ((chunk >> sh) & ((((u64)1) << w) - 1)) | ((u64)w << 32);
+		bit += w;
+	}
+}
+
+const char *aevum_engine_version(void) { return "marin_b200 0.2 (sm_100a) behind the Aevum plugin ABI"; }
+const char *aevum_engine_last_error(void) { return g_err.c_str(); }
+int aevum_engine_resolve_fft(uint32_t exponent, const char *, char *output, size_t output_size)
+{
+	const size_t n = transform_size(exponent);
+	if (n == (size_t)-1) { g_err = "exponent outside the Goldilocks IBDWT range"; return 0; }
+	snprintf(output, output_size, "marin-b200:%zu", n);
+	return 1;
+}
+void *aevum_engine_create(uint32_t exponent, size_t register_count, uint32_t device, int verbose, const char *, const char *)
+{ return mb200_create(exponent, register_count, device, verbose); }
+void aevum_engine_destroy(void *h) { mb200_destroy(h); }
+size_t aevum_engine_transform_size(void *h) { return mb200_transform_size(h); }
+size_t aevum_engine_word_count(void *h) { return h ? ((size_t)E(h)->pl.p + 31) / 32 : 0; }
+int aevum_engine_sync(void *h) { return mb200_sync(h); }
+int aevum_engine_set_u32(void *h, size_t dst, uint32_t v) { return mb200_set_u32(h, dst, v); }
+int aevum_engine_copy(void *h, size_t dst, size_t src) { return mb200_copy(h, dst, src); }
+int aevum_engine_prepare(void *h, size_t dst, size_t src) { return mb200_set_multiplicand(h, dst, src); }
+int aevum_engine_square_mul(void *h, size_t reg, uint32_t f) { return mb200_square_mul(h, reg, f); }
+int aevum_engine_mul(void *h, size_t dst, size_t src, uint32_t f) { return mb200_mul(h, dst, src, f); }
+int aevum_engine_add(void *h, size_t dst, size_t src) { return mb200_add(h, dst, src); }
+int aevum_engine_sub_reg(void *h, size_t dst, size_t src) { return mb200_sub_reg(h, dst, src); }
+int aevum_engine_sub_u32(void *h, size_t dst, uint32_t v) { return mb200_sub_u32(h, dst, v); }
+int aevum_engine_equal(void *h, size_t l, size_t r, int *out) { return mb200_equal(h, l, r, out); }
+int aevum_engine_set_words(void *eng, size_t dst, const uint32_t *words, size_t count)
+{ GUARD(std::vector<u64> enc(E(eng)->pl.n); digits_from_words(E(eng), words, count, enc); E(eng)->set_digits(dst, enc.data())); }
+int aevum_engine_get_words(void *eng, size_t src, uint32_t *words, size_t count)
+{ GUARD(std::vector<u64> enc(E(eng)->pl.n); E(eng)->get_digits(src, enc.data()); words_from_digits(E(eng), enc, words, count)); }
 
 void *mb200_host_alloc(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
 void mb200_host_free(void *p) { if (p) cudaFreeHost(p); }

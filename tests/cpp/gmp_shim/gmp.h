@@ -29,6 +29,8 @@ void __gmpz_add_ui(mpz_ptr, mpz_srcptr, unsigned long);
 void __gmpz_mul(mpz_ptr, mpz_srcptr, mpz_srcptr);
 void __gmpz_mod(mpz_ptr, mpz_srcptr, mpz_srcptr);
 void __gmpz_mul_2exp(mpz_ptr, mpz_srcptr, unsigned long);
+void __gmpz_setbit(mpz_ptr, unsigned long);
+void __gmpz_set(mpz_ptr, mpz_srcptr);
 void __gmpz_powm_ui(mpz_ptr, mpz_srcptr, unsigned long, mpz_srcptr);
 #define mpz_init __gmpz_init
 #define mpz_inits __gmpz_inits
@@ -46,6 +48,8 @@ void __gmpz_powm_ui(mpz_ptr, mpz_srcptr, unsigned long, mpz_srcptr);
 #define mpz_mul __gmpz_mul
 #define mpz_mod __gmpz_mod
 #define mpz_mul_2exp __gmpz_mul_2exp
+#define mpz_setbit __gmpz_setbit
+#define mpz_set __gmpz_set
 #define mpz_powm_ui __gmpz_powm_ui
 #ifdef __cplusplus
 }

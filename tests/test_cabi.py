@@ -24,6 +24,12 @@ def test_header_symbols_are_exported():
         assert hasattr(L, n), n
     assert sorted(pb.exported_symbols()) == names
     assert b"sm_100a" in L.mb200_version()
+    # the reference's own plugin ABI (third_party/aevum/src/EngineApi.h:28-62), exported by the same library
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "marin_b200.h")).read(), flags=re.S)
+    aevum = sorted(set(re.findall(r"\b(aevum_engine_\w+)\s*\(", text)))
+    assert len(aevum) == 19
+    for n in aevum:
+        assert hasattr(L, n), n
 
 
 def test_planner_through_cabi_matches_oracle():

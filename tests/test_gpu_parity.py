@@ -483,3 +483,18 @@ def test_cpp_adapter_against_reference_engine_header():
         pytest.skip("tests/cpp/test_engine_adapter_refhdr not built (needs /root/reference: python __graft_entry__.py)")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "against the reference engine.h passed" in r.stdout, r.stdout + r.stderr
+
+
+def test_reference_plugin_loader_drives_the_engine():
+    """INTEGRATION.md route B: the reference's OWN run-time adapter (src/aevum/EngineAevum.cpp: dlopen of $AEVUM_ENGINE_LIB,
+    `engine_aevum`), compiled unmodified where it lies, loads libmarin_b200.so through the Aevum plugin ABI the library
+    also exports and passes the reference's adapter test sequence (tests/test_aevum_reg_adapter.cpp:27-87) plus a
+    squaring chain at M136279841 against GMP."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_reference_plugin_loader")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/test_reference_plugin_loader not built (needs /root/reference: python __graft_entry__.py)")
+    env = dict(os.environ, AEVUM_ENGINE_LIB=os.path.join(root, "prmers_b200", "libmarin_b200.so"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "test passed" in r.stdout, r.stdout + r.stderr
