@@ -12,8 +12,8 @@ Restated from src/modes/RunEcmTwistedEdwards.cpp of the reference:
   :3126-3153,3264-3283  NAF of the scalar, double-and-add from the top digit
   :2626-2652  curve-equation invariant a X^2 + Y^2 = Z^2 + d T^2
   :3372-3440  stage-1 gcd(T, N), :3542-3566 stage-2 base = affine(Q), :3569-3606,3775-3794 stage-2 chunks
-Not restated (out of the hot path's scope): checkpoint files, Prime95 hand-off, GUI, torsion-16 and family-IV
-curve generators (the a = 1 point operations those use are below for completeness).
+  :723-803,2173-2435  the other curve families: -torsion16 (a = 1, Z/2 x Z/8 torsion) and -iv163 (family IV, a = -1)
+Not restated (out of the hot path's scope): checkpoint files, Prime95 hand-off, GUI, the Montgomery-form driver.
 """
 import math
 
@@ -190,6 +190,170 @@ def curve_from_seed(N, curve_seed):
     return None
 
 
+# ---- the other curve families of the reference (-torsion16, -iv163) -------------------------------------------------
+def _ec_mod4_mul(n, s1, t1, N):
+    """ecm_local::EC_mod4::get (:723-803): n * (s1, t1) on y^2 = x^3 + 4 x - 16 ... by double-and-add from the top bit, affine
+    coordinates modulo N; a non-invertible denominator ends at the point at infinity, reported as (0, 0)."""
+    def inv(d):
+        d %= N
+        if d == 0 or math.gcd(d, N) != 1:
+            return None
+        return pow(d, -1, N)
+
+    def dbl(P):
+        if P is None:
+            return None
+        i = inv(2 * P[1])
+        if i is None:
+            return None
+        lam = (3 * P[0] * P[0] + 4) % N * i % N
+        x3 = (lam * lam - 2 * P[0]) % N
+        return (x3, (lam * (P[0] - x3) - P[1]) % N)
+
+    def add(P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        if P[0] == Q[0]:
+            return None if (P[1] + Q[1]) % N == 0 else dbl(P)
+        i = inv(Q[0] - P[0])
+        if i is None:
+            return None
+        lam = (Q[1] - P[1]) % N * i % N
+        x3 = (lam * lam - P[0] - Q[0]) % N
+        return (x3, (lam * (P[0] - x3) - P[1]) % N)
+
+    P0 = (s1 % N, t1 % N)
+    P = P0
+    for b in range(n.bit_length() - 2, -1, -1):
+        P = dbl(P)
+        if (n >> b) & 1:
+            P = add(P, P0)
+        if P is None:
+            return 0, 0
+    return P
+
+
+def curve_torsion16(N, curve_seed):
+    """-torsion16 (:2228-2370): Edwards curves with a = 1 and torsion Z/2 x Z/8 from the multiples m (4, 8) of a point of
+    infinite order (Gallot / Theorem 2.5 of Bernstein-Birkner-Lange-Peters); up to 128 values of m per curve seed."""
+    for tries in range(128):
+        m = mix64(curve_seed, 0x544F523136 + tries) | 1
+        if m < 3:
+            m += 2
+        s, t = _ec_mod4_mul(m, 4, 8, N)
+        inv = _inv((s - 4) % N, N)
+        if inv is None:
+            continue
+        alpha = (t + 8) % N * inv % N
+        alpha2 = alpha * alpha % N
+        inv = _inv((8 - alpha2) % N, N)
+        if inv is None:
+            continue
+        r = (8 + 2 * alpha) % N * inv % N
+        t1 = (2 * r - 1) % N
+        t1 = t1 * t1 % N
+        inv = _inv(t1 * t1 % N, N)
+        if inv is None:
+            continue
+        dE = (8 * r * r - 8 * r + 1) % N * inv % N
+        if dE in (0, 1, N - 1):
+            continue
+        inv = _inv((2 * s - alpha2 + 4) % N, N)
+        if inv is None:
+            continue
+        X0 = (8 - alpha2) % N * ((2 * r * r - 1) % N) % N * inv % N
+        inv = _inv((4 * r - 3) % N, N)
+        if inv is None:
+            continue
+        Y0 = t1 * inv % N
+        if X0 == 0 or Y0 == 0:
+            continue
+        x2, y2 = X0 * X0 % N, Y0 * Y0 % N
+        if (x2 + y2 - 1 - dE * x2 % N * y2) % N != 0:
+            continue
+        return {"a": 1, "d": dE, "X0": X0, "Y0": Y0, "sigma": None, "tries": tries, "torsion": "16", "m": m}
+    return None
+
+
+def curve_family_iv(N, curve_seed):
+    """-iv163 (:2180-2226,2372-2435): the Gelin-Kleinjung-Lenstra family (a = -1, 16/3 average 2-valuation): a rational
+    point m (5, 8) on y^2 = x^3 - x^2 - 9 x + 9 gives t, e, and from them d = -e^4 and the starting point, computed over Q
+    and only then reduced modulo N (an inversion that fails there exposes a factor)."""
+    from fractions import Fraction as Q
+
+    def padd(P, R):
+        if P is None:
+            return R
+        if R is None:
+            return P
+        if P[0] == R[0] and (P[1] == -R[1] or P[1] == 0):
+            return None
+        if P == R:
+            lam = (3 * P[0] * P[0] - 2 * P[0] - 9) / (2 * P[1])
+        else:
+            lam = (R[1] - P[1]) / (R[0] - P[0])
+        x3 = lam * lam + 1 - P[0] - R[0]
+        return (x3, -P[1] - lam * (x3 - P[0]))
+
+    def pmul(P, k):
+        R = None
+        while k:
+            if k & 1:
+                R = padd(R, P)
+            P = padd(P, P)
+            k >>= 1
+        return R
+
+    def to_mod(q):
+        inv = _inv(q.denominator % N, N)
+        return None if inv is None else q.numerator % N * inv % N
+
+    for tries in range(128):
+        m = 1 + mix64(curve_seed, 0x163163 + tries) % 100
+        Pq = pmul((Q(5), Q(8)), m)
+        if Pq is None or Pq[1] == 4:
+            continue
+        t = (4 * Pq[0] + 4) / (Pq[1] - 4)
+        t2 = t * t
+        if t2 == 4:
+            continue
+        e = (t2 + 4 * t) / (t2 - 4)
+        if e == 0:
+            continue
+        t4 = t2 * t2
+        t6 = t4 * t2
+        den_x = t4 + 6 * t * t2 + 12 * t2 + 16 * t
+        den_y = t6 + 6 * t4 * t + 10 * t4 + 16 * t * t2 + 48 * t2 + 64 * t
+        if den_x == 0 or den_y == 0:
+            continue
+        Xq = (2 * t * t2 + 2 * t2 - 8 * t - 8) / den_x
+        Yq = (t6 + 6 * t4 * t + 10 * t4 - 16 * t * t2 - 48 * t2 - 32 * t - 32) / den_y
+        dE, X0, Y0 = to_mod(-(e ** 4)), to_mod(Xq), to_mod(Yq)
+        if dE is None or X0 is None or Y0 is None:
+            continue
+        aE = N - 1
+        if dE in (0, 1, N - 1) or X0 == 0 or Y0 == 0:
+            continue
+        x2, y2 = X0 * X0 % N, Y0 * Y0 % N
+        if (aE * x2 + y2 - 1 - dE * x2 % N * y2) % N != 0:
+            continue
+        return {"a": aE, "d": dE, "X0": X0, "Y0": Y0, "sigma": None, "tries": tries, "torsion": "family_iv_163", "m": m}
+    return None
+
+
+def curve_for(N, curve_seed, torsion=None):
+    """The curve of one ECM run: default family (Suyama sigma), "16" (-torsion16) or "family_iv_163" (-iv163)."""
+    if torsion in (None, "none"):
+        return curve_from_seed(N, curve_seed)
+    if torsion == "16":
+        return curve_torsion16(N, curve_seed)
+    if torsion == "family_iv_163":
+        return curve_family_iv(N, curve_seed)
+    raise ValueError(f"unknown curve family {torsion!r}")
+
+
 # ---- point operations on engine registers ------------------------------------------------------------
 class EdwardsOps:
     """The reference's op schedules, register for register.  `eng` needs the engine.h methods; the fused helpers
@@ -356,7 +520,7 @@ def check_invariant(eng, p, aE, dE):
     return (aE * X * X + Y * Y - Z * Z - dE * T * T) % N == 0
 
 
-def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None):
+def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None, torsion=None):
     """One curve of RunEcmTwistedEdwards.cpp:1737-3859 on a 51-register engine.  Returns a dict with `status` in
     {"found", "NF", "singular", "nocurve", "invariant"}, `factor`, `stage` (0 = curve generation, 1, 2) and the final
     extended coordinates (for parity checks against a big-integer restatement of the same formulas)."""
@@ -364,7 +528,7 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
     N = (1 << p) - 1
     res = {"curve_seed": curve_seed, "status": "NF", "factor": None, "stage": None, "n": eng.get_size()}
     try:
-        cv = curve if curve is not None else curve_from_seed(N, curve_seed)
+        cv = curve if curve is not None else curve_for(N, curve_seed, torsion)
     except FactorFound as f:
         res.update(status="found", factor=f.g, stage=0)
         return res
@@ -387,7 +551,8 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
     for r, v in ((3, (N - X0) % N if neg else X0), (4, Y0), (5, (N - T0) % N if neg else T0)):
         _set_int(eng, r, v, p)
 
-    ops = EdwardsOps(eng, graphs=graphs)
+    # -torsion16 curves have a = 1 and run the "notwist" schedules (:3255-3272); every other family the general-a ones
+    ops = EdwardsOps(eng, notwist=(torsion == "16"), graphs=graphs)
     def inject(step):
         # -erroriter (:3285-3288): corrupt Z after that many steps; the invariant must catch it
         if step == error_iter:
@@ -457,7 +622,7 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
 
 
 def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), continue_after_factor=False,
-            curve_indices=None, log=None, graphs=None):
+            curve_indices=None, log=None, graphs=None, torsion=None):
     """The curve loop (:1737-1830, 3415-3455): curve c uses curve_seed = mix64(seed, c) on its own engine
     (`engine_factory(p, 51)`), stops at the first new factor unless told to continue.  `curve_indices` restricts
     the loop to a subset (multi-GPU: curve c -> rank c mod world)."""
@@ -470,7 +635,7 @@ def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), con
     for c in (range(curves) if curve_indices is None else curve_indices):
         eng = engine_factory(p, REGS)
         try:
-            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs)
+            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs, torsion=torsion)
         finally:
             if hasattr(eng, "close"):
                 eng.close()

@@ -290,3 +290,60 @@ def test_batched_ecm_config5_gpu():
     for ci in (0, 17, 63):
         seq = ecm.run_ecm(lambda q, r: pb.Engine(q, r), p, 600, 2000, curves=64, seed=7, continue_after_factor=True, curve_indices=[ci])
         assert _curve_key(seq["curves"][0]) == _curve_key(big["curves"][ci])
+
+
+# ---- the other curve families: -torsion16 and -iv163 (round 2) ----------------------------------------------------------------
+def _edwards_group_order(q, a, d):
+    """Order of the group of a x^2 + y^2 = 1 + d x^2 y^2 over F_q (q a small prime), counted on the birationally
+    equivalent Montgomery curve B v^2 = u^3 + A u^2 + u, A = 2 (a + d) / (a - d), B = 4 / (a - d)."""
+    inv = pow((a - d) % q, -1, q)
+    A, Binv = 2 * (a + d) * inv % q, (a - d) * pow(4, -1, q) % q
+    sq = {x * x % q for x in range(1, q)}
+    n = 1
+    for u in range(q):
+        rhs = (u * u * u + A * u * u + u) * Binv % q
+        n += 1 if rhs == 0 else (2 if rhs in sq else 0)
+    return n
+
+
+def test_torsion16_and_family_iv_curves():
+    """Generators of RunEcmTwistedEdwards.cpp:2228-2435: the curves they return satisfy the curve equation with the
+    advertised a (1, resp. -1), and have the advertised torsion: reduced modulo small primes their group order is always
+    divisible by 16 (-torsion16: Z/2 x Z/8) resp. by 8 at least (family IV)."""
+    for p in (701, 1277):
+        N = (1 << p) - 1
+        for c in range(4):
+            cs = ecm.mix64(987654321, c)
+            for tor, a_want in (("16", 1), ("family_iv_163", N - 1)):
+                cv = ecm.curve_for(N, cs, tor)
+                assert cv is not None and cv["a"] == a_want and cv["torsion"] == tor
+                x2, y2 = cv["X0"] ** 2 % N, cv["Y0"] ** 2 % N
+                assert (cv["a"] * x2 + y2 - 1 - cv["d"] * x2 * y2) % N == 0
+    checked = 0
+    for q in (10007, 10009, 20011, 30011):
+        for c in range(6):
+            cs = ecm.mix64(55, c)
+            for tor, div in (("16", 16), ("family_iv_163", 8)):
+                try:
+                    cv = ecm.curve_for(q, cs, tor)
+                except ecm.FactorFound:
+                    continue
+                if cv is None:
+                    continue
+                a, d = cv["a"] % q, cv["d"] % q
+                if d in (0, a):
+                    continue
+                assert _edwards_group_order(q, a, d) % div == 0, (q, c, tor)
+                checked += 1
+    assert checked >= 6
+    with pytest.raises(ValueError):
+        ecm.curve_for((1 << 101) - 1, 1, "bogus")
+
+
+def test_ecm_finds_factors_with_every_curve_family():
+    """The a = 1 ("notwist") schedules with -torsion16 curves and the general-a schedules with family-IV curves on exact
+    arithmetic: invariant holds on every curve, and M67 = 193707721 * 761838257287 is split."""
+    for tor in ("16", "family_iv_163", None):
+        r = ecm.run_ecm(lambda p, regs: IntEngine(p, regs), 67, 4000, 40000, curves=12, seed=11, continue_after_factor=True, torsion=tor)
+        assert all(c["status"] != "invariant" for c in r["curves"])
+        assert r["status"] == "found" and ((1 << 67) - 1) % r["factor"] == 0 and 1 < r["factor"] < (1 << 67) - 1, tor
