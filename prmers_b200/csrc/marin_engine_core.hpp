@@ -65,7 +65,7 @@ public:
 		_rowK = (const u32 *)upload(h.rowK.data(), h.rowK.size() * 4);
 		t.rowroot = (const u64 *)upload(h.rowroot.data(), h.rowroot.size() * 8);
 		t.colroot = (const u64 *)upload(h.colroot.data(), h.colroot.size() * 8);
-		for (int i = 0; i < 4; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
+		for (int i = 0; i < 5; ++i) { t.w5[i] = h.w5[i]; t.w5i[i] = h.w5i[i]; }
 		// natural-order tables for the linear and single-CTA kernels; multi-pass engines unweight / reweight from
 		// the tile-ordered copies instead
 		u64 *w_nat = (u64 *)dev_alloc(n * 8), *winv_nat = (u64 *)dev_alloc(n * 8);

@@ -125,12 +125,20 @@ template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THR
 	{
 		// ---- F0: radix 5, elements j + 1024 q from global memory; F1: radix 4 (s = 256) inside each fifth of the row
 		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		u64 nx[5];                                           // the next butterfly's inputs are requested before this one is computed
+		#pragma unroll
+		for (int q = 0; q < 5; ++q) nx[q] = g[2 * (h + 1024 * q)];
 		#pragma unroll 1
 		for (u32 j = h; j < 1024; j += NTHR / 2)
 		{
 			u64 a[5];
 			#pragma unroll
-			for (int q = 0; q < 5; ++q) a[q] = g[2 * (j + 1024 * q)];
+			for (int q = 0; q < 5; ++q) a[q] = nx[q];
+			if (j + NTHR / 2 < 1024)
+			{
+				#pragma unroll
+				for (int q = 0; q < 5; ++q) nx[q] = g[2 * (j + NTHR / 2 + 1024 * q)];
+			}
 			dft5(a, t.w5);
 			#pragma unroll
 			for (int k = 1; k < 5; ++k) a[k] = gl::mul(a[k], tw0[(k - 1) * 1024 + j]);

@@ -95,8 +95,8 @@ struct Tables
 	const u64 *bl_lo, *bl_hi, *bl_loi, *bl_hii; u32 bl_h; // m-th root: w^(+-e) = lo[e & (2^h - 1)] * hi[e >> h]
 	const u64 *rowroot;          // w_m^(frequency index of the contiguous block) after the strided pass(es)
 	const u64 *colroot;          // w_S^freq(sigma), position order inside a contiguous block
-	u64 w5[4];                   // radix-5 constants (c1, c2, s1, s2), see dft5
-	u64 w5i[4];
+	u64 w5[5];                   // radix-5 constants (u, v, s1, s2 - s1, s1 + s2), see dft5
+	u64 w5i[5];
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -206,17 +206,22 @@ template <bool INV> HD void dft16(u64 *x)
 	}
 }
 
-// 5-point DFT (the only odd radix the Goldilocks IBDWT admits, ibdwt.h:17-22): symmetric form with
-// 8 multiplications; c = (c1, c2, s1, s2) = ((w+w^4)/2, (w^2+w^3)/2, (w-w^4)/2, (w^2-w^3)/2).
+// 5-point DFT (the only odd radix the Goldilocks IBDWT admits, ibdwt.h:17-22) with 5 multiplications (the reference's
+// butterfly5 is a Winograd form too, marin.cl:349-376; this one is re-derived): with c1 = (w + w^4)/2, c2 = (w^2 + w^3)/2,
+// s1 = (w - w^4)/2, s2 = (w^2 - w^3)/2 and a = x1 + x4, b = x1 - x4, e = x2 + x3, d = x2 - x3,
+//   X1,4 = r1 +- i1, X2,3 = r2 +- i2,  r1,2 = x0 + u (a + e) +- v (a - e),  u = (c1 + c2)/2 = -1/4, v = (c1 - c2)/2,
+//   i1 = s1 b + s2 d = P1 + P2, i2 = s2 b - s1 d = P3 - P1,  P1 = s1 (b + d), P2 = (s2 - s1) d, P3 = (s1 + s2) b.
+// c = (u, v, s1, s2 - s1, s1 + s2); the inverse transform uses the same with the three s-constants negated.
 HD void dft5(u64 *x, const u64 *c)
 {
 	const u64 a = gl::add(x[1], x[4]), b = gl::sub(x[1], x[4]);
-	const u64 cc = gl::add(x[2], x[3]), d = gl::sub(x[2], x[3]);
-	const u64 r1 = gl::add(x[0], gl::add(gl::mul(a, c[0]), gl::mul(cc, c[1])));
-	const u64 r2 = gl::add(x[0], gl::add(gl::mul(a, c[1]), gl::mul(cc, c[0])));
-	const u64 i1 = gl::add(gl::mul(b, c[2]), gl::mul(d, c[3]));
-	const u64 i2 = gl::sub(gl::mul(b, c[3]), gl::mul(d, c[2]));
-	x[0] = gl::add(x[0], gl::add(a, cc));
+	const u64 e = gl::add(x[2], x[3]), d = gl::sub(x[2], x[3]);
+	const u64 t5 = gl::add(a, e);
+	const u64 base = gl::add(x[0], gl::mul(t5, c[0])), vv = gl::mul(gl::sub(a, e), c[1]);
+	const u64 r1 = gl::add(base, vv), r2 = gl::sub(base, vv);
+	const u64 p1 = gl::mul(gl::add(b, d), c[2]), p2 = gl::mul(d, c[3]), p3 = gl::mul(b, c[4]);
+	const u64 i1 = gl::add(p1, p2), i2 = gl::sub(p3, p1);
+	x[0] = gl::add(x[0], t5);
 	x[1] = gl::add(r1, i1); x[4] = gl::sub(r1, i1);
 	x[2] = gl::add(r2, i2); x[3] = gl::sub(r2, i2);
 }

@@ -152,7 +152,7 @@ struct HostTables
 {
 	std::vector<u32> wbits, rowK, rowK2;
 	std::vector<u64> twS, twSi, twR, twRi, twR2, twR2i, bl_lo, bl_hi, bl_loi, bl_hii, rowroot, colroot;
-	u64 inv_m = 0, nr2 = 0, nr2_inv = 0, w5[4], w5i[4];
+	u64 inv_m = 0, nr2 = 0, nr2_inv = 0, w5[5], w5i[5];
 	u32 bl_h = 0;
 };
 
@@ -224,9 +224,11 @@ inline void build_tables(const Plan &pl, HostTables &h)
 	for (u32 s = 0; s < pl.S; ++s) h.colroot[s] = gl::pow(rS, freq_of_pos(pl.stS, pl.nstS, s));
 	// radix-5 constants
 	const u64 w = gl::root_of_unity(5), w2 = gl::mul(w, w), w3 = gl::mul(w2, w), w4 = gl::mul(w3, w);
-	h.w5[0] = gl::half(gl::add(w, w4)); h.w5[1] = gl::half(gl::add(w2, w3));
-	h.w5[2] = gl::half(gl::sub(w, w4)); h.w5[3] = gl::half(gl::sub(w2, w3));
-	h.w5i[0] = h.w5[0]; h.w5i[1] = h.w5[1]; h.w5i[2] = gl::neg(h.w5[2]); h.w5i[3] = gl::neg(h.w5[3]);
+	const u64 c1 = gl::half(gl::add(w, w4)), c2 = gl::half(gl::add(w2, w3)), s1 = gl::half(gl::sub(w, w4)), s2 = gl::half(gl::sub(w2, w3));
+	h.w5[0] = gl::half(gl::add(c1, c2)); h.w5[1] = gl::half(gl::sub(c1, c2));          // u = -1/4, v
+	h.w5[2] = s1; h.w5[3] = gl::sub(s2, s1); h.w5[4] = gl::add(s1, s2);
+	h.w5i[0] = h.w5[0]; h.w5i[1] = h.w5[1];
+	for (int i = 2; i < 5; ++i) h.w5i[i] = gl::neg(h.w5[i]);
 }
 
 inline void fill_mid_args(const Plan &pl, MidArgs &A)
