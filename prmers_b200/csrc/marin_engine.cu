@@ -311,12 +311,7 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 2048)); // it also keeps its argument blocks in static shared memory
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID5_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID5_SMEM));
-		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::MID5_SMEM));
+		mid_fast_attr<0>(); mid_fast_attr<1>(); mid_fast_attr<2>(); mid_fast_attr<3>(); mid_fast_attr<4>(); mid_fast_attr<5>();
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
@@ -326,13 +321,32 @@ struct CudaBackend
 	}
 	bool use_fast = true; // the specialised kernels of marin_fast.cuh (same results; MARIN_B200_NO_FAST=1 runs the generic ones: tests, A/B timing)
 
-	static bool fast_mid_shape(const MidArgs &A)
+	template <int SHAPE> static void mid_fast_attr()
 	{
-		return !A.small && A.S == fast::MID_S && A.nst == 3 && A.st[0].radix == 16 && A.st[1].radix == 16 && A.st[2].radix == 16;
+		const int smem = (int)fast::mid_shape_smem(SHAPE);
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_SQR, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_MUL, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		CK(cudaFuncSetAttribute(fast::k_mid_fast<MODE_FWD, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	}
-	static bool fast_mid5_shape(const MidArgs &A)
+	template <int SHAPE> void mid_fast_launch(const MidArgs &A, u32 grid)
 	{
-		return !A.small && A.S == fast::MID5_S && A.nst == 4 && A.st[0].radix == 5 && A.st[1].radix == 4 && A.st[2].radix == 16 && A.st[3].radix == 16;
+		const u32 thr = fast::mid_shape_threads(SHAPE); const size_t smem = fast::mid_shape_smem(SHAPE);
+		if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR, SHAPE>, A, grid, thr, smem);
+		else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL, SHAPE>, A, grid, thr, smem);
+		else launch_windowed(fast::k_mid_fast<MODE_FWD, SHAPE>, A, grid, thr, smem);
+	}
+	// which specialised contiguous-pass kernel serves this row shape, or -1 (the stage list must be the one the kernel hard-codes)
+	static int fast_mid_shape(const MidArgs &A)
+	{
+		if (A.small) return -1;
+		auto is = [&](std::initializer_list<u32> r) { if (A.nst != r.size()) return false; u32 i = 0; for (u32 x : r) if (A.st[i++].radix != x) return false; return true; };
+		if (A.S == 4096 && is({16, 16, 16})) return (int)fast::MID_SHAPE_4096;
+		if (A.S == 5120 && is({5, 4, 16, 16})) return (int)fast::MID_SHAPE_5120;
+		if (A.S == 2048 && is({2, 4, 16, 16})) return (int)fast::MID_SHAPE_2048;
+		if (A.S == 1024 && is({4, 16, 16})) return (int)fast::MID_SHAPE_1024;
+		if (A.S == 2560 && is({5, 2, 16, 16})) return (int)fast::MID_SHAPE_2560;
+		if (A.S == 1280 && is({5, 16, 16})) return (int)fast::MID_SHAPE_1280;
+		return -1;
 	}
 	static bool fast_str_shape(const StridedArgs &A)
 	{
@@ -446,18 +460,18 @@ struct CudaBackend
 		if (fg && fg < grid) grid = fg;
 		if (ft) thr = ft;
 		use();
-		if (use_fast && !ft && fast_mid_shape(A))
+		const int shape = (use_fast && !ft && batch == 1) ? fast_mid_shape(A) : -1;
+		if (shape >= 0)
 		{
-			if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR, false>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
-			else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL, false>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
-			else launch_windowed(fast::k_mid_fast<MODE_FWD, false>, A, grid, fast::MID_THREADS, fast::MID_SMEM);
-			post(); return;
-		}
-		if (use_fast && !ft && fast_mid5_shape(A))
-		{
-			if (A.mode == MODE_SQR) launch_windowed(fast::k_mid_fast<MODE_SQR, true>, A, grid, fast::MID5_THREADS, fast::MID5_SMEM);
-			else if (A.mode == MODE_MUL) launch_windowed(fast::k_mid_fast<MODE_MUL, true>, A, grid, fast::MID5_THREADS, fast::MID5_SMEM);
-			else launch_windowed(fast::k_mid_fast<MODE_FWD, true>, A, grid, fast::MID5_THREADS, fast::MID5_SMEM);
+			switch (shape)
+			{
+				case 0: mid_fast_launch<0>(A, grid); break;
+				case 1: mid_fast_launch<1>(A, grid); break;
+				case 2: mid_fast_launch<2>(A, grid); break;
+				case 3: mid_fast_launch<3>(A, grid); break;
+				case 4: mid_fast_launch<4>(A, grid); break;
+				default: mid_fast_launch<5>(A, grid); break;
+			}
 			post(); return;
 		}
 		launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem, batch); post();

@@ -92,21 +92,33 @@ static constexpr u32 MID_SMEM = (MID_S + MID_S / 16 + 1) * 16;
 // row, then twenty warp-local blocks of 256 pairs; 320 threads, two CTAs per SM.
 static constexpr u32 MID5_S = 5120, MID5_THREADS = 320;
 static constexpr u32 MID5_SMEM = (MID5_S + MID5_S / 16 + 1) * 16;
+// SHAPE 2, 3: rows of S = 2048 = 2 x 4 x 16 x 16 and S = 1024 = 4 x 16 x 16 pairs (n = 2^22 and 2^21 with 1024 rows, so
+// that the strided passes are the specialised R = 1024 kernels): the radix-2 and radix-4 stages across the row are done
+// by one thread on eight (four) elements 256 apart, straight from / to global memory, then one warp-local block per warp.
+// SHAPE 4, 5: S = 2560 = 5 x 2 x 16 x 16 and S = 1280 = 5 x 16 x 16 (n = 5 * 2^20 and 5 * 2^19 with 1024 rows): the radix-5
+// stage (and the radix-2 stage after it) in one thread on elements 256 apart, one warp-local block per warp.
+static constexpr u32 MID_SHAPE_4096 = 0, MID_SHAPE_5120 = 1, MID_SHAPE_2048 = 2, MID_SHAPE_1024 = 3, MID_SHAPE_2560 = 4, MID_SHAPE_1280 = 5;
+__host__ __device__ constexpr u32 mid_shape_S(int shape) { return shape == 0 ? 4096u : shape == 1 ? 5120u : shape == 2 ? 2048u : shape == 3 ? 1024u : shape == 4 ? 2560u : 1280u; }
+__host__ __device__ constexpr u32 mid_shape_threads(int shape) { return shape == 0 ? 256u : shape == 1 ? 320u : shape == 2 ? 256u : shape == 3 ? 128u : shape == 4 ? 320u : 160u; }
+__host__ __device__ constexpr u32 mid_shape_smem(int shape) { return (mid_shape_S(shape) + mid_shape_S(shape) / 16 + 1) * 16; }
+__host__ __device__ constexpr u32 mid_shape_minblocks(int shape) { return shape == 0 ? 3u : shape == 1 ? 2u : shape == 2 ? 3u : shape == 3 ? 6u : shape == 4 ? 2u : 4u; }
 
-template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THREADS : MID_THREADS, FIVE ? 2 : 3) k_mid_fast(const __grid_constant__ MidArgs A)
+template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threads(SHAPE), mid_shape_minblocks(SHAPE)) k_mid_fast(const __grid_constant__ MidArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const Tables &t = A.t;
-	constexpr u32 S = FIVE ? MID5_S : MID_S, NW = FIVE ? 10 : 8, NTHR = 32 * NW;
-	constexpr u32 SB = FIVE ? 2 : 1;                 // index of the s = 16 stage in the stage list
+	constexpr bool FIVE = SHAPE == 1, POW16 = SHAPE == 0, OCT = SHAPE == 2, QUAD = SHAPE == 3, TEN = SHAPE == 4, FIVE1 = SHAPE == 5;
+	constexpr u32 S = mid_shape_S(SHAPE), NTHR = mid_shape_threads(SHAPE), NW = NTHR / 32;
+	constexpr u32 NIT = S / 256 / NW;                // warp-local blocks per warp
+	constexpr u32 SB = (FIVE || OCT || TEN) ? 2 : 1; // index of the s = 16 stage in the stage list
 	const u32 tid = threadIdx.x, lane = tid & 1, h = tid >> 1, wl = tid & 31, warp = tid >> 5;
 	const size_t rowbase = (size_t)blockIdx.x * S;
 	u64 *smw = reinterpret_cast<u64 *>(sm) + lane;
 	const u64 *tw0 = t.twS + A.st[0].toff, *tw1 = t.twS + A.st[SB].toff;
 	const u64 *twi0 = t.twSi + A.st[0].toff, *twi1 = t.twSi + A.st[SB].toff;
 
-	if (!FIVE)
+	if (POW16)
 	{
 		// ---- F0: elements j + 256 q of the row, straight from global memory
 		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
@@ -119,6 +131,82 @@ template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THR
 			dft16<false>(a);
 			tw16<256>(a, tw0 + j);
 			st16_sw<544>(smw + 2 * (j + (j >> 4)), a);
+		}
+	}
+	else if (OCT)
+	{
+		// ---- F0 (radix 2, s = 1024) and F1 (radix 4, s = 256) on the eight elements j + 256 q, from global memory
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		const u64 *twq = t.twS + A.st[1].toff;
+		#pragma unroll 1
+		for (u32 it = 0; it < 2; ++it)
+		{
+			const u32 j = h + 128 * it;
+			u64 a[8];
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) a[q] = g[2 * (j + 256 * q)];
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) { addsub(a[q], a[q + 4]); a[q + 4] = gl::mul(a[q + 4], tw0[j + 256 * q]); }
+			u64 *o = smw + 2 * (j + (j >> 4));
+			#pragma unroll
+			for (int hf = 0; hf < 2; ++hf)
+			{
+				u64 *x = a + 4 * hf;
+				dft4<false>(x[0], x[1], x[2], x[3]);
+				o[hf * 2176] = x[0]; o[hf * 2176 + 544] = gl::mul(x[1], twq[j]);
+				o[hf * 2176 + 1088] = gl::mul(x[2], twq[256 + j]); o[hf * 2176 + 1632] = gl::mul(x[3], twq[512 + j]);
+			}
+		}
+	}
+	else if (TEN)
+	{
+		// ---- F0 (radix 5, s = 512) on j + 512 q and j + 256 + 512 q, then F1 (radix 2, s = 256), from global memory
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		const u64 *twq = t.twS + A.st[1].toff;
+		#pragma unroll 1
+		for (u32 j = h; j < 256; j += NTHR / 2)
+		{
+			u64 a[5], b[5];
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) { a[q] = g[2 * (j + 512 * q)]; b[q] = g[2 * (j + 256 + 512 * q)]; }
+			dft5(a, t.w5); dft5(b, t.w5);
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) { a[k] = gl::mul(a[k], tw0[(k - 1) * 512 + j]); b[k] = gl::mul(b[k], tw0[(k - 1) * 512 + j + 256]); }
+			const u64 w = twq[j];
+			u64 *o = smw + 2 * (j + (j >> 4));
+			#pragma unroll
+			for (int k = 0; k < 5; ++k) { addsub(a[k], b[k]); o[k * 1088] = a[k]; o[k * 1088 + 544] = gl::mul(b[k], w); }
+		}
+	}
+	else if (FIVE1)
+	{
+		// ---- F0 (radix 5, s = 256) on the elements j + 256 q, from global memory
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 j = h; j < 256; j += NTHR / 2)
+		{
+			u64 a[5];
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) a[q] = g[2 * (j + 256 * q)];
+			dft5(a, t.w5);
+			u64 *o = smw + 2 * (j + (j >> 4));
+			o[0] = a[0];
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) o[k * 544] = gl::mul(a[k], tw0[(k - 1) * 256 + j]);
+		}
+	}
+	else if (QUAD)
+	{
+		// ---- F0 (radix 4, s = 256) on the elements j + 256 q, from global memory
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 it = 0; it < 4; ++it)
+		{
+			const u32 j = h + 64 * it;
+			u64 a0 = g[2 * j], a1 = g[2 * (j + 256)], a2 = g[2 * (j + 512)], a3 = g[2 * (j + 768)];
+			dft4<false>(a0, a1, a2, a3);
+			u64 *o = smw + 2 * (j + (j >> 4));
+			o[0] = a0; o[544] = gl::mul(a1, tw0[j]); o[1088] = gl::mul(a2, tw0[256 + j]); o[1632] = gl::mul(a3, tw0[512 + j]);
 		}
 	}
 	else
@@ -163,7 +251,7 @@ template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THR
 	// ---- warp-local part: blocks of 256 pairs
 	const u32 jl = wl >> 1; // butterfly of this thread inside a block (F1: column j, F2: group of 16)
 	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it)
+	for (u32 it = 0; it < NIT; ++it)
 	{
 		const u32 Bk = warp + NW * it;
 		u64 *blk = smw + 2 * (272 * Bk);
@@ -220,7 +308,7 @@ template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THR
 	if (MODE == MODE_FWD) return;
 	__syncthreads();
 
-	if (!FIVE)
+	if (POW16)
 	{
 		// ---- I0: s = 256, back to global memory (in place)
 		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
@@ -233,6 +321,79 @@ template <int MODE, bool FIVE> __global__ void __launch_bounds__(FIVE ? MID5_THR
 			tw16<256>(a, twi0 + j);
 			dft16<true>(a);
 			st16_nat<512>(g + 2 * j, a);
+		}
+	}
+	else if (OCT)
+	{
+		// ---- I1 (radix 4, s = 256) and I0 (radix 2, s = 1024), back to global memory (in place)
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		const u64 *twq = t.twSi + A.st[1].toff;
+		#pragma unroll 1
+		for (u32 it = 0; it < 2; ++it)
+		{
+			const u32 j = h + 128 * it;
+			const u64 *o = smw + 2 * (j + (j >> 4));
+			u64 a[8];
+			#pragma unroll
+			for (int hf = 0; hf < 2; ++hf)
+			{
+				u64 *x = a + 4 * hf;
+				x[0] = o[hf * 2176]; x[1] = gl::mul(o[hf * 2176 + 544], twq[j]);
+				x[2] = gl::mul(o[hf * 2176 + 1088], twq[256 + j]); x[3] = gl::mul(o[hf * 2176 + 1632], twq[512 + j]);
+				dft4<true>(x[0], x[1], x[2], x[3]);
+			}
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) { a[q + 4] = gl::mul(a[q + 4], twi0[j + 256 * q]); addsub(a[q], a[q + 4]); }
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) g[2 * (j + 256 * q)] = a[q];
+		}
+	}
+	else if (TEN)
+	{
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		const u64 *twq = t.twSi + A.st[1].toff;
+		#pragma unroll 1
+		for (u32 j = h; j < 256; j += NTHR / 2)
+		{
+			const u64 w = twq[j];
+			const u64 *o = smw + 2 * (j + (j >> 4));
+			u64 a[5], b[5];
+			#pragma unroll
+			for (int k = 0; k < 5; ++k) { a[k] = o[k * 1088]; b[k] = gl::mul(o[k * 1088 + 544], w); addsub(a[k], b[k]); }
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) { a[k] = gl::mul(a[k], twi0[(k - 1) * 512 + j]); b[k] = gl::mul(b[k], twi0[(k - 1) * 512 + j + 256]); }
+			dft5(a, t.w5i); dft5(b, t.w5i);
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) { g[2 * (j + 512 * q)] = a[q]; g[2 * (j + 256 + 512 * q)] = b[q]; }
+		}
+	}
+	else if (FIVE1)
+	{
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 j = h; j < 256; j += NTHR / 2)
+		{
+			const u64 *o = smw + 2 * (j + (j >> 4));
+			u64 a[5];
+			a[0] = o[0];
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) a[k] = gl::mul(o[k * 544], twi0[(k - 1) * 256 + j]);
+			dft5(a, t.w5i);
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) g[2 * (j + 256 * q)] = a[q];
+		}
+	}
+	else if (QUAD)
+	{
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 it = 0; it < 4; ++it)
+		{
+			const u32 j = h + 64 * it;
+			const u64 *o = smw + 2 * (j + (j >> 4));
+			u64 a0 = o[0], a1 = gl::mul(o[544], twi0[j]), a2 = gl::mul(o[1088], twi0[256 + j]), a3 = gl::mul(o[1632], twi0[512 + j]);
+			dft4<true>(a0, a1, a2, a3);
+			g[2 * j] = a0; g[2 * (j + 256)] = a1; g[2 * (j + 512)] = a2; g[2 * (j + 768)] = a3;
 		}
 	}
 	else
@@ -384,11 +545,18 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(c
 		const u32 ri = (wl >> 2) + 8 * u, row = 4 * G + (ri & 3) + 64 * (ri >> 2);
 		w[u] = ld_stream(wt + (size_t)row * TILE_C + (wl & 3));
 	}
-	#pragma unroll 1
+	// both hand-off slots of the thread are requested before either is examined
+	const u32 rows[2] = {4 * G + (wl & 3) + 64 * (wl >> 2), 4 * G + (wl & 3) + 64 * (wl >> 2) + 512};
+	const size_t si[2] = {slot_before(A, g, rows[0]), slot_before(A, g, rows[1])};
+	const pair_t s0 = marin_ld_slot(&A.slots[si[0]]), s1 = marin_ld_slot(&A.slots[si[1]]);
+	u64 cins[2];
+	cins[0] = (s0.y == (u64)A.epoch) ? s0.x : wait_slot_fast(A, si[0]);
+	cins[1] = (s1.y == (u64)A.epoch) ? s1.x : wait_slot_fast(A, si[1]);
+	#pragma unroll
 	for (u32 u = 0; u < 2; ++u)
 	{
-		const u32 rr = wl + 32 * u, row = 4 * G + (rr & 3) + 64 * (rr >> 2);
-		const u64 cin = wait_slot_fast(A, slot_before(A, g, row));
+		const u32 row = rows[u];
+		const u64 cin = cins[u];
 		if (cin == 0) continue;
 		const pair_t p0 = sm[tile_pair(row, 0)], p1 = sm[tile_pair(row, 1)];
 		u64 d[4] = {p0.x, p0.y, p1.x, p1.y};
@@ -439,22 +607,28 @@ __device__ __forceinline__ void tw16_rt(u64 *a, const u64 *tw, u32 tws)
 	for (int k = 1; k < 16; ++k) a[sw16(k)] = gl::mul(a[sw16(k)], tw[(k - 1) * tws]);
 }
 
-// carry and publish the 64 rows of group G (one thread per row, two rows per thread)
+// carry and publish the 64 rows of group G (one thread per row, two rows per thread: two independent serial chains,
+// written out side by side so that their latencies overlap)
 __device__ __forceinline__ void carry_publish_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl, u32 bits0, u32 bits1)
 {
 	const Tables &t = A.t;
-	#pragma unroll 1
-	for (u32 u = 0; u < 2; ++u)
+	const u32 row0 = 4 * G + (wl & 3) + 64 * (wl >> 2), row1 = row0 + 64 * 8;
+	u64 v0[RUN], v1[RUN];
+	#pragma unroll
+	for (u32 c = 0; c < TILE_C; ++c)
 	{
-		const u32 bits = u ? bits1 : bits0;
-		const u32 rr = wl + 32 * u, row = 4 * G + (rr & 3) + 64 * (rr >> 2);
-		u64 v[RUN];
-		#pragma unroll
-		for (u32 c = 0; c < TILE_C; ++c) { const pair_t pv = sm[tile_pair(row, c)]; v[2 * c] = pv.x; v[2 * c + 1] = pv.y; }
-		const u64 cout = carry_run(v, RUN, t.wbase, bits, A.a, 0);
-		marin_st_slot(&A.slots[(size_t)g * 1024 + row], cout, A.epoch);
-		#pragma unroll
-		for (u32 c = 0; c < TILE_C; ++c) { pair_t pv; pv.x = v[2 * c]; pv.y = v[2 * c + 1]; sm[tile_pair(row, c)] = pv; }
+		const pair_t p0 = sm[tile_pair(row0, c)], p1 = sm[tile_pair(row1, c)];
+		v0[2 * c] = p0.x; v0[2 * c + 1] = p0.y; v1[2 * c] = p1.x; v1[2 * c + 1] = p1.y;
+	}
+	const u64 cout0 = carry_run(v0, RUN, t.wbase, bits0, A.a, 0);
+	const u64 cout1 = carry_run(v1, RUN, t.wbase, bits1, A.a, 0);
+	marin_st_slot(&A.slots[(size_t)g * 1024 + row0], cout0, A.epoch);
+	marin_st_slot(&A.slots[(size_t)g * 1024 + row1], cout1, A.epoch);
+	#pragma unroll
+	for (u32 c = 0; c < TILE_C; ++c)
+	{
+		pair_t p0, p1; p0.x = v0[2 * c]; p0.y = v0[2 * c + 1]; p1.x = v1[2 * c]; p1.y = v1[2 * c + 1];
+		sm[tile_pair(row0, c)] = p0; sm[tile_pair(row1, c)] = p1;
 	}
 }
 

@@ -80,6 +80,31 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta 
 	return k;
 }
 
+// Row length S of the contiguous pass for the transform sizes whose three-pass split was measured on a B200
+// (tools/shape_sweep.py, profiles/r2/shape_sweep.log): the rows the specialised contiguous kernels cover
+// (S = 256 x {4, 8, 16} and 256 x {5, 10, 20}) with 1024 strided rows from n = 2^21 / 5 * 2^19 up, so that both strided
+// passes are the specialised R = 1024 kernels as well; 256 strided rows for the two sizes below.  0 = no entry.
+inline u32 measured_row_length(u32 m)
+{
+	switch (m)
+	{
+		case 1u << 22: return 4096;        // n = 2^23       300 us
+		case 1u << 21: return 2048;        // n = 2^22       166 us (S = 4096, R = 512: 230)
+		case 1u << 20: return 1024;        // n = 2^21        92 us (95)
+		case 1u << 19: return 2048;        // n = 2^20        51 us (66)
+		case 1u << 18: return 1024;        // n = 2^19        39 us (49)
+		case 1u << 15: return 1024;        // n = 2^16        33 us (S = 512: 42)
+		case 1u << 14: return 2048;        // n = 2^15        25 us (S = 256: 35)
+		case 5u << 20: return MID_S5;      // n = 5 * 2^21   432 us
+		case 5u << 19: return 2560;        // n = 5 * 2^20   224 us (S = 4096, R = 640: 323)
+		case 5u << 18: return 1280;        // n = 5 * 2^19   129 us (157)
+		case 5u << 17: return 2560;        // n = 5 * 2^18    77 us (105)
+		case 5u << 16: return 1280;        // n = 5 * 2^17    45 us (55)
+		case 5u << 13: return 2048;        // n = 5 * 2^14    29 us (S = 512: 43)
+		default: return 0;
+	}
+}
+
 inline u32 round_threads(u32 t, u32 cap) { t = (t + 31) / 32 * 32; if (t < 32) t = 32; return t > cap ? cap : t; }
 
 inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 force_R2 = 0)
@@ -100,12 +125,13 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 	{
 		pl.small = false;
 		const u32 five = (m % 5 == 0) ? 5 : 1;
+		const u32 measured_S = force_S ? 0u : measured_row_length(m);
 		if (force_S) { pl.S = force_S; pl.R = m / force_S; }
-		else if (five == 5 && m == 1024u * MID_S5) { pl.S = MID_S5; pl.R = 1024; }   // n = 5 * 2^21 (p ~ 1.7e8 .. 2.1e8)
+		else if (measured_S) { pl.S = measured_S; pl.R = m / measured_S; }
 		else if (m / five >= ((five == 5) ? 16u : 64u) * MID_S) { pl.S = MID_S; pl.R = m / MID_S; }
 		else if (five == 5) { pl.R = 80; pl.S = m / pl.R; }
 		else { pl.R = (m > 8192) ? 64 : 8; pl.S = m / pl.R; } // measured at n = 4096 and n = 16384: few long rows win (latency, not throughput)
-		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || ((pl.S & (pl.S - 1)) != 0 && pl.S != MID_S5) || pl.R < 2) { err = "bad forced split"; return false; }
+		if (pl.R * pl.S != m || pl.S % TILE_C != 0 || ((pl.S & (pl.S - 1)) != 0 && (pl.S % 5 != 0 || ((pl.S / 5) & (pl.S / 5 - 1)) != 0)) || pl.R < 2) { err = "bad forced split"; return false; }
 		// more rows than one tile can hold: split them over two strided passes, R = RA * RB, the radix-5
 		// factor (if any) staying in the first
 		if (pl.R > MAX_R || force_R2)

@@ -32,7 +32,7 @@ def val(e, r):
 
 CASES = [(31, 0), (89, 0), (127, 0), (521, 0), (701, 0), (1279, 0), (3217, 0), (9941, 0), (86243, 0), (216091, 0),
          (9941, 16), (86243, 8), (86243, 64), (86243, 256), (216091, 64), (216091, 128), (1362763, 0), (2500009, 0),
-         (5000011, 0), (20000003, 0)]
+         (5000011, 0), (20000003, 0), (311111, 0), (620003, 0), (1250003, 0), (1560007, 0), (9999991, 0), (12500003, 0)]
 
 
 @pytest.mark.parametrize("p,force_S", CASES)
@@ -79,7 +79,8 @@ def test_register_ops_match_bigint(p, force_S):
 
 
 @pytest.mark.parametrize("p,force_S", [(127, 0), (701, 0), (9941, 0), (9941, 16), (86243, 0), (86243, 64), (216091, 0),
-                                       (216091, 64), (1362763, 0)])
+                                       (216091, 64), (1362763, 0), (311111, 0), (620003, 0), (1250003, 0), (1560007, 0),
+                                       (9999991, 0), (12500003, 0), (20996011, 0)])
 def test_digits_bit_exact_vs_oracle(p, force_S):
     e, o = _engine(p, 2, force_S), mo.OracleEngine(p, 2)
     e.set(0, 3); o.set(0, 3)
@@ -198,10 +199,13 @@ def test_fused_kernels_full_size():
         e.close()
 
 
-def test_specialised_kernels_match_generic_kernels_bit_for_bit():
-    """marin_fast.cuh against the generic phase functions: identical raw register images (MARIN_B200_NO_FAST=1)."""
+@pytest.mark.parametrize("p", [136279841, 205271257, 100000007, 77232917, 50000017, 37156667, 25000009, 20996011,
+                               12500003, 9999991, 1250003, 620003, 311111])
+def test_specialised_kernels_match_generic_kernels_bit_for_bit(p):
+    """marin_fast.cuh against the generic phase functions: identical raw register images (MARIN_B200_NO_FAST=1), at every
+    transform size whose planned split uses a specialised kernel (all six row shapes of the contiguous pass; the R = 1024
+    strided kernels from n = 2^21 / 5 * 2^19 up)."""
     import prmers_b200 as pb
-    p = 136279841
     imgs = []
     for fast in (True, False):
         if not fast:
@@ -321,7 +325,8 @@ def test_extreme_digits_do_not_overflow():
 
 # ---- BASELINE.json full size: n = 2^23 (M136279841) and n = 5 * 2^21 (p = 205271257) ----
 
-@pytest.mark.parametrize("p,n", [(136279841, 1 << 23), (205271257, 5 << 21)])
+@pytest.mark.parametrize("p,n", [(136279841, 1 << 23), (205271257, 5 << 21), (100000007, 5 << 20), (77232917, 1 << 22),
+                                 (50000017, 5 << 19), (37156667, 1 << 21), (25000009, 5 << 18)])
 def test_full_size_squarings_match_oracle_and_identities(p, n):
     e = _engine(p, 6)
     assert e.get_size() == n
