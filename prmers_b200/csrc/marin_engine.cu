@@ -741,3 +741,7 @@ void *mb200_host_alloc(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, 
 void mb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 }
+
+#ifdef MARIN_PHASE_TIMING
+extern "C" void mb200_debug_phase_clocks(long long *out) { cudaMemcpyFromSymbol(out, marin::fast::g_phase_clk, sizeof(marin::fast::g_phase_clk)); }
+#endif

@@ -430,14 +430,25 @@ template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threa
 // global memory and carries the boundary twiddle w_m^(K(row) column).  Tile = R rows x 4 pairs in shared memory with a
 // pitch of 5 pairs.  Blocks of 16 T rows (512 lane elements for T = 4) are warp-local for the two small stages.
 
-static constexpr u32 STR_THREADS = 256, PITCH_W = 2 * TILE_PITCH; // words per tile row
+static constexpr u32 STR_THREADS = 256;
+
+// Tile layout of the R = 1024 kernels: pair (row, c) of the 1024 x 4 tile sits at pair slot
+//   4 row + (row >> 2) + (row >> 6) + c
+// (one pair of padding after every 4 rows, one more after every 64).  Every access pattern of the pass is then free of
+// bank conflicts: the 64-bit accesses of a radix-16 stage (a warp = 4 adjacent rows x 4 columns x 2 lanes = 32
+// consecutive words), the 128-bit accesses of the radix-4 stage on pairs (rows 4 apart: slots 17 apart), of the carry
+// (rows r + 64 b: slots 273 b apart, 273 = 1 mod 8) and of the coalesced re-weighting.  With a plain pitch of 5 pairs the
+// radix-16 stages ran at 3 wavefronts per access instead of 2 and the carry at 8 instead of 4 (ncu: 16.2 M shared
+// wavefronts per launch against 8.6 M ideal).  Rows r0 + 4 q and r0 + 64 q are still equally spaced: 17 and 273 pairs.
+__device__ __forceinline__ constexpr u32 tile_pair(u32 row, u32 c) { return 4 * row + (row >> 2) + (row >> 6) + c; }
+static constexpr u32 ST_SMALL = 2 * 17, ST_BIG = 2 * 273;      // words between rows 4 apart / 64 apart
 
 template <int T> struct SC
 {
 	static constexpr u32 R = 256 * T;
 	static constexpr u32 S0 = 16 * T;          // stride (rows) of the first radix-16 stage
 	static constexpr u32 NB = 16;              // blocks of 16 T rows per tile
-	static constexpr u32 SMEM = R * TILE_PITCH * 16;
+	static constexpr u32 SMEM = (4 * R + R / 4 + R / 64) * 16;
 };
 
 __device__ __forceinline__ u64 wait_slot_fast(const StridedArgs &A, size_t idx)
@@ -480,12 +491,12 @@ __device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, p
 	const Tables &t = A.t;
 	{
 		const u32 lane = wl & 1, cc = (wl >> 1) & 3, j = wl >> 3;
-		u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)(64 * Bk + j) * PITCH_W + 2 * cc + lane;
+		u64 *p = reinterpret_cast<u64 *>(sm) + 2 * tile_pair(64 * Bk + j, cc) + lane;
 		u64 a[16];
-		ld16_nat<4 * PITCH_W>(a, p);
+		ld16_nat<ST_SMALL>(a, p);
 		dft16<false>(a);
 		tw16<4>(a, A.tw + A.st[1].toff + j);
-		st16_sw<4 * PITCH_W>(p, a);
+		st16_sw<ST_SMALL>(p, a);
 	}
 	__syncwarp();
 	const u32 c = wl & 3;
@@ -514,7 +525,7 @@ __device__ __forceinline__ void fwd_small_T4(const StridedArgs &A, pair_t *sm, p
 template <bool FROMG> __device__ __forceinline__ void fwd_big_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 c0, u32 wl)
 {
 	const u32 lane = wl & 1, c = (wl >> 1) & 3, j = 4 * G + (wl >> 3);
-	u64 *p = reinterpret_cast<u64 *>(sm) + (size_t)j * PITCH_W + 2 * c + lane;
+	u64 *p = reinterpret_cast<u64 *>(sm) + 2 * tile_pair(j, c) + lane;
 	u64 a[16];
 	if (FROMG)
 	{
@@ -523,17 +534,18 @@ template <bool FROMG> __device__ __forceinline__ void fwd_big_T4(const StridedAr
 		#pragma unroll
 		for (int q = 0; q < 16; ++q) a[q] = g[q * gs];
 	}
-	else ld16_nat<64 * PITCH_W>(a, p);
+	else ld16_nat<ST_BIG>(a, p);
 	dft16<false>(a);
 	tw16<64>(a, A.tw + A.st[0].toff + j);
-	st16_sw<64 * PITCH_W>(p, a);
+	st16_sw<ST_BIG>(p, a);
 }
 
 // second half, after EVERY run of the tile's warp has been published (a tile never holds back a carry its successor
 // needs while it waits for its own predecessor; tile 0 waits for the last tile: end-around): wait for the run before
 // each row in the previous tile, absorb, re-weight (coalesced; to the register unless the chain keeps the parked
 // transform as the state, back into the tile when the forward pass follows).  The weights are requested before the wait.
-template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl)
+// bits4: the width bits of the first four digits of the thread's two rows (4 + 4 bits), kept from the carry
+template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(const StridedArgs &A, pair_t *sm, u32 G, u32 g, u32 c0, u32 wl, u32 bits4)
 {
 	const Tables &t = A.t;
 	constexpr u32 R = 1024;
@@ -545,8 +557,8 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(c
 		const u32 ri = (wl >> 2) + 8 * u, row = 4 * G + (ri & 3) + 64 * (ri >> 2);
 		w[u] = ld_stream(wt + (size_t)row * TILE_C + (wl & 3));
 	}
-	// both hand-off slots of the thread are requested before either is examined
 	const u32 rows[2] = {4 * G + (wl & 3) + 64 * (wl >> 2), 4 * G + (wl & 3) + 64 * (wl >> 2) + 512};
+	// both hand-off slots of the thread are requested before either is examined
 	const size_t si[2] = {slot_before(A, g, rows[0]), slot_before(A, g, rows[1])};
 	const pair_t s0 = marin_ld_slot(&A.slots[si[0]]), s1 = marin_ld_slot(&A.slots[si[1]]);
 	u64 cins[2];
@@ -560,7 +572,7 @@ template <bool FWD_FOLLOWS> __device__ __forceinline__ void absorb_reweight_T4(c
 		if (cin == 0) continue;
 		const pair_t p0 = sm[tile_pair(row, 0)], p1 = sm[tile_pair(row, 1)];
 		u64 d[4] = {p0.x, p0.y, p1.x, p1.y};
-		carry_absorb(d, 4, t.wbase, run_bits(t, 2 * (row * A.stride + c0), 4), cin);
+		carry_absorb(d, 4, t.wbase, (bits4 >> (4 * u)) & 15u, cin);
 		pair_t q0, q1; q0.x = d[0]; q0.y = d[1]; q1.x = d[2]; q1.y = d[3];
 		sm[tile_pair(row, 0)] = q0; sm[tile_pair(row, 1)] = q1;
 	}
@@ -664,8 +676,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity)
 static constexpr u32 STR_TW = 15 * 64 + 15 * 4;               // stage twiddles of one direction, R = 1024
 static constexpr u32 INV_SMEM_T4 = SC<4>::SMEM + 2 * STR_TW * 8;
 
+// development aid (-DMARIN_PHASE_TIMING, tools/phase_clocks.py): SM cycle counter at the phase boundaries of every warp of
+// four tiles in the middle of the grid
+#ifdef MARIN_PHASE_TIMING
+__device__ long long g_phase_clk[4 * 8 * 32];
+#define MARIN_STAMP(i) do { if (g >= 600 && g < 604 && wl == 0) g_phase_clk[((g - 600) * 8 + warp) * 32 + (i)] = clock64(); } while (0)
+#else
+#define MARIN_STAMP(i) do { } while (0)
+#endif
+
 template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_inv_fast_T4(const __grid_constant__ StridedArgs A)
 {
+#ifdef MARIN_PHASE_TIMING
+	const long long t_entry = clock64();
+#endif
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	u64 *twsm = reinterpret_cast<u64 *>(smraw + SC<4>::SMEM);
@@ -689,6 +713,11 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	const u32 lane = wl & 1, cc = (wl >> 1) & 3, jq = wl >> 3; // radix-16 stages: lane of the pair, column, butterfly of four
 	u64 *smw = reinterpret_cast<u64 *>(sm) + 2 * cc + lane;
 	const size_t gcol = (size_t)c0 + c;
+	u32 keep = 0;                                             // width bits of the first four digits of the thread's four carry rows
+#ifdef MARIN_PHASE_TIMING
+	if (g >= 600 && g < 604 && wl == 0) g_phase_clk[((g - 600) * 8 + warp) * 32 + 0] = t_entry;
+#endif
+	MARIN_STAMP(1);
 	{
 		// ---- inverse: [radix 4 on pairs from global, radix 16 (s = 4)] per block of 64 rows, block barrier,
 		//      [radix 16 (s = 64) + unweight, carry, publish] per group of 4 columns.
@@ -709,13 +738,23 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 		for (u32 b = 0; b < 4; ++b)
 			fq[b] = boundary_tw(t, (u64)A.rowK[64 * (warp + 8 * (b >> 1)) + 4 * ((wl + 32 * (b & 1)) >> 2)] * colscale, true);
 		const BoundaryPow bp = boundary_pow(t, colscale, 256, true);
+		u32 raw0 = 0, raw1 = 0;                                  // words of the width-bit table for the thread's two carry rows
+		auto finish_group = [&](u32 blk)
+		{
+			const u32 r0 = 4 * blk + (wl & 3) + 64 * (wl >> 2);
+			const u32 bits0 = (raw0 >> ((2 * (r0 * A.stride + c0)) & 31)) & 0xffu, bits1 = (raw1 >> ((2 * ((r0 + 512) * A.stride + c0)) & 31)) & 0xffu;
+			keep = (keep << 8) | (bits0 & 15u) | ((bits1 & 15u) << 4);
+			__syncwarp();
+			carry_publish_T4(A, sm, blk, g, c0, wl, bits0, bits1);
+		};
 		#pragma unroll 1
 		for (u32 ph = 0; ph < 4; ++ph)
 		{
 			const u32 blk = warp + 8 * (ph & 1);
 			const bool big = ph >= 2;
+			MARIN_STAMP(2 + 3 * ph);
 			if (ph == 2) __syncthreads();
-			u32 bits0 = 0, bits1 = 0;
+			MARIN_STAMP(3 + 3 * ph);
 			if (!big)
 			{
 				#pragma unroll 1
@@ -755,13 +794,15 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 				const u64 *wp = t.winvs_tile + 2 * (((size_t)g * 1024 + 4 * blk + jq) * TILE_C + cc) + lane;
 				#pragma unroll
 				for (int q = 0; q < 16; ++q) pf[q] = ld_stream(wp + (size_t)q * (64 * TILE_C * 2));
-				bits0 = run_bits(t, 2 * ((4 * blk + (wl & 3) + 64 * (wl >> 2)) * A.stride + c0), RUN);
-				bits1 = run_bits(t, 2 * ((4 * blk + (wl & 3) + 64 * ((wl + 32) >> 2)) * A.stride + c0), RUN);
+				// (the words only: the shift that extracts the eight bits waits until they are needed, so that the loads fly)
+				const u32 r0 = 4 * blk + (wl & 3) + 64 * (wl >> 2);
+				raw0 = t.wbits[(2 * (r0 * A.stride + c0)) >> 5];
+				raw1 = t.wbits[(2 * ((r0 + 512) * A.stride + c0)) >> 5];
 			}
 			const u32 row0 = big ? 4 * blk + jq : 64 * blk + jq;
-			const u32 stw = (big ? 64u : 4u) * PITCH_W, tws = big ? 64u : 4u;
+			const u32 stw = big ? ST_BIG : ST_SMALL, tws = big ? 64u : 4u;
 			const u64 *tw = twsm + (big ? 4 * blk : 960u) + jq;
-			u64 *p = smw + (size_t)row0 * PITCH_W;
+			u64 *p = smw + 2 * tile_pair(row0, 0);
 			u64 a[16];
 			ld16_sw_rt(a, p, stw);
 			if (ph == 0) mbar_wait(&s_bar, 0);                   // the twiddles have landed (long ago: this is the first use)
@@ -780,13 +821,21 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 				for (int q = 0; q < 16; ++q) a[q] = gl::mul(a[q], pf[q]);
 			}
 			st16_nat_rt(p, a, stw);
-			if (big) { __syncwarp(); carry_publish_T4(A, sm, blk, g, c0, wl, bits0, bits1); }
+			MARIN_STAMP(4 + 3 * ph);
+			if (ph == 2) finish_group(blk);
 		}
+		finish_group(warp + 8);
 	}
+	MARIN_STAMP(14);
 	#pragma unroll 1
-	for (u32 it = 0; it < 2; ++it) absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp + 8 * it, g, c0, wl);
+	for (u32 it = 0; it < 2; ++it)
+	{
+		absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp + 8 * it, g, c0, wl, (keep >> (8 - 8 * it)) & 0xffu);
+		MARIN_STAMP(15 + it);
+	}
 	if (!FWD_FOLLOWS) return;
 	__syncthreads();
+	MARIN_STAMP(17);
 	// ---- forward pass of the next squaring: radix 16 (s = 64) per group, block barrier, [radix 16 (s = 4), radix 4 on
 	//      pairs + boundary twiddle -> global] per block
 	u64 fq[4];
@@ -799,11 +848,13 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	{
 		const u32 blk = warp + 8 * (ph & 1);
 		const bool big = ph < 2;
+		MARIN_STAMP(18 + 2 * ph);
 		if (ph == 2) __syncthreads();
+		MARIN_STAMP(19 + 2 * ph);
 		const u32 row0 = big ? 4 * blk + jq : 64 * blk + jq;
-		const u32 stw = (big ? 64u : 4u) * PITCH_W, tws = big ? 64u : 4u;
+		const u32 stw = big ? ST_BIG : ST_SMALL, tws = big ? 64u : 4u;
 		const u64 *tw = twsm + STR_TW + (big ? 4 * blk : 960u) + jq;
-		u64 *p = smw + (size_t)row0 * PITCH_W;
+		u64 *p = smw + 2 * tile_pair(row0, 0);
 		u64 a[16];
 		ld16_nat_rt(a, p, stw);
 		dft16<false>(a);
@@ -831,6 +882,7 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 			}
 		}
 	}
+	MARIN_STAMP(26);
 }
 
 // forward strided pass from a register in global memory
