@@ -5,6 +5,7 @@
 // Replaces ibdwt::transform_size / roots (include/marin/ibdwt.h:17-43,79-108) and the per-n kernel
 // selection tables of engine_gpu_flat (include/marin/engine_gpu.h:108-129,551-691,1568-1630).
 #pragma once
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -53,7 +54,7 @@ struct Plan
 #define MARIN_R_SMALL_FIRST 0
 #endif
 
-inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta = false)
+inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta = false, bool force_r4 = false)
 {
 	// radices: optional 5 first, then 2, 4 and 16s (or 16s first) with product len
 	u32 r[MAX_STAGES], k = 0, rest = len;
@@ -62,7 +63,7 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta 
 	u32 n16 = l2 / 4, rem = l2 % 4;
 	// tiny transforms are pure instruction latency: a radix-16 butterfly is ~900 dependent-ish instructions in a
 	// handful of threads, radix-4 stages are shorter chains on four times the threads
-	if (single_cta && len <= MARIN_SMALL_R4) { n16 = 0; rem = l2; }
+	if ((single_cta && len <= MARIN_SMALL_R4) || force_r4) { n16 = 0; rem = l2; }
 	u32 small_r[MAX_STAGES], ns = 0;
 	if (rem & 1) small_r[ns++] = 2;
 	for (u32 i = 0; i < rem / 2; ++i) small_r[ns++] = 4;
@@ -143,10 +144,12 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 			pl.R2 = rb; pl.R = Rall / rb;
 		}
 		if (pl.R > MAX_R || pl.S > MID_S5) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
-		pl.nstS = factor_stages(pl.S, pl.stS, true);
-		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0);
-		pl.thrMid = round_threads(pl.S / 8, 512);
-		const u32 bf = pl.R * TILE_C * 2 / 16; // radix-16 butterflies x lanes per stage
+		u32 r4mask = 0;
+		if (const char *e = getenv("MARIN_B200_R4MASK")) r4mask = (u32)atoi(e);
+		pl.nstS = factor_stages(pl.S, pl.stS, true, (r4mask & 1) != 0, (r4mask & 1) != 0);
+		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0, (r4mask & 2) != 0, (r4mask & 2) != 0);
+		pl.thrMid = round_threads((r4mask & 1) ? pl.S / 2 : pl.S / 8, 512);
+		const u32 bf = pl.R * TILE_C * 2 / ((r4mask & 2) ? 4 : 16); // butterflies x lanes per stage
 		pl.thrStr = (bf <= 1024) ? round_threads(bf, 1024) : round_threads(bf / 2, 1024);
 		if (pl.R2 > 1)
 		{

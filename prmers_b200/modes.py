@@ -597,6 +597,36 @@ def pm1_stage2_factor(p, accs, known_factors=()):
     return g if 1 < g < m else None
 
 
+def pm1_ultralow_exponent(p, b1, b2, b2_start=0):
+    """E2 = E(B1) * 2 p * Q, Q = product of the primes in (max(B1, b2start), B2] (RunPM1.cpp:1808-1813; buildE
+    is the product of the prime powers only and the reference multiplies 2 p in once, which `pm1_exponent` includes)."""
+    low = max(b1, b2_start)
+    e = pm1_exponent(p, b1)
+    for q in primes_upto(b2):
+        if q > low:
+            e *= q
+    return e
+
+
+def run_pm1_stage2_ultralow(eng, p, b1, b2, b2_start=0, gcd=True, progress=None):
+    """`-pm1-ultralowmem` stage 2 (RunPM1.cpp:1795-1875, the README's MM31 example README.md:88-98): ONE register, no
+    stage-1 residue needed -- 3^(E(B1) 2p Q) is recomputed with the fast3 squarings only (`square_mul(R, 3)` on a set
+    bit), which equals H^Q for the stage-1 result H; the factor is gcd(X - 1, 2^p - 1)."""
+    E2 = pm1_ultralow_exponent(p, b1, b2, b2_start)
+    bits = E2.bit_length()
+    R = 0
+    eng.set(R, 1)
+    for k in range(bits - 1, -1, -1):
+        eng.square_mul(R, 3 if (E2 >> k) & 1 else 1)
+        if progress and (bits - k) % 1000 == 0:
+            progress(bits - k, bits)
+    x = _value(eng, R, p)
+    m = (1 << p) - 1
+    g = hostmath.gcd((x - 1) % m, m) if gcd else 1
+    return {"exponent": p, "worktype": "PM1", "b1": b1, "b2": b2, "bits": bits, "x": x,
+            "factor": g if 1 < g < m else None, "fft_length": eng.get_size()}
+
+
 def split_k_range(b1, b2, D, world):
     """Equal shares of the giant-step range [k_first, k_last] for `world` ranks."""
     k_first, k_last = (b1 + 1 + D // 2) // D, (b2 + D // 2) // D

@@ -380,3 +380,17 @@ def test_prp_checkpoint_resume_emulated(tmp_path):
     log = []
     r4 = modes.run_prp(EmuEngine(p, 8), p, check_level=2, checkpoint_path=path, log=log.append)
     assert not any("Resuming" in s for s in log) and r4["res64"] == full["res64"]
+
+
+def test_pm1_ultralow_one_register_stage2():
+    """-pm1-ultralowmem (RunPM1.cpp:1795-1875): 3^(E(B1) 2p Q) on ONE register with fast3 squarings; the stage-2 vectors
+    of unit_tests.sh:57,60 are found by it too (it computes H^Q), and a bound below the factor's largest prime finds none."""
+    from oracle.int_engine import IntEngine
+    assert modes.pm1_ultralow_exponent(269, 4, 11) == modes.pm1_exponent(269, 4) * 5 * 7 * 11
+    r = modes.run_pm1_stage2_ultralow(IntEngine(269, 1), 269, 4, 2141)
+    assert r["factor"] == 13822297 and r["bits"] == modes.pm1_ultralow_exponent(269, 4, 2141).bit_length()
+    assert modes.run_pm1_stage2_ultralow(IntEngine(269, 1), 269, 4, 2137)["factor"] is None
+    e = EmuEngine(569, 1)
+    assert modes.run_pm1_stage2_ultralow(e, 569, 9, 677)["factor"] == 55470673
+    # -b2start: primes up to it are left out of Q
+    assert modes.pm1_ultralow_exponent(269, 4, 11, b2_start=5) == modes.pm1_exponent(269, 4) * 7 * 11
