@@ -7,6 +7,17 @@ stored as ~crc ^ 0xa23777ac (include/marin/file.h:48-110).  Backend tags: 1 = Ma
 2 = Aevum, **3 = this engine**: raw images are layout specific, so a file written by another backend
 is ignored rather than loaded (the reference does the same for its two backends).
 Rotation: write `<file>.new`, move the current file to `<file>.old`, move `.new` into place.
+
+The other mode loops keep the reference's own field orders (all little endian, CRC word last):
+  LL-safe  (RunLlSafeMarin.cpp:418-477): int32 version = 3, uint32 p, uint32 backend, uint64 iterations done, float64
+           elapsed, uint64 itersave, uint64 jsave, raw image.
+  P-1 stage 1 (RunPM1.cpp:6219-6267): int32 version = 3, uint32 p, uint32 bit index, float64 elapsed, raw image, uint64
+           checkpass, blocks since check, bits in block, current block length, uint8 in_lot, eacc and wbits as
+           length-prefixed hex strings, uint64 chunk index, start prime, uint8 first, uint64 processed bits, bits in
+           chunk; the backend lives in a side file `<file>.backend` (RunPM1.cpp:154-181), here "marin_b200".
+  ECM stage 1 (RunEcmTwistedEdwards.cpp:1866-1930): int32 version, uint32 p, uint32 step, uint32 bits of K, uint64 B1,
+           float64 elapsed, uint64 curve seed, uint8 curve family, raw image.  The reference's file has no backend
+           field, so the version word carries it here: 0x0301 (the reference accepts 1 only and skips the file).
 """
 import os
 import struct
@@ -67,3 +78,144 @@ def load(path, eng, p, mode=MODE_PRP):
 def load_latest(path, eng, p, mode=MODE_PRP):
     """Current file first, then `.old` (RunPrpOrLlMarin.cpp:215-216)."""
     return load(path, eng, p, mode) or load(path + ".old", eng, p, mode)
+
+
+# ---- the other mode loops --------------------------------------------------------------------------------------------
+
+PM1_BACKEND_NAME = "marin_b200"
+ECM_VERSION = 0x0301
+ECM_FAMILY = {None: 0, "none": 0, "16": 1, "iv163": 2}
+
+
+def _raw(eng):
+    data = bytearray(eng.get_checkpoint_size())
+    if not eng.get_checkpoint(data):
+        raise RuntimeError("engine refused the checkpoint buffer")
+    return bytes(data)
+
+
+def _write_rotating(path, body, keep_old=True):
+    """body + CRC word into `<path>.new`, current file to `.old`, `.new` into place."""
+    new, old = path + ".new", path + ".old"
+    with open(new, "wb") as f:
+        f.write(body); f.write(struct.pack("<I", _crc_word(zlib.crc32(body))))
+    if os.path.exists(old):
+        os.remove(old)
+    if os.path.exists(path):
+        os.rename(path, old)
+    os.rename(new, path)
+    if not keep_old and os.path.exists(old):
+        os.remove(old)
+
+
+def _read_verified(path):
+    """File content without its CRC word, or None when missing or damaged."""
+    try:
+        with open(path, "rb") as f:
+            blob = f.read()
+    except OSError:
+        return None
+    if len(blob) < 8:
+        return None
+    (stored,) = struct.unpack_from("<I", blob, len(blob) - 4)
+    return blob[:-4] if stored == _crc_word(zlib.crc32(blob[:-4])) else None
+
+
+_LLS = struct.Struct("<iIIQdQQ")
+
+
+def llsafe_checkpoint_name(p):
+    return f"llsafe_m_{p}.ckpt"
+
+
+def save_llsafe(path, eng, p, iter_done, itersave, jsave, elapsed=0.0):
+    _write_rotating(path, _LLS.pack(3, p, BACKEND_TAG, iter_done, float(elapsed), itersave, jsave) + _raw(eng))
+
+
+def load_llsafe(path, eng, p):
+    """(iter_done, itersave, jsave, elapsed) with the registers restored, or None (missing, damaged, foreign)."""
+    for f in (path, path + ".old"):
+        body = _read_verified(f)
+        if body is None or len(body) != _LLS.size + eng.get_checkpoint_size():
+            continue
+        version, rp, backend, it, et, isave, jsave = _LLS.unpack_from(body)
+        if version != 3 or rp != p or backend != BACKEND_TAG:
+            continue
+        if eng.set_checkpoint(bytearray(body[_LLS.size:])):
+            return it, isave, jsave, et
+    return None
+
+
+def pm1_checkpoint_name(p):
+    return f"pm1_m_{p}.ckpt"
+
+
+def _hexfield(v):
+    h = format(int(v), "x").encode()
+    return struct.pack("<I", len(h)) + h
+
+
+def save_pm1(path, eng, p, bit_index, state, elapsed=0.0):
+    """`state`: checkpass, blocks_since_check, bits_in_block, current_block_len, in_lot, eacc, wbits, processed_bits, bits."""
+    body = struct.pack("<iIId", 3, p, bit_index, float(elapsed)) + _raw(eng)
+    body += struct.pack("<QQQQB", state["checkpass"], state["blocks_since_check"], state["bits_in_block"], state["current_block_len"], 1 if state["in_lot"] else 0)
+    body += _hexfield(state["eacc"]) + _hexfield(state["wbits"])
+    body += struct.pack("<QQBQQ", 0, 0, 1, state["processed_bits"], state["bits"])
+    _write_rotating(path, body, keep_old=False)          # the reference removes `.old` after the rotation (RunPM1.cpp:6222)
+    with open(path + ".backend.new", "w") as f:
+        f.write(PM1_BACKEND_NAME + "\n")
+    os.replace(path + ".backend.new", path + ".backend")
+
+
+def load_pm1(path, eng, p):
+    """(bit_index, state, elapsed) with the registers restored, or None.  A file without the side file that names this
+    backend is not loaded (the reference reads a missing side file as "Marin OpenCL registers")."""
+    try:
+        with open(path + ".backend") as f:
+            if f.read().split()[:1] != [PM1_BACKEND_NAME]:
+                return None
+    except OSError:
+        return None
+    body = _read_verified(path)
+    size = eng.get_checkpoint_size()
+    if body is None or len(body) < 20 + size + 33:
+        return None
+    version, rp, i, et = struct.unpack_from("<iIId", body)
+    if version != 3 or rp != p:
+        return None
+    o = 20 + size
+    chk, blks, bib, cbl, inlot = struct.unpack_from("<QQQQB", body, o); o += 33
+    vals = []
+    for _ in range(2):
+        (ln,) = struct.unpack_from("<I", body, o); o += 4
+        vals.append(int(body[o:o + ln] or b"0", 16)); o += ln
+    _, _, _, processed, bits = struct.unpack_from("<QQBQQ", body, o)
+    if not eng.set_checkpoint(bytearray(body[20:20 + size])):
+        return None
+    return i, {"checkpass": chk, "blocks_since_check": blks, "bits_in_block": bib, "current_block_len": cbl, "in_lot": bool(inlot),
+               "eacc": vals[0], "wbits": vals[1], "processed_bits": processed, "bits": bits}, et
+
+
+_ECM = struct.Struct("<iIIIQdQB")
+
+
+def ecm_checkpoint_name(p, c):
+    return f"ecm_te_m_{p}_c{c}.ckpt"
+
+
+def save_ecm(path, eng, p, step, k_bits, b1, curve_seed, family=None, elapsed=0.0):
+    _write_rotating(path, _ECM.pack(ECM_VERSION, p, step, k_bits, b1, float(elapsed), curve_seed, ECM_FAMILY[family]) + _raw(eng), keep_old=False)
+
+
+def load_ecm(path, eng, p, k_bits, b1, curve_seed, family=None):
+    """Step count of the saved stage-1 state (registers restored), or None: other exponent, bound, curve or backend."""
+    for f in (path, path + ".old"):
+        body = _read_verified(f)
+        if body is None or len(body) != _ECM.size + eng.get_checkpoint_size():
+            continue
+        version, rp, step, nbb, rb1, et, seed, fam = _ECM.unpack_from(body)
+        if version != ECM_VERSION or rp != p or nbb != k_bits or rb1 != b1 or seed != curve_seed or fam != ECM_FAMILY[family]:
+            continue
+        if eng.set_checkpoint(bytearray(body[_ECM.size:])):
+            return step
+    return None

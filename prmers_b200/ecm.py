@@ -502,9 +502,12 @@ def _load_base(eng, p, N, X, Y):
     eng.set_multiplicand(46, 9); eng.set_multiplicand(50, 49)
 
 
-def _scalar_mul(eng, ops, digits, on_step=None):
-    """Q <- k P over the NAF digits (top digit first); the point registers already hold +-P for the top digit."""
+def _scalar_mul(eng, ops, digits, on_step=None, start_step=0):
+    """Q <- k P over the NAF digits (top digit first); the point registers already hold +-P for the top digit.
+    `start_step`: steps already done by a run whose checkpoint has been restored."""
     for step, i in enumerate(range(len(digits) - 2, -1, -1)):
+        if step < start_step:
+            continue
         ops.dbl()
         d = digits[i]
         if d:
@@ -520,10 +523,14 @@ def check_invariant(eng, p, aE, dE):
     return (aE * X * X + Y * Y - Z * Z - dE * T * T) % N == 0
 
 
-def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None, torsion=None):
+def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None, torsion=None,
+              checkpoint_path=None, backup_every=0, stop_at=None):
     """One curve of RunEcmTwistedEdwards.cpp:1737-3859 on a 51-register engine.  Returns a dict with `status` in
     {"found", "NF", "singular", "nocurve", "invariant"}, `factor`, `stage` (0 = curve generation, 1, 2) and the final
-    extended coordinates (for parity checks against a big-integer restatement of the same formulas)."""
+    extended coordinates (for parity checks against a big-integer restatement of the same formulas).
+    Stage-1 checkpoints (:1866-1937, :3090-3243): with `checkpoint_path` the scalar multiplication resumes from that file
+    when it holds this exponent, bound, curve seed and family, saves every `backup_every` steps and, after `stop_at`
+    steps (the reference's SIGINT path), saves and returns status "interrupted"."""
     say = log or (lambda s: None)
     N = (1 << p) - 1
     res = {"curve_seed": curve_seed, "status": "NF", "factor": None, "stage": None, "n": eng.get_size()}
@@ -558,7 +565,30 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
         if step == error_iter:
             eng.sub(1, 2)
             say(f"Injected error at iteration {step}")
-    _scalar_mul(eng, ops, digits, on_step=inject if error_iter else None)
+    start_step = 0
+    if checkpoint_path:
+        from . import checkpoint as ckpt
+        got = ckpt.load_ecm(checkpoint_path, eng, p, K.bit_length(), b1, curve_seed, torsion)
+        if got is not None:
+            start_step = got
+            say(f"Resuming from a checkpoint at step {start_step}.")
+
+    class _Interrupted(Exception):
+        pass
+
+    def on_step(step):
+        if error_iter:
+            inject(step)
+        if checkpoint_path and ((stop_at is not None and step == stop_at) or (backup_every and step % backup_every == 0)):
+            ckpt.save_ecm(checkpoint_path, eng, p, step, K.bit_length(), b1, curve_seed, torsion)
+            if stop_at is not None and step == stop_at:
+                raise _Interrupted()
+    try:
+        _scalar_mul(eng, ops, digits, on_step=on_step if (error_iter or checkpoint_path) else None, start_step=start_step)
+    except _Interrupted:
+        say(f"Interrupted by user, state saved at step {stop_at}")
+        res.update(status="interrupted", stage=1, step=stop_at)
+        return res
     if not check_invariant(eng, p, aE, dE):
         say("[ECM] invariant FAIL")
         res.update(status="invariant", stage=1, point_ops=ops.ops)

@@ -213,7 +213,8 @@ def _fast3_pow(eng, r, e):
         eng.square_mul(r, 3 if (e >> k) & 1 else 1)
 
 
-def run_pm1_stage1(eng, p, b1, reg=0, gcd=True, gerbicz=None, check_level=0, error_iter=0, log=None, max_restores=8):
+def run_pm1_stage1(eng, p, b1, reg=0, gcd=True, gerbicz=None, check_level=0, error_iter=0, log=None, max_restores=8,
+                   checkpoint_path=None, backup_every=0, stop_at=None):
     """P-1 stage 1, "fast3" (RunPM1.cpp:7016-7300): X <- X^2 * (3 if bit else 1) over the bits of
     E = 2 p prod q^floor(log_q B1), MSB first; the factor is gcd(X - 1, 2^p - 1).
 
@@ -224,7 +225,12 @@ def run_pm1_stage1(eng, p, b1, reg=0, gcd=True, gerbicz=None, check_level=0, err
     the blocks since.  On by default when the engine has the 11 registers of the reference's map; `error_iter` injects
     a fault like -erroriter (RunPM1.cpp:7134).  The reference compares its block counter with a variable that stays 0
     (RunPM1.cpp:7155 `gl_checkpass == checkpass`), so its lot check only ever runs at the last bit; here the computed
-    level (every `check_level` full blocks, default the reference's 600 s formula) is honoured."""
+    level (every `check_level` full blocks, default the reference's 600 s formula) is honoured.
+    Checkpoints (RunPM1.cpp:6219-6267; Gerbicz-Li runs only): with `checkpoint_path` the run resumes from that file --
+    all registers plus the bit index and the block bookkeeping (checkpass, blocks since the check, bits in the block,
+    block length, in_lot, eacc, wbits) -- saves every `backup_every` bits and, after `stop_at` bits (the reference's
+    SIGINT path), saves and returns {"interrupted": bits done}."""
+    from . import checkpoint as ckpt
     say = log or (lambda s: None)
     E = pm1_exponent(p, b1)
     bits = E.bit_length()
@@ -251,7 +257,24 @@ def run_pm1_stage1(eng, p, b1, reg=0, gcd=True, gerbicz=None, check_level=0, err
         current_block_len = ((bits - 1) % B) + 1
         in_lot, errordone, restores = False, False, 0
         i = bits
+        got = ckpt.load_pm1(checkpoint_path, eng, p) if checkpoint_path else None
+        if got and got[1]["bits"] == bits:
+            i, st = got[0], got[1]
+            gl_checkpass, blocks_since_check, bits_in_block = st["checkpass"], st["blocks_since_check"], st["bits_in_block"]
+            current_block_len, in_lot, eacc, wbits = st["current_block_len"], st["in_lot"], st["eacc"], st["wbits"]
+            say(f"Resuming from a checkpoint at bit {bits - i}.")
+        elif got:
+            eng.set(PM1_RBASE, 3); eng.set(S, 1)         # a checkpoint of another bound: start over
+        resumed_at = i
         while i > 0:
+            if checkpoint_path and i < resumed_at and ((stop_at is not None and bits - i == stop_at) or (backup_every and (bits - i) % backup_every == 0)):
+                ckpt.save_pm1(checkpoint_path, eng, p, i, {"checkpass": gl_checkpass, "blocks_since_check": blocks_since_check,
+                              "bits_in_block": bits_in_block, "current_block_len": current_block_len, "in_lot": in_lot, "eacc": eacc,
+                              "wbits": wbits, "processed_bits": bits - i, "bits": bits})
+                if stop_at is not None and bits - i == stop_at:
+                    say(f"Interrupted by user, state saved at bit {bits - i}")
+                    return {"exponent": p, "worktype": "PM1", "b1": b1, "interrupted": bits - i, "bits": bits, "errors_gerbicz": errors,
+                            "fft_length": eng.get_size()}
             if bits_in_block == 0:
                 current_block_len = ((i - 1) % B) + 1
                 if current_block_len == B:
@@ -657,24 +680,39 @@ def _pair_mul_by(eng, A, B, Cc, Dd):
     eng.copy(LS_TA, LS_TB); eng.mul(LS_TA, LS_M0); eng.add(B, LS_TA)
 
 
-def run_ll_safe(eng, p, check_level=0, error_iter=0, log=None, max_restores=4):
+def run_ll_safe(eng, p, check_level=0, error_iter=0, log=None, max_restores=4, checkpoint_path=None, backup_every=0, stop_at=None):
     """`prmers p -ll`: (2 + sqrt 3)^(2^(p-1)) in Z[sqrt 3] mod 2^p - 1 is (-1, 0) iff 2^p - 1 is prime; the
     running product of the block-end pairs is checked Gerbicz-Li style and a mismatch restores the last
-    verified pair (RunLlSafeMarin.cpp:539-694).  Needs 18 registers."""
+    verified pair (RunLlSafeMarin.cpp:539-694).  Needs 18 registers.
+    Checkpoints (RunLlSafeMarin.cpp:418-477,577-603): with `checkpoint_path` the run resumes from that file (all 18
+    registers, the iteration count and the last verified iteration), saves every `backup_every` iterations and, at
+    iteration `stop_at` (the reference's SIGINT path), saves and returns {"interrupted": iteration}."""
+    from . import checkpoint as ckpt
     say = log or (lambda s: None)
     m = (1 << p) - 1
     total = p - 1
     B = max(min(int(math.isqrt(p)), total), 1)
     level_auto = int(1000 * 600.0 / B) or 1
     level = check_level if check_level > 0 else max(level_auto, 1)
-    eng.set(LS_RES_A, 2); eng.set(LS_RES_B, 1)
-    eng.set(LS_ACC_A, 1); eng.set(LS_ACC_B, 0)
-    for d, s in ((LS_SAVE_R_A, LS_RES_A), (LS_SAVE_R_B, LS_RES_B), (LS_SAVE_F_A, LS_ACC_A), (LS_SAVE_F_B, LS_ACC_B)):
-        eng.copy(d, s)
+    got = ckpt.load_llsafe(checkpoint_path, eng, p) if checkpoint_path else None
+    if got:
+        ri, itersave, jsave = got[0], got[1], got[2]
+        say(f"Resuming from a checkpoint at iteration {ri}.")
+    else:
+        ri, itersave, jsave = 0, 0, total - 1
+        eng.set(LS_RES_A, 2); eng.set(LS_RES_B, 1)
+        eng.set(LS_ACC_A, 1); eng.set(LS_ACC_B, 0)
+        for d, s in ((LS_SAVE_R_A, LS_RES_A), (LS_SAVE_R_B, LS_RES_B), (LS_SAVE_F_A, LS_ACC_A), (LS_SAVE_F_B, LS_ACC_B)):
+            eng.copy(d, s)
     eng.set(LS_BASE_A, 2); eng.set(LS_BASE_B, 1)
-    itersave, jsave, checkpass, errors, restores, errordone = 0, total - 1, 0, 0, 0, False
-    it, j = 0, total - 1
+    checkpass, errors, restores, errordone = 0, 0, 0, False
+    it, j = ri, total - ri - 1
     while it < total:
+        if checkpoint_path and it > ri and ((stop_at is not None and it == stop_at) or (backup_every and it % backup_every == 0)):
+            ckpt.save_llsafe(checkpoint_path, eng, p, it, itersave, jsave)
+            if stop_at is not None and it == stop_at:
+                say(f"Interrupted by user, state saved at iteration {it} j={j}")
+                return {"exponent": p, "worktype": "LL", "interrupted": it, "errors_gerbicz": errors, "fft_length": eng.get_size()}
         if error_iter > 0 and it + 1 == error_iter and not errordone:
             errordone = True
             eng.sub(LS_RES_A, 2)

@@ -82,3 +82,87 @@ def test_prp_interrupt_and_resume_gpu(tmp_path):
     e2.square_mul_repeat(0, p - 5000)
     assert e2.digit(0).equal_to(9)                               # M9941 is prime
     e2.close()
+
+
+def test_llsafe_pm1_ecm_file_layouts(tmp_path):
+    """Field orders of RunLlSafeMarin.cpp:455-477, RunPM1.cpp:6219-6223 and RunEcmTwistedEdwards.cpp:1866-1889, with this
+    backend's markers; foreign or damaged files load nothing."""
+    e = FakeEngine(1000)
+    keep = bytes(e.blob)
+    # LL-safe
+    path = str(tmp_path / ck.llsafe_checkpoint_name(521))
+    ck.save_llsafe(path, e, 521, 300, 275, 244, 2.5)
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<iIIQdQQ", raw) == (3, 521, 3, 300, 2.5, 275, 244) and raw[44:1044] == keep
+    e.blob[:] = bytes(1000)
+    assert ck.load_llsafe(path, e, 521) == (300, 275, 244, 2.5) and bytes(e.blob) == keep
+    assert ck.load_llsafe(path, e, 523) is None
+    bad = bytearray(raw); bad[8] = 1                                    # the reference's Marin tag: not this backend's image
+    bad[-4:] = struct.pack("<I", (~zlib.crc32(bytes(bad[:-4])) & 0xFFFFFFFF) ^ 0xA23777AC)
+    open(path, "wb").write(bad)
+    assert ck.load_llsafe(path, e, 521) is None
+    # P-1 stage 1
+    path = str(tmp_path / ck.pm1_checkpoint_name(9941))
+    st = {"checkpass": 2, "blocks_since_check": 2, "bits_in_block": 7, "current_block_len": 65, "in_lot": True, "eacc": 0xabcdef0123456789abcdef,
+          "wbits": 0x55, "processed_bits": 1234, "bits": 4321}
+    ck.save_pm1(path, e, 9941, 3087, st, 1.5)
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<iIId", raw) == (3, 9941, 3087, 1.5) and raw[20:1020] == keep
+    assert struct.unpack_from("<QQQQB", raw, 1020) == (2, 2, 7, 65, 1)
+    assert raw[1053:1057] == struct.pack("<I", 22) and raw[1057:1079] == b"abcdef0123456789abcdef"
+    assert open(path + ".backend").read() == "marin_b200\n" and not os.path.exists(path + ".old")
+    e.blob[:] = bytes(1000)
+    assert ck.load_pm1(path, e, 9941) == (3087, st, 1.5) and bytes(e.blob) == keep
+    open(path + ".backend", "w").write("marin\n")                       # a Marin OpenCL image under the same name
+    assert ck.load_pm1(path, e, 9941) is None
+    os.remove(path + ".backend")                                        # no marker = the reference's legacy Marin layout
+    assert ck.load_pm1(path, e, 9941) is None
+    # ECM stage 1
+    path = str(tmp_path / ck.ecm_checkpoint_name(701, 4))
+    ck.save_ecm(path, e, 701, 99, 8650, 6000, 0x1234567890abcdef, None, 0.25)
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<iIIIQdQB", raw) == (0x0301, 701, 99, 8650, 6000, 0.25, 0x1234567890abcdef, 0)
+    assert ck.load_ecm(path, e, 701, 8650, 6000, 0x1234567890abcdef) == 99
+    for args in ((709, 8650, 6000, 0x1234567890abcdef), (701, 8651, 6000, 0x1234567890abcdef), (701, 8650, 6001, 0x1234567890abcdef), (701, 8650, 6000, 5)):
+        assert ck.load_ecm(path, e, *args) is None
+    assert ck.load_ecm(path, e, 701, 8650, 6000, 0x1234567890abcdef, "16") is None
+
+
+def test_mode_loops_resume_from_their_checkpoints_emulated(tmp_path):
+    """LL-safe, P-1 stage 1 (Gerbicz-Li bookkeeping included) and an ECM curve, each interrupted, resumed on a NEW
+    engine from the file alone and compared with the uninterrupted run."""
+    from tests.emu.emu import EmuEngine
+    from prmers_b200 import modes, ecm
+    # LL-safe: M521 is prime; interrupted in the middle of a block
+    path = str(tmp_path / ck.llsafe_checkpoint_name(521))
+    r = modes.run_ll_safe(EmuEngine(521, 18), 521, check_level=2, checkpoint_path=path, stop_at=301)
+    assert r["interrupted"] == 301
+    log = []
+    r = modes.run_ll_safe(EmuEngine(521, 18), 521, check_level=2, checkpoint_path=path, log=log.append)
+    assert r["is_prime"] and any("Resuming" in s for s in log) and r["errors_gerbicz"] == 0
+    whole = modes.run_ll_safe(EmuEngine(607, 18), 607, check_level=3)
+    path = str(tmp_path / ck.llsafe_checkpoint_name(607))
+    modes.run_ll_safe(EmuEngine(607, 18), 607, check_level=3, checkpoint_path=path, backup_every=100, stop_at=433)
+    r = modes.run_ll_safe(EmuEngine(607, 18), 607, check_level=3, checkpoint_path=path, error_iter=500)   # and a fault after the resume
+    assert r["res64"] == whole["res64"] and r["is_prime"] and r["errors_gerbicz"] == 1
+    # P-1 stage 1 with Gerbicz-Li
+    p, b1 = 2151, 256
+    good = modes.run_pm1_stage1(EmuEngine(p, 11), p, b1, check_level=2)
+    for stop in (37, 200, good["bits"] - 3):
+        path = str(tmp_path / f"s{stop}_{ck.pm1_checkpoint_name(p)}")
+        r = modes.run_pm1_stage1(EmuEngine(p, 11), p, b1, check_level=2, checkpoint_path=path, stop_at=stop)
+        assert r["interrupted"] == stop
+        log = []
+        r = modes.run_pm1_stage1(EmuEngine(p, 11), p, b1, check_level=2, checkpoint_path=path, log=log.append, error_iter=stop + 2)
+        assert r["x"] == good["x"] and r["factor"] == 327405968242246366421788399 and r["errors_gerbicz"] == 1
+        assert any("Resuming" in s for s in log)
+    # ECM curve
+    p, seed = 101, ecm.mix64(123456789, 0)
+    whole = ecm.run_curve(EmuEngine(p, ecm.REGS), p, 300, 0, seed)
+    path = str(tmp_path / ck.ecm_checkpoint_name(p, 0))
+    r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, 300, 0, seed, checkpoint_path=path, backup_every=50, stop_at=123)
+    assert r["status"] == "interrupted" and r["step"] == 123
+    log = []
+    r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, 300, 0, seed, checkpoint_path=path, log=log.append)
+    assert (r["status"], r["factor"], r["stage1_T"]) == (whole["status"], whole["factor"], whole["stage1_T"]) and any("Resuming" in s for s in log)
+    assert ecm.run_curve(EmuEngine(p, ecm.REGS), p, 300, 0, seed + 1, checkpoint_path=path, log=log.append)["status"] in ("NF", "found")   # another curve ignores the file
