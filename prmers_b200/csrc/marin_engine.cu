@@ -34,6 +34,7 @@ using namespace marin;
 
 __global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __grid_constant__ MidArgs A0)
 {
+	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
 	const MidArgs A = slab_of(A0, blockIdx.y);
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __
 
 template <bool INV> __global__ void __launch_bounds__(MARIN_STR_MAXT, MARIN_STR_MINB) k_strided(const __grid_constant__ StridedArgs A)
 {
+	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	__shared__ u32 s_tile;
@@ -316,9 +318,11 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
 		use_fast = getenv("MARIN_B200_NO_FAST") == nullptr;
+		use_pdl = getenv("MARIN_B200_NO_PDL") == nullptr;
 		static bool tested[64] = {false};
 		if (dev < 64 && !tested[dev]) { field_selftest(st); tested[dev] = true; }
 	}
+	bool use_pdl = true;  // MARIN_B200_NO_PDL=1: plain stream order (A/B timing)
 	bool use_fast = true; // the specialised kernels of marin_fast.cuh (same results; MARIN_B200_NO_FAST=1 runs the generic ones: tests, A/B timing)
 
 	template <int SHAPE> static void mid_fast_attr()
@@ -443,10 +447,13 @@ struct CudaBackend
 		cudaLaunchConfig_t cfg;
 		memset(&cfg, 0, sizeof(cfg));
 		cfg.gridDim = dim3(grid, gridy); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-		cudaLaunchAttribute at[1];
-		at[0].id = cudaLaunchAttributeAccessPolicyWindow;
-		at[0].val.accessPolicyWindow = win;
-		cfg.attrs = at; cfg.numAttrs = has_win ? 1 : 0;
+		cudaLaunchAttribute at[2];
+		u32 na = 0;
+		if (has_win) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = win; ++na; }
+		// programmatic dependent launch (MARIN_PDL_* in marin_kernels.cuh): every kernel launched from here waits for its
+		// predecessor with griddepcontrol.wait before it reads or writes anything
+		if (use_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+		cfg.attrs = at; cfg.numAttrs = na;
 		CK(cudaLaunchKernelEx(&cfg, kernel, args));
 	}
 	void post() { ++launches; CK(cudaGetLastError()); }

@@ -105,6 +105,7 @@ __host__ __device__ constexpr u32 mid_shape_minblocks(int shape) { return shape 
 
 template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threads(SHAPE), mid_shape_minblocks(SHAPE)) k_mid_fast(const __grid_constant__ MidArgs A)
 {
+	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const Tables &t = A.t;
@@ -695,16 +696,20 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	u64 *twsm = reinterpret_cast<u64 *>(smraw + SC<4>::SMEM);
 	__shared__ u32 s_tile;
 	__shared__ __align__(8) unsigned long long s_bar;
+	MARIN_PDL_TRIGGER();
 	if (threadIdx.x == 0)
 	{
-		// the stage twiddles come in by bulk asynchronous copy while the tile's first loads are in flight
+		// the stage twiddles (constant tables: nothing a predecessor wrote) come in by bulk asynchronous copy while the
+		// contiguous pass before this kernel drains and the tile's first loads are in flight
 		mbar_init(&s_bar, 1);
 		mbar_expect_tx(&s_bar, (FWD_FOLLOWS ? 2u : 1u) * STR_TW * 8);
 		bulk_g2s(twsm, A.twi, STR_TW * 8, &s_bar);
 		if (FWD_FOLLOWS) bulk_g2s(twsm + STR_TW, A.tw, STR_TW * 8, &s_bar);
-		// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket
-		s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
 	}
+	MARIN_PDL_WAIT();
+	// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket (taken after
+	// the wait: the carry pass of the operation before this one hands out tickets from the same counter)
+	if (threadIdx.x == 0) s_tile = (u32)(atomicAdd(A.ticket, 1ull) - A.ticket_base);
 	__syncthreads();
 	const Tables &t = A.t;
 	const u32 g = s_tile, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -888,6 +893,7 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 // forward strided pass from a register in global memory
 __global__ void __launch_bounds__(STR_THREADS, 2) k_fwd_fast_T4(const __grid_constant__ StridedArgs A)
 {
+	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const u32 g = blockIdx.x, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;

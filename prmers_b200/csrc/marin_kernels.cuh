@@ -99,6 +99,20 @@ struct Tables
 	u64 w5i[5];
 };
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The transform kernels of an operation are launched with cudaLaunchAttributeProgrammaticStreamSerialization: each one
+// lets its successor's CTAs become resident while its own last wave drains (griddepcontrol.launch_dependents at entry)
+// and itself touches nothing a predecessor wrote before griddepcontrol.wait returns (predecessor complete, its writes
+// visible).  The kernel boundary then costs neither the launch latency nor the ramp-up of the next grid.  A successor
+// launches only once every CTA of its predecessor is resident, so waiting CTAs never hold a slot the running grid needs.
+#if defined(__CUDA_ARCH__)
+#define MARIN_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define MARIN_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define MARIN_PDL_TRIGGER() do { } while (0)
+#define MARIN_PDL_WAIT() do { } while (0)
+#endif
+
 // ------------------------------------------------------------------ small helpers
 
 HD u32 digit_width(const Tables &t, u32 j) { return t.wbase + ((t.wbits[j >> 5] >> (j & 31)) & 1u); }

@@ -96,6 +96,7 @@ inline u32 measured_row_length(u32 m)
 		case 1u << 18: return 1024;        // n = 2^19        39 us (49)
 		case 1u << 15: return 1024;        // n = 2^16        33 us (S = 512: 42)
 		case 1u << 14: return 2048;        // n = 2^15        25 us (S = 256: 35)
+		case 1u << 12: return 1024;        // n = 2^13        22 us (S = 512: 31)
 		case 5u << 20: return MID_S5;      // n = 5 * 2^21   432 us
 		case 5u << 19: return 2560;        // n = 5 * 2^20   224 us (S = 4096, R = 640: 323)
 		case 5u << 18: return 1280;        // n = 5 * 2^19   129 us (157)
@@ -144,12 +145,16 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 			pl.R2 = rb; pl.R = Rall / rb;
 		}
 		if (pl.R > MAX_R || pl.S > MID_S5) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
-		u32 r4mask = 0;
-		if (const char *e = getenv("MARIN_B200_R4MASK")) r4mask = (u32)atoi(e);
-		pl.nstS = factor_stages(pl.S, pl.stS, true, (r4mask & 1) != 0, (r4mask & 1) != 0);
-		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0, (r4mask & 2) != 0, (r4mask & 2) != 0);
-		pl.thrMid = round_threads((r4mask & 1) ? pl.S / 2 : pl.S / 8, 512);
-		const u32 bf = pl.R * TILE_C * 2 / ((r4mask & 2) ? 4 : 16); // butterflies x lanes per stage
+		// Latency-bound sizes (profiles/r2/lowlat_sweep.log): a pass there is a handful of CTAs walking through dependent
+		// phases, and a radix-16 butterfly is ~1100 instructions in one thread; radix-4 stages put four times the threads
+		// on a quarter of the chain.  Strided passes up to n = 2^18 (n = 65536: 32.8 -> 26.6 us, n = 5 * 2^11: 33.3 -> 24.6),
+		// contiguous passes up to n = 5 * 2^13 unless the row is one of the specialised shapes (n = 4096: 24.6 -> 20.5).
+		const bool fastS = pl.S == 1024 || pl.S == 2048 || pl.S == 4096 || pl.S == 1280 || pl.S == 2560 || pl.S == MID_S5;
+		const bool r4S = !force_S && !fastS && n <= 40960, r4R = !force_S && n <= 262144;
+		pl.nstS = factor_stages(pl.S, pl.stS, true, false, r4S);
+		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0, false, r4R);
+		pl.thrMid = round_threads(r4S ? pl.S / 2 : pl.S / 8, 512);
+		const u32 bf = pl.R * TILE_C * 2 / (r4R ? 4 : 16); // butterflies x lanes per stage
 		pl.thrStr = (bf <= 1024) ? round_threads(bf, 1024) : round_threads(bf / 2, 1024);
 		if (pl.R2 > 1)
 		{
