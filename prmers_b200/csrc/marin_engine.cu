@@ -34,7 +34,8 @@ using namespace marin;
 
 __global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __grid_constant__ MidArgs A0)
 {
-	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
+	if (MARIN_PDL_MODE & 1) MARIN_PDL_TRIGGER();
+	MARIN_PDL_WAIT();
 	const MidArgs A = slab_of(A0, blockIdx.y);
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
@@ -45,11 +46,13 @@ __global__ void __launch_bounds__(MARIN_MID_MAXT, MARIN_MID_MINB) k_mid(const __
 		mid_phase(A, blockIdx.x, ph, threadIdx.x, blockDim.x, sm, smc);
 		__syncthreads();
 	}
+	if (!(MARIN_PDL_MODE & 1)) MARIN_PDL_TRIGGER();
 }
 
 template <bool INV> __global__ void __launch_bounds__(MARIN_STR_MAXT, MARIN_STR_MINB) k_strided(const __grid_constant__ StridedArgs A)
 {
-	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
+	if (MARIN_PDL_MODE & 2) MARIN_PDL_TRIGGER();
+	MARIN_PDL_WAIT();
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	__shared__ u32 s_tile;
@@ -67,6 +70,7 @@ template <bool INV> __global__ void __launch_bounds__(MARIN_STR_MAXT, MARIN_STR_
 		strided_phase<INV>(A, blk, ph, threadIdx.x, blockDim.x, sm);
 		__syncthreads();
 	}
+	if (!(MARIN_PDL_MODE & 2)) MARIN_PDL_TRIGGER();
 }
 
 __global__ void k_lin_p1(const __grid_constant__ LinArgs A0, u32 count)
@@ -442,6 +446,10 @@ struct CudaBackend
 	// kernel's accesses (copies, linear ops) "streaming" misses and slowed them down by up to 2x.
 	cudaAccessPolicyWindow win;
 	bool has_win = false;
+	// rows of 4096 pairs: see MARIN_PDL_MODE in marin_kernels.cuh
+	static bool pdl_shape(const MidArgs &A) { return A.small || A.t.S != 4096; }
+	static bool pdl_shape(const StridedArgs &A) { return A.t.S != 4096; }
+	template <class X> static bool pdl_shape(const X &) { return true; }
 	template <class K, class A> void launch_windowed(K kernel, const A &args, u32 grid, u32 thr, size_t smem, u32 gridy = 1)
 	{
 		cudaLaunchConfig_t cfg;
@@ -452,7 +460,7 @@ struct CudaBackend
 		if (has_win) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = win; ++na; }
 		// programmatic dependent launch (MARIN_PDL_* in marin_kernels.cuh): every kernel launched from here waits for its
 		// predecessor with griddepcontrol.wait before it reads or writes anything
-		if (use_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+		if (use_pdl && pdl_shape(args)) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
 		cfg.attrs = at; cfg.numAttrs = na;
 		CK(cudaLaunchKernelEx(&cfg, kernel, args));
 	}

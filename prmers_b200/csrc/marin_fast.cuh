@@ -105,7 +105,8 @@ __host__ __device__ constexpr u32 mid_shape_minblocks(int shape) { return shape 
 
 template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threads(SHAPE), mid_shape_minblocks(SHAPE)) k_mid_fast(const __grid_constant__ MidArgs A)
 {
-	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
+	if (MARIN_PDL_MODE & 1) MARIN_PDL_TRIGGER();
+	MARIN_PDL_WAIT();
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const Tables &t = A.t;
@@ -306,6 +307,7 @@ template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threa
 			st16_nat<34>(blk + 2 * jl, a);
 		}
 	}
+	if (!(MARIN_PDL_MODE & 1)) MARIN_PDL_TRIGGER();   // late trigger: the last stage below is what is left
 	if (MODE == MODE_FWD) return;
 	__syncthreads();
 
@@ -696,7 +698,7 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	u64 *twsm = reinterpret_cast<u64 *>(smraw + SC<4>::SMEM);
 	__shared__ u32 s_tile;
 	__shared__ __align__(8) unsigned long long s_bar;
-	MARIN_PDL_TRIGGER();
+	if (MARIN_PDL_MODE & 2) MARIN_PDL_TRIGGER();
 	if (threadIdx.x == 0)
 	{
 		// the stage twiddles (constant tables: nothing a predecessor wrote) come in by bulk asynchronous copy while the
@@ -838,6 +840,7 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 		absorb_reweight_T4<FWD_FOLLOWS>(A, sm, warp + 8 * it, g, c0, wl, (keep >> (8 - 8 * it)) & 0xffu);
 		MARIN_STAMP(15 + it);
 	}
+	if (!(MARIN_PDL_MODE & 2)) MARIN_PDL_TRIGGER();   // late trigger: the carries are out, the forward pass of the tile is left
 	if (!FWD_FOLLOWS) return;
 	__syncthreads();
 	MARIN_STAMP(17);
@@ -893,7 +896,8 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 // forward strided pass from a register in global memory
 __global__ void __launch_bounds__(STR_THREADS, 2) k_fwd_fast_T4(const __grid_constant__ StridedArgs A)
 {
-	MARIN_PDL_TRIGGER(); MARIN_PDL_WAIT();
+	if (MARIN_PDL_MODE & 2) MARIN_PDL_TRIGGER();
+	MARIN_PDL_WAIT();
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const u32 g = blockIdx.x, c0 = g * TILE_C, wl = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -100,11 +100,20 @@ struct Tables
 };
 
 // ------------------------------------------------------------------ programmatic dependent launch
-// The transform kernels of an operation are launched with cudaLaunchAttributeProgrammaticStreamSerialization: each one
-// lets its successor's CTAs become resident while its own last wave drains (griddepcontrol.launch_dependents at entry)
-// and itself touches nothing a predecessor wrote before griddepcontrol.wait returns (predecessor complete, its writes
-// visible).  The kernel boundary then costs neither the launch latency nor the ramp-up of the next grid.  A successor
-// launches only once every CTA of its predecessor is resident, so waiting CTAs never hold a slot the running grid needs.
+// The transform kernels of an operation are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel
+// touches nothing a predecessor wrote before griddepcontrol.wait returns (predecessor complete, its writes visible), and
+// releases its successor with griddepcontrol.launch_dependents once its own main work is done, so that the successor's
+// CTAs are resident and past their set-up when the last CTA of this grid exits.  The kernel boundary then costs neither
+// the launch latency nor the ramp-up of the next grid: n = 4096: 20.5 -> 16.8 us per squaring, n = 65536: 26.7 -> 22.7,
+// n = 2^20: 51.3 -> 48.2, n = 2^22: 168.5 -> 163.1 (profiles/r2/pdl_ab.log).  A successor launches only once every CTA of
+// its predecessor is resident, so waiting CTAs never hold a slot the running grid needs.  Triggering at kernel entry
+// instead (MARIN_PDL_MODE bits) was slower at the small sizes (n = 65536: 30 - 36 us) and no faster at the large ones.
+// Rows of 4096 pairs (n >= 2^23) stay on plain stream order: with overlap the squaring took 309 instead of 296 us (the
+// contiguous kernel wants 3 x 68 KB of shared memory per SM, the strided one 2 x 84 KB and the rest as L1: when the two
+// grids share SMs the split cannot follow each kernel).
+#ifndef MARIN_PDL_MODE
+#define MARIN_PDL_MODE 0   // bit 0: contiguous-pass kernels trigger at entry (else after their main work), bit 1: strided-pass kernels
+#endif
 #if defined(__CUDA_ARCH__)
 #define MARIN_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define MARIN_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
