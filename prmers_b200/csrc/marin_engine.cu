@@ -321,11 +321,20 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
+		if (const char *e = getenv("MARIN_B200_CARVE")) // experiment: one shared-memory carve-out for the strided kernels
+		{
+			const int c = atoi(e);
+			CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+			CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+			CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributePreferredSharedMemoryCarveout, c));
+		}
+		pdl_all = getenv("MARIN_B200_PDL_ALL") != nullptr;
 		use_fast = getenv("MARIN_B200_NO_FAST") == nullptr;
 		use_pdl = getenv("MARIN_B200_NO_PDL") == nullptr;
 		static bool tested[64] = {false};
 		if (dev < 64 && !tested[dev]) { field_selftest(st); tested[dev] = true; }
 	}
+	bool pdl_all = false;
 	bool use_pdl = true;  // MARIN_B200_NO_PDL=1: plain stream order (A/B timing)
 	bool use_fast = true; // the specialised kernels of marin_fast.cuh (same results; MARIN_B200_NO_FAST=1 runs the generic ones: tests, A/B timing)
 
@@ -460,7 +469,7 @@ struct CudaBackend
 		if (has_win) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = win; ++na; }
 		// programmatic dependent launch (MARIN_PDL_* in marin_kernels.cuh): every kernel launched from here waits for its
 		// predecessor with griddepcontrol.wait before it reads or writes anything
-		if (use_pdl && pdl_shape(args)) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+		if (use_pdl && (pdl_all || pdl_shape(args))) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
 		cfg.attrs = at; cfg.numAttrs = na;
 		CK(cudaLaunchKernelEx(&cfg, kernel, args));
 	}

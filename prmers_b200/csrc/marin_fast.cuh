@@ -674,10 +674,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 parity)
 }
 
 // inverse strided pass with carry (level 0), optionally followed by the forward strided pass of the next squaring.
-// Shared memory: the tile, then the stage twiddles of the pass (inverse, forward: 2 x 1020 words) -- L1 is a stream of
+// Shared memory: the tile, then the stage twiddles of the direction at work (1020 words) -- L1 is a stream of
 // tile inputs and weights here and a twiddle that misses costs an L2 round trip in the middle of a butterfly.
 static constexpr u32 STR_TW = 15 * 64 + 15 * 4;               // stage twiddles of one direction, R = 1024
-static constexpr u32 INV_SMEM_T4 = SC<4>::SMEM + 2 * STR_TW * 8;
+// ONE twiddle buffer: the inverse tables first, the forward tables copied over them once every warp is through the inverse
+// stages.  Two resident CTAs then need 2 x 76.2 KB, which fits the 164 KB shared-memory configuration of the SM and leaves
+// 64 KB of L1 for the boundary-twiddle and width tables; with both tables resident (2 x 84.2 KB) the SM was configured
+// for 196 KB and 32 KB of L1 (forcing the 228 KB configuration costs this kernel another 17 us: profiles/r2/pdl_ab.log).
+static constexpr u32 INV_SMEM_T4 = SC<4>::SMEM + STR_TW * 8;
 
 // development aid (-DMARIN_PHASE_TIMING, tools/phase_clocks.py): SM cycle counter at the phase boundaries of every warp of
 // four tiles in the middle of the grid
@@ -704,9 +708,8 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 		// the stage twiddles (constant tables: nothing a predecessor wrote) come in by bulk asynchronous copy while the
 		// contiguous pass before this kernel drains and the tile's first loads are in flight
 		mbar_init(&s_bar, 1);
-		mbar_expect_tx(&s_bar, (FWD_FOLLOWS ? 2u : 1u) * STR_TW * 8);
+		mbar_expect_tx(&s_bar, STR_TW * 8);
 		bulk_g2s(twsm, A.twi, STR_TW * 8, &s_bar);
-		if (FWD_FOLLOWS) bulk_g2s(twsm + STR_TW, A.tw, STR_TW * 8, &s_bar);
 	}
 	MARIN_PDL_WAIT();
 	// decoupled look-back needs "the tile I wait for has started": tile numbers come from an atomic ticket (taken after
@@ -843,6 +846,14 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 	if (!(MARIN_PDL_MODE & 2)) MARIN_PDL_TRIGGER();   // late trigger: the carries are out, the forward pass of the tile is left
 	if (!FWD_FOLLOWS) return;
 	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		// every warp is through with the inverse twiddles: the forward ones land in the same buffer while the first
+		// forward butterflies run (they need them only after their 16-point transform)
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		mbar_expect_tx(&s_bar, STR_TW * 8);
+		bulk_g2s(twsm, A.tw, STR_TW * 8, &s_bar);
+	}
 	MARIN_STAMP(17);
 	// ---- forward pass of the next squaring: radix 16 (s = 64) per group, block barrier, [radix 16 (s = 4), radix 4 on
 	//      pairs + boundary twiddle -> global] per block
@@ -861,11 +872,12 @@ template <bool FWD_FOLLOWS> __global__ void __launch_bounds__(STR_THREADS, 2) k_
 		MARIN_STAMP(19 + 2 * ph);
 		const u32 row0 = big ? 4 * blk + jq : 64 * blk + jq;
 		const u32 stw = big ? ST_BIG : ST_SMALL, tws = big ? 64u : 4u;
-		const u64 *tw = twsm + STR_TW + (big ? 4 * blk : 960u) + jq;
+		const u64 *tw = twsm + (big ? 4 * blk : 960u) + jq;
 		u64 *p = smw + 2 * tile_pair(row0, 0);
 		u64 a[16];
 		ld16_nat_rt(a, p, stw);
 		dft16<false>(a);
+		if (ph == 0) mbar_wait(&s_bar, 1);                   // the forward twiddles have landed
 		tw16_rt(a, tw, tws);
 		st16_sw_rt(p, a, stw);
 		if (!big)
