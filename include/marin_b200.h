@@ -29,6 +29,11 @@ size_t mb200_transform_size_for(uint32_t p);
 
 /* engine::create_gpu(q, reg_count, device, verbose) (src/marin/gpu.cpp:52-150, engine.h:301) */
 void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose);
+/* The same with the decomposition of the transform forced (tests and tuning only; every decomposition gives the same
+   results): row_length = pairs per row of the contiguous pass (0 = planner's choice; a non-zero value also sends a
+   small transform down the multi-pass path), second_level_rows = rows of a second strided pass (0 = only if needed).
+   No reference counterpart: the reference picks its kernels per size in a switch (include/marin/engine_gpu.h:238-330). */
+void *mb200_create_split(uint32_t p, size_t reg_count, uint32_t device, int verbose, uint32_t row_length, uint32_t second_level_rows);
 /* Batched engine (no reference counterpart: the reference creates one engine per ECM curve and runs the curves one
    after the other, src/modes/RunEcmTwistedEdwards.cpp:1736-1755): `batch` independent register sets ("slabs") of
    reg_count registers each, driven in lockstep -- every operation below runs on all slabs, one CTA per slab in the

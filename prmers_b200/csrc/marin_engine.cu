@@ -321,20 +321,11 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
-		if (const char *e = getenv("MARIN_B200_CARVE")) // experiment: one shared-memory carve-out for the strided kernels
-		{
-			const int c = atoi(e);
-			CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
-			CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c));
-			CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributePreferredSharedMemoryCarveout, c));
-		}
-		pdl_all = getenv("MARIN_B200_PDL_ALL") != nullptr;
 		use_fast = getenv("MARIN_B200_NO_FAST") == nullptr;
 		use_pdl = getenv("MARIN_B200_NO_PDL") == nullptr;
 		static bool tested[64] = {false};
 		if (dev < 64 && !tested[dev]) { field_selftest(st); tested[dev] = true; }
 	}
-	bool pdl_all = false;
 	bool use_pdl = true;  // MARIN_B200_NO_PDL=1: plain stream order (A/B timing)
 	bool use_fast = true; // the specialised kernels of marin_fast.cuh (same results; MARIN_B200_NO_FAST=1 runs the generic ones: tests, A/B timing)
 
@@ -469,7 +460,7 @@ struct CudaBackend
 		if (has_win) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = win; ++na; }
 		// programmatic dependent launch (MARIN_PDL_* in marin_kernels.cuh): every kernel launched from here waits for its
 		// predecessor with griddepcontrol.wait before it reads or writes anything
-		if (use_pdl && (pdl_all || pdl_shape(args))) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+		if (use_pdl && pdl_shape(args)) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
 		cfg.attrs = at; cfg.numAttrs = na;
 		CK(cudaLaunchKernelEx(&cfg, kernel, args));
 	}
@@ -561,16 +552,15 @@ const char *mb200_version(void) { return "marin_b200 0.1 (sm_100a)"; }
 const char *mb200_last_error(void) { return g_err.c_str(); }
 size_t mb200_transform_size_for(uint32_t p) { return transform_size(p); }
 
-void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose)
+void *mb200_create(uint32_t p, size_t reg_count, uint32_t device, int verbose) { return mb200_create_split(p, reg_count, device, verbose, 0, 0); }
+
+// the same with the decomposition of the transform chosen by the caller (tests and tuning; results do not depend on it)
+void *mb200_create_split(uint32_t p, size_t reg_count, uint32_t device, int verbose, uint32_t row_length, uint32_t second_level_rows)
 {
 	try
 	{
 		g_err.clear();
-		u32 force_S = 0;
-		u32 force_R2 = 0;
-		if (const char *s = getenv("MARIN_B200_FORCE_S")) force_S = (u32)atoi(s);   // test hooks: force the 3-pass path
-		if (const char *s = getenv("MARIN_B200_FORCE_R2")) force_R2 = (u32)atoi(s); // ... and the second strided pass
-		Eng *e = new Eng(p, reg_count, (int)device, force_S, force_R2);
+		Eng *e = new Eng(p, reg_count, (int)device, row_length, second_level_rows);
 		if (verbose)
 			fprintf(stderr, "marin_b200: p = %u, n = %u, %s, R = %u x %u, S = %u, %zu registers, device %u\n", p, e->pl.n,
 				e->pl.small ? "single-CTA path" : (e->pl.R2 > 1 ? "5-pass path" : "3-pass path"), e->pl.R, e->pl.R2, e->pl.S, reg_count, device);

@@ -20,6 +20,7 @@ _SIGS = {
     "mb200_last_error": (C.c_char_p, []),
     "mb200_transform_size_for": (C.c_size_t, [C.c_uint32]),
     "mb200_create": (C.c_void_p, [C.c_uint32, C.c_size_t, C.c_uint32, C.c_int]),
+    "mb200_create_split": (C.c_void_p, [C.c_uint32, C.c_size_t, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32]),
     "mb200_destroy": (None, [C.c_void_p]),
     "mb200_transform_size": (C.c_size_t, [C.c_void_p]),
     "mb200_register_count": (C.c_size_t, [C.c_void_p]),
@@ -100,14 +101,17 @@ class MarinError(RuntimeError):
 class Engine:
     """engine::create_gpu(p, reg_count, device, verbose) and the methods of `class engine`."""
 
-    def __init__(self, p, reg_count, device=0, verbose=False, batch=1):
+    def __init__(self, p, reg_count, device=0, verbose=False, batch=1, force_S=0, force_R2=0):
         """batch > 1: `batch` independent register sets ("slabs") driven in lockstep by every call, one CTA per slab in
-        each launch (single-CTA sizes only: many ECM curves at once); digits are read and written per slab."""
+        each launch (single-CTA sizes only: many ECM curves at once); digits are read and written per slab.
+        force_S / force_R2 (tests and tuning): row length of the contiguous pass / rows of a second strided pass."""
         L = load_library()
         self._L = L
         self.batch = batch
         if batch > 1:
             self._h = L.mb200_create_batch(p, reg_count, device, 1 if verbose else 0, batch)
+        elif force_S or force_R2:
+            self._h = L.mb200_create_split(p, reg_count, device, 1 if verbose else 0, force_S, force_R2)
         else:
             self._h = L.mb200_create(p, reg_count, device, 1 if verbose else 0)
         if not self._h:

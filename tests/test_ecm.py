@@ -187,7 +187,7 @@ def test_ecm_stage2_gpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("p,force_s", [(86243, 64), (216091, 64)])
-def test_ecm_point_ops_on_the_multi_pass_path_gpu(p, force_s, monkeypatch):
+def test_ecm_point_ops_on_the_multi_pass_path_gpu(p, force_s):
     """addsub / mul_copy / sub_reg on 3-pass engines (n = 4096 forced off the single-CTA path, and n = 10240 = 5 * 2^11):
     the Edwards schedules against big integers."""
     import prmers_b200 as pb
@@ -195,8 +195,7 @@ def test_ecm_point_ops_on_the_multi_pass_path_gpu(p, force_s, monkeypatch):
     cv = ecm.curve_from_seed(N, 2024)
     K = ecm.stage1_exponent(60)
     want = ecm.reference_scalar_mul(N, cv["a"], cv["d"], cv["X0"], cv["Y0"], ecm.naf(K))
-    monkeypatch.setenv("MARIN_B200_FORCE_S", str(force_s))
-    eng = pb.Engine(p, ecm.REGS)
+    eng = pb.Engine(p, ecm.REGS, force_S=force_s)
     assert not eng.is_single_cta()
     r = ecm.run_curve(eng, p, 60, 0, 2024, curve=cv, K=K)
     assert r["status"] == "NF" and r["stage1_T"] == want[3] % N

@@ -15,15 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def _engine(p, regs, force_S=0, force_R2=0):
     import prmers_b200 as pb
-    if force_S:
-        os.environ["MARIN_B200_FORCE_S"] = str(force_S)
-    if force_R2:
-        os.environ["MARIN_B200_FORCE_R2"] = str(force_R2)
-    try:
-        return pb.Engine(p, regs)
-    finally:
-        os.environ.pop("MARIN_B200_FORCE_S", None)
-        os.environ.pop("MARIN_B200_FORCE_R2", None)
+    return pb.Engine(p, regs, force_S=force_S, force_R2=force_R2)
 
 
 def val(e, r):

@@ -1,5 +1,6 @@
-"""Development aid: squaring time at the latency-bound sizes per row length S (MARIN_B200_FORCE_S) and radix-4 mask
-(MARIN_B200_R4MASK: 1 = contiguous pass on radix-4 stages, 2 = strided pass)."""
+"""Development aid: squaring time at the latency-bound sizes per row length S and radix-4 mask (1 = contiguous pass on
+radix-4 stages, 2 = strided pass).  The mask was a build-time experiment (MARIN_B200_R4MASK read by make_plan); its outcome
+is the planner's r4S / r4R rule, the log is profiles/r2/lowlat_sweep.log."""
 import os, subprocess, sys
 here = os.path.dirname(os.path.abspath(__file__))
 cases = [int(a) for a in sys.argv[1:]] or [86243, 172001, 350003, 700001, 1362763, 2500009, 4999999]

@@ -4,10 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import prmers_b200 as pb
 
 def run(p, fs=0, r2=0):
-    if fs: os.environ["MARIN_B200_FORCE_S"] = str(fs)
-    if r2: os.environ["MARIN_B200_FORCE_R2"] = str(r2)
-    e = pb.Engine(p, 6)
-    os.environ.pop("MARIN_B200_FORCE_S", None); os.environ.pop("MARIN_B200_FORCE_R2", None)
+    e = pb.Engine(p, 6, force_S=fs, force_R2=r2)
     e.set(0, 3); e.set(1, 5)
     for _ in range(3): e.square_mul(0)
     e.square_mul(0, 3)
