@@ -317,7 +317,7 @@ struct CudaBackend
 		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 2048)); // it also keeps its argument blocks in static shared memory
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-		mid_fast_attr<0>(); mid_fast_attr<1>(); mid_fast_attr<2>(); mid_fast_attr<3>(); mid_fast_attr<4>(); mid_fast_attr<5>();
+		mid_fast_attr<0>(); mid_fast_attr<1>(); mid_fast_attr<2>(); mid_fast_attr<3>(); mid_fast_attr<4>(); mid_fast_attr<5>(); mid_fast_attr<6>(); mid_fast_attr<7>();
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_inv_fast_T4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::INV_SMEM_T4));
 		CK(cudaFuncSetAttribute(fast::k_fwd_fast_T4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SC<4>::SMEM));
@@ -354,6 +354,8 @@ struct CudaBackend
 		if (A.S == 1024 && is({4, 16, 16})) return (int)fast::MID_SHAPE_1024;
 		if (A.S == 2560 && is({5, 2, 16, 16})) return (int)fast::MID_SHAPE_2560;
 		if (A.S == 1280 && is({5, 16, 16})) return (int)fast::MID_SHAPE_1280;
+		if (A.S == 8192 && is({2, 16, 16, 16})) return (int)fast::MID_SHAPE_8192;
+		if (A.S == 10240 && is({5, 2, 4, 16, 16})) return (int)fast::MID_SHAPE_10240;
 		return -1;
 	}
 	static bool fast_str_shape(const StridedArgs &A)
@@ -485,7 +487,9 @@ struct CudaBackend
 				case 2: mid_fast_launch<2>(A, grid); break;
 				case 3: mid_fast_launch<3>(A, grid); break;
 				case 4: mid_fast_launch<4>(A, grid); break;
-				default: mid_fast_launch<5>(A, grid); break;
+				case 5: mid_fast_launch<5>(A, grid); break;
+				case 6: mid_fast_launch<6>(A, grid); break;
+				default: mid_fast_launch<7>(A, grid); break;
 			}
 			post(); return;
 		}

@@ -97,11 +97,18 @@ static constexpr u32 MID5_SMEM = (MID5_S + MID5_S / 16 + 1) * 16;
 // by one thread on eight (four) elements 256 apart, straight from / to global memory, then one warp-local block per warp.
 // SHAPE 4, 5: S = 2560 = 5 x 2 x 16 x 16 and S = 1280 = 5 x 16 x 16 (n = 5 * 2^20 and 5 * 2^19 with 1024 rows): the radix-5
 // stage (and the radix-2 stage after it) in one thread on elements 256 apart, one warp-local block per warp.
-static constexpr u32 MID_SHAPE_4096 = 0, MID_SHAPE_5120 = 1, MID_SHAPE_2048 = 2, MID_SHAPE_1024 = 3, MID_SHAPE_2560 = 4, MID_SHAPE_1280 = 5;
-__host__ __device__ constexpr u32 mid_shape_S(int shape) { return shape == 0 ? 4096u : shape == 1 ? 5120u : shape == 2 ? 2048u : shape == 3 ? 1024u : shape == 4 ? 2560u : 1280u; }
-__host__ __device__ constexpr u32 mid_shape_threads(int shape) { return shape == 0 ? 256u : shape == 1 ? 320u : shape == 2 ? 256u : shape == 3 ? 128u : shape == 4 ? 320u : 160u; }
+// SHAPE 6: rows of S = 8192 = 2 x 16 x 16 x 16 pairs (n = 2^24 with 1024 rows: the transform stays on the three-pass path and
+// on the specialised strided kernels instead of paying two more passes over memory): one thread takes the sixteen elements
+// j + 256 q of BOTH halves of the row, does the radix-2 stage between them and the radix-16 stage of each half, straight
+// from / to global memory; then 32 warp-local blocks over 16 warps.  136 KB of shared memory: one CTA of 512 threads per SM.
+// SHAPE 7: rows of S = 10240 = 5 x 2 x 4 x 16 x 16 pairs (n = 5 * 2^22 with 1024 rows, same reason): the radix-5 stage across
+// the row from / to global memory, the radix-2 and radix-4 stages as one eight-element step in shared memory, then 40
+// warp-local blocks over 20 warps.  170 KB of shared memory: one CTA of 640 threads per SM.
+static constexpr u32 MID_SHAPE_4096 = 0, MID_SHAPE_5120 = 1, MID_SHAPE_2048 = 2, MID_SHAPE_1024 = 3, MID_SHAPE_2560 = 4, MID_SHAPE_1280 = 5, MID_SHAPE_8192 = 6, MID_SHAPE_10240 = 7;
+__host__ __device__ constexpr u32 mid_shape_S(int shape) { return shape == 0 ? 4096u : shape == 1 ? 5120u : shape == 2 ? 2048u : shape == 3 ? 1024u : shape == 4 ? 2560u : shape == 5 ? 1280u : shape == 6 ? 8192u : 10240u; }
+__host__ __device__ constexpr u32 mid_shape_threads(int shape) { return shape == 0 ? 256u : shape == 1 ? 320u : shape == 2 ? 256u : shape == 3 ? 128u : shape == 4 ? 320u : shape == 5 ? 160u : shape == 6 ? 512u : 640u; }
 __host__ __device__ constexpr u32 mid_shape_smem(int shape) { return (mid_shape_S(shape) + mid_shape_S(shape) / 16 + 1) * 16; }
-__host__ __device__ constexpr u32 mid_shape_minblocks(int shape) { return shape == 0 ? 3u : shape == 1 ? 2u : shape == 2 ? 3u : shape == 3 ? 6u : shape == 4 ? 2u : 4u; }
+__host__ __device__ constexpr u32 mid_shape_minblocks(int shape) { return shape == 0 ? 3u : shape == 1 ? 2u : shape == 2 ? 3u : shape == 3 ? 6u : shape == 4 ? 2u : shape == 5 ? 4u : 1u; }
 
 template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threads(SHAPE), mid_shape_minblocks(SHAPE)) k_mid_fast(const __grid_constant__ MidArgs A)
 {
@@ -110,10 +117,10 @@ template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threa
 	extern __shared__ __align__(16) unsigned char smraw[];
 	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
 	const Tables &t = A.t;
-	constexpr bool FIVE = SHAPE == 1, POW16 = SHAPE == 0, OCT = SHAPE == 2, QUAD = SHAPE == 3, TEN = SHAPE == 4, FIVE1 = SHAPE == 5;
+	constexpr bool FIVE = SHAPE == 1, POW16 = SHAPE == 0, OCT = SHAPE == 2, QUAD = SHAPE == 3, TEN = SHAPE == 4, FIVE1 = SHAPE == 5, DBL = SHAPE == 6, FIVE2 = SHAPE == 7;
 	constexpr u32 S = mid_shape_S(SHAPE), NTHR = mid_shape_threads(SHAPE), NW = NTHR / 32;
 	constexpr u32 NIT = S / 256 / NW;                // warp-local blocks per warp
-	constexpr u32 SB = (FIVE || OCT || TEN) ? 2 : 1; // index of the s = 16 stage in the stage list
+	constexpr u32 SB = FIVE2 ? 3 : (FIVE || OCT || TEN || DBL) ? 2 : 1; // index of the s = 16 stage in the stage list
 	const u32 tid = threadIdx.x, lane = tid & 1, h = tid >> 1, wl = tid & 31, warp = tid >> 5;
 	const size_t rowbase = (size_t)blockIdx.x * S;
 	u64 *smw = reinterpret_cast<u64 *>(sm) + lane;
@@ -134,6 +141,72 @@ template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threa
 			tw16<256>(a, tw0 + j);
 			st16_sw<544>(smw + 2 * (j + (j >> 4)), a);
 		}
+	}
+	else if (FIVE2)
+	{
+		// ---- F0: radix 5, elements j + 2048 q from global memory; F1 + F2: radix 2 (s = 1024) and radix 4 (s = 256) on the
+		//      eight elements 256 apart inside each fifth of the row
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		u64 nx[5];
+		#pragma unroll
+		for (int q = 0; q < 5; ++q) nx[q] = g[2 * (h + 2048 * q)];
+		#pragma unroll 1
+		for (u32 j = h; j < 2048; j += NTHR / 2)
+		{
+			u64 a[5];
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) a[q] = nx[q];
+			if (j + NTHR / 2 < 2048)
+			{
+				#pragma unroll
+				for (int q = 0; q < 5; ++q) nx[q] = g[2 * (j + NTHR / 2 + 2048 * q)];
+			}
+			dft5(a, t.w5);
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) a[k] = gl::mul(a[k], tw0[(k - 1) * 2048 + j]);
+			u64 *o = smw + 2 * (j + (j >> 4));
+			#pragma unroll
+			for (int k = 0; k < 5; ++k) o[k * 4352] = a[k];
+		}
+		__syncthreads();
+		const u64 *twa = t.twS + A.st[1].toff, *twq = t.twS + A.st[2].toff;
+		#pragma unroll 1
+		for (u32 rb = h; rb < 1280; rb += NTHR / 2)
+		{
+			const u32 j = rb & 255, base = (rb >> 8) * 2048 + j;
+			u64 *o = smw + 2 * (base + (base >> 4));
+			u64 a[8];
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) a[q] = o[q * 544];
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) { addsub(a[q], a[q + 4]); a[q + 4] = gl::mul(a[q + 4], twa[j + 256 * q]); }
+			#pragma unroll
+			for (int hf = 0; hf < 2; ++hf)
+			{
+				u64 *x = a + 4 * hf;
+				dft4<false>(x[0], x[1], x[2], x[3]);
+				o[hf * 2176] = x[0]; o[hf * 2176 + 544] = gl::mul(x[1], twq[j]);
+				o[hf * 2176 + 1088] = gl::mul(x[2], twq[256 + j]); o[hf * 2176 + 1632] = gl::mul(x[3], twq[512 + j]);
+			}
+		}
+	}
+	else if (DBL)
+	{
+		// ---- F0 (radix 2, s = 4096) between the halves of the row and F1 (radix 16, s = 256) inside each, from global memory
+		const u64 *g = reinterpret_cast<const u64 *>(A.x + rowbase) + lane;
+		const u64 *twh = t.twS + A.st[1].toff;
+		const u32 j = h;
+		u64 a[16], b[16];
+		ld16_nat<512>(a, g + 2 * j);
+		ld16_nat<512>(b, g + 2 * (j + 4096));
+		#pragma unroll
+		for (int q = 0; q < 16; ++q) { addsub(a[q], b[q]); b[q] = gl::mul(b[q], tw0[j + 256 * q]); }
+		dft16<false>(a);
+		tw16<256>(a, twh + j);
+		st16_sw<544>(smw + 2 * (j + (j >> 4)), a);
+		dft16<false>(b);
+		tw16<256>(b, twh + j);
+		st16_sw<544>(smw + 2 * (4352 + j + (j >> 4)), b);
 	}
 	else if (OCT)
 	{
@@ -325,6 +398,61 @@ template <int MODE, int SHAPE> __global__ void __launch_bounds__(mid_shape_threa
 			dft16<true>(a);
 			st16_nat<512>(g + 2 * j, a);
 		}
+	}
+	else if (FIVE2)
+	{
+		const u64 *twa = t.twSi + A.st[1].toff, *twq = t.twSi + A.st[2].toff;
+		#pragma unroll 1
+		for (u32 rb = h; rb < 1280; rb += NTHR / 2)
+		{
+			const u32 j = rb & 255, base = (rb >> 8) * 2048 + j;
+			u64 *o = smw + 2 * (base + (base >> 4));
+			u64 a[8];
+			#pragma unroll
+			for (int hf = 0; hf < 2; ++hf)
+			{
+				u64 *x = a + 4 * hf;
+				x[0] = o[hf * 2176]; x[1] = gl::mul(o[hf * 2176 + 544], twq[j]);
+				x[2] = gl::mul(o[hf * 2176 + 1088], twq[256 + j]); x[3] = gl::mul(o[hf * 2176 + 1632], twq[512 + j]);
+				dft4<true>(x[0], x[1], x[2], x[3]);
+			}
+			#pragma unroll
+			for (int q = 0; q < 4; ++q) { a[q + 4] = gl::mul(a[q + 4], twa[j + 256 * q]); addsub(a[q], a[q + 4]); }
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) o[q * 544] = a[q];
+		}
+		__syncthreads();
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		#pragma unroll 1
+		for (u32 j = h; j < 2048; j += NTHR / 2)
+		{
+			const u64 *o = smw + 2 * (j + (j >> 4));
+			u64 a[5];
+			a[0] = o[0];
+			#pragma unroll
+			for (int k = 1; k < 5; ++k) a[k] = gl::mul(o[k * 4352], twi0[(k - 1) * 2048 + j]);
+			dft5(a, t.w5i);
+			#pragma unroll
+			for (int q = 0; q < 5; ++q) g[2 * (j + 2048 * q)] = a[q];
+		}
+	}
+	else if (DBL)
+	{
+		// ---- I1 (radix 16, s = 256) inside each half and I0 (radix 2, s = 4096) between them, back to global memory (in place)
+		u64 *g = reinterpret_cast<u64 *>(A.x + rowbase) + lane;
+		const u64 *twh = t.twSi + A.st[1].toff;
+		const u32 j = h;
+		u64 a[16], b[16];
+		ld16_sw<544>(a, smw + 2 * (j + (j >> 4)));
+		tw16<256>(a, twh + j);
+		dft16<true>(a);
+		ld16_sw<544>(b, smw + 2 * (4352 + j + (j >> 4)));
+		tw16<256>(b, twh + j);
+		dft16<true>(b);
+		#pragma unroll
+		for (int q = 0; q < 16; ++q) { b[q] = gl::mul(b[q], twi0[j + 256 * q]); addsub(a[q], b[q]); }
+		st16_nat<512>(g + 2 * j, a);
+		st16_nat<512>(g + 2 * (j + 4096), b);
 	}
 	else if (OCT)
 	{

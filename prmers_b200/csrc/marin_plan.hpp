@@ -31,6 +31,7 @@ static constexpr u32 SMALL_MAX_PAIRS = 1024;  // one CTA does the whole operatio
 static constexpr u32 MID_S = 4096;            // contiguous-pass block for large transforms (64 KiB + pad)
 static constexpr u32 MID_S5 = 5120;           // 5 * 2^k transforms with 1024 rows: the radix-5 stage moves into the contiguous pass
                                               // (85 KiB rows), and the strided passes are the specialised R = 1024 kernels
+static constexpr u32 MAX_S = 10240;           // longest row of the contiguous pass (2 x 5120 pairs: 170 KiB of shared memory, one CTA per SM)
 static constexpr u32 MAX_R = 1280;            // strided tile rows: 1280 * 5 pairs (4 + 1 of padding) * 16 B = 100 KiB, two CTAs per SM
 
 struct Plan
@@ -83,12 +84,13 @@ inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta 
 
 // Row length S of the contiguous pass for the transform sizes whose three-pass split was measured on a B200
 // (tools/shape_sweep.py, profiles/r2/shape_sweep.log): the rows the specialised contiguous kernels cover
-// (S = 256 x {4, 8, 16} and 256 x {5, 10, 20}) with 1024 strided rows from n = 2^21 / 5 * 2^19 up, so that both strided
+// (S = 256 x {4, 8, 16, 32} and 256 x {5, 10, 20, 40}) with 1024 strided rows from n = 2^21 / 5 * 2^19 up, so that both strided
 // passes are the specialised R = 1024 kernels as well; 256 strided rows for the two sizes below.  0 = no entry.
 inline u32 measured_row_length(u32 m)
 {
 	switch (m)
 	{
+		case 1u << 23: return 8192;        // n = 2^24       671 us (five passes, R = 64 x 32, S = 4096: 1084)
 		case 1u << 22: return 4096;        // n = 2^23       300 us
 		case 1u << 21: return 2048;        // n = 2^22       166 us (S = 4096, R = 512: 230)
 		case 1u << 20: return 1024;        // n = 2^21        92 us (95)
@@ -97,6 +99,7 @@ inline u32 measured_row_length(u32 m)
 		case 1u << 15: return 1024;        // n = 2^16        33 us (S = 512: 42)
 		case 1u << 14: return 2048;        // n = 2^15        25 us (S = 256: 35)
 		case 1u << 12: return 1024;        // n = 2^13        22 us (S = 512: 31)
+		case 5u << 21: return 10240;       // n = 5 * 2^22   830 us (five passes, R = 80 x 32, S = 4096: 1702)
 		case 5u << 20: return MID_S5;      // n = 5 * 2^21   432 us
 		case 5u << 19: return 2560;        // n = 5 * 2^20   224 us (S = 4096, R = 640: 323)
 		case 5u << 18: return 1280;        // n = 5 * 2^19   129 us (157)
@@ -144,12 +147,12 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 			if (rb < 2 || Rall % rb != 0 || (rb & (rb - 1)) != 0 || Rall / rb < 2) { err = "bad second-level split"; return false; }
 			pl.R2 = rb; pl.R = Rall / rb;
 		}
-		if (pl.R > MAX_R || pl.S > MID_S5) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
+		if (pl.R > MAX_R || pl.S > MAX_S) { err = "transform size n = " + std::to_string(n) + " is outside the supported decompositions"; return false; }
 		// Latency-bound sizes (profiles/r2/lowlat_sweep.log): a pass there is a handful of CTAs walking through dependent
 		// phases, and a radix-16 butterfly is ~1100 instructions in one thread; radix-4 stages put four times the threads
 		// on a quarter of the chain.  Strided passes up to n = 2^18 (n = 65536: 32.8 -> 26.6 us, n = 5 * 2^11: 33.3 -> 24.6),
 		// contiguous passes up to n = 5 * 2^13 unless the row is one of the specialised shapes (n = 4096: 24.6 -> 20.5).
-		const bool fastS = pl.S == 1024 || pl.S == 2048 || pl.S == 4096 || pl.S == 1280 || pl.S == 2560 || pl.S == MID_S5;
+		const bool fastS = pl.S == 1024 || pl.S == 2048 || pl.S == 4096 || pl.S == 8192 || pl.S == 1280 || pl.S == 2560 || pl.S == MID_S5 || pl.S == 10240;
 		const bool r4S = !force_S && !fastS && n <= 40960, r4R = !force_S && n <= 262144;
 		pl.nstS = factor_stages(pl.S, pl.stS, true, false, r4S);
 		pl.nstR = factor_stages(pl.R, pl.stR, MARIN_R_SMALL_FIRST != 0, false, r4R);
