@@ -183,6 +183,15 @@ int emu_set_digits_slab(void *h, uint32_t slab, size_t d, const uint64_t *enc) {
 void emu_destroy(void *h) { delete (Emu *)h; }
 size_t emu_size(void *h) { return ((Emu *)h)->size(); }
 int emu_is_small(void *h) { return ((Emu *)h)->pl.small ? 1 : 0; }
+// the planner alone (no engine, no tables): out = {small, S, R, R2, nstS, nstR, radices of the contiguous pass [8], of the strided pass [8]}
+int emu_plan(uint32_t p, uint32_t *out)
+{
+	marin::Plan pl; std::string err;
+	if (!marin::make_plan(p, pl, err)) { g_err = err; return 0; }
+	out[0] = pl.small; out[1] = pl.S; out[2] = pl.R; out[3] = pl.R2; out[4] = pl.nstS; out[5] = pl.nstR;
+	for (uint32_t i = 0; i < 8; ++i) { out[6 + i] = i < pl.nstS ? pl.stS[i].radix : 0; out[14 + i] = i < pl.nstR ? pl.stR[i].radix : 0; }
+	return 1;
+}
 uint32_t emu_plan_R(void *h) { return ((Emu *)h)->pl.R; }
 uint32_t emu_plan_S(void *h) { return ((Emu *)h)->pl.S; }
 uint32_t emu_plan_R2(void *h) { return ((Emu *)h)->pl.R2; }

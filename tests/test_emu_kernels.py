@@ -262,3 +262,33 @@ def test_two_level_strided_passes(p, force_S, force_R2):
     assert val(e, 0) == x
     e.sub(0, 2); e.square_mul(0); x = (x - 2) ** 2 % m
     assert val(e, 0) == x
+
+
+def test_planner_decompositions():
+    """The measured splits (marin_plan.hpp: measured_row_length, the radix-4 rule of the latency-bound sizes, rows of 8192 /
+    10240 pairs for n = 2^24 / 5 * 2^22): which kernels a size runs on is decided here, so the table is pinned."""
+    import ctypes as C
+    L = lib()
+    L.emu_plan.restype = C.c_int; L.emu_plan.argtypes = [C.c_uint32, C.POINTER(C.c_uint32)]
+    def plan(p):
+        out = (C.c_uint32 * 22)()
+        assert L.emu_plan(p, out)
+        return {"small": out[0], "S": out[1], "R": out[2], "R2": out[3], "stS": [out[6 + i] for i in range(out[4])], "stR": [out[14 + i] for i in range(out[5])]}
+    want = {
+        9941: dict(small=1),
+        86243: dict(small=0, S=256, R=8, R2=1, stS=[4, 4, 4, 4], stR=[4, 2]),                      # n = 4096: radix-4 lists
+        172001: dict(S=1024, R=4, stS=[4, 16, 16]),                                                # n = 8192: a specialised row shape
+        204973: dict(S=64, R=80, stS=[4, 4, 4], stR=[5, 4, 4]),                                    # n = 10240
+        1362763: dict(S=1024, R=32, stS=[4, 16, 16], stR=[4, 4, 2]),                               # n = 65536: strided pass on radix 4
+        4999999: dict(S=2048, R=64, stS=[2, 4, 16, 16], stR=[4, 4, 4]),                            # n = 2^18: last size of the rule
+        7240481: dict(S=1024, R=256, stS=[4, 16, 16], stR=[16, 16]),                               # n = 2^19
+        136279841: dict(S=4096, R=1024, R2=1, stS=[16, 16, 16], stR=[16, 16, 4]),
+        205271257: dict(S=5120, R=1024, R2=1, stS=[5, 4, 16, 16], stR=[16, 16, 4]),
+        300000007: dict(S=8192, R=1024, R2=1, stS=[2, 16, 16, 16], stR=[16, 16, 4]),               # n = 2^24 on three passes
+        340000019: dict(S=10240, R=1024, R2=1, stS=[5, 2, 4, 16, 16], stR=[16, 16, 4]),            # n = 5 * 2^22
+        600000001: dict(S=4096, R=64, R2=64),                                                      # n = 2^25: five passes
+    }
+    for p, w in want.items():
+        got = plan(p)
+        for k, v in w.items():
+            assert got[k] == v, (p, k, got)
