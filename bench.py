@@ -412,6 +412,10 @@ def main():
             line["roofline_int_alu_pipe"] = {"achieved": alu_instr / (ms_iter * 1e-3), "peak": peak_alu, "unit": "warp-inst/s",
                                              "frac": alu_instr / (ms_iter * 1e-3) / peak_alu,
                                              "alu_warp_instructions_per_square_mul": alu_instr,
+                                             "fmaheavy_pipe_busy_pct_under_ncu": summ.get("fmaheavy_pipe_busy_pct"),
+                                             "alu_pipe_busy_pct_under_ncu": summ.get("alu_pipe_busy_pct"),
+                                             "note": "every IMAD goes to the FMA-heavy half of the FMA pipe: both integer pipes are busy 54 - 70 % of the "
+                                                     "time in the two kernels, math-pipe throttle is their top stall reason (profiles/README.md)",
                                              "source": "profiles/ncu_summary.json (ncu capture) + live timing"}
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -1049,5 +1049,53 @@ __global__ void __launch_bounds__(STR_THREADS, 2) k_fwd_fast_T4(const __grid_con
 	for (u32 it = 0; it < 2; ++it) fwd_small_T4(A, sm, A.dst, warp + 8 * it, c0, wl, bpf);
 }
 
+// ================================================================== second-level strided pass with four rows
+// n >= 2^25: m = 1024 x 4 x S.  The first-level pass (1024 rows, stride 4 S) is the specialised kernel above; what is left
+// of the second level is ONE radix-4 butterfly per pair column of every block of 4 S pairs, with the boundary twiddle
+// w_m^(+-K(row) column escale) -- a streaming kernel (coalesced 16-byte accesses, one thread per column and both lanes),
+// not a tile kernel.  Same operation order as the generic stage (marin_kernels.cuh, run_stage_tile / bfly_core).
+static constexpr u32 L1_THREADS = 256;
+template <bool INV> __global__ void __launch_bounds__(L1_THREADS) k_level1_r4(const __grid_constant__ StridedArgs A)
+{
+	MARIN_PDL_WAIT();
+	const Tables &t = A.t;
+	const u32 col = blockIdx.x * L1_THREADS + threadIdx.x;
+	if (col < A.stride)
+	{
+		const size_t base = (size_t)blockIdx.y * A.Lb + col;
+		const u64 colscale = (u64)col * A.escale;
+		const u32 K0 = A.rowK[0];
+		pair_t v[4];
+		#pragma unroll
+		for (u32 q = 0; q < 4; ++q) v[q] = A.src[base + (size_t)q * A.stride];
+		u64 ax[4], ay[4];
+		if (INV)
+		{
+			#pragma unroll
+			for (u32 q = 0; q < 4; ++q)
+			{
+				const u64 f = boundary_tw(t, (u64)(K0 + q) * colscale, true);
+				ax[q] = gl::mul(v[q].x, f); ay[q] = gl::mul(v[q].y, f);
+			}
+			dft4<true>(ax[0], ax[1], ax[2], ax[3]); dft4<true>(ay[0], ay[1], ay[2], ay[3]);
+		}
+		else
+		{
+			#pragma unroll
+			for (u32 q = 0; q < 4; ++q) { ax[q] = v[q].x; ay[q] = v[q].y; }
+			dft4<false>(ax[0], ax[1], ax[2], ax[3]); dft4<false>(ay[0], ay[1], ay[2], ay[3]);
+			#pragma unroll
+			for (u32 k = 0; k < 4; ++k)
+			{
+				const u64 f = boundary_tw(t, (u64)(K0 + k) * colscale, false);
+				ax[k] = gl::mul(ax[k], f); ay[k] = gl::mul(ay[k], f);
+			}
+		}
+		#pragma unroll
+		for (u32 k = 0; k < 4; ++k) { pair_t o; o.x = ax[k]; o.y = ay[k]; A.dst[base + (size_t)k * A.stride] = o; }
+	}
+	MARIN_PDL_TRIGGER();
+}
+
 }} // namespace marin::fast
 #endif

@@ -90,6 +90,8 @@ inline u32 measured_row_length(u32 m)
 {
 	switch (m)
 	{
+		case 1u << 25: return 8192;        // n = 2^26       with 1024 x 4 rows (measured_second_level)
+		case 1u << 24: return 4096;        // n = 2^25       with 1024 x 4 rows
 		case 1u << 23: return 8192;        // n = 2^24       671 us (five passes, R = 64 x 32, S = 4096: 1084)
 		case 1u << 22: return 4096;        // n = 2^23       300 us
 		case 1u << 21: return 2048;        // n = 2^22       166 us (S = 4096, R = 512: 230)
@@ -99,6 +101,8 @@ inline u32 measured_row_length(u32 m)
 		case 1u << 15: return 1024;        // n = 2^16        33 us (S = 512: 42)
 		case 1u << 14: return 2048;        // n = 2^15        25 us (S = 256: 35)
 		case 1u << 12: return 1024;        // n = 2^13        22 us (S = 512: 31)
+		case 5u << 23: return 10240;       // n = 5 * 2^24   with 1024 x 4 rows
+		case 5u << 22: return MID_S5;      // n = 5 * 2^23   with 1024 x 4 rows
 		case 5u << 21: return 10240;       // n = 5 * 2^22   830 us (five passes, R = 80 x 32, S = 4096: 1702)
 		case 5u << 20: return MID_S5;      // n = 5 * 2^21   432 us
 		case 5u << 19: return 2560;        // n = 5 * 2^20   224 us (S = 4096, R = 640: 323)
@@ -106,6 +110,18 @@ inline u32 measured_row_length(u32 m)
 		case 5u << 17: return 2560;        // n = 5 * 2^18    77 us (105)
 		case 5u << 16: return 1280;        // n = 5 * 2^17    45 us (55)
 		case 5u << 13: return 2048;        // n = 5 * 2^14    29 us (S = 512: 43)
+		default: return 0;
+	}
+}
+
+// Rows of the second strided pass for the sizes that need one and were measured: m = 1024 x 4 x S keeps the first level
+// on the specialised strided kernels and leaves a single radix-4 stage for the second (a streaming kernel,
+// marin_fast.cuh: k_level1_r4).  0 = the generic rule below.
+inline u32 measured_second_level(u32 m)
+{
+	switch (m)
+	{
+		case 1u << 24: case 1u << 25: case 5u << 22: case 5u << 23: return 4;
 		default: return 0;
 	}
 }
@@ -142,8 +158,9 @@ inline bool make_plan(u32 p, Plan &pl, std::string &err, u32 force_S = 0, u32 fo
 		if (pl.R > MAX_R || force_R2)
 		{
 			const u32 Rall = pl.R, ramin = (five == 5) ? 80u : 64u;
-			u32 rb = force_R2 ? force_R2 : 128;
-			if (!force_R2) while (rb > 2 && Rall / rb < ramin) rb /= 2;
+			const u32 measured_rb = (force_R2 || force_S) ? 0u : measured_second_level(m);
+			u32 rb = force_R2 ? force_R2 : (measured_rb ? measured_rb : 128);
+			if (!force_R2 && !measured_rb) while (rb > 2 && Rall / rb < ramin) rb /= 2;
 			if (rb < 2 || Rall % rb != 0 || (rb & (rb - 1)) != 0 || Rall / rb < 2) { err = "bad second-level split"; return false; }
 			pl.R2 = rb; pl.R = Rall / rb;
 		}

@@ -419,10 +419,10 @@ def test_two_level_strided_passes_forced(p, force_S, force_R2):
     e.close()
 
 
-@pytest.mark.parametrize("p", [300000007, 400000009, 1100000011, 2200000007])
+@pytest.mark.parametrize("p", [300000007, 400000009, 700000001, 1100000011, 2200000007])
 def test_large_transforms_two_level(p):
-    """n = 2^24 (p = 3.0e8), 2^25 (4.0e8), 2^26 (1.1e9) and 5 * 2^25 (2.2e9): beyond one tile of rows, five kernels per
-    squaring.  Exact small powers (3^(2^k) fits a few digits), then size-independent identities on a
+    """n = 2^24 (p = 3.0e8: rows of 8192 pairs, three passes), 2^25 (4.0e8), 5 * 2^23 (7.0e8), 2^26 (1.1e9) (1024 x 4 rows:
+    the specialised first level and the streaming second level) and 5 * 2^25 (2.2e9: the generic five-pass kernels).  Exact small powers (3^(2^k) fits a few digits), then size-independent identities on a
     dense pseudo-random residue, and one squaring against GMP."""
     e = _engine(p, 5)
     n = e.get_size()

@@ -8,7 +8,7 @@ rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
 summ = {"note": "per launch, from the ncu --set full capture " + os.path.basename(rep) + " (n = 2^23, PRP chain steady state); ncu reports MB = 1e6 bytes",
         "source": outbase + "_ncu_full_raw.csv", "dram_bytes_per_launch": {}, "alu_pipe_warp_instructions_per_launch": {},
-        "warp_instructions_per_launch": {}, "kernel_us_under_ncu": {}, "issue_active_pct": {}, "alu_pipe_pct": {}, "fma_pipe_pct": {}, "stalls_pct": {}}
+        "warp_instructions_per_launch": {}, "kernel_us_under_ncu": {}, "issue_active_pct": {}, "alu_pipe_pct": {}, "fma_pipe_pct": {}, "fmaheavy_pipe_busy_pct": {}, "alu_pipe_busy_pct": {}, "stalls_pct": {}}
 seen = set()
 for r in rows[2:]:
     d = dict(zip(hdr, r))
@@ -29,6 +29,9 @@ for r in rows[2:]:
     summ["issue_active_pct"][key] = f("smsp__issue_active.avg.pct_of_peak_sustained_active")
     summ["alu_pipe_pct"][key] = alu * 100
     summ["fma_pipe_pct"][key] = f("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")
+    # every IMAD* issues to the FMA-heavy half; the combined FMA figure averages it with the idle FMA-lite half
+    summ["fmaheavy_pipe_busy_pct"][key] = f("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed")
+    summ["alu_pipe_busy_pct"][key] = f("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed")
     st = []
     for h in hdr:
         if re.match(r"smsp__pcsamp_warps_issue_stalled_\w+$", h) and "not_issued" not in h:
