@@ -20,6 +20,10 @@ def expect(p):
     x = x * x * 3 % m(p); x = x * 5 % m(p); x = (x + 5 - 5 - 2) % m(p)
     return x
 
-for p, fs, r2 in [(127, 0, 0), (9941, 0, 0), (9941, 16, 0), (86243, 64, 0), (86243, 8, 16), (216091, 64, 0), (1362763, 0, 0)]:
+# single CTA; forced multi-pass splits (generic kernels, second strided level); the planner's radix-4 lists; rows of 8192 and
+# 10240 pairs (k_mid_fast shapes 6, 7); the streaming second level (k_level1_r4); the specialised R = 1024 strided kernels
+CASES = [(127, 0, 0), (9941, 0, 0), (9941, 16, 0), (86243, 64, 0), (86243, 8, 16), (216091, 64, 0), (1362763, 0, 0),
+         (86243, 0, 0), (1362763, 8192, 0), (788023, 10240, 0), (5000011, 256, 4), (40000003, 0, 0)]
+for p, fs, r2 in CASES:
     assert run(p, fs, r2) == expect(p), (p, fs, r2)
 print("sanitize case ok")
