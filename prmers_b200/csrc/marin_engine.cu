@@ -496,22 +496,32 @@ struct CudaBackend
 		launch_windowed(k_mid, A, grid, cap(thr, MARIN_MID_MAXT), smem, batch); post();
 	}
 	// second-level pass of the n >= 2^25 decompositions m = 1024 x 4 x S: one radix-4 stage, a streaming kernel
-	static bool fast_level1_shape(const StridedArgs &A, u32 grid)
+	static u32 fast_level1_shape(const StridedArgs &A, u32 grid)   // rows of the streaming second-level kernel that serves A, or 0
 	{
-		return A.R == 4 && A.nst == 1 && A.st[0].radix == 4 && !A.with_carry && !A.fwd_dst && A.escale > 1
-			&& (size_t)A.Lb == (size_t)4 * A.stride && A.tiles == A.stride / TILE_C && grid % A.tiles == 0 && grid / A.tiles <= 65535;
+		if (A.with_carry || A.fwd_dst || A.escale <= 1 || (size_t)A.Lb != (size_t)A.R * A.stride || A.tiles != A.stride / TILE_C
+			|| grid % A.tiles != 0 || grid / A.tiles > 65535) return 0;
+		if (A.R == 4 && A.nst == 1 && A.st[0].radix == 4) return 4;
+		if (A.R == 8 && A.nst == 2 && A.st[0].radix == 4 && A.st[1].radix == 2) return 8;
+		return 0;
+	}
+	template <bool INV> void level1_launch(const StridedArgs &A, u32 grid, u32 rows)
+	{
+		const u32 gx = (A.stride + fast::L1_THREADS - 1) / fast::L1_THREADS, gy = grid / A.tiles;
+		if (rows == 4) launch_windowed(fast::k_level1_r4<INV>, A, gx, fast::L1_THREADS, 0, gy);
+		else launch_windowed(fast::k_level1_r8<INV>, A, gx, fast::L1_THREADS, 0, gy);
+		post();
 	}
 	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
 	{
 		use();
-		if (use_fast && fast_level1_shape(A, grid)) { launch_windowed(fast::k_level1_r4<false>, A, (A.stride + fast::L1_THREADS - 1) / fast::L1_THREADS, fast::L1_THREADS, 0, grid / A.tiles); post(); return; }
+		if (const u32 rows = use_fast ? fast_level1_shape(A, grid) : 0u) { level1_launch<false>(A, grid, rows); return; }
 		if (use_fast && fast_str_shape(A) && grid == A.tiles) { launch_windowed(fast::k_fwd_fast_T4, A, grid, fast::STR_THREADS, fast::SC<4>::SMEM); post(); return; }
 		launch_windowed(k_strided<false>, A, grid, cap(thr, MARIN_STR_MAXT), smem); post();
 	}
 	void strided_inv(const StridedArgs &A, u32 grid, u32 thr, size_t smem)
 	{
 		use();
-		if (use_fast && fast_level1_shape(A, grid)) { launch_windowed(fast::k_level1_r4<true>, A, (A.stride + fast::L1_THREADS - 1) / fast::L1_THREADS, fast::L1_THREADS, 0, grid / A.tiles); post(); return; }
+		if (const u32 rows = use_fast ? fast_level1_shape(A, grid) : 0u) { level1_launch<true>(A, grid, rows); return; }
 		if (use_fast && A.with_carry && A.ticket && fast_str_shape(A) && grid == A.tiles)
 		{
 			if (A.fwd_dst) launch_windowed(fast::k_inv_fast_T4<true>, A, grid, fast::STR_THREADS, fast::INV_SMEM_T4);

@@ -1097,5 +1097,70 @@ template <bool INV> __global__ void __launch_bounds__(L1_THREADS) k_level1_r4(co
 	MARIN_PDL_TRIGGER();
 }
 
+// The same for eight rows (n = 5 * 2^25 = 2 x 1024 x 8 x 10240: the size of the reference's MM31 example): stage list [4 (s = 2), 2 (s = 1)],
+// both stages in the registers of the thread that owns the column; the radix-2 stage carries the boundary twiddle.
+template <bool INV> __global__ void __launch_bounds__(L1_THREADS) k_level1_r8(const __grid_constant__ StridedArgs A)
+{
+	MARIN_PDL_WAIT();
+	const Tables &t = A.t;
+	const u32 col = blockIdx.x * L1_THREADS + threadIdx.x;
+	if (col < A.stride)
+	{
+		const size_t base = (size_t)blockIdx.y * A.Lb + col;
+		const u64 colscale = (u64)col * A.escale;
+		const u64 *tws = (INV ? A.twi : A.tw) + A.st[0].toff;      // tab[(k - 1) 2 + j] = w_8^(+-j k)
+		u64 x[8], y[8];
+		#pragma unroll
+		for (u32 q = 0; q < 8; ++q) { const pair_t v = A.src[base + (size_t)q * A.stride]; x[q] = v.x; y[q] = v.y; }
+		if (!INV)
+		{
+			#pragma unroll
+			for (u32 j = 0; j < 2; ++j)
+			{
+				dft4<false>(x[j], x[j + 2], x[j + 4], x[j + 6]); dft4<false>(y[j], y[j + 2], y[j + 4], y[j + 6]);
+				#pragma unroll
+				for (u32 k = 1; k < 4; ++k) { const u64 w = tws[(k - 1) * 2 + j]; x[j + 2 * k] = gl::mul(x[j + 2 * k], w); y[j + 2 * k] = gl::mul(y[j + 2 * k], w); }
+			}
+			#pragma unroll
+			for (u32 b = 0; b < 4; ++b)
+			{
+				addsub(x[2 * b], x[2 * b + 1]); addsub(y[2 * b], y[2 * b + 1]);
+				const u32 K0 = A.rowK[2 * b];
+				#pragma unroll
+				for (u32 k = 0; k < 2; ++k)
+				{
+					const u64 f = boundary_tw(t, (u64)(K0 + 4 * k) * colscale, false);
+					x[2 * b + k] = gl::mul(x[2 * b + k], f); y[2 * b + k] = gl::mul(y[2 * b + k], f);
+				}
+			}
+		}
+		else
+		{
+			#pragma unroll
+			for (u32 b = 0; b < 4; ++b)
+			{
+				const u32 K0 = A.rowK[2 * b];
+				#pragma unroll
+				for (u32 k = 0; k < 2; ++k)
+				{
+					const u64 f = boundary_tw(t, (u64)(K0 + 4 * k) * colscale, true);
+					x[2 * b + k] = gl::mul(x[2 * b + k], f); y[2 * b + k] = gl::mul(y[2 * b + k], f);
+				}
+				addsub(x[2 * b], x[2 * b + 1]); addsub(y[2 * b], y[2 * b + 1]);
+			}
+			#pragma unroll
+			for (u32 j = 0; j < 2; ++j)
+			{
+				#pragma unroll
+				for (u32 k = 1; k < 4; ++k) { const u64 w = tws[(k - 1) * 2 + j]; x[j + 2 * k] = gl::mul(x[j + 2 * k], w); y[j + 2 * k] = gl::mul(y[j + 2 * k], w); }
+				dft4<true>(x[j], x[j + 2], x[j + 4], x[j + 6]); dft4<true>(y[j], y[j + 2], y[j + 4], y[j + 6]);
+			}
+		}
+		#pragma unroll
+		for (u32 k = 0; k < 8; ++k) { pair_t o; o.x = x[k]; o.y = y[k]; A.dst[base + (size_t)k * A.stride] = o; }
+	}
+	MARIN_PDL_TRIGGER();
+}
+
 }} // namespace marin::fast
 #endif
