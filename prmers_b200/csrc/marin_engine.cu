@@ -502,13 +502,15 @@ struct CudaBackend
 			|| grid % A.tiles != 0 || grid / A.tiles > 65535) return 0;
 		if (A.R == 4 && A.nst == 1 && A.st[0].radix == 4) return 4;
 		if (A.R == 8 && A.nst == 2 && A.st[0].radix == 4 && A.st[1].radix == 2) return 8;
+		if (A.R == 16 && A.nst == 1 && A.st[0].radix == 16) return 16;
 		return 0;
 	}
 	template <bool INV> void level1_launch(const StridedArgs &A, u32 grid, u32 rows)
 	{
 		const u32 gx = (A.stride + fast::L1_THREADS - 1) / fast::L1_THREADS, gy = grid / A.tiles;
 		if (rows == 4) launch_windowed(fast::k_level1_r4<INV>, A, gx, fast::L1_THREADS, 0, gy);
-		else launch_windowed(fast::k_level1_r8<INV>, A, gx, fast::L1_THREADS, 0, gy);
+		else if (rows == 8) launch_windowed(fast::k_level1_r8<INV>, A, gx, fast::L1_THREADS, 0, gy);
+		else launch_windowed(fast::k_level1_r16<INV>, A, 2 * gx, fast::L1_THREADS, 0, gy);   // one lane per thread
 		post();
 	}
 	void strided_fwd(const StridedArgs &A, u32 grid, u32 thr, size_t smem)

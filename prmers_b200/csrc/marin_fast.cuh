@@ -1162,5 +1162,38 @@ template <bool INV> __global__ void __launch_bounds__(L1_THREADS) k_level1_r8(co
 	MARIN_PDL_TRIGGER();
 }
 
+// Sixteen rows (n = 5 * 2^26): one radix-16 stage; one lane of the pair column per thread.
+template <bool INV> __global__ void __launch_bounds__(L1_THREADS) k_level1_r16(const __grid_constant__ StridedArgs A)
+{
+	MARIN_PDL_WAIT();
+	const Tables &t = A.t;
+	const u32 e = blockIdx.x * L1_THREADS + threadIdx.x, col = e >> 1, lane = e & 1;
+	if (col < A.stride)
+	{
+		const size_t base = 2 * ((size_t)blockIdx.y * A.Lb + col) + lane, rs = 2 * (size_t)A.stride;
+		const u64 *src = reinterpret_cast<const u64 *>(A.src); u64 *dst = reinterpret_cast<u64 *>(A.dst);
+		const u64 colscale = (u64)col * A.escale;
+		const u32 K0 = A.rowK[0];
+		u64 a[16];
+		if (INV)
+		{
+			#pragma unroll
+			for (u32 q = 0; q < 16; ++q) a[sw16(q)] = gl::mul(src[base + q * rs], boundary_tw(t, (u64)(K0 + q) * colscale, true));
+			dft16<true>(a);
+			#pragma unroll
+			for (u32 k = 0; k < 16; ++k) dst[base + k * rs] = a[k];
+		}
+		else
+		{
+			#pragma unroll
+			for (u32 q = 0; q < 16; ++q) a[q] = src[base + q * rs];
+			dft16<false>(a);
+			#pragma unroll
+			for (u32 k = 0; k < 16; ++k) dst[base + k * rs] = gl::mul(a[sw16(k)], boundary_tw(t, (u64)(K0 + k) * colscale, false));
+		}
+	}
+	MARIN_PDL_TRIGGER();
+}
+
 }} // namespace marin::fast
 #endif

@@ -101,6 +101,7 @@ inline u32 measured_row_length(u32 m)
 		case 1u << 15: return 1024;        // n = 2^16        33 us (S = 512: 42)
 		case 1u << 14: return 2048;        // n = 2^15        25 us (S = 256: 35)
 		case 1u << 12: return 1024;        // n = 2^13        22 us (S = 512: 31)
+		case 5u << 25: return 10240;       // n = 5 * 2^26   with 1024 x 16 rows
 		case 5u << 24: return 10240;       // n = 5 * 2^25   with 1024 x 8 rows
 		case 5u << 23: return 10240;       // n = 5 * 2^24   with 1024 x 4 rows
 		case 5u << 22: return MID_S5;      // n = 5 * 2^23   with 1024 x 4 rows
@@ -124,6 +125,7 @@ inline u32 measured_second_level(u32 m)
 	{
 		case 1u << 24: case 1u << 25: case 5u << 22: case 5u << 23: return 4;
 		case 5u << 24: return 8;
+		case 5u << 25: return 16;
 		default: return 0;
 	}
 }

@@ -289,6 +289,7 @@ def test_planner_decompositions():
         600000001: dict(S=4096, R=1024, R2=4, stR=[16, 16, 4]),                                    # n = 2^25: five passes, 1024 x 4 rows
         700000001: dict(S=5120, R=1024, R2=4), 1000000007: dict(S=8192, R=1024, R2=4), 1400000023: dict(S=10240, R=1024, R2=4),
         2147483647: dict(S=10240, R=1024, R2=8, stR=[16, 16, 4]),                                  # n = 5 * 2^25: 1024 x 8 rows
+        3700000001: dict(S=10240, R=1024, R2=16),                                                  # n = 5 * 2^26: 1024 x 16 rows
     }
     for p, w in want.items():
         got = plan(p)
