@@ -184,6 +184,20 @@ def run_workload(args, rank, local_rank, world):
         r = modes.run_pm1_stage2_vtrace(eng, p, b1, b2, None, D=D, k_range=(k_lo, k_lo + steps_k), v1_in_register=True)
         dt = multi.max_over_ranks(time.perf_counter() - t0, device=dev)
         launches = eng.launch_count() - launches0
+        # the slice above is mostly set-up (baby table, Lucas jump, read-back of the accumulator); the cost of a term in a long
+        # run is the difference between a slice of twice the length and this one
+        t1 = time.perf_counter()
+        r2 = modes.run_pm1_stage2_vtrace(eng, p, b1, b2 + steps_k * D, None, D=D, k_range=(k_lo, k_lo + 2 * steps_k), v1_in_register=True)
+        dt2 = time.perf_counter() - t1
+        steady_ms = (dt2 - dt) * 1e3 / max(r2["terms"] - r["terms"], 1) if world == 1 else None
+        steady_ref_ms = None
+        if world == 1 and r.get("fused_terms"):
+            # the same two slices with the reference's own term sequence (copy + add + set_multiplicand + mul)
+            ta = time.perf_counter()
+            modes.run_pm1_stage2_vtrace(eng, p, b1, b2, None, D=D, k_range=(k_lo, k_lo + steps_k), v1_in_register=True, fused_terms=False)
+            tb = time.perf_counter()
+            modes.run_pm1_stage2_vtrace(eng, p, b1, b2 + steps_k * D, None, D=D, k_range=(k_lo, k_lo + 2 * steps_k), v1_in_register=True, fused_terms=False)
+            steady_ref_ms = ((time.perf_counter() - tb) - (tb - ta)) * 1e3 / max(r2["terms"] - r["terms"], 1)
         terms = sum(multi.gather([r["terms"]]))
         if rank == 0:
             peak, peak_src = measured_peak()
@@ -197,6 +211,9 @@ def run_workload(args, rank, local_rank, world):
                                "parallelism": f"giant-step range split over {world} rank(s), no data-path collective"},
                     "terms": terms, "primes": sum(multi.gather([r["primes"]])) if world == 1 else None,
                     "ms_per_square_mul": ms_sq, "ms_per_mul": ms_mul, "ms_per_term": dt * 1e3 / max(r["terms"], 1),
+                    "ms_per_term_steady": steady_ms, "steady_terms_per_s": (1e3 / steady_ms) if steady_ms else None,
+                    "ms_per_term_steady_reference_sequence": steady_ref_ms,
+                    "term_sequence": "add_multiplicand + mul (sum of two multiplicands)" if r.get("fused_terms") else "copy + add + set_multiplicand + mul",
                     "e2e": {"value": terms / dt, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * 8,
                             "note": "the driver runs through the public API; the accumulator residue is read back at the end"},
                     "gpu_launches": int(launches), "clocks": sampler.stop(),

@@ -54,6 +54,11 @@ int mb200_set_u32(void *eng, size_t dst, uint32_t a);               /* engine::s
 int mb200_copy(void *eng, size_t dst, size_t src);                  /* engine::copy, engine.h:49 */
 int mb200_square_mul(void *eng, size_t r, uint32_t a);              /* engine::square_mul, engine.h:51 */
 int mb200_set_multiplicand(void *eng, size_t dst, size_t src);      /* engine::set_multiplicand, engine.h:53 */
+/* dst <- multiplicand of (x + y) from the multiplicands a of x and b of y, in one streaming pass (the transform is linear).
+   No reference counterpart: src/modes/RunPM1.cpp:3790-3814 forms a V-trace term with copy + add + set_multiplicand; the
+   stage-2 driver of this repository uses this instead where the engine allows it.  Needs mb200_max_multiplier() >= 2 (the
+   sum has digits of twice the size); the result must only be used as the multiplicand of a mul with a = 1. */
+int mb200_add_multiplicand(void *eng, size_t dst, size_t a, size_t b);
 int mb200_mul(void *eng, size_t dst, size_t src, uint32_t a);       /* engine::mul, engine.h:60 */
 int mb200_sub_u32(void *eng, size_t r, uint32_t a);                 /* engine::sub, engine.h:62 */
 int mb200_add(void *eng, size_t dst, size_t src);                   /* engine::add, engine.h:64 */

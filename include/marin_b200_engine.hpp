@@ -121,6 +121,8 @@ public:
 	void copy(const Reg dst, const Reg src) const override { ck(mb200_copy(_h, dst, src)); }
 	void square_mul(const Reg src, const uint32 a = 1) const override { ck(mb200_square_mul(_h, src, a)); }
 	void set_multiplicand(const Reg dst, const Reg src) const override { ck(mb200_set_multiplicand(_h, dst, src)); }
+	// extension (no reference counterpart): dst <- multiplicand of (x + y) from the multiplicands a of x and b of y
+	void add_multiplicand(const Reg dst, const Reg a, const Reg b) const { ck(mb200_add_multiplicand(_h, dst, a, b)); }
 	void mul(const Reg dst, const Reg src, const uint32 a = 1) const override { ck(mb200_mul(_h, dst, src, a)); }
 	void sub(const Reg src, const uint32 a) const override { ck(mb200_sub_u32(_h, src, a)); }
 	void add(const Reg dst, const Reg src) const override { ck(mb200_add(_h, dst, src)); }

@@ -26,6 +26,8 @@ class IntEngine:
     def square_mul(self, r, a=1): self.r[r] = self.r[r] * self.r[r] * a % self.N; self.calls += 1
     def set_multiplicand(self, d, s): self.r[d] = self.r[s]; self.calls += 1
     def mul(self, d, s, a=1): self.r[d] = self.r[d] * self.r[s] * a % self.N; self.calls += 1
+    def add_multiplicand(self, d, a, b): self.r[d] = (self.r[a] + self.r[b]) % self.N; self.calls += 1
+    def max_multiplier(self): return 1 << 16
     def sub(self, r, a): self.r[r] = (self.r[r] - a) % self.N; self.calls += 1
     def add(self, d, s): self.r[d] = (self.r[d] + self.r[s]) % self.N; self.calls += 1
     def sub_reg(self, d, s): self.r[d] = (self.r[d] - self.r[s]) % self.N; self.calls += 1

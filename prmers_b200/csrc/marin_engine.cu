@@ -237,6 +237,10 @@ __global__ void k_scale(u64 *x, u64 f, u32 n)
 {
 	scale_thread(x, f, blockIdx.x * blockDim.x + threadIdx.x, n);
 }
+__global__ void k_gl_add(u64 *dst, const u64 *a, const u64 *b, u32 n)
+{
+	gl_add_thread(dst, a, b, blockIdx.x * blockDim.x + threadIdx.x, n);
+}
 __global__ void k_weights(const __grid_constant__ WeightArgs A, u32 n)
 {
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -558,6 +562,7 @@ struct CudaBackend
 	void lin_p2(const LinArgs &A, u32 count, u32 batch = 1) { use(); k_lin_p2<<<dim3((count + 127) / 128, batch), 128, 0, st>>>(A, count); post(); }
 	void unweight(const Tables &t, const u64 *x, u64 *out, u32 n) { use(); k_unweight<<<(n + 255) / 256, 256, 0, st>>>(t, x, out, n); post(); }
 	void scale(u64 *x, u64 f, u32 n) { use(); k_scale<<<(n + 255) / 256, 256, 0, st>>>(x, f, n); post(); }
+	void gl_add(u64 *dst, const u64 *a, const u64 *b, u32 n) { use(); k_gl_add<<<(n + 255) / 256, 256, 0, st>>>(dst, a, b, n); post(); }
 	void weights(const WeightArgs &A, u32 n) { use(); k_weights<<<(n + 255) / 256, 256, 0, st>>>(A, n); post(); }
 };
 
@@ -623,6 +628,7 @@ int mb200_set_u32(void *eng, size_t dst, uint32_t a) { GUARD(E(eng)->set_u32(dst
 int mb200_copy(void *eng, size_t dst, size_t src) { GUARD(E(eng)->copy(dst, src)); }
 int mb200_square_mul(void *eng, size_t r, uint32_t a) { GUARD(E(eng)->square_mul(r, a)); }
 int mb200_set_multiplicand(void *eng, size_t dst, size_t src) { GUARD(E(eng)->set_multiplicand(dst, src)); }
+int mb200_add_multiplicand(void *eng, size_t dst, size_t a, size_t b) { GUARD(E(eng)->add_multiplicand(dst, a, b)); }
 int mb200_mul(void *eng, size_t dst, size_t src, uint32_t a) { GUARD(E(eng)->mul(dst, src, a)); }
 int mb200_sub_u32(void *eng, size_t r, uint32_t a) { GUARD(E(eng)->sub_u32(r, a)); }
 int mb200_add(void *eng, size_t dst, size_t src) { GUARD(E(eng)->add(dst, src)); }

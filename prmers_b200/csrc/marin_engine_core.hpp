@@ -198,6 +198,20 @@ public:
 		MidArgs M = mid_args(R(dst), nullptr, R(dst), MODE_FWD, 1); launch_mid(M);
 	}
 
+	// dst <- multiplicand of (x + y), from the multiplicands a of x and b of y: one streaming pass instead of
+	// copy + add + set_multiplicand (no reference counterpart; the V-trace term V_kD - V_j of P-1 stage 2 is its use).
+	// The sum has digits of up to twice the size, which a later mul must absorb: allowed only where the carry chain has
+	// that bit of headroom (max multiplier >= 2), and the sum itself must not be summed again.
+	void add_multiplicand(size_t dst, size_t a, size_t b)
+	{
+		check(dst); check(a); check(b);
+		if (_recording) throw std::runtime_error("marin_b200: add_multiplicand cannot be recorded");
+		if (_batch > 1) throw std::runtime_error("marin_b200: add_multiplicand is not available on a batched engine");
+		if (pl.a_max < 2) throw std::runtime_error("marin_b200: add_multiplicand needs one bit of headroom in the carry chain (max multiplier >= 2)");
+		touch(dst);
+		be.gl_add(R(dst), R(a), R(b), pl.n);
+	}
+
 	void mul(size_t dst, size_t src, u32 a)
 	{
 		check(dst); check(src); check_a(a);

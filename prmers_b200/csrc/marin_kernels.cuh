@@ -936,6 +936,10 @@ static constexpr u32 LIN_BLOCK = 256; // pairs per CTA of the fast linear kernel
 // x <- x * f, elementwise (the plain inverse strided pass is unnormalised: times 1/R it is the exact inverse)
 HD void scale_thread(u64 *x, u64 f, u32 j, u32 n) { if (j < n) x[j] = gl::mul(x[j], f); }
 
+// dst <- a + b element by element in the field: the sum of two MULTIPLICANDS (transform-domain values) is the multiplicand of
+// the sum of their residues, because the transform is linear
+HD void gl_add_thread(u64 *dst, const u64 *a, const u64 *b, u32 j, u32 n) { if (j < n) dst[j] = gl::add(a[j], b[j]); }
+
 // unweighted digit values (not carried) for the host-side canonical export (engine_gpu.h:1534-1561)
 HD void unweight_thread(const Tables &t, const u64 *x, u64 *out, u32 j) { if (j < t.n) out[j] = gl::mul(x[j], t.winv_nat[j]); }
 

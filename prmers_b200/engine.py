@@ -30,6 +30,7 @@ _SIGS = {
     "mb200_copy": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "mb200_square_mul": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32]),
     "mb200_set_multiplicand": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "mb200_add_multiplicand": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "mb200_mul": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32]),
     "mb200_sub_u32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32]),
     "mb200_add": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
@@ -161,6 +162,10 @@ class Engine:
 
     def set_multiplicand(self, dst, src):
         self._ck(self._L.mb200_set_multiplicand(self._h, dst, src))
+
+    def add_multiplicand(self, dst, a, b):
+        """dst <- multiplicand of (x + y) from the multiplicands a of x and b of y (needs max_multiplier() >= 2)."""
+        self._ck(self._L.mb200_add_multiplicand(self._h, dst, a, b))
 
     def set_multiplicand2(self, dst, src):
         self.set_multiplicand(dst, src)

@@ -507,7 +507,7 @@ def vtrace_plan(p, b1, b2, n, free_bytes, D=None, baby_batch=None, max_regs=4096
     return best
 
 
-def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None, baby_batch=None, v1_in_register=False):
+def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None, baby_batch=None, v1_in_register=False, fused_terms=None):
     """P-1 stage 2 on traces V_n = H^n + H^-n: for every prime B1 < q <= B2 write q = k D +- j and
     accumulate (V_{kD} - V_j); both members of a pair share one term.  Returns the accumulator residue
     (an int) and statistics; the factor is gcd(acc, 2^p - 1) (use pm1_stage2_factor).  `k_range`
@@ -516,8 +516,14 @@ def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None, b
     accumulates its own product.  `baby_batch` keeps only that many baby traces resident and makes
     ceil(m(D) / baby_batch) passes over the giant steps, one per window of the baby table
     (-pm1-vtrace-baby-batch, README.md:520-562); the accumulator runs through all passes.
-    `v1_in_register`: register RV1 already holds V_1 (then H is ignored: no 1/H on the host)."""
+    `v1_in_register`: register RV1 already holds V_1 (then H is ignored: no 1/H on the host).
+    `fused_terms` (default: whenever the engine offers `add_multiplicand` and one bit of carry headroom): the baby traces
+    are kept as MULTIPLICANDS, V_kD is transformed once per giant step, and a term V_kD - V_j is the element-wise sum of
+    two multiplicands (the transform is linear) -- `add_multiplicand; mul` per term instead of the reference's
+    `copy; add; set_multiplicand; mul` (RunPM1.cpp:3790-3814); same accumulator, same registers."""
     m = (1 << p) - 1
+    if fused_terms is None:
+        fused_terms = hasattr(eng, "add_multiplicand") and eng.max_multiplier() >= 2
     D = D or vtrace_choose_D(b1)
     babies = [j for j in range(1, D // 2 + 1) if math.gcd(j, D) == 1]
     batch = min(baby_batch or len(babies), len(babies))
@@ -551,6 +557,8 @@ def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None, b
         for n in range(1, top + 1):
             if n in slot:
                 eng.set(slot[n], 0); eng.sub_reg(slot[n], RBCUR)
+                if fused_terms:
+                    eng.set_multiplicand(slot[n], slot[n])          # in place: the slot now holds the multiplicand of -V_j
             if n == top:
                 if n == D:
                     eng.copy(RVD, RBCUR); have_vd = True
@@ -566,20 +574,26 @@ def run_pm1_stage2_vtrace(eng, p, b1, b2, H, D=None, k_range=None, sieve=None, b
         else:
             _lucas_jump(eng, k_lo)
         for k in range(k_lo, k_hi):
+            giant_ready = False
             for j in window:
                 lo, hi = k * D - j, k * D + j
                 a, b = lo > 0 and is_s2_prime(lo), is_s2_prime(hi)
                 if not (a or b):
                     continue
                 primes += int(a) + int(b)
-                eng.copy(RTMP2, RGCUR); eng.add(RTMP2, slot[j])          # V_kD + (-V_j)
-                eng.set_multiplicand(RMUL_TMP, RTMP2); eng.mul(RACC, RMUL_TMP)
+                if fused_terms:
+                    if not giant_ready:
+                        eng.set_multiplicand(RTMP2, RGCUR); giant_ready = True      # multiplicand of V_kD, once per giant step
+                    eng.add_multiplicand(RMUL_TMP, RTMP2, slot[j]); eng.mul(RACC, RMUL_TMP)
+                else:
+                    eng.copy(RTMP2, RGCUR); eng.add(RTMP2, slot[j])          # V_kD + (-V_j)
+                    eng.set_multiplicand(RMUL_TMP, RTMP2); eng.mul(RACC, RMUL_TMP)
                 terms += 1
             # next giant step: V_{(k+1)D} = V_D V_{kD} - V_{(k-1)D}  (RunPM1.cpp:3788-3797)
             eng.copy(RGNEXT, RGCUR); eng.mul(RGNEXT, RMUL_VD); eng.sub_reg(RGNEXT, RGPREV)
             eng.copy(RGPREV, RGCUR); eng.copy(RGCUR, RGNEXT)
     return {"acc": _value(eng, RACC, p), "terms": terms, "primes": primes, "D": D, "k_range": (k_lo, k_hi),
-            "passes": passes, "baby_batch": batch}
+            "passes": passes, "baby_batch": batch, "fused_terms": bool(fused_terms)}
 
 
 def run_pm1_stage2_sharded(engine_factory, p, b1, b2, H, D=None, baby_batch=None, known_factors=()):

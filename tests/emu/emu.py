@@ -44,7 +44,7 @@ def lib():
         for f in ("emu_is_small", "emu_plan_R", "emu_plan_S", "emu_plan_R2", "emu_a_max"):
             getattr(L, f).argtypes = [vp]; getattr(L, f).restype = u32
         for f, a in (("emu_set_u32", [vp, sz, u32]), ("emu_copy", [vp, sz, sz]), ("emu_square_mul", [vp, sz, u32]),
-                     ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_sub_u32", [vp, sz, u32]),
+                     ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_add_multiplicand", [vp, sz, sz, sz]), ("emu_sub_u32", [vp, sz, u32]),
                      ("emu_add", [vp, sz, sz]), ("emu_sub_reg", [vp, sz, sz]), ("emu_get_digits", [vp, sz, vp]),
                      ("emu_set_digits", [vp, sz, vp]), ("emu_equal", [vp, sz, sz, vp]), ("emu_graph_begin", [vp]),
                      ("emu_graph_end", [vp, vp]), ("emu_graph_launch", [vp, C.c_int]),
@@ -85,6 +85,8 @@ class EmuEngine:
     def square_mul(self, r, a=1): self._ck(lib().emu_square_mul(self._h, r, a))
     def set_multiplicand(self, d, s): self._ck(lib().emu_set_multiplicand(self._h, d, s))
     def mul(self, d, s, a=1): self._ck(lib().emu_mul(self._h, d, s, a))
+    def add_multiplicand(self, d, a, b): self._ck(lib().emu_add_multiplicand(self._h, d, a, b))
+    def max_multiplier(self): return self.a_max
     def sub(self, r, a): self._ck(lib().emu_sub_u32(self._h, r, a))
     def add(self, d, s): self._ck(lib().emu_add(self._h, d, s))
     def sub_reg(self, d, s): self._ck(lib().emu_sub_reg(self._h, d, s))

@@ -156,6 +156,7 @@ struct CpuBackend
 		}
 	}
 	void scale(u64 *x, u64 f, u32 n) { for (u32 j = 0; j < n; ++j) scale_thread(x, f, j, n); }
+	void gl_add(u64 *dst, const u64 *a, const u64 *b, u32 n) { for (u32 j = 0; j < n; ++j) gl_add_thread(dst, a, b, j, n); }
 	void weights(const WeightArgs &A, u32 n)
 	{
 		#pragma omp parallel for schedule(static)
@@ -201,6 +202,7 @@ int emu_copy(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->copy(d, s)) }
 int emu_square_mul(void *h, size_t r, uint32_t a) { GUARD(((Emu *)h)->square_mul(r, a)) }
 int emu_set_multiplicand(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->set_multiplicand(d, s)) }
 int emu_mul(void *h, size_t d, size_t s, uint32_t a) { GUARD(((Emu *)h)->mul(d, s, a)) }
+int emu_add_multiplicand(void *h, size_t d, size_t a, size_t b) { GUARD(((Emu *)h)->add_multiplicand(d, a, b)) }
 int emu_sub_u32(void *h, size_t r, uint32_t a) { GUARD(((Emu *)h)->sub_u32(r, a)) }
 int emu_add(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->add(d, s)) }
 int emu_sub_reg(void *h, size_t d, size_t s) { GUARD(((Emu *)h)->sub_reg(d, s)) }

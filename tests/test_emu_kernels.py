@@ -295,3 +295,22 @@ def test_planner_decompositions():
         got = plan(p)
         for k, v in w.items():
             assert got[k] == v, (p, k, got)
+
+
+@pytest.mark.parametrize("p,force_S", [(127, 0), (9941, 0), (86243, 0), (86243, 64), (216091, 0)])
+def test_add_multiplicand_is_the_multiplicand_of_the_sum(p, force_S):
+    """The transform is linear: the element-wise sum of two multiplicands multiplies like the sum of their residues
+    (mb200_add_multiplicand; the V-trace term of P-1 stage 2).  Inputs include all-ones digits (the largest sums)."""
+    e = EmuEngine(p, 8, force_S)
+    assert e.max_multiplier() >= 2
+    m = mr.mp(p)
+    rng = random.Random(p + 17)
+    for a, b, x in [(rng.randrange(m), rng.randrange(m), rng.randrange(m)), (m - 1, m - 2, m - 3), (0, 5, rng.randrange(m))]:
+        e.set_mpz(0, a); e.set_mpz(1, b); e.set_mpz(2, x)
+        e.set_multiplicand(3, 0); e.set_multiplicand(4, 1)
+        e.add_multiplicand(5, 3, 4)
+        e.mul(2, 5)
+        assert val(e, 2) == x * (a + b) % m
+        e.add_multiplicand(3, 3, 4)                      # in place
+        e.set_mpz(2, x); e.mul(2, 3)
+        assert val(e, 2) == x * (a + b) % m

@@ -394,3 +394,21 @@ def test_pm1_ultralow_one_register_stage2():
     assert modes.run_pm1_stage2_ultralow(e, 569, 9, 677)["factor"] == 55470673
     # -b2start: primes up to it are left out of Q
     assert modes.pm1_ultralow_exponent(269, 4, 11, b2_start=5) == modes.pm1_exponent(269, 4) * 7 * 11
+
+
+def test_vtrace_fused_terms_equal_the_reference_sequence_emulated():
+    """The stage-2 term as the sum of two multiplicands (`add_multiplicand; mul`) against the reference's own sequence
+    (`copy; add; set_multiplicand; mul`, RunPM1.cpp:3790-3814) on the kernels' arithmetic: the same accumulator, with a
+    full baby table and with windows, on a single-CTA and on a multi-pass engine."""
+    for p, b1, b2, D, bb, want in [(569, 9, 677, 30, None, 55470673), (1097, 3, 709, 30, 3, 4576661533441), (4133, 23, 2099, 210, 7, 11173615097)]:
+        H = modes.run_pm1_stage1(EmuEngine(p, 2), p, b1)["x"]
+        regs = modes.BABY_BASE + (bb or modes.euler_phi(D) // 2)
+        a = modes.run_pm1_stage2_vtrace(EmuEngine(p, regs), p, b1, b2, H, D=D, baby_batch=bb, fused_terms=True)
+        b = modes.run_pm1_stage2_vtrace(EmuEngine(p, regs), p, b1, b2, H, D=D, baby_batch=bb, fused_terms=False)
+        assert a["fused_terms"] and not b["fused_terms"] and a["acc"] == b["acc"] and a["terms"] == b["terms"]
+        assert modes.pm1_stage2_factor(p, [a["acc"]]) == want
+    e = EmuEngine(86243, modes.BABY_BASE + 4)                     # multi-pass kernels (n = 4096), a slice of the giant steps
+    e2 = EmuEngine(86243, modes.BABY_BASE + 4)
+    a = modes.run_pm1_stage2_vtrace(e, 86243, 50, 400, 3 ** 41, D=30, k_range=(3, 6))
+    b = modes.run_pm1_stage2_vtrace(e2, 86243, 50, 400, 3 ** 41, D=30, k_range=(3, 6), fused_terms=False)
+    assert a["fused_terms"] and a["acc"] == b["acc"] and a["terms"] > 0
