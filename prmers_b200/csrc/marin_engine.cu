@@ -156,56 +156,101 @@ __global__ void k_canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags)
 	if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
 }
 
-// A recorded sequence of engine ops on a single-CTA engine, run by ONE launch: the CTA walks the list, every op is the
-// same phase functions the stand-alone kernels run, separated by block barriers (registers live in global memory; a
-// barrier orders one op's stores before the next op's loads within the CTA).  At these sizes an op is a few
-// microseconds of launch latency, which is what an ECM point operation (17-27 ops) otherwise consists of.  (Staging
-// registers and tables in shared memory was tried and is no faster: what remains is the serial instruction latency
-// of the tiny transforms, not memory latency.)
+// A recorded sequence of engine ops on a single-CTA engine, run by ONE launch: every op is the same phase functions the
+// stand-alone kernels run (registers live in global memory).  At these sizes an op is a few microseconds of launch
+// latency, which is what an ECM point operation (23-40 ops) otherwise consists of, and inside the kernel it is the serial
+// instruction latency of a tiny transform in a handful of threads (staging registers and tables in shared memory was
+// tried and is no faster).  So the CTA is A.groups warp groups and the list is a schedule over them (schedule_program):
+// a group runs the ops that carry its number, in list order, each with the group's own argument blocks, scratch in
+// shared memory and named barrier between the phases; before an op starts, the group's first thread waits until the
+// other groups have completed as many ops as the op's conflicts ask for (counters in shared memory; release / acquire
+// by __threadfence_block around them, the group barrier passes the order on to the other threads).
+// (immediate barrier numbers: with the number in a register ptxas reserves all 16 barriers for every CTA, and barriers
+// are a per-SM resource that limits how many curves' CTAs are resident)
+__device__ __forceinline__ void group_sync(u32 g, u32 gthr)
+{
+	switch (g)
+	{
+		case 0: asm volatile("bar.sync 1, %0;" :: "r"(gthr) : "memory"); break;
+		case 1: asm volatile("bar.sync 2, %0;" :: "r"(gthr) : "memory"); break;
+		case 2: asm volatile("bar.sync 3, %0;" :: "r"(gthr) : "memory"); break;
+		default: asm volatile("bar.sync 4, %0;" :: "r"(gthr) : "memory"); break;
+	}
+}
+static_assert(PROG_MAX_GROUPS == 4, "group_sync names four barriers");
+
 __global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ ProgArgs A)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
-	pair_t *sm = reinterpret_cast<pair_t *>(smraw);
+	__shared__ LinArgs sLs[PROG_MAX_GROUPS];
+	__shared__ volatile u32 s_done[PROG_MAX_GROUPS];          // ops completed, per group of the schedule
+	const u32 gthr = A.group_threads, grp = threadIdx.x / gthr, tid = threadIdx.x - grp * gthr, ngr = A.groups;
+	const u32 n = A.M.t.n, npairs = n / 2;
+	pair_t *sm = reinterpret_cast<pair_t *>(smraw + (size_t)grp * A.group_smem);
 	u64 *smc = reinterpret_cast<u64 *>(sm + smem_pairs_lin(A.M.S));
-	__shared__ MidArgs sM;
-	__shared__ LinArgs sL;
-	const u32 tid = threadIdx.x, nthr = blockDim.x, n = A.M.t.n, npairs = n / 2;
+	u64 *const carry = reinterpret_cast<u64 *>(sm);           // linear ops: one word per pair / per run, in the idle transform buffer
+	LinArgs &sL = sLs[grp];
 	// batched engines (one ECM curve per CTA): CTA x runs the same op list on its own slab of registers
-	u64 *const reg = A.reg + (size_t)blockIdx.x * A.slab_words, *const carry = A.carry + (size_t)blockIdx.x * A.slab_carry;
-	if (tid == 0) { sM = A.M; sM.carry = carry; sM.slab_pairs = 0; sL.t = A.M.t; sL.carry = carry; sL.D = A.D; sL.digits = nullptr; sL.slab_words = 0; sL.srcA = nullptr; sL.dst2 = sL.cpy = sL.cpy2 = sL.carry2 = nullptr; }
+	u64 *const reg = A.reg + (size_t)blockIdx.x * A.slab_words, *const hid = A.hid + (size_t)blockIdx.x * A.nhid * A.M.t.n;
+	if (tid == 0) { sL.t = A.M.t; sL.carry = carry; sL.D = A.D; sL.digits = nullptr; sL.slab_words = 0; sL.srcA = nullptr; sL.dst2 = sL.cpy = sL.cpy2 = sL.carry2 = nullptr; }
+	if (threadIdx.x < PROG_MAX_GROUPS) s_done[threadIdx.x] = 0;
+	// the op list itself: every group walks all of it (to find its own ops), so a short one is staged in shared memory
+	__shared__ ProgOp s_ops[PROG_SMEM_OPS];
+	const bool staged = A.nops <= PROG_SMEM_OPS;
+	if (staged)
+		for (u32 w = threadIdx.x; w < A.nops * (u32)(sizeof(ProgOp) / 8); w += blockDim.x) reinterpret_cast<u64 *>(s_ops)[w] = reinterpret_cast<const u64 *>(A.ops)[w];
 	__syncthreads();
-	for (u32 k = 0; k < A.nops; ++k)
+	const ProgOp *const ops = staged ? s_ops : A.ops;
+	for (u32 q = 0; q < A.nops; ++q)
 	{
-		const ProgOp op = A.ops[k];
-		u64 *dst = reg + (size_t)op.dst * n;
-		const u64 *src = reg + (size_t)op.src * n;
-		switch (op.code)
+		const u32 sgq = (ops[q].code >> PO_GROUP_SHIFT) & (PROG_MAX_GROUPS - 1);
+		if ((sgq & (ngr - 1)) != grp) continue;                 // fewer groups in the launch than in the schedule: they share (ngr is a power of two)
+		const ProgOp op = ops[q];
+		const u32 code = op.code & PO_CODE_MASK, sg = (op.code >> PO_GROUP_SHIFT) & (PROG_MAX_GROUPS - 1);
+		u64 *dst = prog_reg(A, reg, hid, op.dst);
+		const u64 *src = prog_reg(A, reg, hid, op.src);
+		if (tid == 0)
+		{
+			#pragma unroll
+			for (u32 g = 0; g < PROG_MAX_GROUPS; ++g)
+				if (op.wait[g])
+				{
+					// (bounded: a schedule that could not make progress raises the engine's error word instead of hanging the GPU)
+					u32 spins = 0;
+					while (s_done[g] < op.wait[g]) { if (++spins > 64) MARIN_NANOSLEEP(20); if (spins > (1u << 22)) { MARIN_ST_VOLATILE_U32(A.err, 1u); break; } }
+				}
+			__threadfence_block();
+			switch (code)
+			{
+			case PO_ADD: case PO_SUBREG: case PO_SUBSMALL:
+				sL.dst = dst; sL.src = src; sL.a = op.a; sL.op = (code == PO_ADD) ? LIN_ADD : ((code == PO_SUBREG) ? LIN_SUBREG : LIN_SUBSMALL);
+				break;
+			case PO_SETSMALL:
+				sL.dst = dst; sL.src = dst; sL.a = op.a; sL.op = LIN_SETSMALL;
+				break;
+			default: break;
+			}
+		}
+		group_sync(grp, gthr);
+		switch (code)
 		{
 		case PO_COPY:
-			for (u32 i = tid; i < npairs; i += nthr) reinterpret_cast<pair_t *>(dst)[i] = reinterpret_cast<const pair_t *>(src)[i];
+			for (u32 i = tid; i < npairs; i += gthr) reinterpret_cast<pair_t *>(dst)[i] = reinterpret_cast<const pair_t *>(src)[i];
 			break;
 		case PO_SQR: case PO_MUL: case PO_SETMUL:
 		{
-			if (tid == 0)
-			{
-				sM.x = (pair_t *)((op.code == PO_SETMUL) ? const_cast<u64 *>(src) : dst);
-				sM.y = (op.code == PO_MUL) ? (const pair_t *)src : nullptr;
-				sM.dst = (pair_t *)dst;
-				sM.mode = (op.code == PO_SQR) ? MODE_SQR : ((op.code == PO_MUL) ? MODE_MUL : MODE_FWD);
-				sM.a = op.a;
-			}
-			__syncthreads();
-			const u32 nph = mid_num_phases(sM);
-			for (u32 ph = 0; ph < nph; ++ph) { mid_phase(sM, 0, ph, tid, nthr, sm, smc); __syncthreads(); }
+			// the engine's tables and stages straight from the parameter space, the op's registers in registers
+			const MidOp o{(pair_t *)((code == PO_SETMUL) ? const_cast<u64 *>(src) : dst), (code == PO_MUL) ? (const pair_t *)src : nullptr, (pair_t *)dst,
+				(code == PO_SQR) ? MODE_SQR : ((code == PO_MUL) ? MODE_MUL : MODE_FWD), op.a};
+			const u32 nph = mid_num_phases(A.M, o.mode);
+			for (u32 ph = 0; ph < nph; ++ph) { mid_phase(A.M, o, 0, ph, tid, gthr, sm, smc); if (ph + 1 < nph) group_sync(grp, gthr); }
 			break;
 		}
 		case PO_ADD: case PO_SUBREG: case PO_SUBSMALL:
 		{
-			if (tid == 0) { sL.dst = dst; sL.src = src; sL.a = op.a; sL.op = (op.code == PO_ADD) ? LIN_ADD : ((op.code == PO_SUBREG) ? LIN_SUBREG : LIN_SUBSMALL); }
-			__syncthreads();
-			for (u32 i = tid; i < npairs; i += nthr) carry[i] = lin_pair_carry(sL, i);      // from the ORIGINAL content
-			__syncthreads();
-			for (u32 i = tid; i < npairs; i += nthr)
+			for (u32 i = tid; i < npairs; i += gthr) carry[i] = lin_pair_carry(sL, i);      // from the ORIGINAL content
+			group_sync(grp, gthr);
+			for (u32 i = tid; i < npairs; i += gthr)
 			{
 				u64 u0, u1; u32 w0, w1;
 				lin_pair_compute(sL, i, u0, u1, w0, w1);
@@ -215,16 +260,15 @@ __global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ Prog
 		}
 		default: // PO_SETSMALL
 		{
-			if (tid == 0) { sL.dst = dst; sL.src = dst; sL.a = op.a; sL.op = LIN_SETSMALL; }
-			__syncthreads();
 			const u32 runs = n / A.D;
-			for (u32 r = tid; r < runs; r += nthr) lin_p1_thread(sL, r);
-			__syncthreads();
-			for (u32 r = tid; r < runs; r += nthr) lin_p2_thread(sL, r);
+			for (u32 r = tid; r < runs; r += gthr) lin_p1_thread(sL, r);
+			group_sync(grp, gthr);
+			for (u32 r = tid; r < runs; r += gthr) lin_p2_thread(sL, r);
 			break;
 		}
 		}
-		__syncthreads();
+		group_sync(grp, gthr);   // every thread of the group is through: the op is complete (and the group's scratch is free)
+		if (tid == 0) { __threadfence_block(); s_done[sg] = s_done[sg] + 1; }
 	}
 }
 
@@ -318,7 +362,7 @@ struct CudaBackend
 		CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 		const int maxsm = (int)pr.sharedMemPerBlockOptin - 1024; // room for the kernels' few static shared words
 		CK(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 2048)); // it also keeps its argument blocks in static shared memory
+		CK(cudaFuncSetAttribute(k_program, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 8192)); // it also keeps the argument blocks of its warp groups in static shared memory
 		CK(cudaFuncSetAttribute(k_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		CK(cudaFuncSetAttribute(k_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
 		mid_fast_attr<0>(); mid_fast_attr<1>(); mid_fast_attr<2>(); mid_fast_attr<3>(); mid_fast_attr<4>(); mid_fast_attr<5>(); mid_fast_attr<6>(); mid_fast_attr<7>();
@@ -388,12 +432,32 @@ struct CudaBackend
 		progs.push_back(d); prog_len.push_back((u32)ops.size());
 		return (int)progs.size() - 1;
 	}
-	void prog_launch(int id, ProgArgs A, u32 thr, size_t smem, u32 batch = 1)
+	void prog_launch(int id, ProgArgs A, u32 batch = 1)
 	{
 		if (id < 0 || (size_t)id >= progs.size()) throw std::runtime_error("marin_b200: unknown graph id");
 		use();
 		A.ops = progs[(size_t)id]; A.nops = prog_len[(size_t)id];
-		k_program<<<batch, thr, smem, st>>>(A); post();
+		if (A.nops == 0) return;
+		// warp groups shorten one slab's chain of ops; a batch that no longer fits the GPU in ONE wave of CTAs with them
+		// (hundreds of ECM curves) is after throughput instead: fewer groups per CTA, more CTAs resident
+		u32 g = A.groups;
+		while (g > 1 && (uint64_t)prog_resident_ctas(g, A.group_threads, A.group_smem) < batch) g >>= 1;
+		A.groups = g;
+		k_program<<<batch, g * A.group_threads, (size_t)g * A.group_smem, st>>>(A); post();
+	}
+	int sm_count = 0;
+	u32 occ_key[PROG_MAX_GROUPS + 1] = {0, 0, 0, 0, 0}, occ_val[PROG_MAX_GROUPS + 1] = {0, 0, 0, 0, 0};
+	u32 prog_resident_ctas(u32 g, u32 thr, u32 smem)
+	{
+		const u32 key = thr * 65536u + smem / 16u + 1u;
+		if (occ_key[g] != key)
+		{
+			int nb = 0;
+			if (!sm_count) CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program, (int)(g * thr), (size_t)g * smem));
+			occ_key[g] = key; occ_val[g] = (u32)nb * (u32)sm_count;
+		}
+		return occ_val[g];
 	}
 
 	void use() { CK(cudaSetDevice(dev)); }

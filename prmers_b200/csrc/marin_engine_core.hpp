@@ -4,6 +4,7 @@
 // and launches: the CUDA backend in marin_engine.cu is the product; tests/emu instantiates the same
 // template with a CPU emulator of the kernels to check the host logic without a GPU.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -11,6 +12,141 @@
 #include "marin_plan.hpp"
 
 namespace marin {
+
+// Schedule of a recorded op sequence (k_program), two steps.
+// (1) Renaming.  The schedules of the callers reuse one scratch register over and over (the Edwards formulas of ECM:
+// set_multiplicand(11, x); mul(., 11) five times in a point addition), which chains otherwise independent products one
+// behind the other.  A LIFETIME of register r starts at an op that writes r without reading it (copy, set_multiplicand
+// from another register, set) and ends at the last read before the next such op.  The first lifetime of r holds
+// what the caller put there, the last one what the caller finds there afterwards; the ones in between are the engine's
+// business, and each moves to one of `nhidden` registers behind the caller's (index nregs + h) that is free at that point
+// of the recorded order, if there is one.
+// (2) List scheduling over G warp groups.  Op i must wait for every earlier op it conflicts with -- it reads a register
+// that op writes, writes one that op reads, or both write the same one; nothing else orders two ops.  With the measured
+// cost of an op inside the kernel (a transform with its carry ~ 4.5 us at the ECM sizes, a forward transform alone ~ 2.5,
+// a linear op ~ 1) the ops go, longest remaining chain first, to the group that can start them earliest.  An Edwards
+// doubling (23 ops, 65 us one after the other) has a critical chain of 8 ops.
+// Output: the ops in start-time order with their group and, per other group, the number of that group's ops that must be
+// complete before the op starts (a group runs its own ops in list order).
+struct ProgRW { u32 w, r0, r1; };                     // register written, registers read (~0u = none)
+inline ProgRW prog_rw(const ProgOp &o)
+{
+	switch (o.code & PO_CODE_MASK)
+	{
+		case PO_COPY: case PO_SETMUL: return ProgRW{o.dst, o.src, ~0u};
+		case PO_SQR: case PO_SUBSMALL: return ProgRW{o.dst, o.dst, ~0u};
+		case PO_SETSMALL: return ProgRW{o.dst, ~0u, ~0u};
+		default: return ProgRW{o.dst, o.dst, o.src};      // PO_MUL, PO_ADD, PO_SUBREG
+	}
+}
+inline bool prog_pure_def(const ProgOp &o)
+{
+	const u32 c = o.code & PO_CODE_MASK;
+	return c == PO_SETSMALL || ((c == PO_COPY || c == PO_SETMUL) && o.dst != o.src);
+}
+inline u32 prog_cost(const ProgOp &o)
+{
+	const u32 c = o.code & PO_CODE_MASK;
+	return (c == PO_SQR || c == PO_MUL) ? 45u : ((c == PO_SETMUL) ? 25u : 10u);
+}
+
+inline std::vector<ProgOp> schedule_program(const std::vector<ProgOp> &recorded, u32 nregs = 0, u32 nhidden = 0, u32 G = PROG_MAX_GROUPS)
+{
+	std::vector<ProgOp> ops = recorded;
+	const size_t k = ops.size();
+	for (ProgOp &o : ops) { o.code &= PO_CODE_MASK; for (u32 g = 0; g < PROG_MAX_GROUPS; ++g) o.wait[g] = 0; }
+	if (k > 4096 || G <= 1) return ops;                  // one group, recorded order (the conflict search below is quadratic)
+	if (G > PROG_MAX_GROUPS) G = PROG_MAX_GROUPS;
+	if (nhidden)
+	{
+		std::vector<size_t> busy_until(nhidden, 0);       // hidden register h is free for a lifetime that starts after this op index
+		std::vector<bool> used(nhidden, false);
+		for (size_t i = 0; i < k; ++i)
+		{
+			if (!prog_pure_def(ops[i]) || ops[i].dst >= nregs) continue;
+			const u32 r = ops[i].dst;
+			// the lifetime that op i starts: up to the next pure definition of r (none: it is the last one and stays in r)
+			size_t next_def = k, last_use = i;
+			for (size_t j = i + 1; j < k; ++j)
+			{
+				if (prog_pure_def(ops[j]) && ops[j].dst == r) { next_def = j; break; }
+				const ProgRW b = prog_rw(ops[j]);
+				if (b.w == r || b.r0 == r || b.r1 == r) last_use = j;
+			}
+			if (next_def == k) continue;
+			// the free hidden register that has been idle longest: a fresh one does not tie this lifetime to the last one's readers
+			u32 h = nhidden;
+			for (u32 c = 0; c < nhidden; ++c)
+				if (!used[c]) { h = c; break; }
+				else if (busy_until[c] < i && (h == nhidden || busy_until[c] < busy_until[h])) h = c;
+			if (h == nhidden) continue;
+			used[h] = true; busy_until[h] = last_use;
+			const u32 nr = nregs + h;
+			// every reference to r from op i to last_use is a reference to this lifetime
+			for (size_t j = i; j <= last_use; ++j)
+			{
+				if (ops[j].dst == r) ops[j].dst = nr;
+				if (ops[j].src == r) ops[j].src = nr;
+			}
+		}
+	}
+	// conflicts, and the length of the longest chain of ops that hangs on each op
+	std::vector<std::vector<u32>> pred(k);
+	std::vector<u32> chain(k), npend(k, 0);
+	for (size_t i = 0; i < k; ++i)
+	{
+		const ProgRW a = prog_rw(ops[i]);
+		for (size_t j = 0; j < i; ++j)
+		{
+			const ProgRW b = prog_rw(ops[j]);
+			const bool raw = (a.r0 == b.w || a.r1 == b.w), waw = (a.w == b.w), war = (a.w == b.r0 || a.w == b.r1);
+			if (raw || waw || war) pred[i].push_back((u32)j);
+		}
+		chain[i] = prog_cost(ops[i]);
+	}
+	for (size_t i = k; i-- > 0;)
+		for (u32 j : pred[i]) if (chain[j] < prog_cost(ops[j]) + chain[i]) chain[j] = prog_cost(ops[j]) + chain[i];
+	std::vector<u32> start(k, 0), finish(k, 0), grp(k, 0), pos(k, 0), gfree(G, 0), gcount(G, 0);
+	std::vector<bool> done(k, false);
+	std::vector<u32> order;
+	order.reserve(k);
+	for (size_t step = 0; step < k; ++step)
+	{
+		// among the ops whose predecessors are all placed: the one that can start first, the longest chain on a tie
+		size_t best = k; u32 best_start = 0, best_g = 0;
+		for (size_t i = 0; i < k; ++i)
+		{
+			if (done[i]) continue;
+			u32 ready = 0, home = 0; bool ok = true;
+			for (u32 j : pred[i]) { if (!done[j]) { ok = false; break; } if (finish[j] >= ready) { ready = finish[j]; home = grp[j]; } }
+			if (!ok) continue;
+			// the group that can start it first; on a tie the group of the op it waits for longest (no hand-off between groups)
+			u32 g = 0, st = ~0u;
+			for (u32 c = 0; c < G; ++c) { const u32 s0 = (gfree[c] > ready) ? gfree[c] : ready; if (s0 < st || (s0 == st && c == home && !pred[i].empty())) { st = s0; g = c; } }
+			if (best == k || st < best_start || (st == best_start && chain[i] > chain[best])) { best = i; best_start = st; best_g = g; }
+		}
+		const size_t i = best;
+		done[i] = true; start[i] = best_start; finish[i] = best_start + prog_cost(ops[i]); grp[i] = best_g;
+		gfree[best_g] = finish[i]; pos[i] = gcount[best_g]++;
+		order.push_back((u32)i);
+	}
+	// start-time order (placement order is not: an op with a long chain may be placed before an earlier-starting one of
+	// another group); a group's own ops keep their order, and every predecessor starts before its successor
+	std::stable_sort(order.begin(), order.end(), [&](u32 x, u32 y) { return start[x] < start[y]; });
+	// positions inside the groups follow the sorted list
+	std::fill(gcount.begin(), gcount.end(), 0u);
+	for (u32 i : order) pos[i] = gcount[grp[i]]++;
+	std::vector<ProgOp> out;
+	out.reserve(k);
+	for (u32 i : order)
+	{
+		ProgOp o = ops[i];
+		o.code |= grp[i] << PO_GROUP_SHIFT;
+		for (u32 j : pred[i]) if (grp[j] != grp[i] && o.wait[grp[j]] < pos[j] + 1) o.wait[grp[j]] = (unsigned short)(pos[j] + 1);
+		out.push_back(o);
+	}
+	return out;
+}
 
 template <class Backend> class EngineCore
 {
@@ -40,6 +176,7 @@ public:
 		_carry = (u64 *)dev_alloc(_batch * ncarry * 8);
 		_carry2 = (u64 *)dev_alloc(_batch * ncarry * 8);
 		_scratch = (u64 *)dev_alloc(n * 8);
+		if (pl.small) { _hid = (u64 *)dev_alloc(_batch * PROG_HIDDEN * n * 8); be.memset0(_hid, _batch * PROG_HIDDEN * n * 8); } // recorded programs: renamed lifetimes
 		_canon_D = (n % 16 == 0) ? 16 : ((n % 8 == 0) ? 8 : 4);
 		_cc[0] = (u64 *)dev_alloc((n / _canon_D) * 8); _cc[1] = (u64 *)dev_alloc((n / _canon_D) * 8);
 		_words = (u32 *)dev_alloc(16); be.memset0(_words, 16);   // [0], [1] carries still pending after a canon round, [2] comparison flags
@@ -119,8 +256,10 @@ public:
 	{
 		if (!_recording) throw std::runtime_error("marin_b200: graph_end without graph_begin");
 		_recording = false;
-		return be.prog_upload(_rec);
+		return be.prog_upload(schedule_program(_rec, (u32)_regs, PROG_HIDDEN, prog_groups()));
 	}
+	// warp groups of a program launch: 4, 4, 2, 1 for groups of 64, 128, 256, 512 threads (a power of two; the CTA has 512 threads at most)
+	u32 prog_groups() const { const u32 thr = pl.thrMid < 64 ? 64 : pl.thrMid; u32 g = 1; while (2 * g <= PROG_MAX_GROUPS && 2 * g * thr <= 512) g *= 2; return g; }
 	void graph_launch(int id)
 	{
 		blocking("graph_launch");
@@ -129,7 +268,14 @@ public:
 		A.M = mid_args(nullptr, nullptr, nullptr, MODE_SQR, 1);
 		A.reg = _reg; A.D = pl.D; A.carry = _carry;
 		A.slab_words = (u32)slab_words(); A.slab_carry = (u32)_ncarry;
-		be.prog_launch(id, A, pl.thrMid < 64 ? 64 : pl.thrMid, mid_smem(), _batch);
+		A.hid = _hid; A.nregs = (u32)_regs; A.nhid = PROG_HIDDEN;
+		// warp groups: the independent ops of a level side by side, each group with its own scratch in shared memory
+		// (the transform buffer doubles as the carry words of the linear ops: one per pair <= the buffer's 2 S words)
+		A.group_threads = pl.thrMid < 64 ? 64 : pl.thrMid;
+		A.groups = prog_groups();
+		A.err = _flags + (size_t)(pl.R2 * pl.S / TILE_C);
+		A.group_smem = (u32)((mid_smem() + 15) / 16 * 16);
+		be.prog_launch(id, A, _batch);
 	}
 
 	void set_u32(size_t dst, u32 a)
@@ -467,6 +613,7 @@ private:
 	size_t _regs;
 	u32 _batch = 1; size_t _ncarry = 0;
 	void check_slab(u32 slab) const { if (slab >= _batch) throw std::runtime_error("marin_b200: slab index out of range"); }
+	u64 *_hid = nullptr;
 	u64 *_reg = nullptr, *_carry = nullptr, *_carry2 = nullptr, *_scratch = nullptr, *_scratch2 = nullptr, *_cc[2] = {nullptr, nullptr}, *_cc2[2] = {nullptr, nullptr};
 	u32 *_words = nullptr, _canon_D = 16;
 	pair_t *_slots = nullptr; size_t _nslots = 0;
@@ -504,7 +651,7 @@ private:
 
 	bool _recording = false;
 	std::vector<ProgOp> _rec;
-	bool rec(u32 code, size_t dst, size_t src, u32 a) { if (!_recording) return false; _rec.push_back(ProgOp{code, (u32)dst, (u32)src, a}); return true; }
+	bool rec(u32 code, size_t dst, size_t src, u32 a) { if (!_recording) return false; _rec.push_back(ProgOp{code, (u32)dst, (u32)src, a, {0, 0, 0, 0}}); return true; }
 	size_t mid_smem() const { return (size_t)smem_pairs_lin(pl.S) * 16 + (pl.small ? ((size_t)pl.n / pl.D) * 8 : 0); }
 	void blocking(const char *what) const { if (_recording) throw std::runtime_error(std::string("marin_b200: ") + what + " is not allowed while a graph is being recorded"); }
 	void check_range(size_t r) const { if (r >= _regs) throw std::runtime_error("marin_b200: register index out of range"); }

@@ -496,21 +496,27 @@ template <bool INV> HD void dispatch_stage_lin(const View &in, const View &out, 
 
 // ---- contiguous pass -------------------------------------------------------------------------
 // phases: 0 .. nst-1 forward stages (the last has s = 1: no twiddles), nst pointwise on pairs,
-// nst+1 .. 2 nst inverse stages, then for single-CTA engines: carry, absorb + store.
-HD u32 mid_num_phases(const MidArgs &A) { return (A.mode == MODE_FWD) ? A.nst : (2 * A.nst + 1 + (A.small ? 2 : 0)); }
+// nst+1 .. 2 nst inverse stages, then for single-CTA engines: unweight, carry, absorb, re-weight + store.
+// What differs from op to op on one engine, apart from the tables and stages of MidArgs: a recorded program (k_program)
+// keeps ONE MidArgs in the kernel's parameter space (constant bank) and hands the registers of each op in here, instead
+// of rewriting an argument block in shared memory per op and reading every field of it through LDS.
+struct MidOp { pair_t *x; const pair_t *y; pair_t *dst; int mode; u32 a; };
+HD MidOp mid_op_of(const MidArgs &A) { return MidOp{A.x, A.y, A.dst, A.mode, A.a}; }
+HD u32 mid_num_phases(const MidArgs &A, int mode) { return (mode == MODE_FWD) ? A.nst : (2 * A.nst + 1 + (A.small ? 4 : 0)); }
+HD u32 mid_num_phases(const MidArgs &A) { return mid_num_phases(A, A.mode); }
 
-HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc)
+HD void mid_phase(const MidArgs &A, const MidOp &o, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc)
 {
 	const Tables &t = A.t;
 	const u32 S = A.S, nst = A.nst;
-	pair_t *xg = A.x + (size_t)blk * S;
+	pair_t *xg = o.x + (size_t)blk * S;
 	const View G = view_global(xg, 0, 1, 0), Sv = view_lin(sm, 0);
 	if (ph < nst)
 	{
 		const Stage &sg = A.st[ph];
 		const Tw tw{(sg.s > 1) ? t.twS + sg.toff : nullptr, sg.s};
-		const View Gd = view_global(A.dst + (size_t)blk * S, 0, 1, 0);
-		dispatch_stage_lin<false>((ph == 0) ? G : Sv, (A.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
+		const View Gd = view_global(o.dst + (size_t)blk * S, 0, 1, 0);
+		dispatch_stage_lin<false>((ph == 0) ? G : Sv, (o.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
 	if (ph == nst)
@@ -522,7 +528,7 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 			const u64 cr = t.colroot[i];
 			const u64 u = A.use_rowroot ? gl::mul(rr, cr) : cr;
 			pair_t &v = sm[lin_pair(i)];
-			v = (A.mode == MODE_SQR) ? sqr22(v, u) : mul22(v, A.y[(size_t)blk * S + i], u);
+			v = (o.mode == MODE_SQR) ? sqr22(v, u) : mul22(v, o.y[(size_t)blk * S + i], u);
 		}
 		return;
 	}
@@ -534,45 +540,60 @@ HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *
 		dispatch_stage_lin<true>(Sv, (si == 0 && !A.small) ? G : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
-	// ---- small engines only: whole register is in shared memory (natural order)
+	// ---- small engines only: whole register is in shared memory (natural order).  Four phases: unweight (every thread,
+	// a pair each), carry (one thread per run of D digits: additions only), absorb the carry of the run before (the same
+	// thread, four digits), re-weight and store (every thread).  With the multiplications inside the per-run loops a
+	// thread did 2 D of them one after the other while most of the CTA idled: at the ECM sizes that was a third of an op.
 	const u32 D = A.D, nruns = t.n / D;
 	if (ph == 2 * nst + 1)
+	{
+		for (u32 i = tid; i < S; i += nthr)
+		{
+			pair_t pv = sm[lin_pair(i)];
+			pv.x = gl::mul(pv.x, t.winvs_nat[2 * i]); pv.y = gl::mul(pv.y, t.winvs_nat[2 * i + 1]);
+			if (A.add_src)
+			{
+				const pair_t av = A.add_src[i];
+				pv.x = gl::add(pv.x, gl::mul(av.x, t.winv_nat[2 * i])); pv.y = gl::add(pv.y, gl::mul(av.y, t.winv_nat[2 * i + 1]));
+			}
+			sm[lin_pair(i)] = pv;
+		}
+		return;
+	}
+	if (ph == 2 * nst + 2)
 	{
 		for (u32 r = tid; r < nruns; r += nthr)
 		{
 			u64 v[MAXRUN];
 			const u32 j0 = r * D;
-			for (u32 i = 0; i < D; i += 2)
-			{
-				const pair_t pv = sm[lin_pair((j0 + i) >> 1)];
-				v[i] = gl::mul(pv.x, t.winvs_nat[j0 + i]);
-				v[i + 1] = gl::mul(pv.y, t.winvs_nat[j0 + i + 1]);
-				if (A.add_src)
-				{
-					const pair_t av = A.add_src[(j0 + i) >> 1];
-					v[i] = gl::add(v[i], gl::mul(av.x, t.winv_nat[j0 + i])); v[i + 1] = gl::add(v[i + 1], gl::mul(av.y, t.winv_nat[j0 + i + 1]));
-				}
-			}
-			smc[r] = carry_run(v, D, t.wbase, run_bits(t, j0, D), A.a, 0);
+			for (u32 i = 0; i < D; i += 2) { const pair_t pv = sm[lin_pair((j0 + i) >> 1)]; v[i] = pv.x; v[i + 1] = pv.y; }
+			smc[r] = carry_run(v, D, t.wbase, run_bits(t, j0, D), o.a, 0);
 			for (u32 i = 0; i < D; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; sm[lin_pair((j0 + i) >> 1)] = pv; }
 		}
 		return;
 	}
-	for (u32 r = tid; r < nruns; r += nthr)
+	if (ph == 2 * nst + 3)
 	{
-		u64 v[MAXRUN];
-		const u32 j0 = r * D;
-		for (u32 i = 0; i < D; i += 2) { const pair_t pv = sm[lin_pair((j0 + i) >> 1)]; v[i] = pv.x; v[i + 1] = pv.y; }
-		carry_absorb(v, (D < 4) ? D : 4, t.wbase, run_bits(t, j0, D), smc[(r == 0) ? nruns - 1 : r - 1]);
-		for (u32 i = 0; i < D; i += 2)
+		for (u32 r = tid; r < nruns; r += nthr)
 		{
-			pair_t pv;
-			pv.x = gl::mul(v[i], t.w_nat[j0 + i]); pv.y = gl::mul(v[i + 1], t.w_nat[j0 + i + 1]);
-			xg[(j0 + i) >> 1] = pv;
-			if (A.dst2) A.dst2[(j0 + i) >> 1] = pv;
+			u64 v[4];
+			const u32 j0 = r * D, na = (D < 4) ? D : 4;
+			for (u32 i = 0; i < na; i += 2) { const pair_t pv = sm[lin_pair((j0 + i) >> 1)]; v[i] = pv.x; v[i + 1] = pv.y; }
+			carry_absorb(v, na, t.wbase, run_bits(t, j0, D), smc[(r == 0) ? nruns - 1 : r - 1]);
+			for (u32 i = 0; i < na; i += 2) { pair_t pv; pv.x = v[i]; pv.y = v[i + 1]; sm[lin_pair((j0 + i) >> 1)] = pv; }
 		}
+		return;
+	}
+	for (u32 i = tid; i < S; i += nthr)
+	{
+		pair_t pv = sm[lin_pair(i)];
+		pv.x = gl::mul(pv.x, t.w_nat[2 * i]); pv.y = gl::mul(pv.y, t.w_nat[2 * i + 1]);
+		xg[i] = pv;
+		if (A.dst2) A.dst2[i] = pv;
 	}
 }
+
+HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc) { mid_phase(A, mid_op_of(A), blk, ph, tid, nthr, sm, smc); }
 
 // ---- strided passes ----------------------------------------------------------------------------
 // Tile = R rows x TILE_C (4) pair columns (64-byte row segments); butterfly id b -> lane b & 1, column (b >> 1) & 3, row-butterfly b >> 3.
@@ -1006,7 +1027,15 @@ HD u32 canon_cmp_digit(u64 el, u64 er)
 
 // ---- recorded op sequences for single-CTA engines ("programs"): one kernel launch runs the whole list ------------
 enum ProgCode : u32 { PO_COPY = 0, PO_SQR, PO_SETMUL, PO_MUL, PO_ADD, PO_SUBREG, PO_SUBSMALL, PO_SETSMALL };
-struct ProgOp { u32 code, dst, src, a; };
+// A program is stored as a list schedule over up to PROG_MAX_GROUPS warp groups (marin_engine_core.hpp,
+// schedule_program): the list is in start-time order, every op names its group (bits 8-9 of `code`) and, per group, how
+// many ops of that group must have finished before it may start (`wait`: the ops it conflicts with -- a register one of
+// them writes and the other reads or writes).  A group runs its own ops in list order; the groups meet nowhere else.
+static constexpr u32 PO_CODE_MASK = 0xffu, PO_GROUP_SHIFT = 8;
+static constexpr u32 PROG_MAX_GROUPS = 4;   // warp groups of k_program (named barriers 1 .. 4)
+struct ProgOp { u32 code, dst, src, a; unsigned short wait[PROG_MAX_GROUPS]; };
+static_assert(sizeof(ProgOp) == 24, "ProgOp is copied as three 64-bit words");
+static constexpr u32 PROG_SMEM_OPS = 128;   // programs up to this length are staged in shared memory by k_program
 struct ProgArgs
 {
 	MidArgs M;          // tables and stages of the engine; x / y / dst / mode / a are set per op
@@ -1015,7 +1044,12 @@ struct ProgArgs
 	u32 D;              // digits per run of the set-small path
 	u64 *carry;         // one word per run (set-small), one per pair (linear ops)
 	u32 slab_words, slab_carry; // batched engines: CTA x of the grid runs the program on slab x
+	u32 groups, group_threads, group_smem; // warp groups per CTA, threads and bytes of dynamic shared memory of each
+	u32 *err;                   // the engine's sticky device error word
+	u64 *hid; u32 nregs, nhid;  // registers nregs .. nregs + nhid - 1 of a program are the engine's own (renamed lifetimes), nhid per slab
 };
+static constexpr u32 PROG_HIDDEN = 4;
+HD u64 *prog_reg(const ProgArgs &A, u64 *reg, u64 *hid, u32 r) { return (r < A.nregs) ? reg + (size_t)r * A.M.t.n : hid + (size_t)(r - A.nregs) * A.M.t.n; }
 
 // batched engines: the argument block of CTA `y`, every register pointer moved to slab y
 HD MidArgs slab_of(const MidArgs &A, u32 y)

@@ -47,7 +47,7 @@ def lib():
                      ("emu_set_multiplicand", [vp, sz, sz]), ("emu_mul", [vp, sz, sz, u32]), ("emu_add_multiplicand", [vp, sz, sz, sz]), ("emu_sub_u32", [vp, sz, u32]),
                      ("emu_add", [vp, sz, sz]), ("emu_sub_reg", [vp, sz, sz]), ("emu_get_digits", [vp, sz, vp]),
                      ("emu_set_digits", [vp, sz, vp]), ("emu_equal", [vp, sz, sz, vp]), ("emu_graph_begin", [vp]),
-                     ("emu_graph_end", [vp, vp]), ("emu_graph_launch", [vp, C.c_int]),
+                     ("emu_graph_end", [vp, vp]), ("emu_graph_launch", [vp, C.c_int]), ("emu_graph_shape", [vp, C.c_int, vp, vp]),
                      ("emu_addsub", [vp, sz, sz, sz, sz]), ("emu_addsub_copy", [vp, sz, sz, sz, sz, sz, sz]),
                      ("emu_square_mul_copy", [vp, sz, sz, u32]), ("emu_mul_copy", [vp, sz, sz, sz, u32]),
                      ("emu_mul_add", [vp, sz, sz, sz, u32])):
@@ -106,6 +106,11 @@ class EmuEngine:
         return gid.value
 
     def graph_launch(self, gid): self._ck(lib().emu_graph_launch(self._h, gid))
+
+    def graph_shape(self, gid):
+        lv, ops = C.c_int(0), C.c_int(0)
+        self._ck(lib().emu_graph_shape(self._h, gid, C.byref(lv), C.byref(ops)))
+        return lv.value, ops.value
 
     def get_checkpoint_size(self): return lib().emu_checkpoint_size(self._h)
 

@@ -110,17 +110,50 @@ struct CpuBackend
 	// recorded op sequences: the emulated k_program -- the same op order, each op through the same phase functions
 	std::vector<std::vector<ProgOp>> progs;
 	int prog_upload(const std::vector<ProgOp> &ops) { progs.push_back(ops); return (int)progs.size() - 1; }
-	void prog_launch(int id, ProgArgs A0, u32 thr, size_t smem, u32 batch = 1)
+	// The device runs the groups of a program side by side, ordered by nothing but the `wait` counts of the ops
+	// (schedule_program).  Here the groups are played in an order as far from the recorded one as those counts allow: the
+	// LAST group that can move runs as far as it can, then the one before it, ... -- a conflict the scheduler failed to
+	// turn into a wait changes the registers.  A program that cannot make progress is an error.
+	void prog_launch(int id, ProgArgs A0, u32 batch = 1)
 	{
 		if (id < 0 || (size_t)id >= progs.size()) throw std::runtime_error("marin_b200: unknown graph id");
 		const u32 n = A0.M.t.n, npairs = n / 2;
+		const u32 thr = A0.group_threads;
+		const size_t smem = A0.group_smem;
+		std::vector<ProgOp> order;
+		{
+			const std::vector<ProgOp> &pr = progs[(size_t)id];
+			std::vector<size_t> next(PROG_MAX_GROUPS, 0);       // per group: index into pr of the next op to look at
+			u32 done[PROG_MAX_GROUPS] = {0, 0, 0, 0};
+			while (order.size() < pr.size())
+			{
+				bool moved = false;
+				for (u32 g = PROG_MAX_GROUPS; g-- > 0;)
+				{
+					for (;;)
+					{
+						size_t q = next[g];
+						while (q < pr.size() && ((pr[q].code >> PO_GROUP_SHIFT) & (PROG_MAX_GROUPS - 1)) != g) ++q;
+						next[g] = q;
+						if (q == pr.size()) break;
+						bool ok = true;
+						for (u32 c = 0; c < PROG_MAX_GROUPS; ++c) if (done[c] < pr[q].wait[c]) ok = false;
+						if (!ok) break;
+						ProgOp o = pr[q]; o.code &= PO_CODE_MASK; order.push_back(o);
+						++done[g]; ++next[g]; moved = true;
+					}
+				}
+				if (!moved) throw std::runtime_error("marin_b200 emulator: the program schedule deadlocks");
+			}
+		}
 		for (u32 y = 0; y < batch; ++y)
-		for (const ProgOp &op : progs[(size_t)id])
+		for (const ProgOp &op : order)
 		{
 			ProgArgs A = A0;
 			A.reg += (size_t)y * A0.slab_words; A.carry += (size_t)y * A0.slab_carry; A.M.carry = A.carry; A.M.slab_pairs = 0;
-			u64 *dst = A.reg + (size_t)op.dst * n;
-			const u64 *src = A.reg + (size_t)op.src * n;
+			u64 *const hid = A0.hid + (size_t)y * A0.nhid * n;
+			u64 *dst = prog_reg(A0, A.reg, hid, op.dst);
+			const u64 *src = prog_reg(A0, A.reg, hid, op.src);
 			LinArgs L{A.M.t, dst, src, nullptr, A.carry, 0, op.a, A.D};
 			switch (op.code)
 			{
@@ -216,6 +249,29 @@ int emu_set_digits(void *h, size_t d, const uint64_t *enc) { GUARD(((Emu *)h)->s
 int emu_graph_begin(void *h) { GUARD(((Emu *)h)->graph_begin()) }
 int emu_graph_end(void *h, int *id) { GUARD(*id = ((Emu *)h)->graph_end()) }
 int emu_graph_launch(void *h, int id) { GUARD(((Emu *)h)->graph_launch(id)) }
+// test aid: levels and ops of a stored program (schedule_program)
+int emu_graph_shape(void *h, int id, int *length, int *ops)
+{
+	// length of the stored schedule in the units of the scheduler's cost model (0.1 us): the start times replayed
+	try
+	{
+		const auto &pr = ((Emu *)h)->be.progs.at((size_t)id);
+		*ops = (int)pr.size();
+		std::vector<std::vector<unsigned>> fin(PROG_MAX_GROUPS);
+		unsigned gfree[PROG_MAX_GROUPS] = {0, 0, 0, 0}, end = 0;
+		for (const ProgOp &o : pr)
+		{
+			const unsigned g = (o.code >> PO_GROUP_SHIFT) & (PROG_MAX_GROUPS - 1);
+			unsigned st = gfree[g];
+			for (unsigned c = 0; c < PROG_MAX_GROUPS; ++c) if (o.wait[c]) st = std::max(st, fin[c].at(o.wait[c] - 1u));
+			const unsigned f = st + prog_cost(o);
+			fin[g].push_back(f); gfree[g] = f; end = std::max(end, f);
+		}
+		*length = (int)end;
+		return 1;
+	}
+	catch (const std::exception &e) { g_err = e.what(); return 0; }
+}
 int emu_equal(void *h, size_t l, size_t r, int *out) { GUARD(*out = ((Emu *)h)->equal(l, r) ? 1 : 0) }
 size_t emu_checkpoint_size(void *h) { Emu *e = (Emu *)h; return e->size() * 8 * e->regs() * e->batch(); }
 int emu_get_checkpoint(void *h, void *buf) { GUARD(((Emu *)h)->get_all(buf)) }
