@@ -169,6 +169,7 @@ __global__ void k_canon_cmp(const u64 *l, const u64 *r, u32 n, u32 *flags)
 // are a per-SM resource that limits how many curves' CTAs are resident)
 __device__ __forceinline__ void group_sync(u32 g, u32 gthr)
 {
+	if (gthr == 32) { __syncwarp(); return; }                  // a group of one warp
 	switch (g)
 	{
 		case 0: asm volatile("bar.sync 1, %0;" :: "r"(gthr) : "memory"); break;

@@ -258,8 +258,9 @@ public:
 		_recording = false;
 		return be.prog_upload(schedule_program(_rec, (u32)_regs, PROG_HIDDEN, prog_groups()));
 	}
-	// warp groups of a program launch: 4, 4, 2, 1 for groups of 64, 128, 256, 512 threads (a power of two; the CTA has 512 threads at most)
-	u32 prog_groups() const { const u32 thr = pl.thrMid < 64 ? 64 : pl.thrMid; u32 g = 1; while (2 * g <= PROG_MAX_GROUPS && 2 * g * thr <= 512) g *= 2; return g; }
+	// warp groups of a program launch: 4, 4, 4, 2, 1 for groups of 32, 64, 128, 256, 512 threads (a power of two; the CTA has 512 threads at most)
+	u32 prog_group_threads() const { return pl.thrMid < 32 ? 32 : pl.thrMid; }   // one warp per group up to n = 128: its barrier is a __syncwarp
+	u32 prog_groups() const { const u32 thr = prog_group_threads(); u32 g = 1; while (2 * g <= PROG_MAX_GROUPS && 2 * g * thr <= 512) g *= 2; return g; }
 	void graph_launch(int id)
 	{
 		blocking("graph_launch");
@@ -271,7 +272,7 @@ public:
 		A.hid = _hid; A.nregs = (u32)_regs; A.nhid = PROG_HIDDEN;
 		// warp groups: the independent ops of a level side by side, each group with its own scratch in shared memory
 		// (the transform buffer doubles as the carry words of the linear ops: one per pair <= the buffer's 2 S words)
-		A.group_threads = pl.thrMid < 64 ? 64 : pl.thrMid;
+		A.group_threads = prog_group_threads();
 		A.groups = prog_groups();
 		A.err = _flags + (size_t)(pl.R2 * pl.S / TILE_C);
 		A.group_smem = (u32)((mid_smem() + 15) / 16 * 16);
