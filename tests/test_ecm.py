@@ -291,15 +291,41 @@ def test_level_schedule_shapes_of_the_edwards_programs():
     assert shapes["dbl"][0] <= 200 and shapes["add+"][0] <= 210 and shapes["add-"][0] <= 210, shapes
 
 
+def test_long_programs_emulated():
+    """Programs longer than the shared-memory staging area of k_program (128 ops) and longer than the scheduler's limit
+    (4096 ops: recorded order, one group) replay like the direct calls."""
+    import random
+    p, regs = 701, 7
+    m = (1 << p) - 1
+    for count in (300, 3000):
+        a, b = EmuEngine(p, regs), EmuEngine(p, regs)
+        rng = random.Random(count)
+        for r in range(regs):
+            v = rng.randrange(m)
+            a.set_mpz(r, v); b.set_mpz(r, v)
+        a.set_multiplicand(regs - 1, 0); b.set_multiplicand(regs - 1, 0)
+        b.graph_begin()
+        _random_program(b, random.Random(5), regs, count)
+        g = b.graph_end()
+        assert b.graph_shape(g)[1] >= count
+        _random_program(a, random.Random(5), regs, count)
+        b.graph_launch(g)
+        for r in range(regs - 1):
+            assert a.get_mpz(r) == b.get_mpz(r), (count, r)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("p", [701, 9941])
-def test_level_schedule_of_recorded_programs_gpu(p):
-    """The same on the device (n = 32: four warp groups of 64 threads; n = 512: four of 128), batched and not."""
+@pytest.mark.parametrize("p,batches,count", [(701, (1, 3), 80), (9941, (1, 3), 80), (701, (1, 2500), 300), (40009, (1,), 3000)])
+def test_level_schedule_of_recorded_programs_gpu(p, batches, count):
+    """The same on the device (n = 32: four warp groups of one warp; n = 512: four of 128 threads; n = 2048: one of 512),
+    batched and not; 2500 slabs do not fit the GPU in one wave with four groups per CTA, so the launch shares the
+    schedule's groups among fewer (k_program: group of the schedule modulo groups of the launch); 300 ops are read from
+    global memory instead of the staging area, 3000 recorded calls (> 4096 ops) run in recorded order on one group."""
     import random
     import prmers_b200 as pb
     regs = 7
     m = (1 << p) - 1
-    for batch in (1, 3):
+    for batch in batches:
         a, b = pb.Engine(p, regs, batch=batch), pb.Engine(p, regs, batch=batch)
         rng = random.Random(7)
         for s in range(batch):
@@ -308,12 +334,12 @@ def test_level_schedule_of_recorded_programs_gpu(p):
                 (a.slab(s) if batch > 1 else a).set_mpz(r, v); (b.slab(s) if batch > 1 else b).set_mpz(r, v)
         a.set_multiplicand(regs - 1, 0); b.set_multiplicand(regs - 1, 0)
         b.graph_begin()
-        _random_program(b, random.Random(11), regs, 80)
+        _random_program(b, random.Random(11), regs, count)
         g = b.graph_end()
-        for _ in range(3):
-            _random_program(a, random.Random(11), regs, 80)
+        for _ in range(3 if count <= 300 else 1):
+            _random_program(a, random.Random(11), regs, count)
             b.graph_launch(g)
-        for s in range(batch):
+        for s in (range(batch) if batch <= 8 else (0, 1, batch // 2, batch - 1)):
             va, vb = (a.slab(s), b.slab(s)) if batch > 1 else (a, b)
             for r in range(regs - 1):
                 assert va.get_mpz(r) == vb.get_mpz(r), (batch, s, r)
