@@ -224,14 +224,14 @@ def run_workload(args, rank, local_rank, world):
         eng.close()
         return
     # config 5: ECM on M701, B1 = 6000, B2 = 33333, K = 8 curves (twisted Edwards, default family), fixed seed; curve c on rank c mod world
-    # K = 8 is BASELINE's count (one launch now carries all 8: one CTA per curve); K = 592 fills the GPU (4 CTAs per SM)
+    # K = 8 is BASELINE's count (one launch now carries all 8: one CTA per curve); K = 740 fills the GPU (5 CTAs per SM)
     p, b1, b2, K, seed = 701, 6000, 33333, 8, 123456789
     bfactory = lambda q, regs, b: pb.Engine(q, regs, device=local_rank, batch=b)
     ecm.run_ecm(factory, p, b1, b2, curves=1, seed=seed, continue_after_factor=True)      # warm-up curve (tables, graphs)
     t0 = time.perf_counter()
     seq = ecm.run_ecm(factory, p, b1, b2, curves=K, seed=seed, continue_after_factor=True, curve_indices=multi.assign(list(range(K)), rank, world))
     dt_seq = multi.max_over_ranks(time.perf_counter() - t0, device=dev)
-    Kbig = 592 * world          # four CTAs of 128 threads and 128 registers per SM: the curves one wave of the GPU holds
+    Kbig = 740 * world          # five CTAs of 128 threads and 94 registers per SM: the curves one wave of the GPU holds
     t0 = time.perf_counter()
     big = ecm.run_ecm_sharded(factory, p, b1, b2, curves=Kbig, seed=seed, batch_engine_factory=bfactory)
     dt_big = multi.max_over_ranks(time.perf_counter() - t0, device=dev)

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ Prog
 			const MidOp o{(pair_t *)((code == PO_SETMUL) ? const_cast<u64 *>(src) : dst), (code == PO_MUL) ? (const pair_t *)src : nullptr, (pair_t *)dst,
 				(code == PO_SQR) ? MODE_SQR : ((code == PO_MUL) ? MODE_MUL : MODE_FWD), op.a};
 			const u32 nph = mid_num_phases(A.M, o.mode);
-			for (u32 ph = 0; ph < nph; ++ph) { mid_phase(A.M, o, 0, ph, tid, gthr, sm, smc); if (ph + 1 < nph) group_sync(grp, gthr); }
+			for (u32 ph = 0; ph < nph; ++ph) { mid_phase<true>(A.M, o, 0, ph, tid, gthr, sm, smc); if (ph + 1 < nph) group_sync(grp, gthr); }   // no radix-16 stage in a single-CTA engine
 			break;
 		}
 		case PO_ADD: case PO_SUBREG: case PO_SUBSMALL:

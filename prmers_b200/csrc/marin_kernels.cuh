@@ -483,11 +483,13 @@ template <int R, bool INV> HD void run_stage_lin(View in, View out, const Stage 
 	}
 }
 
-template <bool INV> HD void dispatch_stage_lin(const View &in, const View &out, const Stage &sg, const Tw &tw, u32 S, u32 tid, u32 nthr, const Tables &t)
+// NO16: the caller knows that the stage list holds no radix-16 stage (single-CTA engines: factor_stages gives them radix
+// 4 / 2 / 5 lists, marin_plan.hpp) and does without that butterfly's code and registers
+template <bool INV, bool NO16 = false> HD void dispatch_stage_lin(const View &in, const View &out, const Stage &sg, const Tw &tw, u32 S, u32 tid, u32 nthr, const Tables &t)
 {
 	switch (sg.radix)
 	{
-	case 16: run_stage_lin<16, INV>(in, out, sg, tw, S, tid, nthr, t); break;
+	case 16: if (!NO16) run_stage_lin<16, INV>(in, out, sg, tw, S, tid, nthr, t); break;
 	case 4: run_stage_lin<4, INV>(in, out, sg, tw, S, tid, nthr, t); break;
 	case 2: run_stage_lin<2, INV>(in, out, sg, tw, S, tid, nthr, t); break;
 	case 5: run_stage_lin<5, INV>(in, out, sg, tw, S, tid, nthr, t); break;
@@ -505,7 +507,7 @@ HD MidOp mid_op_of(const MidArgs &A) { return MidOp{A.x, A.y, A.dst, A.mode, A.a
 HD u32 mid_num_phases(const MidArgs &A, int mode) { return (mode == MODE_FWD) ? A.nst : (2 * A.nst + 1 + (A.small ? 4 : 0)); }
 HD u32 mid_num_phases(const MidArgs &A) { return mid_num_phases(A, A.mode); }
 
-HD void mid_phase(const MidArgs &A, const MidOp &o, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc)
+template <bool NO16 = false> HD void mid_phase(const MidArgs &A, const MidOp &o, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc)
 {
 	const Tables &t = A.t;
 	const u32 S = A.S, nst = A.nst;
@@ -516,7 +518,7 @@ HD void mid_phase(const MidArgs &A, const MidOp &o, u32 blk, u32 ph, u32 tid, u3
 		const Stage &sg = A.st[ph];
 		const Tw tw{(sg.s > 1) ? t.twS + sg.toff : nullptr, sg.s};
 		const View Gd = view_global(o.dst + (size_t)blk * S, 0, 1, 0);
-		dispatch_stage_lin<false>((ph == 0) ? G : Sv, (o.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
+		dispatch_stage_lin<false, NO16>((ph == 0) ? G : Sv, (o.mode == MODE_FWD && ph == nst - 1) ? Gd : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
 	if (ph == nst)
@@ -537,7 +539,7 @@ HD void mid_phase(const MidArgs &A, const MidOp &o, u32 blk, u32 ph, u32 tid, u3
 		const u32 si = 2 * nst - ph; // nst-1 .. 0
 		const Stage &sg = A.st[si];
 		const Tw tw{(sg.s > 1) ? t.twSi + sg.toff : nullptr, sg.s};
-		dispatch_stage_lin<true>(Sv, (si == 0 && !A.small) ? G : Sv, sg, tw, S, tid, nthr, t);
+		dispatch_stage_lin<true, NO16>(Sv, (si == 0 && !A.small) ? G : Sv, sg, tw, S, tid, nthr, t);
 		return;
 	}
 	// ---- small engines only: whole register is in shared memory (natural order).  Four phases: unweight (every thread,
@@ -593,7 +595,7 @@ HD void mid_phase(const MidArgs &A, const MidOp &o, u32 blk, u32 ph, u32 tid, u3
 	}
 }
 
-HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc) { mid_phase(A, mid_op_of(A), blk, ph, tid, nthr, sm, smc); }
+HD void mid_phase(const MidArgs &A, u32 blk, u32 ph, u32 tid, u32 nthr, pair_t *sm, u64 *smc) { mid_phase<false>(A, mid_op_of(A), blk, ph, tid, nthr, sm, smc); }
 
 // ---- strided passes ----------------------------------------------------------------------------
 // Tile = R rows x TILE_C (4) pair columns (64-byte row segments); butterfly id b -> lane b & 1, column (b >> 1) & 3, row-butterfly b >> 3.

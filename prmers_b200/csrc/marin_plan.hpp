@@ -55,6 +55,7 @@ struct Plan
 #define MARIN_R_SMALL_FIRST 0
 #endif
 
+static_assert(MARIN_SMALL_R4 >= SMALL_MAX_PAIRS, "k_program is compiled without the radix-16 stage: single-CTA engines must get radix-4 lists");
 inline u32 factor_stages(u32 len, Stage *st, bool sixteen_last, bool single_cta = false, bool force_r4 = false)
 {
 	// radices: optional 5 first, then 2, 4 and 16s (or 16s first) with product len
