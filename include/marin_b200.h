@@ -107,7 +107,11 @@ int mb200_is_single_cta(void *eng);
    clEnqueueNDRangeKernel per op, include/marin/engine_gpu.h:886-1248, which is all an ECM curve at n = 32 costs,
    src/modes/RunEcmTwistedEdwards.cpp:2717-2945).  Between graph_begin and graph_end the asynchronous ops (set_u32,
    copy, square_mul, set_multiplicand, mul, add, sub_reg, sub_u32 and their fused forms) are recorded, not run;
-   blocking calls fail.  graph_launch runs the recorded list inside one CTA (k_program).  Single-CTA engines
+   blocking calls fail.  graph_launch runs the recorded list inside one CTA (k_program): the engine orders the ops by
+   their register conflicts only and runs independent ones side by side on the warp groups of the CTA, so the registers
+   afterwards are those of the calls made one after the other, in less time (an Edwards doubling of 23 ops: 8 in a chain).
+   A register that the list overwrites completely more than once may live in an engine-private register in between;
+   its contents DURING a replay are unspecified, its contents afterwards are not.  Single-CTA engines
    (mb200_is_single_cta, n <= 2048: the ECM sizes) only. */
 int mb200_graph_begin(void *eng);
 int mb200_graph_end(void *eng, int *graph_id);
