@@ -194,12 +194,16 @@ __global__ void __launch_bounds__(512, 1) k_program(const __grid_constant__ Prog
 	// batched engines (one ECM curve per CTA): CTA x runs the same op list on its own slab of registers
 	u64 *const reg = A.reg + (size_t)blockIdx.x * A.slab_words, *const hid = A.hid + (size_t)blockIdx.x * A.nhid * A.M.t.n;
 	if (tid == 0) { sL.t = A.M.t; sL.carry = carry; sL.D = A.D; sL.digits = nullptr; sL.slab_words = 0; sL.srcA = nullptr; sL.dst2 = sL.cpy = sL.cpy2 = sL.carry2 = nullptr; }
+	// programmatic dependent launch: the next replay's CTA may become resident and stage its op list while this one runs;
+	// nothing a predecessor wrote (the registers) is touched before the wait below
+	MARIN_PDL_TRIGGER();
 	if (threadIdx.x < PROG_MAX_GROUPS) s_done[threadIdx.x] = 0;
 	// the op list itself: every group walks all of it (to find its own ops), so a short one is staged in shared memory
 	__shared__ ProgOp s_ops[PROG_SMEM_OPS];
 	const bool staged = A.nops <= PROG_SMEM_OPS;
 	if (staged)
 		for (u32 w = threadIdx.x; w < A.nops * (u32)(sizeof(ProgOp) / 8); w += blockDim.x) reinterpret_cast<u64 *>(s_ops)[w] = reinterpret_cast<const u64 *>(A.ops)[w];
+	MARIN_PDL_WAIT();
 	__syncthreads();
 	const ProgOp *const ops = staged ? s_ops : A.ops;
 	for (u32 q = 0; q < A.nops; ++q)
@@ -444,7 +448,7 @@ struct CudaBackend
 		u32 g = A.groups;
 		while (g > 1 && (uint64_t)prog_resident_ctas(g, A.group_threads, A.group_smem) < batch) g >>= 1;
 		A.groups = g;
-		k_program<<<batch, g * A.group_threads, (size_t)g * A.group_smem, st>>>(A); post();
+		launch_windowed(k_program, A, batch, g * A.group_threads, (size_t)g * A.group_smem); post();
 	}
 	int sm_count = 0;
 	u32 occ_key[PROG_MAX_GROUPS + 1] = {0, 0, 0, 0, 0}, occ_val[PROG_MAX_GROUPS + 1] = {0, 0, 0, 0, 0};
