@@ -108,6 +108,7 @@ class EmuEngine:
     def graph_launch(self, gid): self._ck(lib().emu_graph_launch(self._h, gid))
 
     def graph_shape(self, gid):
+        """(length of the stored schedule in the scheduler's cost units of 0.1 us, number of ops) of a recorded program."""
         lv, ops = C.c_int(0), C.c_int(0)
         self._ck(lib().emu_graph_shape(self._h, gid, C.byref(lv), C.byref(ops)))
         return lv.value, ops.value
