@@ -18,6 +18,11 @@ The other mode loops keep the reference's own field orders (all little endian, C
   ECM stage 1 (RunEcmTwistedEdwards.cpp:1866-1930): int32 version, uint32 p, uint32 step, uint32 bits of K, uint64 B1,
            float64 elapsed, uint64 curve seed, uint8 curve family, raw image.  The reference's file has no backend
            field, so the version word carries it here: 0x0301 (the reference accepts 1 only and skips the file).
+  ECM stage 2 (RunEcmTwistedEdwards.cpp:1940-2068, version 6): int32 version, uint32 p, uint32 index of the next stage-2
+           prime, uint32 number of stage-2 primes, uint64 B1, uint64 B2, uint64 curve seed, uint8 curve family, float64
+           elapsed, uint8 in_chunk, uint32 chunk start index, chunk end index, chunk bits, steps done inside the chunk,
+           uint8 has_base (+ six length-prefixed hex strings: X, Y, T of the affine base and of its negative), raw image.
+           Version word 0x0306 for the same reason (the reference accepts 2 ... 6).
 """
 import os
 import struct
@@ -219,3 +224,52 @@ def load_ecm(path, eng, p, k_bits, b1, curve_seed, family=None):
         if eng.set_checkpoint(bytearray(body[_ECM.size:])):
             return step
     return None
+
+
+ECM2_VERSION = 0x0306
+_ECM2 = struct.Struct("<iIIIQQQBdBIIIIB")
+
+
+def ecm2_checkpoint_name(p, c):
+    return f"ecm2_te_m_{p}_c{c}.ckpt"
+
+
+def save_ecm2(path, eng, p, idx, count, b1, b2, curve_seed, family=None, elapsed=0.0, chunk=None, base=None):
+    """Stage-2 state: `idx` = index of the next stage-2 prime (the start of the chunk at work when `chunk` is given),
+    `chunk` = (start index, end index, bits of the chunk scalar, steps done) when the scalar multiplication of a chunk was
+    interrupted, `base` = the six residues X, Y, T, -X, Y, -T of the affine base of that chunk (save_ckpt2_ex)."""
+    c = chunk or (0, 0, 0, 0)
+    head = _ECM2.pack(ECM2_VERSION, p, idx, count, b1, b2, curve_seed, ECM_FAMILY[family], float(elapsed),
+                      1 if chunk else 0, c[0], c[1], c[2], c[3], 1 if base else 0)
+    blobs = b"".join(_hexfield(v) for v in (base or ()))
+    _write_rotating(path, head + blobs + _raw(eng), keep_old=True)
+
+
+def load_ecm2(path, eng, p, count, b1, b2, curve_seed, family=None):
+    """{"idx", "elapsed", "chunk" (or None), "base" (or None)} with the registers restored, or None: other exponent,
+    bounds, prime count, curve, family or backend (read_ckpt2_one; the file, then `.old`)."""
+    size = eng.get_checkpoint_size()
+    for f in (path, path + ".old"):
+        body = _read_verified(f)
+        if body is None or len(body) < _ECM2.size + size:
+            continue
+        version, rp, idx, cnt, rb1, rb2, seed, fam, et, in_chunk, cs, ce, cb, cd, has_base = _ECM2.unpack_from(body)
+        if version != ECM2_VERSION or rp != p or cnt != count or rb1 != b1 or rb2 != b2 or seed != curve_seed or fam != ECM_FAMILY[family]:
+            continue
+        o, base = _ECM2.size, None
+        if has_base:
+            base = []
+            for _ in range(6):
+                (ln,) = struct.unpack_from("<I", body, o); o += 4
+                base.append(int(body[o:o + ln] or b"0", 16)); o += ln
+        if len(body) != o + size or not eng.set_checkpoint(bytearray(body[o:o + size])):
+            continue
+        return {"idx": idx, "elapsed": et, "chunk": (cs, ce, cb, cd) if in_chunk else None, "base": base}
+    return None
+
+
+def remove_ecm2(path):
+    """A finished stage 2 leaves no file behind (:3838-3846)."""
+    for f in (path, path + ".old", path + ".new"):
+        if os.path.exists(f):
+            os.remove(f)

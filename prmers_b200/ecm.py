@@ -524,13 +524,18 @@ def check_invariant(eng, p, aE, dE):
 
 
 def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None, torsion=None,
-              checkpoint_path=None, backup_every=0, stop_at=None):
+              checkpoint_path=None, backup_every=0, stop_at=None, checkpoint2_path=None, stop_at2=None, s2_bits=None):
     """One curve of RunEcmTwistedEdwards.cpp:1737-3859 on a 51-register engine.  Returns a dict with `status` in
     {"found", "NF", "singular", "nocurve", "invariant"}, `factor`, `stage` (0 = curve generation, 1, 2) and the final
     extended coordinates (for parity checks against a big-integer restatement of the same formulas).
     Stage-1 checkpoints (:1866-1937, :3090-3243): with `checkpoint_path` the scalar multiplication resumes from that file
     when it holds this exponent, bound, curve seed and family, saves every `backup_every` steps and, after `stop_at`
-    steps (the reference's SIGINT path), saves and returns status "interrupted"."""
+    steps (the reference's SIGINT path), saves and returns status "interrupted".
+    Stage-2 checkpoints (:1940-2078, :3092, :3640-3664, :3797-3822): with `checkpoint2_path` a stage 2 that a file of this
+    exponent, bounds, curve seed and family describes is resumed instead of running stage 1 again -- at a chunk boundary,
+    or inside a chunk at the saved step with the saved affine base; the state is saved after every chunk, every
+    `backup_every` steps inside a chunk and at `stop_at2` = (chunk number, steps) before returning "interrupted"; a
+    finished stage 2 removes the file.  `s2_bits` overrides the chunk size (tests)."""
     say = log or (lambda s: None)
     N = (1 << p) - 1
     res = {"curve_seed": curve_seed, "status": "NF", "factor": None, "stage": None, "n": eng.get_size()}
@@ -566,8 +571,16 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
             eng.sub(1, 2)
             say(f"Injected error at iteration {step}")
     start_step = 0
-    if checkpoint_path:
+    if checkpoint_path or checkpoint2_path:
         from . import checkpoint as ckpt
+    if b2 > b1 and primes_s2 is None:
+        primes_s2 = ecm_primes(b1, b2)[1]
+    resume2 = None
+    if checkpoint2_path and b2 > b1:
+        resume2 = ckpt.load_ecm2(checkpoint2_path, eng, p, len(primes_s2), b1, b2, curve_seed, torsion)
+        if resume2 is not None:
+            say(f"Resuming stage 2 at prime index {resume2['idx']}" + (f", step {resume2['chunk'][3]} of its chunk." if resume2["chunk"] else "."))
+    if checkpoint_path and resume2 is None:
         got = ckpt.load_ecm(checkpoint_path, eng, p, K.bit_length(), b1, curve_seed, torsion)
         if got is not None:
             start_step = got
@@ -584,11 +597,85 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
             if stop_at is not None and step == stop_at:
                 raise _Interrupted()
     try:
-        _scalar_mul(eng, ops, digits, on_step=on_step if (error_iter or checkpoint_path) else None, start_step=start_step)
+        if resume2 is None:
+            _scalar_mul(eng, ops, digits, on_step=on_step if (error_iter or checkpoint_path) else None, start_step=start_step)
     except _Interrupted:
         say(f"Interrupted by user, state saved at step {stop_at}")
         res.update(status="interrupted", stage=1, step=stop_at)
         return res
+    if resume2 is None:
+        early = _after_stage1(eng, p, N, aE, dE, ops, res, say)
+        if early is not None:
+            return early
+
+    if b2 > b1:
+        chunks = s2_chunks(primes_s2, s2_bits or s2_chunk_bits(eng.get_size()))
+        for ci, (i0, i1, echunk) in enumerate(chunks):
+            if resume2 is not None and i0 < resume2["idx"]:
+                continue                                         # chunks a saved state is already past
+            d2 = naf(echunk)
+            in_chunk = resume2 is not None and resume2["chunk"] is not None and resume2["chunk"][0] == i0
+            if in_chunk:
+                # the registers (point, base, multiplicands) are the saved ones; the saved base is what they were made from
+                base, step0 = resume2["base"], resume2["chunk"][3]
+            else:
+                # setup_te_stage2_base (:3542-3566): the current point, made affine, becomes the base
+                Xv, Yv, Zv = (_value(eng, r, p) for r in (3, 4, 1))
+                try:
+                    iz = _inv(Zv, N)
+                except FactorFound as f:
+                    res.update(status="found", factor=f.g, stage=2)
+                    return res
+                if iz is None:
+                    res.update(status="singular", stage=2)
+                    return res
+                Xa, Ya = Xv * iz % N, Yv * iz % N
+                Ta = Xa * Ya % N
+                base, step0 = [Xa, Ya, Ta, (N - Xa) % N, Ya, (N - Ta) % N], 0
+                _load_base(eng, p, N, Xa, Ya)
+                if d2:
+                    eng.set(1, 1)
+                    for dst, src in (((3, 47), (4, 48), (5, 49)) if d2[-1] < 0 else ((3, 6), (4, 7), (5, 9))):
+                        eng.copy(dst, src)
+            resume2 = None
+
+            def on_step2(step, ci=ci, i0=i0, i1=i1, nb=len(d2), base=base):
+                stop = stop_at2 is not None and stop_at2 == (ci, step)
+                if stop or (backup_every and step % backup_every == 0):
+                    ckpt.save_ecm2(checkpoint2_path, eng, p, i0, len(primes_s2), b1, b2, curve_seed, torsion, chunk=(i0, i1, nb, step), base=base)
+                    if stop:
+                        raise _Interrupted()
+            if d2:
+                try:
+                    _scalar_mul(eng, ops, d2, on_step=on_step2 if checkpoint2_path else None, start_step=step0)
+                except _Interrupted:
+                    say(f"Interrupted by user in stage 2, state saved at step {stop_at2[1]} of chunk {ci}")
+                    res.update(status="interrupted", stage=2, step=stop_at2[1], chunk=ci)
+                    return res
+            T = _value(eng, 5, p)
+            g = math.gcd(T, N)
+            res["stage2_T"] = T
+            res["point_ops"] = ops.ops
+            say(f"[ECM] Stage2 chunk end | next_prime_idx={i1} | gcd(T,N)={g}")
+            if g == N:
+                res.update(status="singular", stage=2)
+            elif g > 1:
+                res.update(status="found", factor=g, stage=2)
+            if res["status"] != "NF" or ci == len(chunks) - 1:
+                if checkpoint2_path:
+                    ckpt.remove_ecm2(checkpoint2_path)
+                return res
+            if checkpoint2_path:
+                ckpt.save_ecm2(checkpoint2_path, eng, p, i1, len(primes_s2), b1, b2, curve_seed, torsion)
+                if stop_at2 is not None and stop_at2 == (ci, None):
+                    say(f"Interrupted by user after stage-2 chunk {ci}")
+                    res.update(status="interrupted", stage=2, chunk=ci)
+                    return res
+    return res
+
+
+def _after_stage1(eng, p, N, aE, dE, ops, res, say):
+    """Invariant, gcd on T and the two inversions that end stage 1 (:3372-3413): the finished result, or None to go on."""
     if not check_invariant(eng, p, aE, dE):
         say("[ECM] invariant FAIL")
         res.update(status="invariant", stage=1, point_ops=ops.ops)
@@ -614,41 +701,7 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
     except FactorFound as f:
         res.update(status="found", factor=f.g, stage=1)
         return res
-
-    if b2 > b1:
-        if primes_s2 is None:
-            primes_s2 = ecm_primes(b1, b2)[1]
-        for (i0, i1, echunk) in s2_chunks(primes_s2, s2_chunk_bits(eng.get_size())):
-            # setup_te_stage2_base (:3542-3566): the current point, made affine, becomes the base
-            Xv, Yv, Zv = (_value(eng, r, p) for r in (3, 4, 1))
-            try:
-                iz = _inv(Zv, N)
-            except FactorFound as f:
-                res.update(status="found", factor=f.g, stage=2)
-                return res
-            if iz is None:
-                res.update(status="singular", stage=2)
-                return res
-            Xa, Ya = Xv * iz % N, Yv * iz % N
-            _load_base(eng, p, N, Xa, Ya)
-            d2 = naf(echunk)
-            if d2:
-                eng.set(1, 1)
-                for dst, src in (((3, 47), (4, 48), (5, 49)) if d2[-1] < 0 else ((3, 6), (4, 7), (5, 9))):
-                    eng.copy(dst, src)
-                _scalar_mul(eng, ops, d2)
-            T = _value(eng, 5, p)
-            g = math.gcd(T, N)
-            res["stage2_T"] = T
-            res["point_ops"] = ops.ops
-            say(f"[ECM] Stage2 chunk end | next_prime_idx={i1} | gcd(T,N)={g}")
-            if g == N:
-                res.update(status="singular", stage=2)
-                return res
-            if g > 1:
-                res.update(status="found", factor=g, stage=2)
-                return res
-    return res
+    return None
 
 
 def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), continue_after_factor=False,

@@ -166,3 +166,37 @@ def test_mode_loops_resume_from_their_checkpoints_emulated(tmp_path):
     r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, 300, 0, seed, checkpoint_path=path, log=log.append)
     assert (r["status"], r["factor"], r["stage1_T"]) == (whole["status"], whole["factor"], whole["stage1_T"]) and any("Resuming" in s for s in log)
     assert ecm.run_curve(EmuEngine(p, ecm.REGS), p, 300, 0, seed + 1, checkpoint_path=path, log=log.append)["status"] in ("NF", "found")   # another curve ignores the file
+
+
+def test_ecm_stage2_checkpoints_emulated(tmp_path):
+    """Stage 2 of a curve interrupted inside a chunk, inside a later chunk and at a chunk boundary resumes from the file
+    alone (fresh engine) to the result of the uninterrupted run; a finished stage 2 leaves no file; a file of another
+    curve is ignored (RunEcmTwistedEdwards.cpp:1940-2078, 3640-3664, 3797-3822)."""
+    from tests.emu.emu import EmuEngine
+    from prmers_b200 import ecm
+    p, b1, b2, bits = 701, 50, 400, 300
+    for seed_idx, expect in ((1, "NF"), (3, "found")):
+        seed = ecm.mix64(7, seed_idx)
+        whole = ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2, seed, s2_bits=bits)
+        assert whole["status"] == expect and (expect == "NF" or whole["stage"] == 2)
+        path = str(tmp_path / ck.ecm2_checkpoint_name(p, seed_idx))
+        for stop in ((0, 40), (1, 10), (0, None)):
+            if expect == "found" and stop[0] == 1 and whole["point_ops"] < 600:
+                continue                                     # the factor appears at the end of the first chunk
+            r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2, seed, s2_bits=bits, checkpoint2_path=path, backup_every=25, stop_at2=stop)
+            if r["status"] != "interrupted":
+                assert expect == "found" and (r["status"], r["factor"]) == (whole["status"], whole["factor"])
+                continue
+            assert r["stage"] == 2 and os.path.exists(path)
+            log = []
+            assert ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2, seed + 2, s2_bits=bits, checkpoint2_path=path + ".other")["status"] in ("NF", "found")
+            r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2, seed, s2_bits=bits, checkpoint2_path=path, log=log.append)
+            assert (r["status"], r["factor"], r.get("stage2_T")) == (whole["status"], whole["factor"], whole.get("stage2_T")), stop
+            assert any("Resuming stage 2" in s for s in log) and not os.path.exists(path)
+    # a file of another curve / other bounds is not loaded
+    seed = ecm.mix64(7, 1)
+    path = str(tmp_path / "foreign.ckpt")
+    assert ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2, seed, s2_bits=bits, checkpoint2_path=path, stop_at2=(0, 30))["status"] == "interrupted"
+    log = []
+    r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2 + 100, seed, s2_bits=bits, checkpoint2_path=path, log=log.append)
+    assert not any("Resuming stage 2" in s for s in log) and r["status"] in ("NF", "found")
