@@ -200,3 +200,25 @@ def test_ecm_stage2_checkpoints_emulated(tmp_path):
     log = []
     r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, b2 + 100, seed, s2_bits=bits, checkpoint2_path=path, log=log.append)
     assert not any("Resuming stage 2" in s for s in log) and r["status"] in ("NF", "found")
+
+
+@pytest.mark.gpu
+def test_ecm_stage1_and_stage2_checkpoints_gpu(tmp_path):
+    """The same on the device (recorded point operations, i.e. programs with renamed registers: a checkpoint between two
+    replays holds everything that is live): stage 1 interrupted and resumed, then stage 2 interrupted inside its second
+    chunk and resumed, equals the uninterrupted run."""
+    import prmers_b200 as pb
+    from prmers_b200 import ecm
+    p, b1, b2, bits = 701, 50, 400, 300
+    seed = ecm.mix64(7, 1)
+    make = lambda: pb.Engine(p, ecm.REGS)
+    whole = ecm.run_curve(make(), p, b1, b2, seed, s2_bits=bits)
+    p1, p2 = str(tmp_path / ck.ecm_checkpoint_name(p, 1)), str(tmp_path / ck.ecm2_checkpoint_name(p, 1))
+    r = ecm.run_curve(make(), p, b1, b2, seed, s2_bits=bits, checkpoint_path=p1, checkpoint2_path=p2, stop_at=33)
+    assert r["status"] == "interrupted" and r["stage"] == 1
+    r = ecm.run_curve(make(), p, b1, b2, seed, s2_bits=bits, checkpoint_path=p1, checkpoint2_path=p2, stop_at2=(1, 10))
+    assert r["status"] == "interrupted" and r["stage"] == 2 and r["chunk"] == 1
+    log = []
+    r = ecm.run_curve(make(), p, b1, b2, seed, s2_bits=bits, checkpoint_path=p1, checkpoint2_path=p2, log=log.append)
+    assert (r["status"], r["factor"], r["stage2_T"]) == (whole["status"], whole["factor"], whole["stage2_T"])
+    assert any("Resuming stage 2" in s for s in log) and not os.path.exists(p2)
