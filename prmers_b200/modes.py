@@ -664,6 +664,49 @@ def run_pm1_stage2_ultralow(eng, p, b1, b2, b2_start=0, gcd=True, progress=None)
             "factor": g if 1 < g < m else None, "fft_length": eng.get_size()}
 
 
+def run_pm1_stage2_lowmem(eng, p, b1, b2, H, gcd=True, progress=None):
+    """`-pm1-lowmem` stage 2 (RunPM1.cpp:1878-1926): THREE registers and no baby table -- for every prime q in (B1, B2] the
+    stage-1 residue H is restored from the host, RQ = H^q by the engine's square-and-multiply (engine.h:160-170),
+    RACC <- RACC (H^q - 1); one gcd at the end.  Returns the accumulator; the factor is gcd(acc, 2^p - 1)."""
+    RH, RACC, RQ = 0, 1, 2
+    m = (1 << p) - 1
+    primes = [q for q in primes_upto(b2) if q > b1]
+    eng.set(RACC, 1)
+    _set_int(eng, RH, H % m, p)
+    raw = None
+    if hasattr(eng, "get_data") and hasattr(eng, "set_data"):
+        raw = bytearray(eng.get_register_data_size())
+        if not eng.get_data(raw, RH):
+            raw = None
+    powf = eng.pow if hasattr(eng, "pow") else (lambda d, s_, e: _pow(eng, d, s_, e))
+    for i, q in enumerate(primes):
+        if i:
+            if raw is not None:
+                eng.set_data(RH, raw)                    # pow turned RH into a multiplicand: the weighted digits come back from the host
+            else:
+                _set_int(eng, RH, H % m, p)
+        powf(RQ, RH, q)
+        eng.sub(RQ, 1)
+        eng.set_multiplicand(RQ, RQ)
+        eng.mul(RACC, RQ)
+        if progress and (i + 1) % 100 == 0:
+            progress(i + 1, len(primes))
+    acc = _value(eng, RACC, p)
+    g = hostmath.gcd(acc, m) if gcd else 1
+    return {"exponent": p, "worktype": "PM1", "b1": b1, "b2": b2, "primes": len(primes), "acc": acc,
+            "factor": g if 1 < g < m else None, "fft_length": eng.get_size()}
+
+
+def _pow(eng, dst, src, e):
+    """engine::pow (engine.h:160-170) for engines without their own: dst = src^e, src becomes a multiplicand."""
+    eng.set_multiplicand(src, src)
+    eng.set(dst, 1)
+    for i in range(int(e).bit_length() - 1, -1, -1):
+        eng.square_mul(dst)
+        if (e >> i) & 1:
+            eng.mul(dst, src)
+
+
 def split_k_range(b1, b2, D, world):
     """Equal shares of the giant-step range [k_first, k_last] for `world` ranks."""
     k_first, k_last = (b1 + 1 + D // 2) // D, (b2 + D // 2) // D

@@ -293,6 +293,42 @@ def test_pm1_two_stage_vectors_bigint(p, b1, b2, s1, s2):
     assert modes.pm1_stage2_factor(p, [acc]) == s2
 
 
+@pytest.mark.parametrize("p,b1,b2,factor", [(269, 4, 2141, 13822297), (569, 9, 677, 55470673), (1097, 3, 709, 4576661533441),
+                                            (269, 192, 457, None)])
+def test_pm1_stage2_lowmem_vectors(p, b1, b2, factor):
+    """`-pm1-lowmem` three-register streamed stage 2 (RunPM1.cpp:1878-1926) on the reference's stage-2 vectors
+    (unit_tests.sh:57-62), emulated kernels and exact arithmetic; the accumulator is prod (H^q - 1) over the primes."""
+    from oracle.int_engine import IntEngine
+    H = modes.run_pm1_stage1(IntEngine(p, 11), p, b1)["x"]
+    m = (1 << p) - 1
+    want = 1
+    for q in modes.primes_upto(b2):
+        if q > b1:
+            want = want * (pow(H, q, m) - 1) % m
+    for eng in (IntEngine(p, 3), EmuEngine(p, 3)):
+        r = modes.run_pm1_stage2_lowmem(eng, p, b1, b2, H)
+        assert r["acc"] % m == want % m and r["factor"] == factor
+
+
+@pytest.mark.gpu
+def test_pm1_stage2_lowmem_gpu():
+    """The same on the device: H comes back from the host as a raw register image for every prime (set_data), as in the
+    reference; unit_tests.sh:61-62 and the n = 4096 size (the accumulator against big-integer arithmetic)."""
+    import prmers_b200 as pb
+    from oracle.int_engine import IntEngine
+    for p, b1, b2, factor in ((1097, 3, 709, 4576661533441), (569, 9, 677, 55470673), (86243, 20, 60, None)):
+        H = modes.run_pm1_stage1(IntEngine(p, 11), p, b1)["x"]
+        m = (1 << p) - 1
+        want = 1
+        for q in modes.primes_upto(b2):
+            if q > b1:
+                want = want * (pow(H, q, m) - 1) % m
+        e = pb.Engine(p, 3)
+        r = modes.run_pm1_stage2_lowmem(e, p, b1, b2, H)
+        assert r["acc"] % m == want and r["factor"] == factor
+        e.close()
+
+
 @pytest.mark.gpu
 def test_pm1_stage1_gerbicz_li_gpu():
     """-erroriter on the P-1 exponentiation: p = 9941 (unit-test size) and BASELINE config 4's exponent (n = 5 * 2^21) at
