@@ -697,6 +697,61 @@ def run_pm1_stage2_lowmem(eng, p, b1, b2, H, gcd=True, progress=None):
             "factor": g if 1 < g < m else None, "fft_length": eng.get_size()}
 
 
+def read_pm1_resume(base_path, p=None, b1=None):
+    """Stage-1 residue from `resume_p<p>_B1_<b1>.save` or `.p95` (RunPM1.cpp:1518-1560 tries the path as given, then
+    `.save`, then `.p95`); the exponent and bound of the file must be the ones asked for."""
+    import os
+    for path, binary in ((base_path, base_path.endswith(".p95")), (base_path + ".save", False), (base_path + ".p95", True)):
+        if not os.path.isfile(path):
+            continue
+        if binary:
+            with open(path, "rb") as f:
+                got = parse_pm1_p95(f.read())
+        else:
+            with open(path) as f:
+                got = parse_pm1_resume_line(f.readline())
+        if (p is not None and got["p"] != p) or (b1 is not None and got["b1"] != b1):
+            raise ValueError(f"{path}: resume file of another exponent or B1")
+        return got
+    raise FileNotFoundError(base_path)
+
+
+def run_pm1_stage2_resume2reg(eng, p, b1, b2, H, chunk_bits=200000, gcd=True, progress=None):
+    """`-pm1-ultralowmem -pm1-s2-resume2reg` stage 2 (RunPM1.cpp:1507-1793): TWO registers, H from a stage-1 resume file
+    (read_pm1_resume) -- the primes of (B1, B2] are multiplied into chunks Q of at most `chunk_bits` bits and
+    RSTATE <- RSTATE^Q chunk by chunk (RBASE = the multiplicand of the state the chunk starts from, RSTATE restarts at 1);
+    the factor is gcd(H^(prod Q) - 1, 2^p - 1)."""
+    RSTATE_, RBASE = 0, 1
+    m = (1 << p) - 1
+    primes = [q for q in primes_upto(b2) if q > b1]
+    _set_int(eng, RSTATE_, H % m, p)
+    i, chunks, bits_done = 0, 0, 0
+    chunk_bits = max(int(chunk_bits), 1024)
+    while i < len(primes):
+        Q, i0 = 1, i
+        while i < len(primes):
+            cand = Q * primes[i]
+            if i > i0 and cand.bit_length() > chunk_bits:
+                break
+            Q = cand; i += 1
+            if Q.bit_length() >= chunk_bits:
+                break
+        chunks += 1
+        eng.set_multiplicand(RBASE, RSTATE_)
+        eng.set(RSTATE_, 1)
+        for k in range(Q.bit_length() - 1, -1, -1):
+            eng.square_mul(RSTATE_)
+            if (Q >> k) & 1:
+                eng.mul(RSTATE_, RBASE)
+        bits_done += Q.bit_length()
+        if progress:
+            progress(i, len(primes))
+    x = _value(eng, RSTATE_, p)
+    g = hostmath.gcd((x - 1) % m, m) if gcd else 1
+    return {"exponent": p, "worktype": "PM1", "b1": b1, "b2": b2, "primes": len(primes), "chunks": chunks, "bits": bits_done, "x": x,
+            "factor": g if 1 < g < m else None, "fft_length": eng.get_size()}
+
+
 def _pow(eng, dst, src, e):
     """engine::pow (engine.h:160-170) for engines without their own: dst = src^e, src becomes a multiplicand."""
     eng.set_multiplicand(src, src)

@@ -310,6 +310,29 @@ def test_pm1_stage2_lowmem_vectors(p, b1, b2, factor):
         assert r["acc"] % m == want % m and r["factor"] == factor
 
 
+@pytest.mark.parametrize("p,b1,b2,factor", [(269, 4, 2141, 13822297), (569, 9, 677, 55470673), (1097, 3, 709, 4576661533441),
+                                            (269, 192, 457, None)])
+def test_pm1_stage2_resume2reg_vectors(p, b1, b2, factor, tmp_path):
+    """`-pm1-s2-resume2reg` (RunPM1.cpp:1507-1793): H read back from the stage-1 resume files (.save and .p95), H^Q chunk by
+    chunk on two registers; the reference's stage-2 vectors, emulated kernels and exact arithmetic, small chunks."""
+    from oracle.int_engine import IntEngine
+    H = modes.run_pm1_stage1(IntEngine(p, 11), p, b1)["x"]
+    save, p95 = modes.write_pm1_resume(str(tmp_path), p, b1, H)
+    base = save[:-5]
+    assert modes.read_pm1_resume(base, p, b1)["x"] == H and modes.read_pm1_resume(p95, p, b1)["x"] == H
+    with pytest.raises(ValueError):
+        modes.read_pm1_resume(base, p, b1 + 1)
+    m = (1 << p) - 1
+    Q = 1
+    for q in modes.primes_upto(b2):
+        if q > b1:
+            Q *= q
+    want = pow(H, Q, m)
+    for eng, cb in ((IntEngine(p, 2), 200000), (EmuEngine(p, 2), 1024)):
+        r = modes.run_pm1_stage2_resume2reg(eng, p, b1, b2, modes.read_pm1_resume(base, p, b1)["x"], chunk_bits=cb)
+        assert r["x"] == want and r["factor"] == factor and (cb != 1024 or b2 < 1000 or r["chunks"] > 1)
+
+
 @pytest.mark.gpu
 def test_pm1_stage2_lowmem_gpu():
     """The same on the device: H comes back from the host as a raw register image for every prime (set_data), as in the
@@ -326,6 +349,8 @@ def test_pm1_stage2_lowmem_gpu():
         e = pb.Engine(p, 3)
         r = modes.run_pm1_stage2_lowmem(e, p, b1, b2, H)
         assert r["acc"] % m == want and r["factor"] == factor
+        r2 = modes.run_pm1_stage2_resume2reg(e, p, b1, b2, H, chunk_bits=1024)          # -pm1-s2-resume2reg on the same engine
+        assert r2["factor"] == factor and (p > 5000 or r2["x"] == pow(H, __import__("math").prod(q for q in modes.primes_upto(b2) if q > b1), m))
         e.close()
 
 
