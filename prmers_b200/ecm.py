@@ -705,10 +705,14 @@ def _after_stage1(eng, p, N, aE, dE, ops, res, say):
 
 
 def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), continue_after_factor=False,
-            curve_indices=None, log=None, graphs=None, torsion=None):
+            curve_indices=None, log=None, graphs=None, torsion=None, checkpoint_dir=None, backup_every=0, stop=None, s2_bits=None):
     """The curve loop (:1737-1830, 3415-3455): curve c uses curve_seed = mix64(seed, c) on its own engine
     (`engine_factory(p, 51)`), stops at the first new factor unless told to continue.  `curve_indices` restricts
-    the loop to a subset (multi-GPU: curve c -> rank c mod world)."""
+    the loop to a subset (multi-GPU: curve c -> rank c mod world).
+    With `checkpoint_dir` every curve keeps the reference's two files there (`ecm_te_m_<p>_c<c>.ckpt`,
+    `ecm2_te_m_<p>_c<c>.ckpt`, :1826-1830): a curve whose files describe a stage 1 or stage 2 under way resumes from them,
+    and `stop` = (curve, 1, step) or (curve, 2, (chunk, step)) is the interruption of the reference's SIGINT path: the
+    state is saved, the loop ends with status "interrupted" and the same call made again carries on from the files."""
     say = log or (lambda s: None)
     K = stage1_exponent(b1)
     primes_s2 = ecm_primes(b1, b2)[1] if b2 > b1 else []
@@ -717,14 +721,27 @@ def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), con
            "curves": [], "k_bits": K.bit_length()}
     for c in (range(curves) if curve_indices is None else curve_indices):
         eng = engine_factory(p, REGS)
+        kw = {}
+        if checkpoint_dir:
+            import os
+            from . import checkpoint as ckpt
+            kw = {"checkpoint_path": os.path.join(checkpoint_dir, ckpt.ecm_checkpoint_name(p, c)),
+                  "checkpoint2_path": os.path.join(checkpoint_dir, ckpt.ecm2_checkpoint_name(p, c)), "backup_every": backup_every}
+            if stop is not None and stop[0] == c:
+                kw["stop_at" if stop[1] == 1 else "stop_at2"] = stop[2]
         try:
-            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs, torsion=torsion)
+            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs, torsion=torsion, s2_bits=s2_bits, **kw)
         finally:
             if hasattr(eng, "close"):
                 eng.close()
         r["curve"] = c
         out["curves"].append(r)
         out["fft_length"] = r["n"]
+        if r["status"] == "interrupted":
+            out.update(status="interrupted", interrupted_curve=c)
+            break
+        if checkpoint_dir and os.path.exists(kw["checkpoint_path"]):
+            os.remove(kw["checkpoint_path"])                  # a finished curve leaves no stage-1 file behind (:3440-3446)
         if r["status"] == "found":
             if r["factor"] in known:
                 say(f"[ECM] Curve {c + 1}/{curves} | known factor={r['factor']}")

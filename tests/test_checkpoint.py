@@ -202,6 +202,31 @@ def test_ecm_stage2_checkpoints_emulated(tmp_path):
     assert not any("Resuming stage 2" in s for s in log) and r["status"] in ("NF", "found")
 
 
+def test_ecm_curve_loop_with_checkpoint_files_emulated(tmp_path):
+    """run_ecm with a checkpoint directory: interrupted in stage 1 of one curve, then in stage 2 of another, the same call
+    made again carries on from the files and ends with the results of the uninterrupted loop."""
+    from tests.emu.emu import EmuEngine
+    from prmers_b200 import ecm
+    p, b1, b2, bits, curves, seed = 701, 50, 400, 300, 4, 7
+    fac = lambda q, regs: EmuEngine(q, regs)
+    key = lambda out: [(c["curve"], c["status"], c["factor"], c.get("stage2_T")) for c in out["curves"]]
+    whole = ecm.run_ecm(fac, p, b1, b2, curves=curves, seed=seed, continue_after_factor=True, s2_bits=bits)
+    d = str(tmp_path)
+    done = []
+    for stop in ((0, 1, 20), (1, 2, (0, 35)), (2, 2, (1, 5)), None):
+        out = ecm.run_ecm(fac, p, b1, b2, curves=curves, seed=seed, continue_after_factor=True, s2_bits=bits, checkpoint_dir=d, backup_every=10,
+                          stop=stop, curve_indices=range(len(done), curves))
+        if stop is not None and out["status"] == "interrupted":
+            assert out["interrupted_curve"] == stop[0]
+            done += [c for c in out["curves"] if c["status"] != "interrupted"]
+        else:
+            done += out["curves"]
+            if stop is None:
+                break
+    assert [(c["curve"], c["status"], c["factor"], c.get("stage2_T")) for c in done] == key(whole)
+    assert not [f for f in os.listdir(d) if f.endswith(".ckpt")]
+
+
 @pytest.mark.gpu
 def test_ecm_stage1_and_stage2_checkpoints_gpu(tmp_path):
     """The same on the device (recorded point operations, i.e. programs with renamed registers: a checkpoint between two
