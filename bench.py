@@ -258,7 +258,7 @@ def run_workload(args, rank, local_rank, world):
                 "factors": sorted({str(c["factor"]) for c in res["curves"] if c.get("factor")}),
                 "e2e": {"value": K * reps / dt, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "host loop through the public API, gcds on the host"},
-                "gpu_launches": None, "clocks": sampler.stop(), "roofline": None, "cpu_baseline": None}
+                "gpu_launches": res.get("gpu_launches"), "clocks": sampler.stop(), "roofline": None, "cpu_baseline": None}
         print(json.dumps(line), flush=True)
 
 

@@ -873,6 +873,8 @@ def run_ecm_batched(batch_engine_factory, p, b1, b2=0, curves=1, seed=1, known_f
                     finish(s, status="singular", stage=2)
                 elif g > 1:
                     finish(s, status="found", factor=g, stage=2)
+    if hasattr(eng, "launch_count"):
+        out["gpu_launches"] = int(eng.launch_count())
     if hasattr(eng, "close"):
         eng.close()
     known = {int(f) for f in known_factors}
@@ -902,6 +904,8 @@ def run_ecm_sharded(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors
     allc = sorted(multi.gather(local["curves"]), key=lambda c: c["curve"])
     out = {k: local[k] for k in ("exponent", "worktype", "b1", "b2", "seed", "k_bits")}
     out.update(status="NF", factor=None, curves=allc, world=world)
+    if "gpu_launches" in local:
+        out["gpu_launches"] = local["gpu_launches"]              # this rank's launches
     known = {int(f) for f in known_factors}
     for c in allc:
         if c["status"] == "found" and c["factor"] not in known:
