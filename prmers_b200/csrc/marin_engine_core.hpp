@@ -47,7 +47,7 @@ inline bool prog_pure_def(const ProgOp &o)
 inline u32 prog_cost(const ProgOp &o)
 {
 	const u32 c = o.code & PO_CODE_MASK;
-	return (c == PO_SQR || c == PO_MUL) ? 45u : ((c == PO_SETMUL) ? 25u : 10u);
+	return (c == PO_SQR || c == PO_MUL) ? 45u : ((c == PO_SETMUL) ? 17u : ((c == PO_COPY) ? 5u : 10u));   // 0.1 us, profiles/r2/prog_probe_*.log
 }
 
 inline std::vector<ProgOp> schedule_program(const std::vector<ProgOp> &recorded, u32 nregs = 0, u32 nhidden = 0, u32 G = PROG_MAX_GROUPS)
