@@ -202,6 +202,52 @@ def pm1_exponent(p, b1):
     return e
 
 
+def pm1_exponent_increment(b1_old, b1_new):
+    """buildE_incremental_fast (RunPM1.cpp:5771-5870): E(B1_new) / E(B1_old) = the new primes and the prime powers that
+    fit under the higher bound only (the factor 2 p is in both)."""
+    if b1_new <= b1_old:
+        return 1
+    e = 1
+    for q in primes_upto(b1_new):
+        k_old = k_new = 0
+        qk = q
+        while qk <= b1_new:
+            k_new += 1
+            if qk <= b1_old:
+                k_old += 1
+            qk *= q
+        e *= q ** (k_new - k_old)
+    return e
+
+
+def run_pm1_stage1_extend(eng, p, b1_old, b1_new, H_old, gcd=True, resume_dir=None, progress=None):
+    """Stage 1 extended from a finished lower bound (`-b1old`, RunPM1.cpp:5901-5945, 6070-6122, 6271-6300, 6334-6345): the
+    residue H_old of bound B1_old comes from its resume file (read_pm1_resume), H_new = H_old^(E(B1_new) / E(B1_old)) by
+    square-and-multiply with H_old as the multiplicand (RBASE) -- the base is no longer 3, so this is not the fast3
+    chain -- and the new residue is what a stage 1 at B1_new gives.  Writes the resume files of the new bound into
+    `resume_dir` (RunPM1.cpp:7268-7274)."""
+    m = (1 << p) - 1
+    E = pm1_exponent_increment(b1_old, b1_new)
+    bits = E.bit_length()
+    rbase = PM1_RBASE if getattr(eng, "reg_count", 11) > PM1_RBASE else 1     # the reference's register map, or two registers
+    _set_int(eng, rbase, H_old % m, p)
+    eng.set_multiplicand(rbase, rbase)
+    eng.set(PM1_RSTATE, 1)
+    for k in range(bits - 1, -1, -1):
+        eng.square_mul(PM1_RSTATE)
+        if (E >> k) & 1:
+            eng.mul(PM1_RSTATE, rbase)
+        if progress and (bits - k) % 1000 == 0:
+            progress(bits - k, bits)
+    x = _value(eng, PM1_RSTATE, p)
+    g = hostmath.gcd((x - 1) % m, m) if gcd else 1
+    out = {"exponent": p, "worktype": "PM1", "b1": b1_new, "b1_old": b1_old, "bits": bits, "x": x,
+           "factor": g if 1 < g < m else None, "fft_length": eng.get_size()}
+    if resume_dir:
+        out["resume_files"] = write_pm1_resume(resume_dir, p, b1_new, x)
+    return out
+
+
 # register map of runPM1Marin (RunPM1.cpp:6206-6216)
 PM1_RSTATE, PM1_RACC_L, PM1_RACC_R, PM1_RCHK, PM1_RPOW, PM1_RTMP, PM1_RSTART, PM1_RSAVE_S, PM1_RSAVE_L, PM1_RSAVE_R, PM1_RBASE = range(11)
 

@@ -333,6 +333,36 @@ def test_pm1_stage2_resume2reg_vectors(p, b1, b2, factor, tmp_path):
         assert r["x"] == want and r["factor"] == factor and (cb != 1024 or b2 < 1000 or r["chunks"] > 1)
 
 
+@pytest.mark.parametrize("p,b1_old,b1_new,factor", [(2151, 100, 256, 327405968242246366421788399), (367, 5000, 11981, 646300400639), (269, 4, 192, None)])
+def test_pm1_stage1_extend_vectors(p, b1_old, b1_new, factor, tmp_path):
+    """`-b1old` (RunPM1.cpp:5901-5945, 6271-6345): a stage 1 taken from B1_old to B1_new through the resume file of the
+    lower bound gives the residue (and the factor, unit_tests.sh:59-63) of a stage 1 run at B1_new from the start."""
+    from oracle.int_engine import IntEngine
+    assert modes.pm1_exponent(p, b1_new) == modes.pm1_exponent(p, b1_old) * modes.pm1_exponent_increment(b1_old, b1_new)
+    low = modes.run_pm1_stage1(IntEngine(p, 11), p, b1_old)
+    full = modes.run_pm1_stage1(IntEngine(p, 11), p, b1_new)
+    save, _ = modes.write_pm1_resume(str(tmp_path), p, b1_old, low["x"])
+    H = modes.read_pm1_resume(save[:-5], p, b1_old)["x"]
+    for eng in (IntEngine(p, 11), EmuEngine(p, 2)):
+        r = modes.run_pm1_stage1_extend(eng, p, b1_old, b1_new, H, resume_dir=str(tmp_path))
+        assert r["x"] == full["x"] and r["factor"] == factor == full["factor"]
+        assert modes.read_pm1_resume(r["resume_files"][0][:-5], p, b1_new)["x"] == full["x"]
+
+
+@pytest.mark.gpu
+def test_pm1_stage1_extend_gpu():
+    """The same on the device, with the 11-register map and with two registers, incl. a multi-pass size (n = 4096)."""
+    import prmers_b200 as pb
+    from oracle.int_engine import IntEngine
+    for p, b1_old, b1_new, regs in ((2151, 100, 256, 11), (86243, 30, 120, 2)):
+        low = modes.run_pm1_stage1(IntEngine(p, 2), p, b1_old, gcd=False)
+        full = modes.run_pm1_stage1(IntEngine(p, 2), p, b1_new)
+        e = pb.Engine(p, regs)
+        r = modes.run_pm1_stage1_extend(e, p, b1_old, b1_new, low["x"])
+        assert r["x"] == full["x"] and r["factor"] == full["factor"]
+        e.close()
+
+
 @pytest.mark.gpu
 def test_pm1_stage2_lowmem_gpu():
     """The same on the device: H comes back from the host as a raw register image for every prime (set_data), as in the
