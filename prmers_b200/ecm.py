@@ -135,6 +135,33 @@ def _inv(a, N):
     return None
 
 
+_CHKSUMMOD = 4294967291
+
+
+def ecm_resume_line(p, b1, A, x, program="PrMers b200", who="", when=""):
+    """One GMP-ECM / Prime95 resume line for a finished stage 1 (append_ecm_stage1_resume_line, :1287-1330): the curve as
+    its Montgomery coefficient A = 2 (a + d) / (a - d), the point as its Montgomery x = (Z + Y) / (Z - Y)."""
+    N = (1 << p) - 1
+    A, x = A % N, x % N
+    chk = b1 * (A % _CHKSUMMOD) * (N % _CHKSUMMOD) * (x % _CHKSUMMOD) % _CHKSUMMOD
+    return (f"METHOD=ECM; B1={b1}; N=2^{p}-1; X=0x{x:x}; A={A}; CHECKSUM={chk}; PROGRAM={program}; X0=0x0; Y0=0x0;"
+            + (f" WHO={who};" if who else "") + f" TIME={when};\n")
+
+
+def parse_ecm_resume_line(line):
+    """The fields back, checksum verified."""
+    f = dict(kv.strip().split("=", 1) for kv in line.strip().rstrip(";").split(";") if "=" in kv)
+    b1, p, x, A = int(f["B1"]), int(f["N"][2:].split("-")[0]), int(f["X"], 16), int(f["A"])
+    N = (1 << p) - 1
+    if int(f["CHECKSUM"]) != b1 * (A % _CHKSUMMOD) * (N % _CHKSUMMOD) * (x % _CHKSUMMOD) % _CHKSUMMOD:
+        raise ValueError("ECM resume line: checksum mismatch")
+    return {"p": p, "b1": b1, "x": x, "A": A}
+
+
+def ecm_resume_name(p, b1):
+    return f"resume_p{p}_ECM_TE_B1_{b1}.save"
+
+
 def curve_from_sigma(N, sigma):
     """Suyama parametrisation -> Montgomery (A + 2, B) -> twisted Edwards a = (A+2)/B, d = (A-2)/B and the point
     (X0, Y0); None when the sigma is singular for this modulus (the reference then tries the next one)."""
@@ -524,7 +551,7 @@ def check_invariant(eng, p, aE, dE):
 
 
 def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, error_iter=0, log=None, graphs=None, torsion=None,
-              checkpoint_path=None, backup_every=0, stop_at=None, checkpoint2_path=None, stop_at2=None, s2_bits=None):
+              checkpoint_path=None, backup_every=0, stop_at=None, checkpoint2_path=None, stop_at2=None, s2_bits=None, resume_path=None):
     """One curve of RunEcmTwistedEdwards.cpp:1737-3859 on a 51-register engine.  Returns a dict with `status` in
     {"found", "NF", "singular", "nocurve", "invariant"}, `factor`, `stage` (0 = curve generation, 1, 2) and the final
     extended coordinates (for parity checks against a big-integer restatement of the same formulas).
@@ -535,7 +562,9 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
     exponent, bounds, curve seed and family describes is resumed instead of running stage 1 again -- at a chunk boundary,
     or inside a chunk at the saved step with the saved affine base; the state is saved after every chunk, every
     `backup_every` steps inside a chunk and at `stop_at2` = (chunk number, steps) before returning "interrupted"; a
-    finished stage 2 removes the file.  `s2_bits` overrides the chunk size (tests)."""
+    finished stage 2 removes the file.  `s2_bits` overrides the chunk size (tests).
+    `resume_path`: a stage 1 that ends without a factor appends its GMP-ECM resume line there (:1287-1330, :3396-3426);
+    the two values are also returned as `resume_x` and `resume_A`."""
     say = log or (lambda s: None)
     N = (1 << p) - 1
     res = {"curve_seed": curve_seed, "status": "NF", "factor": None, "stage": None, "n": eng.get_size()}
@@ -604,7 +633,8 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
         res.update(status="interrupted", stage=1, step=stop_at)
         return res
     if resume2 is None:
-        early = _after_stage1(eng, p, N, aE, dE, ops, res, say)
+        res["b1"] = b1
+        early = _after_stage1(eng, p, N, aE, dE, ops, res, say, resume_path)
         if early is not None:
             return early
 
@@ -674,7 +704,7 @@ def run_curve(eng, p, b1, b2, curve_seed, curve=None, K=None, primes_s2=None, er
     return res
 
 
-def _after_stage1(eng, p, N, aE, dE, ops, res, say):
+def _after_stage1(eng, p, N, aE, dE, ops, res, say, resume_path=None):
     """Invariant, gcd on T and the two inversions that end stage 1 (:3372-3413): the finished result, or None to go on."""
     if not check_invariant(eng, p, aE, dE):
         say("[ECM] invariant FAIL")
@@ -696,8 +726,15 @@ def _after_stage1(eng, p, N, aE, dE, ops, res, say):
     # g == 1: the Montgomery resume values need 1/(Z - Y) and 1/(a - d); either inversion may split N (:3396-3413)
     Zv, Yv = _value(eng, 1, p), _value(eng, 4, p)
     try:
-        if _inv((Zv - Yv) % N, N) is not None:
-            _inv((aE - dE) % N, N)
+        iu = _inv((Zv - Yv) % N, N)
+        if iu is not None:
+            ia = _inv((aE - dE) % N, N)
+            if ia is not None:
+                res["resume_x"] = (Zv + Yv) * iu % N          # Montgomery x of the stage-1 point
+                res["resume_A"] = 2 * (aE + dE) * ia % N      # Montgomery coefficient of the curve
+                if resume_path:
+                    with open(resume_path, "a") as f:
+                        f.write(ecm_resume_line(p, res.get("b1", 0), res["resume_A"], res["resume_x"]))
     except FactorFound as f:
         res.update(status="found", factor=f.g, stage=1)
         return res
@@ -705,14 +742,17 @@ def _after_stage1(eng, p, N, aE, dE, ops, res, say):
 
 
 def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), continue_after_factor=False,
-            curve_indices=None, log=None, graphs=None, torsion=None, checkpoint_dir=None, backup_every=0, stop=None, s2_bits=None):
+            curve_indices=None, log=None, graphs=None, torsion=None, checkpoint_dir=None, backup_every=0, stop=None, s2_bits=None,
+            resume_path=None):
     """The curve loop (:1737-1830, 3415-3455): curve c uses curve_seed = mix64(seed, c) on its own engine
     (`engine_factory(p, 51)`), stops at the first new factor unless told to continue.  `curve_indices` restricts
     the loop to a subset (multi-GPU: curve c -> rank c mod world).
     With `checkpoint_dir` every curve keeps the reference's two files there (`ecm_te_m_<p>_c<c>.ckpt`,
     `ecm2_te_m_<p>_c<c>.ckpt`, :1826-1830): a curve whose files describe a stage 1 or stage 2 under way resumes from them,
     and `stop` = (curve, 1, step) or (curve, 2, (chunk, step)) is the interruption of the reference's SIGINT path: the
-    state is saved, the loop ends with status "interrupted" and the same call made again carries on from the files."""
+    state is saved, the loop ends with status "interrupted" and the same call made again carries on from the files.
+    `resume_path`: every curve whose stage 1 ends without a factor appends its GMP-ECM resume line to that file
+    (`resume_p<p>_ECM_TE_B1_<B1>.save` in the reference, :1269-1272)."""
     say = log or (lambda s: None)
     K = stage1_exponent(b1)
     primes_s2 = ecm_primes(b1, b2)[1] if b2 > b1 else []
@@ -730,7 +770,8 @@ def run_ecm(engine_factory, p, b1, b2=0, curves=1, seed=1, known_factors=(), con
             if stop is not None and stop[0] == c:
                 kw["stop_at" if stop[1] == 1 else "stop_at2"] = stop[2]
         try:
-            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs, torsion=torsion, s2_bits=s2_bits, **kw)
+            r = run_curve(eng, p, b1, b2, mix64(seed, c), K=K, primes_s2=primes_s2, log=log, graphs=graphs, torsion=torsion, s2_bits=s2_bits,
+                          resume_path=resume_path, **kw)
         finally:
             if hasattr(eng, "close"):
                 eng.close()

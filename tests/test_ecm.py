@@ -227,6 +227,36 @@ def test_graph_replay_equals_direct_calls_gpu():
     assert np.array_equal(e.get(0), e.get(3))
 
 
+def test_ecm_stage1_resume_line(tmp_path):
+    """A stage 1 without a factor appends the GMP-ECM resume line (RunEcmTwistedEdwards.cpp:1287-1330, 3396-3426): the
+    Montgomery x of K P and the coefficient A of the curve, against the big-integer double-and-add on the Edwards curve
+    (u = (1 + y) / (1 - y), A = 2 (a + d) / (a - d)); the line's checksum is the reference's."""
+    p, b1 = 701, 50
+    N = (1 << p) - 1
+    seed = ecm.mix64(7, 1)                                       # this curve ends stage 1 without a factor
+    path = str(tmp_path / ecm.ecm_resume_name(p, b1))
+    r = ecm.run_curve(EmuEngine(p, ecm.REGS), p, b1, 0, seed, resume_path=path)
+    assert r["status"] == "NF" and "resume_x" in r
+    cv = ecm.curve_from_seed(N, seed)
+    X, Y, Z, T = ecm.reference_scalar_mul(N, cv["a"], cv["d"], cv["X0"], cv["Y0"], ecm.naf(ecm.stage1_exponent(b1)))
+    assert r["resume_x"] == (Z + Y) * pow((Z - Y) % N, -1, N) % N
+    assert r["resume_A"] == 2 * (cv["a"] + cv["d"]) * pow((cv["a"] - cv["d"]) % N, -1, N) % N
+    got = ecm.parse_ecm_resume_line(open(path).read().splitlines()[-1])
+    assert got == {"p": p, "b1": b1, "x": r["resume_x"], "A": r["resume_A"]}
+    # the point lies on the Montgomery curve B v^2 = u^3 + A u^2 + u for SOME B: u (u^2 + A u + 1) is B times a square;
+    # cheaper and sharper: the same u comes out of the affine Edwards point
+    y = Y * pow(Z, -1, N) % N
+    assert r["resume_x"] == (1 + y) * pow((1 - y) % N, -1, N) % N
+    with pytest.raises(ValueError):
+        ecm.parse_ecm_resume_line(open(path).read().replace("B1=50", "B1=51"))
+    # the curve loop appends one line per curve that ends stage 1 without a factor
+    path2 = str(tmp_path / "loop.save")
+    out = ecm.run_ecm(lambda q, regs: EmuEngine(q, regs), p, b1, 0, curves=3, seed=7, continue_after_factor=True, resume_path=path2)
+    lines = open(path2).read().splitlines()
+    assert len(lines) == sum(1 for c in out["curves"] if "resume_x" in c) >= 1
+    assert [ecm.parse_ecm_resume_line(l)["x"] for l in lines] == [c["resume_x"] for c in out["curves"] if "resume_x" in c]
+
+
 def _random_program(e, rng, regs, count):
     """A hazard-rich op list on registers 0 .. regs-1 (register regs-1 is kept as a multiplicand slot)."""
     M = regs - 1
