@@ -170,6 +170,57 @@ def run_prp(eng, p, gerbicz=True, check_level=0, error_iter=0, log=None, max_res
             "residue_type": rtype, "errors_gerbicz": errors, "fft_length": eng.get_size(), "iterations": total}
 
 
+def result_json(r, known_factors=(), program_version="b200"):
+    """The result line of a finished run with the reference's field names, order and values (JsonBuilder.cpp:342-470: status,
+    exponent, worktype, factors / known-factors, b1, b2, res64, res2048, residue-type, errors, shift-count, curve fields,
+    fft-length, program) -- the parity surface of the drivers.  `r`: the dict a driver of this module or
+    of ecm.py returns.  The proof, os, user, timestamp and checksum fields of the reference belong to its I/O shell."""
+    import json
+    wt = r.get("worktype", "")
+    out = {}
+    if wt == "PRP-3":
+        out["status"] = "P" if r["is_prp"] else "C"
+    elif wt == "LL":
+        out["status"] = "P" if r["is_prime"] else "C"
+    else:
+        out["status"] = "F" if r.get("factor") else "NF"
+    out["exponent"] = r["exponent"]
+    out["worktype"] = wt
+    known = [str(int(f)) for f in known_factors]
+    if wt in ("PRP-3", "LL"):
+        if known:
+            out["known-factors"] = known
+    else:
+        if r.get("factor"):
+            out["factors"] = [str(r["factor"])]
+        if known:
+            out["known-factors"] = known
+    if r.get("b1"):
+        out["b1"] = r["b1"]
+        if r.get("b2", 0) > r["b1"]:
+            out["b2"] = r["b2"]
+    if wt in ("PRP-3", "LL"):
+        out["res64"] = r["res64"]
+        if wt == "PRP-3":
+            out["res2048"] = r["res2048"]
+            out["residue-type"] = r["residue_type"]
+        out["errors"] = {"gerbicz": r.get("errors_gerbicz", 0)}
+        out["shift-count"] = 0
+    elif wt == "ECM":
+        if r.get("curves_tested_for_found"):
+            out["curves"] = r["curves_tested_for_found"]
+        out["curve-type"] = "Edwards"
+        out["torsion-subgroup"] = {None: 0, "none": 0, "16": 16}.get(r.get("torsion"), 8)
+        out["base-seed"] = r.get("seed")
+        out["errors"] = {"invariant": sum(1 for c in r.get("curves", []) if c.get("status") == "invariant")}
+    elif wt == "PM1":
+        out["errors"] = {"gerbicz": r.get("errors_gerbicz", 0)}
+    if r.get("fft_length"):
+        out["fft-length"] = r["fft_length"]
+    out["program"] = {"name": "prmers", "version": program_version}
+    return json.dumps(out, separators=(",", ":"))
+
+
 def run_ll(eng, p, error_iter=0):
     """Classic Lucas-Lehmer (-llunsafe, RunPrpOrLlMarin.cpp:229,322-324): s <- s^2 - 2, p - 2 times from 4."""
     eng.set(R0, 4)

@@ -270,6 +270,30 @@ def test_vtrace_windows_forced_D_and_planner():
     assert modes.pm1_stage2_factor(p, [0], known_factors=()) is None
 
 
+def test_result_json_fields():
+    """The reference's result-line fields (JsonBuilder.cpp:342-470) from the driver results: a composite and a prime PRP, an
+    LL, a P-1 factor (unit_tests.sh:63), a P-1 run with a known factor, an ECM factor."""
+    import json
+    from oracle.int_engine import IntEngine
+    from prmers_b200 import ecm
+    r = modes.run_prp(IntEngine(1277, 8), 1277)
+    j = json.loads(modes.result_json(r))
+    assert list(j)[:3] == ["status", "exponent", "worktype"]
+    assert (j["status"], j["worktype"], j["residue-type"], j["errors"], j["shift-count"]) == ("C", "PRP-3", 1, {"gerbicz": 0}, 0)
+    assert (j["res64"], j["res2048"]) == (r["res64"], r["res2048"]) and len(j["res64"]) == 16 and len(j["res2048"]) == 512
+    j = json.loads(modes.result_json(modes.run_prp(IntEngine(521, 8), 521)))
+    assert j["status"] == "P" and j["res64"] == "0000000000000001"
+    j = json.loads(modes.result_json(modes.run_ll(IntEngine(127, 2), 127)))
+    assert (j["status"], j["worktype"], "res2048" in j) == ("P", "LL", False)
+    j = json.loads(modes.result_json(modes.run_pm1_stage1(IntEngine(2151, 11), 2151, 256)))
+    assert (j["status"], j["factors"], j["b1"], j["worktype"]) == ("F", ["327405968242246366421788399"], 256, "PM1") and "b2" not in j
+    j = json.loads(modes.result_json(modes.run_pm1_stage1(IntEngine(269, 2), 269, 192), known_factors=[13822297]))
+    assert (j["status"], j["known-factors"]) == ("NF", ["13822297"]) and "factors" not in j
+    r = ecm.run_ecm(lambda q, regs: IntEngine(q, regs), 101, 300, 2000, curves=3, seed=123456789)
+    j = json.loads(modes.result_json(r))
+    assert (j["status"], j["factors"], j["curves"], j["curve-type"], j["torsion-subgroup"], j["b2"]) == ("F", ["7432339208719"], 1, "Edwards", 0, 2000)
+
+
 def test_cofactor_prp_m2699():
     """unit_tests.sh:216-234: M2699 over four known factors is composite, over five is a probable prime."""
     f4 = [5399, 307687, 1187561, 7570504839257]
